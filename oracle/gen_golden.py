@@ -1,0 +1,253 @@
+"""Generate tests/golden/*.npz by RUNNING THE REAL REFERENCE (build container only).
+
+TEST INFRASTRUCTURE.  Usage:  python -m oracle.gen_golden [--only name,...]
+The reference (AmazingDD/daisyRec) has no tests or golden vectors of its own, so the
+parity pins of this repo are outputs of the reference's own code, imported from
+/root/reference through oracle/ref_harness.py (3 library-compat shims, documented there).
+Each fixture stores the exact inputs and the reference's outputs; the files are small and
+committed, because /root/reference does not exist on the GPU box.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _save(name, **arrs):
+    os.makedirs(GOLD, exist_ok=True)
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def _ur_from(users, items):
+    import pandas as pd
+    from daisy.utils.utils import get_ur
+    return get_ur(pd.DataFrame({"user": users, "item": items}))
+
+
+def _synthetic_inter(rng, U, I, nnz, dense_user=None):
+    """Random implicit-feedback COO (unique (u,i) pairs), every user >= 1 item."""
+    pairs = set()
+    for u in range(U):
+        pairs.add((u, int(rng.integers(I))))
+    while len(pairs) < nnz:
+        pairs.add((int(rng.integers(U)), int(min(I - 1, rng.zipf(1.3) - 1 if rng.random() < .5 else rng.integers(I)))))
+    if dense_user is not None:               # a user who has seen all but 1 / all but 3 items
+        for it in range(I):
+            if it != 7:
+                pairs.add((dense_user, it))
+        for it in range(I):
+            if it not in (2, 3, I - 1):
+                pairs.add((dense_user + 1, it))
+        pairs.discard((dense_user, 7))
+        for it in (2, 3, I - 1):
+            pairs.discard((dense_user + 1, it))
+    pairs = np.array(sorted(pairs), dtype=np.int64)
+    order = rng.permutation(len(pairs))       # "time" order
+    return pairs[order, 0].astype(np.int32), pairs[order, 1].astype(np.int32)
+
+
+# --------------------------------------------------------------------------- sampler
+def gen_sampler_small():
+    """daisy/utils/sampler.py:55-103 on a small synthetic set (incl. near-full users, G=1..5)."""
+    import pandas as pd
+    from daisy.utils.sampler import BasicNegtiveSampler
+    rng = np.random.default_rng(7)
+    out = {}
+    for case, (U, I, nnz, G, seed, dense) in enumerate([(50, 80, 600, 4, 2022, 10), (31, 1025, 900, 1, 5, None),
+                                                         (17, 33, 200, 5, 123456789, 3), (64, 4096, 3000, 3, 0, None)]):
+        cu, ci = _synthetic_inter(rng, U, I, nnz, dense)
+        df = pd.DataFrame({"user": cu, "item": ci, "rating": 1.0, "timestamp": np.arange(len(cu))})
+        cfg = rh.make_config("mf", user_num=U, item_num=I, num_ng=G, train_ur=_ur_from(cu, ci))
+        np.random.seed(seed)
+        triples = BasicNegtiveSampler(df, cfg).sampling()
+        nxt = np.random.randint(0, 2 ** 31 - 1, size=3)            # pins how many MT words were consumed
+        out.update({f"c{case}_coo_u": cu, f"c{case}_coo_i": ci, f"c{case}_triples": triples,
+                    f"c{case}_meta": np.array([U, I, G, seed], np.int64), f"c{case}_next": nxt})
+    out["ncases"] = np.array(4)
+    _save("sampler_small", **out)
+
+
+def _ml100k(factors=32, epochs=1, **kw):
+    cfg = rh.make_config("mf", factors=factors, epochs=epochs, **kw)
+    rh.seed_everything(cfg["seed"])
+    art = rh.load_ml100k(cfg)
+    return cfg, art
+
+
+def gen_ml100k_pipeline():
+    """Config 1 of BASELINE.json: test.py:41-120 with MF+BPR, factors=32, 1 epoch, CPU, seed 2022.
+
+    Follows the driver's order of RNG consumption: seed -> (data, split: no RNG) -> MF(config)
+    [torch RNG: init] -> sampling() [numpy RNG] -> fit [torch RNG: DataLoader permutation] ->
+    build_candidates_set [numpy RNG] -> rank.
+    """
+    import torch
+    from daisy.model.MFRecommender import MF
+    from daisy.utils.sampler import BasicNegtiveSampler
+    from daisy.utils.dataset import BasicDataset, CandidatesDataset, get_dataloader
+    from daisy.utils.utils import build_candidates_set
+    from daisy.utils.metrics import calc_ranking_results
+    cfg, art = _ml100k()
+    train_set, test_ur, train_ur = art["train_set"], art["test_ur"], art["train_ur"]
+    model = MF(cfg)
+    P0 = model.embed_user.weight.detach().numpy().copy()
+    Q0 = model.embed_item.weight.detach().numpy().copy()
+    coo_u = train_set["user"].values.astype(np.int32)
+    coo_i = train_set["item"].values.astype(np.int32)
+    triples = BasicNegtiveSampler(train_set, cfg).sampling()
+
+    class Rec(BasicDataset):                                   # records the DataLoader's index order
+        def __init__(self, s):
+            super().__init__(s)
+            self.order = []
+
+        def __getitem__(self, idx):
+            self.order.append(idx)
+            return super().__getitem__(idx)
+
+    ds = Rec(triples)
+    loader = get_dataloader(ds, batch_size=cfg["batch_size"], shuffle=True, num_workers=0)
+    torch_state = torch.get_rng_state().numpy().copy()          # state right before fit()
+    step_losses = []
+    orig = model.calc_loss
+
+    def rec_loss(batch):
+        l = orig(batch)
+        step_losses.append(float(l.item()))
+        return l
+
+    model.calc_loss = rec_loss
+    model.fit(loader)
+    perm = np.array(ds.order, np.int32)
+    P1 = model.embed_user.weight.detach().numpy().copy()
+    Q1 = model.embed_item.weight.detach().numpy().copy()
+
+    test_u, test_ucands = build_candidates_set(test_ur, train_ur, cfg)
+    cands = np.stack([c[1] for c in test_ucands]).astype(np.int16)
+    gt_flat = np.concatenate([np.array(list(test_ur[u]), np.int32) for u in test_u])
+    gt_len = np.array([len(test_ur[u]) for u in test_u], np.int32)
+    nxt = np.random.randint(0, 2 ** 31 - 1, size=3)
+    loader_t = get_dataloader(CandidatesDataset(test_ucands), batch_size=128, shuffle=False, num_workers=0)
+    preds = model.rank(loader_t)
+    full = np.stack([model.full_rank(int(u)) for u in test_u[:16]])
+    pred_pairs = np.array([model.predict(int(test_u[k]), int(cands[k][-1])) for k in range(8)], np.float32)
+    import tempfile
+    cfg['res_path'] = tempfile.mkdtemp() + '/'
+    res = calc_ranking_results(test_ur, preds, test_u, cfg)
+
+    _save("ml100k_sampler", coo_u=coo_u.astype(np.int16), coo_i=coo_i.astype(np.int16), triples_j=triples[:, 2].astype(np.int16),
+          meta=np.array([cfg["user_num"], cfg["item_num"], cfg["num_ng"], cfg["seed"]], np.int64))
+    _save("ml100k_fit", P0=P0, Q0=Q0, P1=P1, Q1=Q1, perm=perm, step_losses=np.array(step_losses, np.float64),
+          torch_state=torch_state,
+          hyper=np.array([cfg["lr"], cfg["reg_1"], cfg["reg_2"], cfg["batch_size"], cfg["factors"]], np.float64))
+    _save("ml100k_rank", test_u=np.array(test_u, np.int32), cands=cands, gt_flat=gt_flat, gt_len=gt_len,
+          next=nxt, preds=preds, full=full, pred_pairs=pred_pairs, topk=np.array(cfg["topk"]),
+          kpi=res.values[:, 1:].astype(np.float64) if res.shape[1] > 1 else res.values.astype(np.float64))
+    print(res)
+
+
+# --------------------------------------------------------------------------- steps
+def gen_mf_steps():
+    """MF.calc_loss + backward + optimizer.step (MFRecommender.py:70-97, AbstractRecommender.py:119-126)
+    on small random tables: several F, reg on/off, duplicate-heavy batches, SGD and Adam, 3 steps each."""
+    import torch
+    from daisy.model.MFRecommender import MF
+    out = {}
+    cases = [  # U, I, F, B, lr, reg1, reg2, opt, seed
+        (40, 60, 8, 64, 0.01, 0.001, 0.001, "sgd", 1),
+        (40, 60, 32, 256, 0.05, 0.0, 0.0, "sgd", 2),
+        (25, 30, 100, 200, 0.01, 0.01, 0.02, "sgd", 3),     # reference default F=100 (not a power of two)
+        (13, 9, 6, 50, 0.01, 0.001, 0.001, "sgd", 4),       # F%4 != 0, heavy duplicates
+        (40, 60, 64, 128, 0.001, 0.001, 0.001, "adam", 5),
+        (20, 20, 7, 33, 0.01, 0.0, 0.001, "adam", 6),       # odd F
+    ]
+    for k, (U, I, F, B, lr, r1, r2, opt, seed) in enumerate(cases):
+        cfg = rh.make_config("mf", user_num=U, item_num=I, factors=F, lr=lr, reg_1=r1, reg_2=r2, optimizer=opt,
+                             epochs=1)
+        torch.manual_seed(seed)
+        model = MF(cfg)
+        with torch.no_grad():                                 # larger weights so the loss is not ~log 2 everywhere
+            model.embed_user.weight.mul_(30.0)
+            model.embed_item.weight.mul_(30.0)
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        P = [model.embed_user.weight.detach().numpy().copy()]
+        Q = [model.embed_item.weight.detach().numpy().copy()]
+        batches, losses = [], []
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            P.append(model.embed_user.weight.detach().numpy().copy())
+            Q.append(model.embed_item.weight.detach().numpy().copy())
+        out.update({f"c{k}_P": np.stack(P), f"c{k}_Q": np.stack(Q), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64),
+                    f"c{k}_hyper": np.array([lr, r1, r2, 0 if opt == "sgd" else 1], np.float64)})
+    out["ncases"] = np.array(len(cases))
+    _save("mf_steps", **out)
+
+
+# --------------------------------------------------------------------------- rank
+def gen_mf_rank():
+    """MF.rank / full_rank / predict (MFRecommender.py:99-133) on fixed random tables; candidate
+    lists contain duplicates (sampled with replacement, utils.py:79); 130 users = batches 128 + 2."""
+    import torch
+    from daisy.model.MFRecommender import MF
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [(300, 2000, 32, 130, 1000, 50, 11), (90, 700, 100, 40, 1000, 50, 12), (50, 120, 64, 7, 100, 10, 13),
+             (64, 1500, 128, 9, 1000, 50, 14)]
+    for k, (U, I, F, n, C, K, seed) in enumerate(cases):
+        cfg = rh.make_config("mf", user_num=U, item_num=I, factors=F, topk=K, cand_num=C)
+        torch.manual_seed(seed)
+        model = MF(cfg)
+        rng = np.random.default_rng(seed)
+        users = rng.permutation(U)[:n].astype(np.int64)
+        cands = rng.integers(I, size=(n, C)).astype(np.int64)
+        cands[:, -3:] = cands[:, :3]                           # forced duplicates
+        ucands = [[int(users[r]), cands[r]] for r in range(n)]
+        loader = get_dataloader(CandidatesDataset(ucands), batch_size=128, shuffle=False, num_workers=0)
+        preds = model.rank(loader)
+        P = model.embed_user.weight.detach().numpy().copy()
+        Q = model.embed_item.weight.detach().numpy().copy()
+        # ambiguity screen: reference fp32 scores (float64 recomputation) gaps inside the top-(K+1)
+        sc = np.einsum("nf,ncf->nc", P[users].astype(np.float64), Q[cands].astype(np.float64))
+        srt = -np.sort(-sc, axis=1)[:, :K + 1]
+        gaps = srt[:, :-1] - srt[:, 1:]
+        gaps[gaps == 0] = np.inf                               # exact duplicates
+        min_gap_rel = float((gaps / np.abs(srt[:, :-1]).clip(1e-30)).min())
+        full = np.stack([model.full_rank(int(u)) for u in users[:5]])
+        out.update({f"c{k}_P": P, f"c{k}_Q": Q, f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32),
+                    f"c{k}_preds": preds, f"c{k}_full": full, f"c{k}_K": np.array(K),
+                    f"c{k}_min_gap_rel": np.array(min_gap_rel)})
+        print(f"rank case {k}: preds {preds.shape} {preds.dtype}, min relative score gap in top-K+1 = {min_gap_rel:.3e}")
+    out["ncases"] = np.array(len(cases))
+    _save("mf_rank", **out)
+
+
+ALL = {"sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+       "mf_rank": gen_mf_rank}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    rh.import_reference()
+    for name, fn in ALL.items():
+        if a.only and name not in a.only.split(","):
+            continue
+        print(f"== {name}")
+        fn()

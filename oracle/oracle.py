@@ -1,0 +1,186 @@
+"""ctypes binding of oracle/bpr_oracle.c (the CPU checker) + small numpy helpers.
+
+TEST INFRASTRUCTURE ONLY -- see the header of bpr_oracle.c.  Parity is pinned by
+tests/golden/ fixtures generated from the real reference (oracle/gen_golden.py).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libbpr_oracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "bpr_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+class Hyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("reg_1", C.c_float), ("reg_2", C.c_float), ("opt", C.c_int32),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+def hyper(lr=0.01, reg_1=0.001, reg_2=0.001, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8):
+    return Hyper(lr, reg_1, reg_2, 0 if opt == "sgd" else 1, beta1, beta2, eps)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_mt_next.restype = C.c_uint32
+        _lib.orc_dot.restype = C.c_float
+        _lib.orc_mf_bpr_step.restype = C.c_double
+        _lib.orc_mf_bpr_epoch.restype = C.c_double
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _f32(a):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return _p(a, C.c_float)
+
+
+def _i32(a):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return _p(a, C.c_int32)
+
+
+def _i64(a):
+    assert a.dtype == np.int64 and a.flags.c_contiguous
+    return _p(a, C.c_int64)
+
+
+# ---------------------------------------------------------------- RNG
+def mt_seed(seed):
+    """np.random.seed(int) -> uint32[625] state (key + pos)."""
+    st = np.zeros(625, np.uint32)
+    lib().orc_mt_seed(_p(st, C.c_uint32), C.c_uint32(seed & 0xFFFFFFFF))
+    return st
+
+
+def mt_from_numpy(rs=None):
+    """Snapshot numpy's (global or given) legacy RandomState into the oracle layout."""
+    s = (np.random if rs is None else rs).get_state()
+    st = np.zeros(625, np.uint32)
+    st[:624] = s[1]
+    st[624] = s[2]
+    return st
+
+
+def mt_to_numpy(st, rs=None):
+    (np.random if rs is None else rs).set_state(("MT19937", st[:624].copy(), int(st[624]), 0, 0.0))
+
+
+def mt_next(st):
+    return int(lib().orc_mt_next(_p(st, C.c_uint32)))
+
+
+# ---------------------------------------------------------------- sampler
+def csr_from_ur(ur, user_num):
+    """dict[int -> set[int]] (config['train_ur']) -> (row_ptr int64[U+1], col int32 sorted)."""
+    deg = np.zeros(user_num + 1, np.int64)
+    for u in range(user_num):
+        deg[u + 1] = len(ur[u]) if u in ur else 0
+    row_ptr = np.cumsum(deg)
+    col = np.empty(int(row_ptr[-1]), np.int32)
+    for u in range(user_num):
+        if u in ur and len(ur[u]):
+            col[row_ptr[u]:row_ptr[u + 1]] = sorted(ur[u])
+    return row_ptr, col
+
+
+def sample_negatives(mt_state, row_ptr, col, user_num, item_num, num_ng):
+    js = np.zeros((user_num, num_ng), np.int32)
+    rc = lib().orc_sample_negatives(_p(mt_state, C.c_uint32), _i64(row_ptr), _i32(col), user_num, item_num, num_ng,
+                                    _i32(js))
+    if rc != 0:
+        raise ValueError("a cannot be empty (user %d has interacted with every item)" % (-rc - 1))
+    return js
+
+
+def explode_triples(coo_u, coo_i, js):
+    n, g = len(coo_u), js.shape[1]
+    out = np.empty((n * g, 3), np.int32)
+    lib().orc_explode_triples(_i32(coo_u), _i32(coo_i), C.c_int64(n), _i32(js), g, _i32(out))
+    return out
+
+
+def build_candidates_user(mt_state, gt, train, item_num, cand_num):
+    gt = np.ascontiguousarray(gt, np.int32)
+    train = np.ascontiguousarray(train, np.int32)
+    out = np.empty(cand_num, np.int64)
+    rc = lib().orc_build_candidates_user(_p(mt_state, C.c_uint32), _i32(gt), len(gt), _i32(train), len(train),
+                                         item_num, cand_num, _i64(out))
+    if rc != 0:
+        raise ValueError("a cannot be empty")
+    return out
+
+
+# ---------------------------------------------------------------- model
+def dot(a, b):
+    return float(lib().orc_dot(_f32(a), _f32(b), len(a)))
+
+
+def mf_predict(P, Q, u, i):
+    out = np.empty(len(u), np.float32)
+    lib().orc_mf_predict(_f32(P), _f32(Q), P.shape[1], _i32(u), _i32(i), C.c_int64(len(u)), _f32(out))
+    return out
+
+
+def mf_bpr_step(P, Q, bu, bi, bj, hp, apply=True, adam_state=None, step_count=1):
+    """In-place step on P,Q (float32 [U,F],[I,F]).  Returns (loss, parts[8])."""
+    parts = np.zeros(8, np.float64)
+    mP = vP = mQ = vQ = None
+    if adam_state is not None:
+        mP, vP, mQ, vQ = adam_state
+    loss = lib().orc_mf_bpr_step(_f32(P), _f32(Q), P.shape[0], Q.shape[0], P.shape[1], _i32(bu), _i32(bi), _i32(bj),
+                                 C.c_int64(len(bu)), C.byref(hp), int(apply),
+                                 None if mP is None else _f32(mP), None if vP is None else _f32(vP),
+                                 None if mQ is None else _f32(mQ), None if vQ is None else _f32(vQ),
+                                 C.c_int64(step_count), _p(parts, C.c_double))
+    return loss, parts
+
+
+def mf_bpr_epoch(P, Q, triples, perm, batch, hp, adam_state=None, first_step_count=1):
+    T = len(triples)
+    nsteps = (T + batch - 1) // batch
+    step_loss = np.zeros(nsteps, np.float64)
+    mP = vP = mQ = vQ = None
+    if adam_state is not None:
+        mP, vP, mQ, vQ = adam_state
+    total = lib().orc_mf_bpr_epoch(_f32(P), _f32(Q), P.shape[0], Q.shape[0], P.shape[1], _i32(triples), C.c_int64(T),
+                                   None if perm is None else _i64(perm), C.c_int64(batch), C.byref(hp),
+                                   None if mP is None else _f32(mP), None if vP is None else _f32(vP),
+                                   None if mQ is None else _f32(mQ), None if vQ is None else _f32(vQ),
+                                   C.c_int64(first_step_count), _p(step_loss, C.c_double))
+    return total, step_loss
+
+
+def mf_rank(P, Q, users, cands, topk):
+    users = np.ascontiguousarray(users, np.int64)
+    cands = np.ascontiguousarray(cands, np.int64)
+    out = np.empty((len(users), topk), np.float32)
+    lib().orc_mf_rank(_f32(P), _f32(Q), P.shape[1], _i64(users), C.c_int64(len(users)), _i64(cands), cands.shape[1],
+                      topk, _f32(out))
+    return out
+
+
+def mf_full_rank(P, Q, users, topk):
+    users = np.ascontiguousarray(users, np.int64)
+    out = np.empty((len(users), topk), np.int64)
+    lib().orc_mf_full_rank(_f32(P), _f32(Q), P.shape[1], Q.shape[0], _i64(users), C.c_int64(len(users)), topk,
+                           _i64(out))
+    return out
