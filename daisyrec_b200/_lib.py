@@ -1,0 +1,91 @@
+"""ctypes loader for libdaisyrec_b200.so -- the C ABI declared in include/daisyrec_b200.h.
+
+The product path has NO CPU fallback: if the shared object is missing (and cannot be built
+because nvcc is absent) or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+_lib = None
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_NAN_LOSS, DRB_ERR_EMPTY_SET, DRB_ERR_NO_DEVICE = range(6)
+OPT_SGD, OPT_ADAM = 0, 1
+
+
+class Hyper(C.Structure):
+    """struct drb_hyper"""
+    _fields_ = [("lr", C.c_float), ("reg_1", C.c_float), ("reg_2", C.c_float), ("opt", C.c_int32),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol of include/daisyrec_b200.h
+SIGNATURES = {
+    "drb_version": (C.c_int, []),
+    "drb_last_error": (C.c_char_p, []),
+    "drb_device_query": (C.c_int, [c_i32p, c_i32p, c_i32p, c_i64p]),
+    "drb_mt19937_seed": (C.c_int, [vp, C.c_uint32]),
+    "drb_sampler_draw_mt19937": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, c_i32p]),
+    "drb_sampler_draw_philox": (C.c_int, [C.c_uint64, C.c_uint64, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
+    "drb_sampler_kth_complement": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "drb_sampler_explode": (C.c_int, [vp, vp, C.c_int64, vp, C.c_int32, vp, vp]),
+    "drb_sample_triples_host": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp,
+                                          c_i32p]),
+    "drb_gather_triples": (C.c_int, [vp, vp, C.c_int64, vp, vp, vp, vp]),
+    "drb_mf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "drb_mf_workspace_init": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),
+    "drb_mf_bpr_train_steps": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int64, C.POINTER(Hyper), C.c_int64, vp, C.c_int32, c_i64p, vp]),
+    "drb_mf_bpr_loss": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, C.POINTER(Hyper),
+                                  vp, vp]),
+    "drb_mf_bpr_train_step_host": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64,
+                                             C.POINTER(Hyper), C.c_int64, vp, c_f64p, vp]),
+    "drb_mf_rank": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int64, vp, C.c_int32, C.c_int32, vp, vp]),
+    "drb_mf_full_rank": (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, C.c_int64, C.c_int32, vp, vp]),
+    "drb_mf_predict": (C.c_int, [vp, vp, C.c_int32, vp, vp, C.c_int64, vp, vp]),
+    "drb_mf_rank_host": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int64, vp, C.c_int32, C.c_int32, vp]),
+}
+
+
+def so_path():
+    return _build.SO
+
+
+def lib():
+    """Load (building first if the .so is absent and nvcc is present).  Fails loudly otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = so_path()
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                f"libdaisyrec_b200.so is missing ({path}) and could not be built: {e}. "
+                "The B200 path has no CPU fallback; run `python -c 'import __graft_entry__ as g; g.build()'`.") from e
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)          # AttributeError here == header and library out of sync
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+class DrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[libdaisyrec_b200 rc={code}] {msg}")
+        self.code = code
+
+
+def check(rc):
+    if rc != DRB_OK:
+        raise DrbError(rc, (lib().drb_last_error() or b"").decode(errors="replace"))

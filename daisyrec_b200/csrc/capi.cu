@@ -1,0 +1,60 @@
+// capi.cu -- library-level entry points and error plumbing of libdaisyrec_b200.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace drb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();  // clear the sticky-less error state
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice ||
+        e == cudaErrorInvalidDeviceFunction)
+        return DRB_ERR_NO_DEVICE;
+    return DRB_ERR_CUDA;
+}
+
+int sm_count()
+{
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace drb
+
+extern "C" int drb_version(void) { return 100; }
+
+extern "C" const char *drb_last_error(void) { return drb::g_err; }
+
+extern "C" int drb_device_query(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *l2_bytes)
+{
+    int dev = 0;
+    DRB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    DRB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+    return DRB_OK;
+}

@@ -1,0 +1,606 @@
+// mf_bpr.cu -- the BPR-MF training step as ONE persistent cooperative sm_100a kernel.
+//
+// Stands behind GeneralRecommender.fit's step loop (daisy/model/AbstractRecommender.py:112-128)
+// with MF.calc_loss (daisy/model/MFRecommender.py:70-97), BPRLoss (daisy/utils/loss.py:11),
+// autograd's embedding backward (:125) and optim.SGD/Adam.step (:126, :53-56).
+//
+// Synchronous-step semantics (every gradient of a step is taken at the PRE-step weights, the
+// Frobenius norms couple the whole batch) are kept exactly, without ever materialising the
+// reference's table-sized dense gradient:
+//
+//   phase 1 (read-only on P,Q)   per triple (u,i,j): index tile staged by TMA (cp.async.bulk) into
+//       shared memory; a group of W lanes gathers the three factor rows with 128-bit L2 loads,
+//       reduces the two dot products with xor-shuffles (canonical order), evaluates
+//       s = sigmoid(x), loss = -log(1e-10+s), c = -s(1-s)/(1e-10+s) and issues vector
+//       RED.ADD.F32x4 reductions of the BPR part of the gradient into the L2-resident
+//       accumulators gP/gQ:  gP[u] += c(q_i-q_j), gQ[i] += c p_u, gQ[j] -= c p_u; it also counts how
+//       often each row occurs (cntU, cntI = pos | neg<<32) and accumulates the six batch norms.
+//   -- grid barrier --           (norms and loss are now final; nobody reads P,Q any more)
+//   phase 2                      every touched row is applied exactly once:
+//       g = gP[r] + cnt * (reg_1 sgn(theta) + reg_2 theta / ||.||_F);  theta -= lr g  (or Adam);
+//       the accumulator row and its counter are reset for the next step.  Rows are found either
+//       by a dense sweep (large batches: every row is touched) or by claiming the counter with
+//       atomicExch from the triple that touched it (small batches).
+//   -- grid barrier --           next step.
+//
+// A NaN loss (ValueError in the reference, :122-123) stops the loop before the update of that step.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace drb {
+
+constexpr int kThreads = 256;
+constexpr int kTileMax = 512;  // triples per staged index tile
+
+struct WsHeader {
+    unsigned long long barrier;  // grid barrier ticket counter
+    long long nan_step;          // -1, or the step whose loss was NaN
+    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, -]
+    int status;
+    int pad[15];
+};
+static_assert(sizeof(WsHeader) <= 256, "header must fit its slot");
+
+struct Workspace {
+    WsHeader *hdr;
+    float *gP, *gQ;
+    unsigned *cntU;
+    unsigned long long *cntI;
+    float *mP, *vP, *mQ, *vQ;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t carve(void *base, int U, int I, int F, int opt, Workspace *w)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) {
+        char *p = b ? b + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    Workspace t;
+    t.hdr = (WsHeader *)take(256);
+    t.gP = (float *)take(sizeof(float) * (size_t)U * F);
+    t.gQ = (float *)take(sizeof(float) * (size_t)I * F);
+    t.cntU = (unsigned *)take(sizeof(unsigned) * (size_t)U);
+    t.cntI = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)I);
+    t.mP = t.vP = t.mQ = t.vQ = nullptr;
+    if (opt == DRB_OPT_ADAM) {
+        t.mP = (float *)take(sizeof(float) * (size_t)U * F);
+        t.vP = (float *)take(sizeof(float) * (size_t)U * F);
+        t.mQ = (float *)take(sizeof(float) * (size_t)I * F);
+        t.vQ = (float *)take(sizeof(float) * (size_t)I * F);
+    }
+    if (w) *w = t;
+    return off;
+}
+
+struct StepParams {
+    float *P, *Q;
+    Workspace ws;
+    const int32_t *bu, *bi, *bj;
+    long long n, batch, first_step, n_steps;
+    int U, I, F, tile;
+    float lr, reg1, reg2;
+    int opt;
+    float beta1, beta2, eps;
+    long long adam_step0;
+    double *step_loss;
+    int apply;
+};
+
+// ------------------------------------------------------------------ device pieces
+__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+
+struct Norms {
+    float inv_u, inv_i, inv_j;  // 1/||.||_F, 0 when the norm is 0 (zero subgradient)
+};
+
+struct AdamCoef {
+    float step_size, bc2_sqrt;
+};
+
+// Apply the accumulated gradient of ONE table row (all W lanes of the group cooperate).
+// cnt_a / cnt_b: occurrences weighted by inv_a / inv_b (user rows: cnt_b = 0).
+template <int VEC, int W, int NCH, int OPT>
+__device__ __forceinline__ void apply_row(float *theta_row, float *g_row, float *m_row, float *v_row, int gl,
+                                          int chunks, float cnt_a, float inv_a, float cnt_b, float inv_b,
+                                          const StepParams &p, const AdamCoef &ac, bool touched)
+{
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        int c = gl + ch * W;
+        if (c >= chunks) continue;
+        float *tp = theta_row + c * VEC;
+        Vec<VEC> th = ld_row<VEC>(tp);
+        Vec<VEC> g;
+        if (touched) {
+            g = ld_row<VEC>(g_row + c * VEC);
+            Vec<VEC> z;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) z.v[e] = 0.f;
+            st_row<VEC>(g_row + c * VEC, z);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) g.v[e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            float t = th.v[e];
+            float gg = g.v[e];
+            if (touched) {
+                float sg = p.reg1 * sgnf(t);
+                gg += cnt_a * (sg + p.reg2 * t * inv_a) + cnt_b * (sg + p.reg2 * t * inv_b);
+            }
+            g.v[e] = gg;
+        }
+        if constexpr (OPT == DRB_OPT_SGD) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) th.v[e] = th.v[e] - p.lr * g.v[e];
+        } else {
+            Vec<VEC> m = ld_row<VEC>(m_row + c * VEC), v = ld_row<VEC>(v_row + c * VEC);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                float gk = g.v[e];
+                m.v[e] = m.v[e] + (gk - m.v[e]) * (1.f - p.beta1);
+                v.v[e] = v.v[e] * p.beta2 + (1.f - p.beta2) * gk * gk;
+                float denom = sqrtf(v.v[e]) / ac.bc2_sqrt + p.eps;
+                th.v[e] = th.v[e] - ac.step_size * (m.v[e] / denom);
+            }
+            st_row<VEC>(m_row + c * VEC, m);
+            st_row<VEC>(v_row + c * VEC, v);
+        }
+        st_row<VEC>(tp, th);
+    }
+}
+
+template <int VEC, int W, int NCH>
+__global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
+{
+    constexpr int GPW = 32 / W;                  // lane groups per warp
+    constexpr int GROUPS = (kThreads / 32) * GPW;  // lane groups per CTA
+    constexpr int UNR = (NCH * VEC <= 4) ? 2 : 1;  // triples in flight per group
+
+    __shared__ __align__(128) int32_t s_idx[2][3][kTileMax];
+    __shared__ uint64_t s_bar[2];
+    __shared__ double s_red[8][kThreads / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gl = lane % W, gw = lane / W;
+    const int group = warp * GPW + gw;
+    const int chunks = p.F / VEC;
+    const int F = p.F;
+    WsHeader *hdr = p.ws.hdr;
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t par0 = 0, par1 = 0;
+    unsigned long long epoch = 0;
+    const int tile = p.tile;
+
+    // stage one index tile: TMA bulk copy when full and 16-byte aligned, plain loads otherwise
+    auto stage = [&](long long tbase, int cnt, int b) {
+        const int32_t *su = p.bu + tbase, *si = p.bi + tbase, *sj = p.bj + tbase;
+        bool bulk = (cnt % 4 == 0) && ((((uintptr_t)su | (uintptr_t)si | (uintptr_t)sj) & 15) == 0);
+        if (bulk) {
+            if (tid == 0) {
+                uint32_t bytes = (uint32_t)cnt * 4u;
+                mbar_expect_tx(&s_bar[b], 3u * bytes);
+                tma_load_1d(&s_idx[b][0][0], su, bytes, &s_bar[b]);
+                tma_load_1d(&s_idx[b][1][0], si, bytes, &s_bar[b]);
+                tma_load_1d(&s_idx[b][2][0], sj, bytes, &s_bar[b]);
+            }
+        } else {
+            for (int k = tid; k < cnt; k += kThreads) {
+                s_idx[b][0][k] = __ldg(su + k);
+                s_idx[b][1][k] = __ldg(si + k);
+                s_idx[b][2][k] = __ldg(sj + k);
+            }
+            __syncthreads();
+            if (tid == 0) mbar_arrive(&s_bar[b]);
+        }
+    };
+
+    for (long long s = 0; s < p.n_steps; ++s) {
+        const long long step = p.first_step + s;
+        const long long base = step * p.batch;
+        const long long nb = min(p.batch, p.n - base);
+        const long long ntiles = (nb + tile - 1) / tile;
+        double *acc = hdr->acc[s & 1];
+        const bool has_reg = (p.reg1 != 0.f) || (p.reg2 != 0.f);
+
+        // ------------------------------------------------------------ phase 1
+        double a_loss = 0, a_l1u = 0, a_l1i = 0, a_l1j = 0, a_s2u = 0, a_s2i = 0, a_s2j = 0;
+        int buf = 0;
+        long long t_i = blockIdx.x;
+        if (t_i < ntiles) stage(base + t_i * tile, (int)min((long long)tile, nb - t_i * tile), 0);
+        for (; t_i < ntiles; t_i += gridDim.x) {
+            long long t_n = t_i + gridDim.x;
+            if (t_n < ntiles) stage(base + t_n * tile, (int)min((long long)tile, nb - t_n * tile), buf ^ 1);
+            if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1; } else { mbar_wait(&s_bar[1], par1); par1 ^= 1; }
+            const int cnt = (int)min((long long)tile, nb - t_i * tile);
+            const int32_t *xu = s_idx[buf][0], *xi = s_idx[buf][1], *xj = s_idx[buf][2];
+
+            for (int tb = 0; tb < cnt; tb += GROUPS * UNR) {
+                Row<VEC, W, NCH> rp[UNR], rqi[UNR], rqj[UNR];
+                int iu[UNR], ii[UNR], ij[UNR];
+                bool ok[UNR];
+#pragma unroll
+                for (int r = 0; r < UNR; ++r) {
+                    int t = tb + r * GROUPS + group;
+                    ok[r] = t < cnt;
+                    iu[r] = ok[r] ? xu[t] : 0;
+                    ii[r] = ok[r] ? xi[t] : 0;
+                    ij[r] = ok[r] ? xj[t] : 0;
+                    rp[r] = load_row<VEC, W, NCH>(p.P + (size_t)iu[r] * F, gl, chunks, ok[r]);
+                    rqi[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ii[r] * F, gl, chunks, ok[r]);
+                    rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < UNR; ++r) {
+                    float pos = dot_rows<VEC, W, NCH>(rp[r], rqi[r]);
+                    float neg = dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
+                    if (!ok[r]) continue;
+                    float x = pos - neg;
+                    float sg = 1.f / (1.f + expf(-x));
+                    if (gl == 0) a_loss += (double)(-logf(1e-10f + sg));
+                    float c = -(sg * (1.f - sg)) / (1e-10f + sg);
+                    if (has_reg) {
+                        float l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) {
+                                float a = rp[r].c[ch].v[e], b = rqi[r].c[ch].v[e], d = rqj[r].c[ch].v[e];
+                                l1u += fabsf(a); s2u = fmaf(a, a, s2u);
+                                l1i += fabsf(b); s2i = fmaf(b, b, s2i);
+                                l1j += fabsf(d); s2j = fmaf(d, d, s2j);
+                            }
+                        a_l1u += l1u; a_l1i += l1i; a_l1j += l1j;
+                        a_s2u += s2u; a_s2i += s2i; a_s2j += s2j;
+                    }
+                    if (p.apply) {
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ++ch) {
+                            int cc = gl + ch * W;
+                            if (cc >= chunks) continue;
+                            Vec<VEC> gu, gi, gj;
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) {
+                                gu.v[e] = c * (rqi[r].c[ch].v[e] - rqj[r].c[ch].v[e]);
+                                gi.v[e] = c * rp[r].c[ch].v[e];
+                                gj.v[e] = -gi.v[e];
+                            }
+                            red_row<VEC>(p.ws.gP + (size_t)iu[r] * F + cc * VEC, gu);
+                            red_row<VEC>(p.ws.gQ + (size_t)ii[r] * F + cc * VEC, gi);
+                            red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
+                        }
+                        if (gl == 0) {
+                            atomicAdd(p.ws.cntU + iu[r], 1u);
+                            atomicAdd(p.ws.cntI + ii[r], 1ull);
+                            atomicAdd(p.ws.cntI + ij[r], 1ull << 32);
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // tile buffer free for re-staging
+            buf ^= 1;
+        }
+        // CTA reduction of the 7 partial sums -> one fp64 atomic each
+        {
+            double vals[7] = {a_loss, a_l1u, a_l1i, a_l1j, a_s2u, a_s2i, a_s2j};
+            const int nv = has_reg ? 7 : 1;
+            for (int k = 0; k < nv; ++k) {
+                double v = warp_sum(vals[k]);
+                if (lane == 0) s_red[k][warp] = v;
+            }
+            __syncthreads();
+            if (tid < nv) {
+                double v = 0;
+                for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
+                if (v != 0.0) atomicAdd(&acc[tid], v);
+            }
+        }
+        grid_barrier(&hdr->barrier, epoch);
+
+        // ------------------------------------------------------------ phase 2
+        double bpr, l1u, l1i, l1j, s2u, s2i, s2j;
+        {
+            const volatile double *va = acc;
+            bpr = va[0]; l1u = va[1]; l1i = va[2]; l1j = va[3]; s2u = va[4]; s2i = va[5]; s2j = va[6];
+        }
+        double nu = sqrt(s2u), ni = sqrt(s2i), nj = sqrt(s2j);
+        // fp32 assembly of the scalar loss, in the reference's order (MFRecommender.py:88-95)
+        float loss = (float)bpr;
+        loss += p.reg1 * ((float)l1i + (float)l1j);
+        loss += p.reg2 * ((float)ni + (float)nj);
+        loss += p.reg1 * (float)l1u;
+        loss += p.reg2 * (float)nu;
+        if (blockIdx.x == 0 && tid == 0) p.step_loss[s] = (double)loss;
+        if (blockIdx.x == 0 && tid < 8) hdr->acc[(s + 1) & 1][tid] = 0.0;  // recycle the other accumulator
+        if (isnan(loss)) {
+            if (blockIdx.x == 0 && tid == 0) {
+                hdr->status = DRB_ERR_NAN_LOSS;
+                hdr->nan_step = step;
+            }
+            break;  // uniform across the grid: every CTA computed the same loss
+        }
+        if (p.apply) {
+            Norms nm;
+            nm.inv_u = nu > 0 ? (float)(1.0 / nu) : 0.f;
+            nm.inv_i = ni > 0 ? (float)(1.0 / ni) : 0.f;
+            nm.inv_j = nj > 0 ? (float)(1.0 / nj) : 0.f;
+            AdamCoef ac;
+            ac.step_size = 0.f;
+            ac.bc2_sqrt = 1.f;
+            if (p.opt == DRB_OPT_ADAM) {
+                double t = (double)(p.adam_step0 + s + 1);
+                ac.step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, t)));
+                ac.bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, t));
+            }
+            const bool dense = (p.opt == DRB_OPT_ADAM) || (3 * nb >= ((long long)p.U + p.I) / 4);
+            if (dense) {
+                const long long rows = (long long)p.U + p.I;
+                for (long long r = (long long)blockIdx.x * GROUPS + group; r < rows; r += (long long)gridDim.x * GROUPS) {
+                    if (r < p.U) {
+                        unsigned c = __ldcg(p.ws.cntU + r);
+                        if (c != 0 || p.opt == DRB_OPT_ADAM) {
+                            size_t o = (size_t)r * F;
+                            if (p.opt == DRB_OPT_SGD)
+                                apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.P + o, p.ws.gP + o, nullptr, nullptr, gl, chunks,
+                                                                    (float)c, nm.inv_u, 0.f, 0.f, p, ac, true);
+                            else
+                                apply_row<VEC, W, NCH, DRB_OPT_ADAM>(p.P + o, p.ws.gP + o, p.ws.mP + o, p.ws.vP + o, gl,
+                                                                     chunks, (float)c, nm.inv_u, 0.f, 0.f, p, ac, c != 0);
+                            if (gl == 0 && c != 0) p.ws.cntU[r] = 0u;
+                        }
+                    } else {
+                        long long it = r - p.U;
+                        unsigned long long c = __ldcg(p.ws.cntI + it);
+                        if (c != 0 || p.opt == DRB_OPT_ADAM) {
+                            size_t o = (size_t)it * F;
+                            float cp = (float)(unsigned)(c & 0xffffffffull), cn = (float)(unsigned)(c >> 32);
+                            if (p.opt == DRB_OPT_SGD)
+                                apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.Q + o, p.ws.gQ + o, nullptr, nullptr, gl, chunks, cp,
+                                                                    nm.inv_i, cn, nm.inv_j, p, ac, true);
+                            else
+                                apply_row<VEC, W, NCH, DRB_OPT_ADAM>(p.Q + o, p.ws.gQ + o, p.ws.mQ + o, p.ws.vQ + o, gl,
+                                                                     chunks, cp, nm.inv_i, cn, nm.inv_j, p, ac, c != 0);
+                            if (gl == 0 && c != 0) p.ws.cntI[it] = 0ull;
+                        }
+                    }
+                }
+            } else {
+                // claim mode (SGD only): the first group to swap a row's counter to zero applies it
+                for (long long t0 = (long long)blockIdx.x * tile; t0 < nb; t0 += (long long)gridDim.x * tile) {
+                    const int cnt = (int)min((long long)tile, nb - t0);
+                    for (int tb = 0; tb < cnt; tb += GROUPS) {
+                        int t = tb + group;
+                        bool ok = t < cnt;
+                        int u = 0, i = 0, j = 0;
+                        if (ok) {
+                            u = __ldg(p.bu + base + t0 + t);
+                            i = __ldg(p.bi + base + t0 + t);
+                            j = __ldg(p.bj + base + t0 + t);
+                        }
+                        unsigned cu = 0;
+                        unsigned long long ci = 0, cj = 0;
+                        if (ok && gl == 0) {
+                            cu = atomicExch(p.ws.cntU + u, 0u);
+                            ci = atomicExch(p.ws.cntI + i, 0ull);
+                            cj = atomicExch(p.ws.cntI + j, 0ull);
+                        }
+                        cu = __shfl_sync(0xffffffffu, cu, gw * W);
+                        ci = __shfl_sync(0xffffffffu, ci, gw * W);
+                        cj = __shfl_sync(0xffffffffu, cj, gw * W);
+                        if (cu != 0) {
+                            size_t o = (size_t)u * F;
+                            apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.P + o, p.ws.gP + o, nullptr, nullptr, gl, chunks, (float)cu,
+                                                                nm.inv_u, 0.f, 0.f, p, ac, true);
+                        }
+                        if (ci != 0) {
+                            size_t o = (size_t)i * F;
+                            apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.Q + o, p.ws.gQ + o, nullptr, nullptr, gl, chunks,
+                                                                (float)(unsigned)(ci & 0xffffffffull), nm.inv_i,
+                                                                (float)(unsigned)(ci >> 32), nm.inv_j, p, ac, true);
+                        }
+                        if (cj != 0) {
+                            size_t o = (size_t)j * F;
+                            apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.Q + o, p.ws.gQ + o, nullptr, nullptr, gl, chunks,
+                                                                (float)(unsigned)(cj & 0xffffffffull), nm.inv_i,
+                                                                (float)(unsigned)(cj >> 32), nm.inv_j, p, ac, true);
+                        }
+                    }
+                }
+            }
+        }
+        if (s + 1 < p.n_steps) grid_barrier(&hdr->barrier, epoch);
+    }
+}
+
+// b?[k] = triples[perm[k], ?]
+__global__ void gather_triples_kernel(const int32_t *__restrict__ triples, const int64_t *__restrict__ perm, long long n,
+                                      int32_t *__restrict__ bu, int32_t *__restrict__ bi, int32_t *__restrict__ bj)
+{
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        long long src = perm ? perm[k] : k;
+        const int32_t *t = triples + 3 * src;
+        bu[k] = __ldg(t);
+        bi[k] = __ldg(t + 1);
+        bj[k] = __ldg(t + 2);
+    }
+}
+
+// ------------------------------------------------------------------ host dispatch
+typedef void (*StepKernel)(StepParams);
+
+template <int VEC>
+static StepKernel pick_kernel_v(int W, int NCH)
+{
+#define DRB_CASE(w, n) \
+    if (W == w && NCH == n) return mf_bpr_steps_kernel<VEC, w, n>;
+    DRB_CASE(1, 1) DRB_CASE(2, 1) DRB_CASE(4, 1) DRB_CASE(8, 1) DRB_CASE(16, 1) DRB_CASE(32, 1)
+    DRB_CASE(32, 2) DRB_CASE(32, 4) DRB_CASE(32, 8)
+#undef DRB_CASE
+    return nullptr;
+}
+
+static StepKernel pick_kernel(int F)
+{
+    if (F <= 0) return nullptr;
+    RowGeom g = row_geom(F);
+    if (g.vec == 4) return pick_kernel_v<4>(g.width, g.nch);
+    if (g.vec == 2) return pick_kernel_v<2>(g.width, g.nch);
+    return pick_kernel_v<1>(g.width, g.nch);
+}
+
+static int launch_steps(StepParams &p, cudaStream_t st)
+{
+    StepKernel k = pick_kernel(p.F);
+    DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
+    int per_sm = 0;
+    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0));
+    DRB_REQUIRE(per_sm > 0, "step kernel does not fit on an SM");
+    const int max_grid = per_sm * sm_count();
+    // tile: as large as possible (<= kTileMax) while still giving every CTA work
+    long long want = (p.batch + max_grid - 1) / max_grid;
+    int tile = (int)((want + 15) / 16 * 16);
+    if (tile < 16) tile = 16;
+    if (tile > kTileMax) tile = kTileMax;
+    p.tile = tile;
+    long long tiles = (p.batch + tile - 1) / tile;
+    long long rows_work = ((long long)p.U + p.I + 63) / 64;
+    bool dense = (p.opt == DRB_OPT_ADAM) || (3 * p.batch >= ((long long)p.U + p.I) / 4);
+    long long want_grid = (dense && p.apply) ? (tiles > rows_work ? tiles : rows_work) : tiles;
+    int grid = (int)(want_grid < 1 ? 1 : (want_grid > max_grid ? max_grid : want_grid));
+    DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, sizeof(WsHeader), st));
+    void *args[] = {&p};
+    DRB_CUDA(cudaLaunchCooperativeKernel((void *)k, dim3(grid), dim3(kThreads), args, 0, st));
+    return DRB_OK;
+}
+
+}  // namespace drb
+
+using namespace drb;
+
+extern "C" size_t drb_mf_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_t opt)
+{
+    return carve(nullptr, U, I, F, opt, nullptr);
+}
+
+extern "C" int drb_mf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F, int32_t opt, void *stream)
+{
+    DRB_REQUIRE(d_ws != nullptr && U > 0 && I > 0 && F > 0, "workspace_init: bad arguments");
+    size_t bytes = carve(nullptr, U, I, F, opt, nullptr);
+    DRB_CUDA(cudaMemsetAsync(d_ws, 0, bytes, (cudaStream_t)stream));
+    return DRB_OK;
+}
+
+static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu,
+                       const int32_t *bi, const int32_t *bj, long long n, long long batch, long long first, long long nsteps,
+                       const drb_hyper *h, long long adam_step0, double *d_step_loss, int apply)
+{
+    DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
+    DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
+    DRB_REQUIRE(h->opt == DRB_OPT_SGD || h->opt == DRB_OPT_ADAM, "unknown optimizer id %d", h->opt);
+    DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0, "steps [%lld,%lld) exceed %lld triples", first,
+                first + nsteps, n);
+    p.P = P; p.Q = Q;
+    carve(d_ws, U, I, F, h->opt, &p.ws);
+    p.bu = bu; p.bi = bi; p.bj = bj;
+    p.n = n; p.batch = batch; p.first_step = first; p.n_steps = nsteps;
+    p.U = U; p.I = I; p.F = F; p.tile = kTileMax;
+    p.lr = h->lr; p.reg1 = h->reg_1; p.reg2 = h->reg_2; p.opt = h->opt;
+    p.beta1 = h->beta1; p.beta2 = h->beta2; p.eps = h->eps;
+    p.adam_step0 = adam_step0;
+    p.step_loss = d_step_loss;
+    p.apply = apply;
+    return DRB_OK;
+}
+
+static int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step)
+{
+    WsHeader h;
+    DRB_CUDA(cudaMemcpyAsync(&h, d_ws, sizeof(WsHeader), cudaMemcpyDeviceToHost, st));
+    DRB_CUDA(cudaStreamSynchronize(st));
+    if (h.status == DRB_ERR_NAN_LOSS) {
+        if (nan_step) *nan_step = h.nan_step;
+        set_error("Loss=Nan or Infinity at step %lld: current settings does not fit the recommender", h.nan_step);
+        return DRB_ERR_NAN_LOSS;
+    }
+    if (nan_step) *nan_step = -1;
+    return DRB_OK;
+}
+
+extern "C" int drb_mf_bpr_train_steps(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
+                                      const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
+                                      int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *hyper,
+                                      int64_t adam_step0, double *d_step_loss, int32_t sync_and_check,
+                                      int64_t *nan_step, void *stream)
+{
+    StepParams p;
+    int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu, d_bi, d_bj, n, batch, first_step, n_steps, hyper, adam_step0,
+                         d_step_loss, 1);
+    if (rc != DRB_OK) return rc;
+    if (n_steps == 0) return DRB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_steps(p, st);
+    if (rc != DRB_OK) return rc;
+    if (sync_and_check) return check_nan(d_ws, st, nan_step);
+    return DRB_OK;
+}
+
+extern "C" int drb_mf_bpr_loss(const float *d_P, const float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
+                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t batch,
+                               const drb_hyper *hyper, double *d_loss, void *stream)
+{
+    StepParams p;
+    int rc = fill_params(p, (float *)d_P, (float *)d_Q, d_ws, U, I, F, d_bu, d_bi, d_bj, batch, batch, 0, 1, hyper, 0,
+                         d_loss, 0);
+    if (rc != DRB_OK) return rc;
+    return launch_steps(p, (cudaStream_t)stream);
+}
+
+extern "C" int drb_mf_bpr_train_step_host(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
+                                          const int32_t *h_bu, const int32_t *h_bi, const int32_t *h_bj, int64_t batch,
+                                          const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage, double *h_loss,
+                                          void *stream)
+{
+    DRB_REQUIRE(h_bu && h_bi && h_bj && d_stage && h_loss && batch > 0, "train_step_host: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t stride = (size_t)((batch + 3) / 4 * 4);  // keep each array 16-byte aligned for the TMA path
+    size_t bytes = sizeof(int32_t) * (size_t)batch;
+    DRB_CUDA(cudaMemcpyAsync(d_stage, h_bu, bytes, cudaMemcpyHostToDevice, st));
+    DRB_CUDA(cudaMemcpyAsync(d_stage + stride, h_bi, bytes, cudaMemcpyHostToDevice, st));
+    DRB_CUDA(cudaMemcpyAsync(d_stage + 2 * stride, h_bj, bytes, cudaMemcpyHostToDevice, st));
+    double *d_loss = (double *)(d_stage + 3 * stride);
+    StepParams p;
+    int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_stage, d_stage + stride, d_stage + 2 * stride, batch, batch, 0, 1,
+                         hyper, adam_step0, d_loss, 1);
+    if (rc != DRB_OK) return rc;
+    rc = launch_steps(p, st);
+    if (rc != DRB_OK) return rc;
+    DRB_CUDA(cudaMemcpyAsync(h_loss, d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
+    int64_t nan_step = -1;
+    return check_nan(d_ws, st, &nan_step);
+}
+
+extern "C" int drb_gather_triples(const int32_t *d_triples, const int64_t *d_perm, int64_t n, int32_t *d_bu,
+                                  int32_t *d_bi, int32_t *d_bj, void *stream)
+{
+    DRB_REQUIRE(d_triples && d_bu && d_bi && d_bj && n >= 0, "gather_triples: bad arguments");
+    if (n == 0) return DRB_OK;
+    long long blocks = (n + 255) / 256;
+    long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    gather_triples_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_triples, d_perm, n, d_bu, d_bi, d_bj);
+    DRB_CUDA(cudaGetLastError());
+    return DRB_OK;
+}

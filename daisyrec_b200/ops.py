@@ -1,0 +1,221 @@
+"""Tensor-level bindings of the C ABI (include/daisyrec_b200.h).
+
+torch is plumbing here: device memory (``tensor.data_ptr()``) and the current CUDA stream.
+Every function forwards to libdaisyrec_b200.so; nothing is computed by torch ops.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _dev(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError(f"{name}: expected a contiguous CUDA tensor of dtype {dtype}")
+    return t
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("daisyrec_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def hyper(lr, reg_1, reg_2, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8):
+    return L.Hyper(lr, reg_1, reg_2, L.OPT_SGD if opt == "sgd" else L.OPT_ADAM, beta1, beta2, eps)
+
+
+def device_query():
+    sm, ma, mi, l2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    L.check(L.lib().drb_device_query(C.byref(sm), C.byref(ma), C.byref(mi), C.byref(l2)))
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value), l2_bytes=l2.value)
+
+
+# ------------------------------------------------------------------ sampler
+def mt19937_seed(seed):
+    st = np.zeros(625, np.uint32)
+    L.check(L.lib().drb_mt19937_seed(st.ctypes.data, C.c_uint32(seed & 0xFFFFFFFF)))
+    return st
+
+
+def mt19937_from_numpy(rs=None):
+    s = (np.random if rs is None else rs).get_state()
+    st = np.zeros(625, np.uint32)
+    st[:624] = s[1]
+    st[624] = s[2]
+    return st
+
+
+def mt19937_to_numpy(st, rs=None):
+    (np.random if rs is None else rs).set_state(("MT19937", st[:624].copy(), int(st[624]), 0, 0.0))
+
+
+def sampler_draw_mt19937(state, row_ptr, user_num, item_num, num_ng):
+    """Host: the reference's per-user bounded draws (advances ``state`` in place)."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    draws = np.empty((user_num, num_ng), np.int32)
+    bad = C.c_int32(-1)
+    rc = L.lib().drb_sampler_draw_mt19937(state.ctypes.data, row_ptr.ctypes.data, user_num, item_num, num_ng,
+                                          draws.ctypes.data, C.byref(bad))
+    if rc == L.DRB_ERR_EMPTY_SET:
+        raise ValueError("'a' cannot be empty unless no samples are taken")
+    L.check(rc)
+    return draws
+
+
+def sampler_draw_philox(seed, offset, d_row_ptr, user_num, item_num, num_ng):
+    _dev(d_row_ptr, torch.int64, "row_ptr")
+    draws = torch.empty((user_num, num_ng), dtype=torch.int32, device=d_row_ptr.device)
+    bad = torch.empty(1, dtype=torch.int32, device=d_row_ptr.device)
+    L.check(L.lib().drb_sampler_draw_philox(C.c_uint64(seed), C.c_uint64(offset), _ptr(d_row_ptr), user_num, item_num,
+                                            num_ng, _ptr(draws), _ptr(bad), _stream()))
+    return draws, bad
+
+
+def sampler_kth_complement(d_row_ptr, d_col, d_draws, item_num):
+    _dev(d_row_ptr, torch.int64, "row_ptr"); _dev(d_col, torch.int32, "col"); _dev(d_draws, torch.int32, "draws")
+    U, G = d_draws.shape
+    js = torch.empty_like(d_draws)
+    L.check(L.lib().drb_sampler_kth_complement(_ptr(d_row_ptr), _ptr(d_col), _ptr(d_draws), U, item_num, G, _ptr(js),
+                                               _stream()))
+    return js
+
+
+def sampler_explode(d_coo_u, d_coo_i, d_js):
+    _dev(d_coo_u, torch.int32, "coo_u"); _dev(d_coo_i, torch.int32, "coo_i"); _dev(d_js, torch.int32, "js")
+    nnz, G = d_coo_u.numel(), d_js.shape[1]
+    tr = torch.empty((nnz * G, 3), dtype=torch.int32, device=d_js.device)
+    L.check(L.lib().drb_sampler_explode(_ptr(d_coo_u), _ptr(d_coo_i), nnz, _ptr(d_js), G, _ptr(tr), _stream()))
+    return tr
+
+
+def sample_triples_host(state, row_ptr, col, coo_u, coo_i, user_num, item_num, num_ng):
+    """All-host-buffer convenience call (H2D/D2H inside the library)."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    col = np.ascontiguousarray(col, np.int32)
+    coo_u = np.ascontiguousarray(coo_u, np.int32)
+    coo_i = np.ascontiguousarray(coo_i, np.int32)
+    js = np.empty((user_num, num_ng), np.int32)
+    tr = np.empty((len(coo_u) * num_ng, 3), np.int32)
+    bad = C.c_int32(-1)
+    rc = L.lib().drb_sample_triples_host(state.ctypes.data, row_ptr.ctypes.data, col.ctypes.data, coo_u.ctypes.data,
+                                         coo_i.ctypes.data, len(coo_u), user_num, item_num, num_ng, js.ctypes.data,
+                                         tr.ctypes.data, C.byref(bad))
+    if rc == L.DRB_ERR_EMPTY_SET:
+        raise ValueError("'a' cannot be empty unless no samples are taken")
+    L.check(rc)
+    return js, tr
+
+
+# ------------------------------------------------------------------ train feed
+def gather_triples(d_triples, d_perm=None):
+    _dev(d_triples, torch.int32, "triples")
+    n = d_triples.shape[0] if d_perm is None else d_perm.numel()
+    if d_perm is not None:
+        _dev(d_perm, torch.int64, "perm")
+    n4 = (n + 3) // 4 * 4                                   # 16-byte aligned planes for the TMA path
+    soa = torch.empty((3, n4), dtype=torch.int32, device=d_triples.device)
+    L.check(L.lib().drb_gather_triples(_ptr(d_triples), None if d_perm is None else _ptr(d_perm), n, _ptr(soa[0]),
+                                       _ptr(soa[1]), _ptr(soa[2]), _stream()))
+    return soa[0][:n], soa[1][:n], soa[2][:n]
+
+
+# ------------------------------------------------------------------ training
+class MFWorkspace:
+    """Device scratch of the step kernel: gradient accumulators, row counters, Adam moments."""
+
+    def __init__(self, user_num, item_num, factors, opt, device):
+        self.U, self.I, self.F = user_num, item_num, factors
+        self.opt = L.OPT_SGD if opt == "sgd" else L.OPT_ADAM
+        nbytes = L.lib().drb_mf_workspace_bytes(user_num, item_num, factors, self.opt)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.reset()
+
+    def reset(self):
+        L.check(L.lib().drb_mf_workspace_init(_ptr(self.buf), self.U, self.I, self.F, self.opt, _stream()))
+
+
+def mf_bpr_train_steps(P, Q, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, check=True, out=None):
+    _dev(P, torch.float32, "P"); _dev(Q, torch.float32, "Q")
+    for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
+        _dev(t, torch.int32, nm)
+    n = bu.numel()
+    losses = out if out is not None else torch.empty(max(n_steps, 1), dtype=torch.float64, device=P.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_mf_bpr_train_steps(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, _ptr(bu), _ptr(bi), _ptr(bj),
+                                        n, batch, first_step, n_steps, C.byref(hp), adam_step0, _ptr(losses),
+                                        1 if check else 0, C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]
+
+
+def mf_bpr_loss(P, Q, ws, bu, bi, bj, hp):
+    _dev(P, torch.float32, "P"); _dev(Q, torch.float32, "Q")
+    loss = torch.empty(1, dtype=torch.float64, device=P.device)
+    L.check(L.lib().drb_mf_bpr_loss(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, _ptr(bu), _ptr(bi), _ptr(bj),
+                                    bu.numel(), C.byref(hp), _ptr(loss), _stream()))
+    return loss
+
+
+def stage_buffer(batch, device):
+    stride = (batch + 3) // 4 * 4
+    return torch.empty(3 * stride + 4, dtype=torch.int32, device=device)
+
+
+def mf_bpr_train_step_host(P, Q, ws, h_bu, h_bi, h_bj, hp, stage, adam_step0=0):
+    """One end-to-end step from HOST batch arrays (numpy int32 or CPU tensors, ideally pinned)."""
+    def hp_(a):
+        return a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data
+    n = len(h_bu)
+    loss = C.c_double(0.0)
+    rc = L.lib().drb_mf_bpr_train_step_host(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, hp_(h_bu), hp_(h_bi),
+                                            hp_(h_bj), n, C.byref(hp), adam_step0, _ptr(stage), C.byref(loss), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return loss.value
+
+
+# ------------------------------------------------------------------ inference
+def mf_rank(P, Q, users, cands, topk):
+    _dev(users, torch.int64, "users"); _dev(cands, torch.int64, "cands")
+    n, Cn = cands.shape
+    out = torch.empty((n, topk), dtype=torch.float32, device=P.device)
+    L.check(L.lib().drb_mf_rank(_ptr(P), _ptr(Q), P.shape[1], _ptr(users), n, _ptr(cands), Cn, topk, _ptr(out),
+                                _stream()))
+    return out
+
+
+def mf_full_rank(P, Q, users, topk):
+    _dev(users, torch.int64, "users")
+    out = torch.empty((users.numel(), topk), dtype=torch.int64, device=P.device)
+    L.check(L.lib().drb_mf_full_rank(_ptr(P), _ptr(Q), P.shape[1], Q.shape[0], _ptr(users), users.numel(), topk,
+                                     _ptr(out), _stream()))
+    return out
+
+
+def mf_predict(P, Q, u, i):
+    _dev(u, torch.int32, "u"); _dev(i, torch.int32, "i")
+    out = torch.empty(u.numel(), dtype=torch.float32, device=P.device)
+    L.check(L.lib().drb_mf_predict(_ptr(P), _ptr(Q), P.shape[1], _ptr(u), _ptr(i), u.numel(), _ptr(out), _stream()))
+    return out
+
+
+def mf_rank_host(P, Q, users, cands, topk):
+    users = np.ascontiguousarray(users, np.int64)
+    cands = np.ascontiguousarray(cands, np.int64)
+    out = np.empty((len(users), topk), np.float32)
+    L.check(L.lib().drb_mf_rank_host(_ptr(P), _ptr(Q), P.shape[1], users.ctypes.data, len(users), cands.ctypes.data,
+                                     cands.shape[1], topk, out.ctypes.data))
+    return out

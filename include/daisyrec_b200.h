@@ -1,0 +1,137 @@
+/*
+ * daisyrec_b200.h -- C ABI of the B200-native BPR hot path (libdaisyrec_b200.so).
+ *
+ * The reference (AmazingDD/daisyRec v2.3.0) is pure Python: it has no FFI, so the
+ * "boundary" it offers is the duck-typed model / sampler contract consumed by
+ * run_examples/test.py:87-95,118-120 and run_examples/tune.py:180-188,210-212
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference interface it
+ * stands behind (file:line, relative to the reference root); the Python host in
+ * daisyrec_b200/ (same class / method names as the reference) binds them with ctypes,
+ * and INTEGRATION.md shows the stub a daisyRec maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - "d_" = device pointer, "h_" = host pointer.  Device buffers are allocated by the
+ *     caller (any allocator: cudaMalloc, torch) on the current device.
+ *   - stream: a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns DRB_OK (0) or a DRB_ERR_* code; drb_last_error() returns a
+ *     thread-local message for the last failure.  Nothing aborts the process.
+ *   - tables are row-major fp32: P[user_num, factors], Q[item_num, factors]
+ *     (== MF.embed_user.weight / MF.embed_item.weight, daisy/model/MFRecommender.py:53-54).
+ *   - index arrays are int32 for batches (the sampler's dtype, daisy/utils/sampler.py:101)
+ *     and int64 for rank inputs (torch.tensor of python ints, daisy/utils/dataset.py:37-38).
+ */
+#ifndef DAISYREC_B200_H
+#define DAISYREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRB_OK 0
+#define DRB_ERR_INVALID 1     /* bad argument (null pointer, unsupported factors, ...)            */
+#define DRB_ERR_CUDA 2        /* a CUDA runtime call failed; see drb_last_error()                 */
+#define DRB_ERR_NAN_LOSS 3    /* loss became NaN: ValueError of AbstractRecommender.py:122-123    */
+#define DRB_ERR_EMPTY_SET 4   /* a user has no un-interacted item: numpy "a cannot be empty"      */
+#define DRB_ERR_NO_DEVICE 5   /* no sm_100 device / kernel image not loadable on this device     */
+
+#define DRB_OPT_SGD 0         /* optim.SGD(lr)   AbstractRecommender.py:55-56                     */
+#define DRB_OPT_ADAM 1        /* optim.Adam(lr)  AbstractRecommender.py:53-54 (dense, torch defaults) */
+
+typedef struct drb_hyper {
+    float lr;                 /* config['lr']                                                      */
+    float reg_1;              /* config['reg_1']  L1 coefficient  (MFRecommender.py:88,94)        */
+    float reg_2;              /* config['reg_2']  Frobenius coefficient (MFRecommender.py:89,95)  */
+    int32_t opt;              /* DRB_OPT_*                                                         */
+    float beta1, beta2, eps;  /* Adam (torch defaults 0.9, 0.999, 1e-8)                           */
+} drb_hyper;
+
+/* ---- library / device ----------------------------------------------------------- */
+int drb_version(void);
+const char *drb_last_error(void);
+/* sm_count, compute capability, L2 bytes of the current device */
+int drb_device_query(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *l2_bytes);
+
+/* ---- pair-wise sampler: BasicNegtiveSampler.sampling(), uniform + BPR branch ------
+ * daisy/utils/sampler.py:55-103 (js table :63,84-89; explode :91,99-101).
+ * CSR = config['train_ur'] as sorted, duplicate-free user->item rows.
+ * Parity mode replays numpy's legacy MT19937 stream (np.random.seed, daisy/utils/config.py:34):
+ * the word stream is inherently sequential, so the O(U*G) bounded draws run on the host
+ * (drb_sampler_draw_mt19937) and everything proportional to nnz runs on the device. */
+int drb_mt19937_seed(uint32_t *h_state625, uint32_t seed); /* numpy RandomState.seed(int) */
+/* h_draws[u*G+g] = randint(0, item_num - deg(u)); advances the state exactly like the
+ * reference's np.random.choice calls.  *bad_user receives the offending user on DRB_ERR_EMPTY_SET. */
+int drb_sampler_draw_mt19937(uint32_t *h_state625, const int64_t *h_row_ptr, int32_t user_num, int32_t item_num,
+                             int32_t num_ng, int32_t *h_draws, int32_t *bad_user);
+/* counter-based (Philox4x32-10) draws on the device: throughput mode, NOT the reference stream */
+int drb_sampler_draw_philox(uint64_t seed, uint64_t offset, const int64_t *d_row_ptr, int32_t user_num,
+                            int32_t item_num, int32_t num_ng, int32_t *d_draws, int32_t *d_bad_user, void *stream);
+/* js[u,g] = the draws[u,g]-th smallest item NOT in row u  (== setdiff1d(arange(I), past)[k]) */
+int drb_sampler_kth_complement(const int64_t *d_row_ptr, const int32_t *d_col, const int32_t *d_draws,
+                               int32_t user_num, int32_t item_num, int32_t num_ng, int32_t *d_js, void *stream);
+/* triples[(r*G+g), :] = (coo_u[r], coo_i[r], js[coo_u[r], g])  -- int32 [nnz*G, 3] */
+int drb_sampler_explode(const int32_t *d_coo_u, const int32_t *d_coo_i, int64_t nnz, const int32_t *d_js,
+                        int32_t num_ng, int32_t *d_triples, void *stream);
+/* host-buffer convenience: CSR + COO in, triples out (H2D / D2H inside) */
+int drb_sample_triples_host(uint32_t *h_state625, const int64_t *h_row_ptr, const int32_t *h_col,
+                            const int32_t *h_coo_u, const int32_t *h_coo_i, int64_t nnz, int32_t user_num,
+                            int32_t item_num, int32_t num_ng, int32_t *h_js, int32_t *h_triples, int32_t *bad_user);
+
+/* ---- pair-wise train feed: BasicDataset + DataLoader(shuffle=True) ------------------
+ * daisy/utils/dataset.py:5-27.  Gathers the epoch's permuted triples into the SoA batch
+ * arrays the step kernel streams with TMA: b?[k] = triples[perm[k], ?] (perm NULL = identity). */
+int drb_gather_triples(const int32_t *d_triples, const int64_t *d_perm, int64_t n, int32_t *d_bu, int32_t *d_bi,
+                       int32_t *d_bj, void *stream);
+
+/* ---- BPR-MF training: GeneralRecommender.fit step loop ------------------------------
+ * daisy/model/AbstractRecommender.py:112-128 with MF.calc_loss (MFRecommender.py:70-97),
+ * BPRLoss (daisy/utils/loss.py:11), autograd backward (:125) and optimizer.step (:126).
+ * One persistent cooperative kernel runs n_steps synchronous steps: every gradient of a
+ * step is taken at the pre-step weights, exactly like the reference. */
+size_t drb_mf_workspace_bytes(int32_t user_num, int32_t item_num, int32_t factors, int32_t opt);
+int drb_mf_workspace_init(void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t opt,
+                          void *stream);
+/* Steps first_step .. first_step+n_steps-1 over the SoA batch arrays (n triples total, step s
+ * covers [s*batch, min((s+1)*batch, n)); the last batch may be partial, drop_last=False).
+ * d_step_loss[n_steps]: fp32-assembled loss of each step (what loss.item() returns, :128).
+ * adam_step0: number of optimizer steps already taken (Adam bias correction).
+ * Returns DRB_ERR_NAN_LOSS after synchronising if a step produced NaN (tables keep their
+ * pre-step values from that step on); *nan_step receives the step index. */
+int drb_mf_bpr_train_steps(float *d_P, float *d_Q, void *d_ws, int32_t user_num, int32_t item_num, int32_t factors,
+                           const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
+                           int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                           double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+/* MF.calc_loss(batch) only (no update): MFRecommender.py:70-97 */
+int drb_mf_bpr_loss(const float *d_P, const float *d_Q, void *d_ws, int32_t user_num, int32_t item_num,
+                    int32_t factors, const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t batch,
+                    const drb_hyper *hyper, double *d_loss, void *stream);
+/* End-to-end step with HOST batch arrays (what calc_loss receives from the DataLoader,
+ * MFRecommender.py:71-72,83): H2D of 3*batch int32, one step, D2H of the loss. */
+int drb_mf_bpr_train_step_host(float *d_P, float *d_Q, void *d_ws, int32_t user_num, int32_t item_num,
+                               int32_t factors, const int32_t *h_bu, const int32_t *h_bi, const int32_t *h_bj,
+                               int64_t batch, const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage,
+                               double *h_loss, void *stream);
+
+/* ---- inference ------------------------------------------------------------------------
+ * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,
+ *   descending sort, first topk ids as float32 (the reference's dtype quirk, :107).
+ * MF.full_rank :126-133: all items, first topk ids as int64, no train-item masking.
+ * MF.predict :99-104 / MF.forward :63-68.
+ * Scores use the canonical fp32 summation order documented in DESIGN.md; equal scores
+ * order by lower candidate position (rank) / lower item id (full_rank). */
+int drb_mf_rank(const float *d_P, const float *d_Q, int32_t factors, const int64_t *d_users, int64_t n_users,
+                const int64_t *d_cands, int32_t cand_num, int32_t topk, float *d_out, void *stream);
+int drb_mf_full_rank(const float *d_P, const float *d_Q, int32_t factors, int32_t item_num, const int64_t *d_users,
+                     int64_t n_users, int32_t topk, int64_t *d_out, void *stream);
+int drb_mf_predict(const float *d_P, const float *d_Q, int32_t factors, const int32_t *d_u, const int32_t *d_i,
+                   int64_t n, float *d_out, void *stream);
+int drb_mf_rank_host(const float *d_P, const float *d_Q, int32_t factors, const int64_t *h_users, int64_t n_users,
+                     const int64_t *h_cands, int32_t cand_num, int32_t topk, float *h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAISYREC_B200_H */
