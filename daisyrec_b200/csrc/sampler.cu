@@ -128,6 +128,28 @@ __global__ void kth_complement_kernel(const int64_t *__restrict__ row_ptr, const
     }
 }
 
+// variable number of draws per row: row m owns draws[offsets[m] .. offsets[m+1])
+__global__ void kth_complement_var_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                          const int64_t *__restrict__ offsets, const int32_t *__restrict__ draws,
+                                          long long rows, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long m = warp; m < rows; m += nwarps) {          // one warp per row
+        long long b = row_ptr[m], e = row_ptr[m + 1];
+        for (long long d = offsets[m] + lane; d < offsets[m + 1]; d += 32) {
+            int k = draws[d];
+            long long lo = 0, hi = e - b;
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if ((long long)__ldg(col + b + mid) - mid <= (long long)k) lo = mid + 1; else hi = mid;
+            }
+            out[d] = k + (int)lo;
+        }
+    }
+}
+
 __global__ void explode_kernel(const int32_t *__restrict__ coo_u, const int32_t *__restrict__ coo_i, long long nnz,
                                const int32_t *__restrict__ js, int G, int32_t *__restrict__ triples)
 {
@@ -180,6 +202,33 @@ extern "C" int drb_sampler_draw_mt19937(uint32_t *st, const int64_t *h_row_ptr, 
         }
         for (int32_t g = 0; g < G; ++g) h_draws[(int64_t)u * G + g] = (int32_t)mt.bounded((uint32_t)n);
     }
+    return DRB_OK;
+}
+
+extern "C" int drb_bounded_draws_mt19937(uint32_t *st, const int64_t *h_n, const int64_t *h_offsets, int64_t rows,
+                                         int32_t *h_draws, int64_t *bad_row)
+{
+    DRB_REQUIRE(st && h_n && h_offsets && h_draws && rows >= 0, "bounded_draws_mt19937: bad arguments");
+    Mt mt{st, st + 624};
+    for (int64_t m = 0; m < rows; ++m) {
+        if (h_offsets[m + 1] > h_offsets[m] && h_n[m] <= 0) {
+            if (bad_row) *bad_row = m;
+            set_error("'a' cannot be empty: row %lld has an empty population", (long long)m);
+            return DRB_ERR_EMPTY_SET;
+        }
+        for (int64_t d = h_offsets[m]; d < h_offsets[m + 1]; ++d) h_draws[d] = (int32_t)mt.bounded((uint32_t)h_n[m]);
+    }
+    return DRB_OK;
+}
+
+extern "C" int drb_kth_complement_var(const int64_t *d_row_ptr, const int32_t *d_col, const int64_t *d_offsets,
+                                      const int32_t *d_draws, int64_t rows, int32_t *d_out, void *stream)
+{
+    DRB_REQUIRE(d_row_ptr && d_offsets && d_draws && d_out && rows >= 0, "kth_complement_var: bad arguments");
+    if (rows == 0) return DRB_OK;
+    kth_complement_var_kernel<<<grid_for(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(d_row_ptr, d_col, d_offsets,
+                                                                                          d_draws, rows, d_out);
+    DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }
 

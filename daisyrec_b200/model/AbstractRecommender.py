@@ -1,0 +1,210 @@
+"""Host side of the B200 recommenders: the reference's plug-in surface
+(daisy/model/AbstractRecommender.py:10-137) without nn.Module / autograd / torch.optim.
+
+``GeneralRecommender.fit(train_loader)`` keeps the reference contract -- a
+``torch.utils.data.DataLoader`` over ``BasicDataset(samples)``, ``batch_size`` and ``shuffle`` read
+from the loader, epoch loss accumulated from per-step losses, ``ValueError`` on a NaN loss, early
+stop on |delta epoch loss| < 1e-5 -- but runs each epoch as ONE persistent kernel launch:
+the epoch's permutation is produced with the DataLoader's own RNG protocol (so batches are the
+reference's batches), gathered into SoA index planes on the device, and consumed by
+``drb_mf_bpr_train_steps``.
+"""
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import RandomSampler, SequentialSampler, BatchSampler
+from tqdm import tqdm
+
+from .. import ops
+
+
+class _Table:
+    """Stand-in for nn.Embedding: ``.weight`` is the raw fp32 [rows, factors] table."""
+
+    def __init__(self, weight):
+        self.weight = weight
+
+    @property
+    def num_embeddings(self):
+        return self.weight.shape[0]
+
+    @property
+    def embedding_dim(self):
+        return self.weight.shape[1]
+
+
+def _init_table(rows, cols, method):
+    """Reproduce the reference's CPU init stream: nn.Embedding's own N(0,1) reset first
+    (torch/nn/modules/sparse.py reset_parameters), re-initialised later by ``_apply_init``."""
+    return torch.empty(rows, cols, dtype=torch.float32).normal_(0.0, 1.0)
+
+
+_INIT = {
+    # AbstractRecommender.py:19-31 (initializer_param_config / initializer_config)
+    'normal': lambda w: torch.nn.init.normal_(w, mean=0.0, std=0.01),
+    'uniform': lambda w: torch.nn.init.uniform_(w, a=0.0, b=1.0),
+    'xavier_normal': lambda w: torch.nn.init.xavier_normal_(w, gain=1.0),
+    'xavier_uniform': lambda w: torch.nn.init.xavier_uniform_(w, gain=1.0),
+}
+
+
+def epoch_permutation(n, shuffle, generator=None):
+    """Index order of one DataLoader epoch (torch/utils/data/dataloader.py:706-710 draws
+    ``_base_seed``; sampler.py RandomSampler.__iter__ draws a seed, seeds a private generator and
+    yields ``torch.randperm(n, generator)``).  Consumes the global torch RNG identically."""
+    torch.empty((), dtype=torch.int64).random_(generator=generator)           # _base_seed (discarded)
+    if not shuffle:
+        return None
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
+class AbstractRecommender(object):
+    def __init__(self):
+        self.optimizer = None
+        self.initializer = None
+        self.loss_type = None
+        self.lr = 0.01
+        self.logger = None
+        self.training = False
+
+    # -- reference surface (AbstractRecommender.py:33-46)
+    def calc_loss(self, batch):
+        raise NotImplementedError
+
+    def fit(self, train_loader):
+        raise NotImplementedError
+
+    def rank(self, test_loader):
+        raise NotImplementedError
+
+    def full_rank(self, u):
+        raise NotImplementedError
+
+    def predict(self, u, i):
+        raise NotImplementedError
+
+    # -- nn.Module look-alikes used by drivers
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def _optimizer_name(self):
+        """AbstractRecommender.py:48-67: unknown names fall back to Adam with a log line."""
+        name = str(self.optimizer).lower()
+        if name in ('sgd', 'adam'):
+            return name
+        if name in ('adagrad', 'rmsprop', 'sparse_adam'):
+            raise NotImplementedError(f"optimizer '{name}' is outside the B200 hot path (sgd / adam are native)")
+        if self.logger is not None:
+            self.logger.info('Received unrecognized optimizer, set default Adam optimizer')
+        return 'adam'
+
+    def _check_loss_type(self):
+        lt = str(self.loss_type).upper()
+        if lt == 'BPR':
+            return
+        if lt in ('CL', 'SL', 'HL', 'TL'):
+            raise NotImplementedError(f"loss_type '{lt}' is outside the B200 hot path (BPR is native)")
+        raise NotImplementedError(f'Invalid loss type: {self.loss_type}...')
+
+
+class GeneralRecommender(AbstractRecommender):
+    def __init__(self, config):
+        super().__init__()
+        gpu = str(config.get('gpu', '') or '')
+        if gpu and not torch.cuda.is_initialized() and 'LOCAL_RANK' not in os.environ:
+            os.environ['CUDA_VISIBLE_DEVICES'] = gpu             # AbstractRecommender.py:99
+        ops.require_cuda()
+        local = int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))
+        self.device = torch.device('cuda', local if local < torch.cuda.device_count() else 0)
+        torch.cuda.set_device(self.device)
+        self.logger = config['logger']
+        self.steps_per_launch = int(config.get('steps_per_launch', 0))   # 0 = whole epoch in one launch
+        self.show_progress = bool(config.get('progress', True))
+
+    # subclasses provide: _tables() -> (P, Q); _hyper(); _workspace()
+    def _loader_plan(self, train_loader):
+        """Decode a DataLoader into (triples ndarray, batch_size, shuffle, drop_last) or None."""
+        ds = getattr(train_loader, 'dataset', None)
+        data = getattr(ds, 'data', None)
+        bs = getattr(train_loader, 'batch_size', None)
+        if not isinstance(data, np.ndarray) or data.ndim != 2 or data.shape[1] != 3 or bs is None:
+            return None
+        sampler = getattr(train_loader, 'sampler', None)
+        if not isinstance(getattr(train_loader, 'batch_sampler', None), BatchSampler):
+            return None
+        if isinstance(sampler, RandomSampler) and not sampler.replacement and sampler._num_samples is None:
+            shuffle, gen = True, sampler.generator
+        elif isinstance(sampler, SequentialSampler):
+            shuffle, gen = False, None
+        else:
+            return None
+        if gen is not None:
+            return None
+        return data, int(bs), shuffle, bool(train_loader.drop_last), train_loader.generator
+
+    def fit(self, train_loader):
+        self._check_loss_type()
+        opt = self._optimizer_name()
+        self._begin_fit(opt)
+        plan = self._loader_plan(train_loader)
+        last_loss = 0.
+        for epoch in range(1, self.epochs + 1):
+            self.train()
+            if plan is not None:
+                current_loss = self._fit_epoch_bulk(plan, epoch)
+            else:
+                current_loss = self._fit_epoch_generic(train_loader, epoch)
+            self.eval()
+            delta_loss = float(current_loss - last_loss)
+            if (abs(delta_loss) < 1e-5) and self.early_stop:
+                self.logger.info('Satisfy early stop mechanism')
+                break
+            else:
+                last_loss = current_loss
+
+    def _fit_epoch_bulk(self, plan, epoch):
+        data, bs, shuffle, drop_last, gen = plan
+        T = data.shape[0]
+        d_triples = getattr(data, '_drb_device', None)
+        if d_triples is None or d_triples.device != self.device:
+            if getattr(self, '_triples_key', None) != (id(data), T):
+                self._triples_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.int32)).to(self.device)
+                self._triples_key = (id(data), T)
+            d_triples = self._triples_dev
+        perm = epoch_permutation(T, shuffle, gen)
+        d_perm = None if perm is None else perm.to(self.device, non_blocking=False)
+        bu, bi, bj = ops.gather_triples(d_triples, d_perm)
+        n_use = (T // bs) * bs if drop_last else T
+        nsteps = (n_use + bs - 1) // bs
+        if n_use != T:
+            bu, bi, bj = bu[:n_use], bi[:n_use], bj[:n_use]
+        chunk = self.steps_per_launch if self.steps_per_launch > 0 else nsteps
+        pbar = tqdm(total=nsteps, disable=not self.show_progress)
+        pbar.set_description(f'[Epoch {epoch:03d}]')
+        current_loss = 0.
+        for first in range(0, nsteps, chunk):
+            k = min(chunk, nsteps - first)
+            losses = self._train_steps(bu, bi, bj, bs, first, k)           # raises ValueError on NaN
+            current_loss += float(losses.sum().item())
+            pbar.update(k)
+        pbar.set_postfix(loss=current_loss)
+        pbar.close()
+        return current_loss
+
+    def _fit_epoch_generic(self, train_loader, epoch):
+        """Any other iterable of (user, pos, neg) batches: one end-to-end step per batch."""
+        current_loss = 0.
+        pbar = tqdm(train_loader, disable=not self.show_progress)
+        pbar.set_description(f'[Epoch {epoch:03d}]')
+        for batch in pbar:
+            current_loss += self.train_step(batch)
+        pbar.set_postfix(loss=current_loss)
+        return current_loss

@@ -1,0 +1,155 @@
+"""BPR-MF on the B200 path, with the reference's class name, config keys and methods
+(daisy/model/MFRecommender.py:25-133).
+
+No nn.Embedding, no autograd, no torch.optim: the two factor tables are raw fp32 device tensors
+(still reachable as ``embed_user.weight`` / ``embed_item.weight``) and every method forwards to
+hand-written CUDA through the C ABI (include/daisyrec_b200.h):
+
+    fit        -> drb_gather_triples + drb_mf_bpr_train_steps   (one persistent launch per epoch)
+    calc_loss  -> drb_mf_bpr_loss
+    train_step -> drb_mf_bpr_train_step_host                     (host batch in, loss out)
+    rank       -> drb_mf_rank        full_rank -> drb_mf_full_rank        predict -> drb_mf_predict
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from .AbstractRecommender import GeneralRecommender, _Table, _init_table, _INIT
+
+
+class MF(GeneralRecommender):
+    def __init__(self, config):
+        """Same keys as the reference (MFRecommender.py:46-59): lr, reg_1, reg_2, epochs, topk,
+        user_num, item_num, factors, loss_type, optimizer, init_method, early_stop (+ gpu, logger)."""
+        super().__init__(config)
+        self.lr = config['lr']
+        self.reg_1 = config['reg_1']
+        self.reg_2 = config['reg_2']
+        self.epochs = config['epochs']
+        self.topk = config['topk']
+        self.user_num, self.item_num, self.factors = config['user_num'], config['item_num'], config['factors']
+
+        self.loss_type = config['loss_type']
+        self.optimizer = config['optimizer'] if config['optimizer'] != 'default' else 'sgd'
+        self.initializer = config['init_method'] if config['init_method'] != 'default' else 'normal'
+        self.early_stop = config['early_stop']
+
+        # Same CPU RNG consumption as the reference: two nn.Embedding constructors (N(0,1) each),
+        # then self.apply(_init_weight) over embed_user, embed_item (AbstractRecommender.py:69-77).
+        wu = _init_table(self.user_num, self.factors, None)
+        wi = _init_table(self.item_num, self.factors, None)
+        _INIT[self.initializer](wu)
+        _INIT[self.initializer](wi)
+        self.embed_user = _Table(wu.to(self.device))
+        self.embed_item = _Table(wi.to(self.device))
+        self._ws = None
+        self._opt_steps = 0
+        self._stage = None
+
+    # ------------------------------------------------------------------ plumbing
+    def parameters(self):
+        return [self.embed_user.weight, self.embed_item.weight]
+
+    def state_dict(self):
+        return {'embed_user.weight': self.embed_user.weight, 'embed_item.weight': self.embed_item.weight}
+
+    def load_state_dict(self, sd):
+        self.embed_user.weight.copy_(sd['embed_user.weight'])
+        self.embed_item.weight.copy_(sd['embed_item.weight'])
+
+    def to(self, device):
+        return self
+
+    def _hyper(self, opt=None):
+        return ops.hyper(self.lr, self.reg_1, self.reg_2, opt or self._optimizer_name())
+
+    def _begin_fit(self, opt):
+        """fit() builds a fresh optimizer (AbstractRecommender.py:105): fresh Adam moments / step count."""
+        self._ws = ops.MFWorkspace(self.user_num, self.item_num, self.factors, opt, self.device)
+        self._opt_steps = 0
+        self._hp = self._hyper(opt)
+
+    def _ensure_ws(self):
+        if self._ws is None:
+            self._begin_fit(self._optimizer_name())
+
+    def _train_steps(self, bu, bi, bj, batch, first, n_steps):
+        losses = ops.mf_bpr_train_steps(self.embed_user.weight, self.embed_item.weight, self._ws, bu, bi, bj, batch,
+                                        first, n_steps, self._hp, adam_step0=self._opt_steps)
+        self._opt_steps += n_steps
+        return losses
+
+    @staticmethod
+    def _host_i32(x):
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+        return np.ascontiguousarray(x, dtype=np.int32)
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, user, item):
+        """MFRecommender.py:63-68: pred = (P[user] * Q[item]).sum(-1) for index tensors."""
+        u = torch.as_tensor(user).to(self.device, torch.int32).reshape(-1).contiguous()
+        i = torch.as_tensor(item).to(self.device, torch.int32).reshape(-1).contiguous()
+        return ops.mf_predict(self.embed_user.weight, self.embed_item.weight, u, i)
+
+    __call__ = forward
+
+    def calc_loss(self, batch):
+        """MFRecommender.py:70-97 (BPR branch): 0-d fp32 loss of one (user, pos, neg) batch; no update."""
+        self._check_loss_type()
+        self._ensure_ws()
+        bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
+        loss = ops.mf_bpr_loss(self.embed_user.weight, self.embed_item.weight, self._ws, bu, bi, bj, self._hp)
+        return loss.to(torch.float32).reshape(())
+
+    def train_step(self, batch):
+        """zero_grad + calc_loss + backward + optimizer.step on one HOST batch
+        (AbstractRecommender.py:119-128); returns loss.item()."""
+        self._check_loss_type()
+        self._ensure_ws()
+        hb = [self._host_i32(b) for b in batch[:3]]
+        n = len(hb[0])
+        if self._stage is None or self._stage.numel() < 3 * ((n + 3) // 4 * 4) + 4:
+            self._stage = ops.stage_buffer(n, self.device)
+        loss = ops.mf_bpr_train_step_host(self.embed_user.weight, self.embed_item.weight, self._ws, hb[0], hb[1], hb[2],
+                                          self._hp, self._stage, adam_step0=self._opt_steps)
+        self._opt_steps += 1
+        return loss
+
+    def predict(self, u, i):
+        """MFRecommender.py:99-104 -> python float."""
+        return float(self.forward([u], [i]).item())
+
+    def rank(self, test_loader):
+        """MFRecommender.py:106-123 -> float32 ndarray [n_test_users, topk], rows in loader order."""
+        ds = getattr(test_loader, 'dataset', None)
+        data = getattr(ds, 'data', None)
+        if isinstance(data, (list, tuple)) and len(data) and len(data[0]) == 2:
+            users = np.fromiter((int(r[0]) for r in data), np.int64, len(data))
+            cands = np.stack([np.asarray(r[1], dtype=np.int64) for r in data])
+        else:                                                   # any iterable of (us, cands_ids) batches
+            us, cs = [], []
+            for b_us, b_c in test_loader:
+                us.append(torch.as_tensor(b_us).reshape(-1).to(torch.int64))
+                cs.append(torch.as_tensor(b_c).to(torch.int64).reshape(us[-1].numel(), -1))
+            if not us:
+                return np.zeros((0,), np.float32)
+            users, cands = torch.cat(us).numpy(), torch.cat(cs).numpy()
+        if len(users) == 0:
+            return np.zeros((0,), np.float32)
+        k = min(self.topk, cands.shape[1])
+        out = ops.mf_rank(self.embed_user.weight, self.embed_item.weight,
+                          torch.from_numpy(users).to(self.device), torch.from_numpy(np.ascontiguousarray(cands)).to(self.device), k)
+        return out.cpu().numpy()
+
+    def full_rank(self, u):
+        """MFRecommender.py:126-133 -> int64 ndarray [topk]; no masking of train items."""
+        users = torch.tensor([int(u)], dtype=torch.int64, device=self.device)
+        k = min(self.topk, self.item_num)
+        return ops.mf_full_rank(self.embed_user.weight, self.embed_item.weight, users, k)[0].cpu().numpy()
+
+    def full_rank_users(self, users):
+        """Batched full_rank (B200 extension): int64 ndarray [len(users), topk]."""
+        users = torch.as_tensor(np.asarray(users, dtype=np.int64)).to(self.device)
+        k = min(self.topk, self.item_num)
+        return ops.mf_full_rank(self.embed_user.weight, self.embed_item.weight, users, k).cpu().numpy()

@@ -56,7 +56,9 @@ def mt19937_from_numpy(rs=None):
 
 
 def mt19937_to_numpy(st, rs=None):
-    (np.random if rs is None else rs).set_state(("MT19937", st[:624].copy(), int(st[624]), 0, 0.0))
+    tgt = np.random if rs is None else rs
+    old = tgt.get_state()
+    tgt.set_state(("MT19937", st[:624].copy(), int(st[624]), old[3], old[4]))
 
 
 def sampler_draw_mt19937(state, row_ptr, user_num, item_num, num_ng):
@@ -114,6 +116,29 @@ def sample_triples_host(state, row_ptr, col, coo_u, coo_i, user_num, item_num, n
         raise ValueError("'a' cannot be empty unless no samples are taken")
     L.check(rc)
     return js, tr
+
+
+def bounded_draws_mt19937(state, n, offsets):
+    """Host: row m draws offsets[m+1]-offsets[m] values from [0, n[m]) off numpy's MT19937 stream."""
+    n = np.ascontiguousarray(n, np.int64)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    draws = np.empty(int(offsets[-1]), np.int32)
+    bad = C.c_int64(-1)
+    rc = L.lib().drb_bounded_draws_mt19937(state.ctypes.data, n.ctypes.data, offsets.ctypes.data, len(n),
+                                           draws.ctypes.data, C.byref(bad))
+    if rc == L.DRB_ERR_EMPTY_SET:
+        raise ValueError("'a' cannot be empty unless no samples are taken")
+    L.check(rc)
+    return draws
+
+
+def kth_complement_var(d_row_ptr, d_col, d_offsets, d_draws):
+    _dev(d_row_ptr, torch.int64, "row_ptr"); _dev(d_col, torch.int32, "col")
+    _dev(d_offsets, torch.int64, "offsets"); _dev(d_draws, torch.int32, "draws")
+    out = torch.empty_like(d_draws)
+    L.check(L.lib().drb_kth_complement_var(_ptr(d_row_ptr), _ptr(d_col), _ptr(d_offsets), _ptr(d_draws),
+                                           d_row_ptr.numel() - 1, _ptr(out), _stream()))
+    return out
 
 
 # ------------------------------------------------------------------ train feed

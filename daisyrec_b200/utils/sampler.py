@@ -1,0 +1,92 @@
+"""Pair-wise negative sampler with the reference's class name and config keys
+(daisy/utils/sampler.py:3-103), computed on the device through the C ABI.
+
+Reference semantics kept bit for bit in the uniform + pair-wise branch: per USER, ``num_ng``
+draws (with replacement) from the sorted complement of the user's train positives, using numpy's
+global legacy RandomState; every positive row is then paired with its user's negatives
+(``explode``).  The global numpy RNG is advanced exactly as the reference would advance it.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class TripleArray(np.ndarray):
+    """int32 [T,3] host array that remembers its device twin (saves fit() a 12*T-byte H2D)."""
+    _drb_device = None
+
+    def __array_finalize__(self, obj):
+        self._drb_device = None
+
+
+def csr_from_ur(ur, user_num):
+    """config['train_ur'] (dict[int -> set[int]], daisy/utils/utils.py:19-34) -> sorted CSR."""
+    lens = np.fromiter((len(ur[u]) if u in ur else 0 for u in range(user_num)), np.int64, user_num)
+    row_ptr = np.zeros(user_num + 1, np.int64)
+    np.cumsum(lens, out=row_ptr[1:])
+    total = int(row_ptr[-1])
+    col = np.fromiter((i for u in range(user_num) if u in ur for i in ur[u]), np.int64, total)
+    key = np.repeat(np.arange(user_num, dtype=np.int64), lens) * (1 << 32) + col
+    key.sort()
+    return row_ptr, (key & 0xFFFFFFFF).astype(np.int32)
+
+
+class AbstractSampler(object):
+    def __init__(self, config):
+        self.uid_name = config['UID_NAME']
+        self.iid_name = config['IID_NAME']
+        self.item_num = config['item_num']
+        self.ur = config['train_ur']
+
+    def sampling(self):
+        raise NotImplementedError
+
+
+class BasicNegtiveSampler(AbstractSampler):
+    def __init__(self, df, config):
+        super().__init__(config)
+        self.user_num = config['user_num']
+        self.num_ng = config['num_ng']
+        self.inter_name = config['INTER_NAME']
+        self.sample_method = config['sample_method']
+        self.sample_ratio = config['sample_ratio']
+        self.loss_type = config['loss_type'].upper()
+        # optional B200 keys (absent == reference behaviour)
+        self.rng_engine = config.get('sampler_rng', 'numpy')       # 'numpy' (MT19937 replay) | 'philox'
+        self.csr = config.get('train_csr', None)                   # (row_ptr int64, col int32) to skip the dict walk
+
+        assert self.sample_method in ['uniform', 'low-pop', 'high-pop'], f'Invalid sampling method: {self.sample_method}'
+        assert 0 <= self.sample_ratio <= 1, 'Invalid sample ratio value'
+        self.df = df
+
+    def sampling(self):
+        if self.num_ng == 0:
+            raise NotImplementedError('loss function (BPR, TL, HL) need num_ng > 0')
+        if self.sample_method != 'uniform' or self.loss_type not in ('BPR', 'HL', 'TL'):
+            raise NotImplementedError(
+                'daisyrec_b200 accelerates the uniform pair-wise branch (sampler.py:84-89,99-101); '
+                f'sample_method={self.sample_method!r} / loss_type={self.loss_type!r} is outside the B200 hot path')
+        ops.require_cuda()
+        U, I, G = self.user_num, self.item_num, self.num_ng
+        row_ptr, col = self.csr if self.csr is not None else csr_from_ur(self.ur, U)
+        coo_u = np.ascontiguousarray(self.df[self.uid_name].values, dtype=np.int32)
+        coo_i = np.ascontiguousarray(self.df[self.iid_name].values, dtype=np.int32)
+        d_row_ptr = torch.from_numpy(np.ascontiguousarray(row_ptr, np.int64)).cuda()
+        d_col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).cuda()
+        if self.rng_engine == 'numpy':
+            state = ops.mt19937_from_numpy()
+            draws = ops.sampler_draw_mt19937(state, row_ptr, U, I, G)         # host: sequential MT19937 words
+            ops.mt19937_to_numpy(state)                                       # numpy's stream moves on as in the reference
+            d_draws = torch.from_numpy(draws).cuda()
+        else:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            d_draws, bad = ops.sampler_draw_philox(seed, 0, d_row_ptr, U, I, G)
+            if int(bad.item()) < U:
+                raise ValueError("'a' cannot be empty unless no samples are taken")
+        d_js = ops.sampler_kth_complement(d_row_ptr, d_col, d_draws, I)
+        d_tr = ops.sampler_explode(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
+        self.js = d_js
+        out = d_tr.cpu().numpy().view(TripleArray)
+        out._drb_device = d_tr
+        return out

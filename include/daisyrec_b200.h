@@ -80,6 +80,17 @@ int drb_sample_triples_host(uint32_t *h_state625, const int64_t *h_row_ptr, cons
                             const int32_t *h_coo_u, const int32_t *h_coo_i, int64_t nnz, int32_t user_num,
                             int32_t item_num, int32_t num_ng, int32_t *h_js, int32_t *h_triples, int32_t *bad_user);
 
+/* ---- candidate sets for ranking: build_candidates_set ------------------------------------
+ * daisy/utils/utils.py:53-85.  Per test user the reference draws cand_num-|gt| ids from the
+ * complement of gt + train positives (or, when |gt| >= cand_num, cand_num ids from gt itself).
+ * Generic form: row m draws offsets[m+1]-offsets[m] values uniformly from [0, n[m]) off numpy's
+ * MT19937 stream (host, sequential); the complement lookup runs on the device over the CSR of
+ * each row's excluded ids (one warp per row). */
+int drb_bounded_draws_mt19937(uint32_t *h_state625, const int64_t *h_n, const int64_t *h_offsets, int64_t rows,
+                              int32_t *h_draws, int64_t *bad_row);
+int drb_kth_complement_var(const int64_t *d_row_ptr, const int32_t *d_col, const int64_t *d_offsets,
+                           const int32_t *d_draws, int64_t rows, int32_t *d_out, void *stream);
+
 /* ---- pair-wise train feed: BasicDataset + DataLoader(shuffle=True) ------------------
  * daisy/utils/dataset.py:5-27.  Gathers the epoch's permuted triples into the SoA batch
  * arrays the step kernel streams with TMA: b?[k] = triples[perm[k], ?] (perm NULL = identity). */

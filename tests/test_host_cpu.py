@@ -1,0 +1,117 @@
+"""CPU suite for the host side: the C-ABI library loads and exports every symbol the header declares
+(no compute calls without a GPU), host-only entry points (MT19937 seeding / bounded draws) match
+numpy, the DataLoader permutation protocol, the init stream, and loud failure without a device.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden, csr_from_coo
+
+
+def test_library_exports_every_header_symbol():
+    from daisyrec_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "daisyrec_b200.h")).read()
+    declared = set(re.findall(r"\b(drb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = C.CDLL(_lib.so_path()) if os.path.exists(_lib.so_path()) else _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().drb_version() >= 100
+
+
+def test_host_mt19937_entry_points_match_numpy():
+    from daisyrec_b200 import ops
+    for seed in (0, 2022, 2 ** 32 - 1):
+        st = ops.mt19937_seed(seed)
+        assert np.array_equal(st, ops.mt19937_from_numpy(np.random.RandomState(seed)))
+    # per-user bounded draws == np.random.choice(arange(n), size=G) user after user
+    U, I, G = 40, 50, 4
+    rng = np.random.default_rng(1)
+    deg = rng.integers(0, 49, size=U)
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    st = ops.mt19937_seed(5)
+    draws = ops.sampler_draw_mt19937(st, row_ptr, U, I, G)
+    np.random.seed(5)
+    want = np.stack([np.random.choice(np.arange(I - d), size=G) for d in deg])
+    assert np.array_equal(draws, want)
+    assert np.array_equal(st, ops.mt19937_from_numpy())
+    # variable-count form used by build_candidates_set
+    n = np.array([7, 1, 1000, 33], np.int64)
+    off = np.array([0, 5, 9, 9, 20], np.int64)
+    st = ops.mt19937_seed(9)
+    d = ops.bounded_draws_mt19937(st, n, off)
+    np.random.seed(9)
+    want = np.concatenate([np.random.choice(np.arange(n[k]), size=off[k + 1] - off[k]) for k in range(4)])
+    assert np.array_equal(d, want)
+    with pytest.raises(ValueError):
+        ops.sampler_draw_mt19937(ops.mt19937_seed(1), np.array([0, 3], np.int64), 1, 3, 2)
+
+
+def test_epoch_permutation_is_the_dataloaders():
+    from torch.utils.data import DataLoader, TensorDataset
+    from daisyrec_b200.model.AbstractRecommender import epoch_permutation
+    n = 1000
+    ds = TensorDataset(torch.arange(n))
+    for shuffle in (True, False):
+        torch.manual_seed(3)
+        loader = DataLoader(ds, batch_size=64, shuffle=shuffle)
+        want = [torch.cat([b[0] for b in loader]) for _ in range(2)]          # two epochs
+        torch.manual_seed(3)
+        for e in range(2):
+            p = epoch_permutation(n, shuffle)
+            got = torch.arange(n) if p is None else p
+            assert torch.equal(got, want[e])
+    g = golden("ml100k_fit")
+    torch.set_rng_state(torch.from_numpy(g["torch_state"]))
+    assert np.array_equal(epoch_permutation(313452, True).numpy().astype(np.int32), g["perm"])
+
+
+def test_init_stream_matches_reference():
+    from daisyrec_b200.model.AbstractRecommender import _init_table, _INIT
+    g = golden("ml100k_fit")
+    torch.manual_seed(2022)
+    wu, wi = _init_table(943, 32, None), _init_table(1152, 32, None)
+    _INIT['normal'](wu); _INIT['normal'](wi)
+    assert np.array_equal(wu.numpy(), g["P0"]) and np.array_equal(wi.numpy(), g["Q0"])
+
+
+def test_csr_from_ur_and_get_ur():
+    import pandas as pd
+    from daisyrec_b200.utils.sampler import csr_from_ur
+    from daisyrec_b200.utils.utils import get_ur
+    rng = np.random.default_rng(0)
+    df = pd.DataFrame({"user": rng.integers(30, size=400), "item": rng.integers(50, size=400)})
+    ur = get_ur(df)
+    ref = {}
+    for u, i in zip(df["user"], df["item"]):
+        ref.setdefault(int(u), set()).add(int(i))
+    assert dict(ur) == ref and list(ur.keys()) == list(ref.keys())
+    row_ptr, col = csr_from_ur(ur, 30)
+    rp2, col2 = csr_from_coo(df["user"].values.astype(np.int32), df["item"].values.astype(np.int32), 30)
+    assert np.array_equal(row_ptr, rp2) and np.array_equal(col, col2)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_silent_cpu_fallback():
+    import logging
+    from daisyrec_b200.model.MFRecommender import MF
+    cfg = dict(gpu='', logger=logging.getLogger(), lr=.01, reg_1=0, reg_2=0, epochs=1, topk=5, user_num=4, item_num=4,
+               factors=8, loss_type='BPR', optimizer='default', init_method='default', early_stop=False)
+    with pytest.raises(RuntimeError):
+        MF(cfg)
+
+
+def test_synthetic_generator_shape():
+    from daisyrec_b200.utils.synthetic import make_interactions
+    d = make_interactions(2000, 1500, 60000, seed=1)
+    assert d["nnz"] == 60000 == int(d["row_ptr"][-1])
+    key = d["coo_u"].to(torch.int64) * 1500 + d["coo_i"]
+    assert torch.unique(key).numel() == 60000                         # unique pairs
+    deg = d["row_ptr"][1:] - d["row_ptr"][:-1]
+    assert int(deg.min()) >= 1
