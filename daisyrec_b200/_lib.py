@@ -58,7 +58,8 @@ SIGNATURES = {
 
 
 def so_path():
-    return _build.SO
+    # DRB_LIB_PATH: developer override used by scripts/tune_variants.sh to A/B kernel builds
+    return os.environ.get("DRB_LIB_PATH") or _build.SO
 
 
 def lib():

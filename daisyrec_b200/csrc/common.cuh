@@ -111,6 +111,15 @@ __device__ __forceinline__ void red_row(float *p, const Vec<VEC> &r)
     }
 }
 
+__device__ __forceinline__ void red_add_u32(unsigned *p, unsigned v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // xor-butterfly sum over the W lanes of a group (W consecutive lanes, W | 32)
 template <int W>
 __device__ __forceinline__ float group_sum(float x)

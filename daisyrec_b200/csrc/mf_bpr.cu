@@ -32,6 +32,12 @@ namespace drb {
 
 constexpr int kThreads = 256;
 constexpr int kTileMax = 512;  // triples per staged index tile
+#ifndef DRB_MINB
+#define DRB_MINB 2             // resident CTAs per SM the register allocator must allow
+#endif
+#ifndef DRB_UNR
+#define DRB_UNR 2              // triples in flight per lane group (memory-level parallelism)
+#endif
 
 struct WsHeader {
     unsigned long long barrier;  // grid barrier ticket counter
@@ -157,12 +163,99 @@ __device__ __forceinline__ void apply_row(float *theta_row, float *g_row, float 
     }
 }
 
+// Dense phase-2 sweep: lane groups walk ALL rows of P then Q, R rows in flight each.  Counter, theta
+// and gradient accumulator of the R rows are loaded unconditionally and up front (one memory round
+// trip instead of three dependent ones); an untouched SGD row has cnt == 0 and g == 0, so nothing is
+// written for it.  Adam moves every row (dense optimiser semantics of the reference).
+template <int VEC, int W, int NCH, int OPT>
+__device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm, const AdamCoef &ac, int gl, int group,
+                                            int groups_per_cta, int chunks)
+{
+    constexpr int R = (OPT == DRB_OPT_SGD) ? ((NCH * VEC <= 4) ? 4 : 2) : ((NCH * VEC <= 4) ? 2 : 1);
+    const long long rows = (long long)p.U + p.I;
+    const long long tg = (long long)gridDim.x * groups_per_cta;
+    const int F = p.F;
+    for (long long r0 = (long long)blockIdx.x * groups_per_cta + group; r0 < rows; r0 += tg * R) {
+        float *th_p[R], *g_p[R], *m_p[R], *v_p[R];
+        unsigned long long cnt[R];
+        bool act[R], is_user[R];
+        Row<VEC, W, NCH> th[R], g[R], m[R], v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            long long r = r0 + (long long)k * tg;
+            act[k] = r < rows;
+            is_user[k] = r < p.U;
+            long long it = is_user[k] ? r : r - p.U;
+            size_t o = (size_t)(act[k] ? it : 0) * F;
+            th_p[k] = (is_user[k] ? p.P : p.Q) + o;
+            g_p[k] = (is_user[k] ? p.ws.gP : p.ws.gQ) + o;
+            cnt[k] = 0;
+            if (act[k]) cnt[k] = is_user[k] ? (unsigned long long)__ldcg(p.ws.cntU + it) : __ldcg(p.ws.cntI + it);
+            th[k] = load_row<VEC, W, NCH>(th_p[k], gl, chunks, act[k]);
+            g[k] = load_row<VEC, W, NCH>(g_p[k], gl, chunks, act[k]);
+            if constexpr (OPT == DRB_OPT_ADAM) {
+                m_p[k] = (is_user[k] ? p.ws.mP : p.ws.mQ) + o;
+                v_p[k] = (is_user[k] ? p.ws.vP : p.ws.vQ) + o;
+                m[k] = load_row<VEC, W, NCH>(m_p[k], gl, chunks, act[k]);
+                v[k] = load_row<VEC, W, NCH>(v_p[k], gl, chunks, act[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const bool touched = cnt[k] != 0;
+            if (!act[k] || (OPT == DRB_OPT_SGD && !touched)) continue;
+            const float ca = (float)(unsigned)(cnt[k] & 0xffffffffull), cb = (float)(unsigned)(cnt[k] >> 32);
+            const float ia = is_user[k] ? nm.inv_u : nm.inv_i, ib = nm.inv_j;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                int c = gl + ch * W;
+                if (c >= chunks) continue;
+                Vec<VEC> &t = th[k].c[ch];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    float x = t.v[e], gg = g[k].c[ch].v[e];
+                    if (touched) {
+                        float sg = p.reg1 * sgnf(x);
+                        gg += ca * (sg + p.reg2 * x * ia) + cb * (sg + p.reg2 * x * ib);
+                    }
+                    if constexpr (OPT == DRB_OPT_SGD) {
+                        t.v[e] = x - p.lr * gg;
+                    } else {
+                        float mm = m[k].c[ch].v[e], vv = v[k].c[ch].v[e];
+                        mm = mm + (gg - mm) * (1.f - p.beta1);
+                        vv = vv * p.beta2 + (1.f - p.beta2) * gg * gg;
+                        float denom = sqrtf(vv) / ac.bc2_sqrt + p.eps;
+                        t.v[e] = x - ac.step_size * (mm / denom);
+                        m[k].c[ch].v[e] = mm;
+                        v[k].c[ch].v[e] = vv;
+                    }
+                }
+                st_row<VEC>(th_p[k] + c * VEC, t);
+                if constexpr (OPT == DRB_OPT_ADAM) {
+                    st_row<VEC>(m_p[k] + c * VEC, m[k].c[ch]);
+                    st_row<VEC>(v_p[k] + c * VEC, v[k].c[ch]);
+                }
+                if (touched) {
+                    Vec<VEC> z;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) z.v[e] = 0.f;
+                    st_row<VEC>(g_p[k] + c * VEC, z);
+                }
+            }
+            if (touched && gl == 0) {
+                long long r = r0 + (long long)k * tg;
+                if (is_user[k]) p.ws.cntU[r] = 0u; else p.ws.cntI[r - p.U] = 0ull;
+            }
+        }
+    }
+}
+
 template <int VEC, int W, int NCH>
-__global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
+__global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepParams p)
 {
     constexpr int GPW = 32 / W;                  // lane groups per warp
     constexpr int GROUPS = (kThreads / 32) * GPW;  // lane groups per CTA
-    constexpr int UNR = (NCH * VEC <= 4) ? 2 : 1;  // triples in flight per group
+    constexpr int UNR = (NCH * VEC <= 4) ? DRB_UNR : 1;  // triples in flight per group
 
     __shared__ __align__(128) int32_t s_idx[2][3][kTileMax];
     __shared__ uint64_t s_bar[2];
@@ -217,7 +310,8 @@ __global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
         const bool has_reg = (p.reg1 != 0.f) || (p.reg2 != 0.f);
 
         // ------------------------------------------------------------ phase 1
-        double a_loss = 0, a_l1u = 0, a_l1i = 0, a_l1j = 0, a_s2u = 0, a_s2i = 0, a_s2j = 0;
+        if (tid < 8 * (kThreads / 32)) (&s_red[0][0])[tid] = 0.0;   // per-warp fp64 accumulators of this step
+        __syncthreads();
         int buf = 0;
         long long t_i = blockIdx.x;
         if (t_i < ntiles) stage(base + t_i * tile, (int)min((long long)tile, nb - t_i * tile), 0);
@@ -227,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
             if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1; } else { mbar_wait(&s_bar[1], par1); par1 ^= 1; }
             const int cnt = (int)min((long long)tile, nb - t_i * tile);
             const int32_t *xu = s_idx[buf][0], *xi = s_idx[buf][1], *xj = s_idx[buf][2];
+            float t_loss = 0.f, t_l1u = 0.f, t_l1i = 0.f, t_l1j = 0.f, t_s2u = 0.f, t_s2i = 0.f, t_s2j = 0.f;
 
             for (int tb = 0; tb < cnt; tb += GROUPS * UNR) {
                 Row<VEC, W, NCH> rp[UNR], rqi[UNR], rqj[UNR];
@@ -250,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
                     if (!ok[r]) continue;
                     float x = pos - neg;
                     float sg = 1.f / (1.f + expf(-x));
-                    if (gl == 0) a_loss += (double)(-logf(1e-10f + sg));
+                    if (gl == 0) t_loss += -logf(1e-10f + sg);
                     float c = -(sg * (1.f - sg)) / (1e-10f + sg);
                     if (has_reg) {
                         float l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
@@ -263,8 +358,8 @@ __global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
                                 l1i += fabsf(b); s2i = fmaf(b, b, s2i);
                                 l1j += fabsf(d); s2j = fmaf(d, d, s2j);
                             }
-                        a_l1u += l1u; a_l1i += l1i; a_l1j += l1j;
-                        a_s2u += s2u; a_s2i += s2i; a_s2j += s2j;
+                        t_l1u += l1u; t_l1i += l1i; t_l1j += l1j;
+                        t_s2u += s2u; t_s2i += s2i; t_s2j += s2j;
                     }
                     if (p.apply) {
 #pragma unroll
@@ -283,30 +378,33 @@ __global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
                             red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
                         }
                         if (gl == 0) {
-                            atomicAdd(p.ws.cntU + iu[r], 1u);
-                            atomicAdd(p.ws.cntI + ii[r], 1ull);
-                            atomicAdd(p.ws.cntI + ij[r], 1ull << 32);
+                            red_add_u32(p.ws.cntU + iu[r], 1u);
+                            red_add_u64(p.ws.cntI + ii[r], 1ull);
+                            red_add_u64(p.ws.cntI + ij[r], 1ull << 32);
                         }
                     }
+                }
+            }
+            // per-thread fp32 partials cover <= tile/GROUPS triples: warp-reduce, widen to fp64 in smem
+            {
+                float tv[7] = {t_loss, t_l1u, t_l1i, t_l1j, t_s2u, t_s2i, t_s2j};
+                const int nv = has_reg ? 7 : 1;
+                for (int k = 0; k < nv; ++k) {
+                    float v = tv[k];
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if (lane == 0) s_red[k][warp] += (double)v;
                 }
             }
             __syncthreads();  // tile buffer free for re-staging
             buf ^= 1;
         }
         // CTA reduction of the 7 partial sums -> one fp64 atomic each
-        {
-            double vals[7] = {a_loss, a_l1u, a_l1i, a_l1j, a_s2u, a_s2i, a_s2j};
-            const int nv = has_reg ? 7 : 1;
-            for (int k = 0; k < nv; ++k) {
-                double v = warp_sum(vals[k]);
-                if (lane == 0) s_red[k][warp] = v;
-            }
-            __syncthreads();
-            if (tid < nv) {
-                double v = 0;
-                for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
-                if (v != 0.0) atomicAdd(&acc[tid], v);
-            }
+        __syncthreads();
+        if (tid < (has_reg ? 7 : 1)) {
+            double v = 0;
+            for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
+            if (v != 0.0) atomicAdd(&acc[tid], v);
         }
         grid_barrier(&hdr->barrier, epoch);
 
@@ -347,36 +445,10 @@ __global__ void __launch_bounds__(kThreads, 2) mf_bpr_steps_kernel(StepParams p)
             }
             const bool dense = (p.opt == DRB_OPT_ADAM) || (3 * nb >= ((long long)p.U + p.I) / 4);
             if (dense) {
-                const long long rows = (long long)p.U + p.I;
-                for (long long r = (long long)blockIdx.x * GROUPS + group; r < rows; r += (long long)gridDim.x * GROUPS) {
-                    if (r < p.U) {
-                        unsigned c = __ldcg(p.ws.cntU + r);
-                        if (c != 0 || p.opt == DRB_OPT_ADAM) {
-                            size_t o = (size_t)r * F;
-                            if (p.opt == DRB_OPT_SGD)
-                                apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.P + o, p.ws.gP + o, nullptr, nullptr, gl, chunks,
-                                                                    (float)c, nm.inv_u, 0.f, 0.f, p, ac, true);
-                            else
-                                apply_row<VEC, W, NCH, DRB_OPT_ADAM>(p.P + o, p.ws.gP + o, p.ws.mP + o, p.ws.vP + o, gl,
-                                                                     chunks, (float)c, nm.inv_u, 0.f, 0.f, p, ac, c != 0);
-                            if (gl == 0 && c != 0) p.ws.cntU[r] = 0u;
-                        }
-                    } else {
-                        long long it = r - p.U;
-                        unsigned long long c = __ldcg(p.ws.cntI + it);
-                        if (c != 0 || p.opt == DRB_OPT_ADAM) {
-                            size_t o = (size_t)it * F;
-                            float cp = (float)(unsigned)(c & 0xffffffffull), cn = (float)(unsigned)(c >> 32);
-                            if (p.opt == DRB_OPT_SGD)
-                                apply_row<VEC, W, NCH, DRB_OPT_SGD>(p.Q + o, p.ws.gQ + o, nullptr, nullptr, gl, chunks, cp,
-                                                                    nm.inv_i, cn, nm.inv_j, p, ac, true);
-                            else
-                                apply_row<VEC, W, NCH, DRB_OPT_ADAM>(p.Q + o, p.ws.gQ + o, p.ws.mQ + o, p.ws.vQ + o, gl,
-                                                                     chunks, cp, nm.inv_i, cn, nm.inv_j, p, ac, c != 0);
-                            if (gl == 0 && c != 0) p.ws.cntI[it] = 0ull;
-                        }
-                    }
-                }
+                if (p.opt == DRB_OPT_SGD)
+                    dense_sweep<VEC, W, NCH, DRB_OPT_SGD>(p, nm, ac, gl, group, GROUPS, chunks);
+                else
+                    dense_sweep<VEC, W, NCH, DRB_OPT_ADAM>(p, nm, ac, gl, group, GROUPS, chunks);
             } else {
                 // claim mode (SGD only): the first group to swap a row's counter to zero applies it
                 for (long long t0 = (long long)blockIdx.x * tile; t0 < nb; t0 += (long long)gridDim.x * tile) {

@@ -9,7 +9,7 @@ torch.manual_seed(0)
 P = (torch.randn(U, F, device="cuda") * 0.01)
 Q = (torch.randn(I, F, device="cuda") * 0.01)
 g = torch.Generator(device="cuda"); g.manual_seed(1)
-for B in [256, 8192, 65536, 1 << 20, 1 << 22]:
+for B in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 else '256,8192,65536,1048576,4194304'.split(','))]:
     K = max(4, min(200, (1 << 25) // B))
     n = B * K
     bu = torch.randint(0, U, (n,), device="cuda", dtype=torch.int32, generator=g)
@@ -17,7 +17,7 @@ for B in [256, 8192, 65536, 1 << 20, 1 << 22]:
     r = torch.rand(n, device="cuda", generator=g)
     bi = (I * r.pow(3.0)).to(torch.int32).clamp_(0, I - 1)
     bj = torch.randint(0, I, (n,), device="cuda", dtype=torch.int32, generator=g)
-    for reg in (0.001, 0.0):
+    for reg in (0.001,):
         hp = ops.hyper(0.01, reg, reg)
         ws = ops.MFWorkspace(U, I, F, "sgd", "cuda")
         ops.mf_bpr_train_steps(P, Q, ws, bu, bi, bj, B, 0, min(K, 3), hp)

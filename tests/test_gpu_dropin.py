@@ -57,8 +57,7 @@ def test_ml100k_driver_sequence():
     preds = model.rank(test_loader)                                   # test.py:120
     assert preds.dtype == np.float32 and preds.shape == (304, 50)
     # tables differ from the reference's by fp32 noise -> compare ranking quality, not ids
-    agree = np.mean([len(set(a) & set(b)) / 50 for a, b in zip(preds, gr["preds"])])
-    assert agree > 0.98
+    assert (preds == gr["preds"]).mean() > 0.98
     # with the reference's own trained tables the ids are bit-identical
     model.load_state_dict({'embed_user.weight': torch.from_numpy(gf["P1"]).cuda(),
                            'embed_item.weight': torch.from_numpy(gf["Q1"]).cuda()})
