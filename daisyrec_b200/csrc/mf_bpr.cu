@@ -40,12 +40,13 @@ constexpr int kTileMax = 512;  // triples per staged index tile
 #endif
 
 struct WsHeader {
-    unsigned long long barrier;  // grid barrier ticket counter
-    long long nan_step;          // -1, or the step whose loss was NaN
-    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, -]
+    unsigned long long barrier;  // grid barrier ticket counter          } reset before every phase-1 launch
+    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, -]  }
+    long long nan_step;          // step whose loss was NaN               } sticky in split (multi-GPU) mode
     int status;
-    int pad[15];
+    int pad[13];
 };
+constexpr size_t kHdrResetBytes = sizeof(unsigned long long) + sizeof(double) * 16;
 static_assert(sizeof(WsHeader) <= 256, "header must fit its slot");
 
 struct Workspace {
@@ -96,6 +97,8 @@ struct StepParams {
     long long adam_step0;
     double *step_loss;
     int apply;
+    int phases;      // bit 0: phase 1 (accumulate), bit 1: phase 2 (apply); 3 = fused persistent steps
+    int dense_hint;  // -1 auto, 0 claim, 1 dense sweep (multi-GPU: always dense, counters are global)
 };
 
 // ------------------------------------------------------------------ device pieces
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
         fence_mbar_init();
     }
     __syncthreads();
+    if (*(volatile int *)&hdr->status != 0) return;   // split mode: a previous step already raised NaN
     uint32_t par0 = 0, par1 = 0;
     unsigned long long epoch = 0;
     const int tile = p.tile;
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
         const bool has_reg = (p.reg1 != 0.f) || (p.reg2 != 0.f);
 
         // ------------------------------------------------------------ phase 1
+        if (p.phases & 1) {
         if (tid < 8 * (kThreads / 32)) (&s_red[0][0])[tid] = 0.0;   // per-warp fp64 accumulators of this step
         __syncthreads();
         int buf = 0;
@@ -406,7 +411,9 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
             for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
             if (v != 0.0) atomicAdd(&acc[tid], v);
         }
-        grid_barrier(&hdr->barrier, epoch);
+        }  // phase 1
+        if (p.phases == 3) grid_barrier(&hdr->barrier, epoch);
+        if (!(p.phases & 2)) break;   // split mode: the host reduces gQ / counters / acc across ranks now
 
         // ------------------------------------------------------------ phase 2
         double bpr, l1u, l1i, l1j, s2u, s2i, s2j;
@@ -443,7 +450,8 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                 ac.step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, t)));
                 ac.bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, t));
             }
-            const bool dense = (p.opt == DRB_OPT_ADAM) || (3 * nb >= ((long long)p.U + p.I) / 4);
+            const bool dense = p.dense_hint >= 0 ? (p.dense_hint != 0)
+                                                 : ((p.opt == DRB_OPT_ADAM) || (3 * nb >= ((long long)p.U + p.I) / 4));
             if (dense) {
                 if (p.opt == DRB_OPT_SGD)
                     dense_sweep<VEC, W, NCH, DRB_OPT_SGD>(p, nm, ac, gl, group, GROUPS, chunks);
@@ -549,10 +557,11 @@ static int launch_steps(StepParams &p, cudaStream_t st)
     p.tile = tile;
     long long tiles = (p.batch + tile - 1) / tile;
     long long rows_work = ((long long)p.U + p.I + 63) / 64;
-    bool dense = (p.opt == DRB_OPT_ADAM) || (3 * p.batch >= ((long long)p.U + p.I) / 4);
+    bool dense = p.dense_hint >= 0 ? (p.dense_hint != 0)
+                                   : ((p.opt == DRB_OPT_ADAM) || (3 * p.batch >= ((long long)p.U + p.I) / 4));
     long long want_grid = (dense && p.apply) ? (tiles > rows_work ? tiles : rows_work) : tiles;
     int grid = (int)(want_grid < 1 ? 1 : (want_grid > max_grid ? max_grid : want_grid));
-    DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, sizeof(WsHeader), st));
+    if (p.phases & 1) DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, p.phases == 3 ? sizeof(WsHeader) : kHdrResetBytes, st));
     void *args[] = {&p};
     DRB_CUDA(cudaLaunchCooperativeKernel((void *)k, dim3(grid), dim3(kThreads), args, 0, st));
     return DRB_OK;
@@ -582,7 +591,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
     DRB_REQUIRE(h->opt == DRB_OPT_SGD || h->opt == DRB_OPT_ADAM, "unknown optimizer id %d", h->opt);
-    DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0, "steps [%lld,%lld) exceed %lld triples", first,
+    DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0 || n == 0, "steps [%lld,%lld) exceed %lld triples", first,
                 first + nsteps, n);
     p.P = P; p.Q = Q;
     carve(d_ws, U, I, F, h->opt, &p.ws);
@@ -594,6 +603,8 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.adam_step0 = adam_step0;
     p.step_loss = d_step_loss;
     p.apply = apply;
+    p.phases = 3;
+    p.dense_hint = -1;
     return DRB_OK;
 }
 
@@ -675,4 +686,33 @@ extern "C" int drb_gather_triples(const int32_t *d_triples, const int64_t *d_per
     gather_triples_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_triples, d_perm, n, d_bu, d_bi, d_bj);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
+}
+
+extern "C" int drb_mf_workspace_layout(int32_t U, int32_t I, int32_t F, int32_t opt, int64_t *out8)
+{
+    DRB_REQUIRE(out8 && U > 0 && I > 0 && F > 0, "workspace_layout: bad arguments");
+    Workspace w;
+    carve((void *)(uintptr_t)256, U, I, F, opt, &w);   // fake non-null base: pointers become offsets + 256
+    auto off = [](const void *p) { return (int64_t)((uintptr_t)p - 256); };
+    out8[0] = off(&w.hdr->acc[0][0]);  out8[1] = 8 * sizeof(double);
+    out8[2] = off(w.gQ);               out8[3] = (int64_t)sizeof(float) * I * F;
+    out8[4] = off(w.cntI);             out8[5] = (int64_t)sizeof(unsigned long long) * I;
+    out8[6] = off(w.gP);               out8[7] = off(w.cntU);
+    return DRB_OK;
+}
+
+extern "C" int drb_mf_bpr_phase(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F, const int32_t *d_bu,
+                                const int32_t *d_bi, const int32_t *d_bj, int64_t begin, int64_t count, int32_t phase,
+                                const drb_hyper *hyper, int64_t adam_step0, double *d_loss, void *stream)
+{
+    DRB_REQUIRE(phase == 1 || phase == 2, "mf_bpr_phase: phase must be 1 or 2");
+    DRB_REQUIRE(begin >= 0 && count >= 0, "mf_bpr_phase: bad range");
+    StepParams p;
+    // count may be 0 on a rank (its users have no triple in this global batch): phases still run (loss, sweep)
+    int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu + begin, d_bi + begin, d_bj + begin, count, count > 0 ? count : 1,
+                         0, 1, hyper, adam_step0, d_loss, 1);
+    if (rc != DRB_OK) return rc;
+    p.phases = phase;
+    p.dense_hint = 1;
+    return launch_steps(p, (cudaStream_t)stream);
 }

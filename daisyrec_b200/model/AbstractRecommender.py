@@ -128,6 +128,10 @@ class GeneralRecommender(AbstractRecommender):
         self.logger = config['logger']
         self.steps_per_launch = int(config.get('steps_per_launch', 0))   # 0 = whole epoch in one launch
         self.show_progress = bool(config.get('progress', True))
+        # one process per GPU (torchrun): user-sharded training / ranking, see daisyrec_b200/parallel.py
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank_id = dist.get_rank() if self.world > 1 else 0
 
     # subclasses provide: _tables() -> (P, Q); _hyper(); _workspace()
     def _loader_plan(self, train_loader):
@@ -158,7 +162,9 @@ class GeneralRecommender(AbstractRecommender):
         last_loss = 0.
         for epoch in range(1, self.epochs + 1):
             self.train()
-            if plan is not None:
+            if plan is not None and self.world > 1:
+                current_loss = self._fit_epoch_sharded(plan, epoch)
+            elif plan is not None:
                 current_loss = self._fit_epoch_bulk(plan, epoch)
             else:
                 current_loss = self._fit_epoch_generic(train_loader, epoch)
@@ -195,6 +201,40 @@ class GeneralRecommender(AbstractRecommender):
             losses = self._train_steps(bu, bi, bj, bs, first, k)           # raises ValueError on NaN
             current_loss += float(losses.sum().item())
             pbar.update(k)
+        pbar.set_postfix(loss=current_loss)
+        pbar.close()
+        return current_loss
+
+    def _device_triples(self, data):
+        T = data.shape[0]
+        d_triples = getattr(data, '_drb_device', None)
+        if d_triples is None or d_triples.device != self.device:
+            if getattr(self, '_triples_key', None) != (id(data), T):
+                self._triples_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.int32)).to(self.device)
+                self._triples_key = (id(data), T)
+            d_triples = self._triples_dev
+        return d_triples
+
+    def _fit_epoch_sharded(self, plan, epoch):
+        """N > 1: same global batches as the single-GPU run; this rank trains the triples of its users."""
+        data, bs, shuffle, drop_last, gen = plan
+        T = data.shape[0]
+        d_triples = self._device_triples(data)
+        trainer = self._sharded_trainer(d_triples)
+        perm = epoch_permutation(T, shuffle, gen)                  # identical on every rank (same torch seed)
+        d_perm = None if perm is None else perm.to(self.device)
+        nsteps = trainer.prepare_epoch(d_triples, d_perm, bs)
+        if drop_last and T % bs:
+            nsteps -= 1
+        pbar = tqdm(total=nsteps, disable=not self.show_progress or self.rank_id != 0)
+        pbar.set_description(f'[Epoch {epoch:03d}]')
+        losses = torch.empty(nsteps, dtype=torch.float64, device=self.device)
+        for s in range(nsteps):
+            trainer.step(s)
+            losses[s] = trainer.loss[0]
+        trainer.check_nan()
+        current_loss = float(losses.sum().item())
+        pbar.update(nsteps)
         pbar.set_postfix(loss=current_loss)
         pbar.close()
         return current_loss

@@ -40,8 +40,12 @@ class MF(GeneralRecommender):
         wi = _init_table(self.item_num, self.factors, None)
         _INIT[self.initializer](wu)
         _INIT[self.initializer](wi)
-        self.embed_user = _Table(wu.to(self.device))
         self.embed_item = _Table(wi.to(self.device))
+        if self.world > 1:
+            # user rows are sharded at fit()/rank() time, once the interaction counts are known
+            self._P_full_cpu, self.embed_user, self._bounds, self._trainer = wu, None, None, None
+        else:
+            self.embed_user = _Table(wu.to(self.device))
         self._ws = None
         self._opt_steps = 0
         self._stage = None
@@ -60,14 +64,54 @@ class MF(GeneralRecommender):
     def to(self, device):
         return self
 
+    # ------------------------------------------------------------------ multi-GPU (user-sharded P)
+    def _shard(self, bounds):
+        from ..parallel import ShardedTrainer
+        if self._bounds is not None and np.array_equal(bounds, self._bounds):
+            return
+        if self._bounds is not None:                               # re-shard: collect the current rows first
+            self._P_full_cpu = self.gather_user_table().cpu()
+        self._bounds = np.asarray(bounds, np.int64)
+        lo, hi = int(bounds[self.rank_id]), int(bounds[self.rank_id + 1])
+        self.embed_user = _Table(self._P_full_cpu[lo:hi].contiguous().to(self.device))
+        self._P_full_cpu = None
+        self._trainer = None
+
+    def _default_bounds(self):
+        from ..parallel import partition_users
+        return partition_users(np.ones(self.user_num, np.int64), self.world)
+
+    def _sharded_trainer(self, d_triples):
+        from ..parallel import ShardedTrainer, partition_users
+        if self._bounds is None:
+            w = torch.bincount(d_triples[:, 0].to(torch.int64), minlength=self.user_num).cpu().numpy()
+            self._shard(partition_users(w, self.world))
+        if self._trainer is None:
+            self._trainer = ShardedTrainer(self.embed_user.weight, self.embed_item.weight, self._bounds, self.rank_id,
+                                           self.world, self._hp, self._optimizer_name())
+        return self._trainer
+
+    def gather_user_table(self):
+        """Full [user_num, factors] user table on every rank (one all-gather of the shards)."""
+        if self.world == 1:
+            return self.embed_user.weight
+        import torch.distributed as dist
+        from ..parallel import allgather_rows
+        lo, hi = int(self._bounds[self.rank_id]), int(self._bounds[self.rank_id + 1])
+        pos = torch.arange(lo, hi, device=self.device)
+        return allgather_rows(self.embed_user.weight, pos, self.user_num)
+
     def _hyper(self, opt=None):
         return ops.hyper(self.lr, self.reg_1, self.reg_2, opt or self._optimizer_name())
 
     def _begin_fit(self, opt):
         """fit() builds a fresh optimizer (AbstractRecommender.py:105): fresh Adam moments / step count."""
-        self._ws = ops.MFWorkspace(self.user_num, self.item_num, self.factors, opt, self.device)
-        self._opt_steps = 0
         self._hp = self._hyper(opt)
+        self._opt_steps = 0
+        if self.world > 1:
+            self._trainer = None                                   # fresh optimiser state per fit()
+            return
+        self._ws = ops.MFWorkspace(self.user_num, self.item_num, self.factors, opt, self.device)
 
     def _ensure_ws(self):
         if self._ws is None:
@@ -138,8 +182,26 @@ class MF(GeneralRecommender):
         if len(users) == 0:
             return np.zeros((0,), np.float32)
         k = min(self.topk, cands.shape[1])
+        if self.world > 1:
+            return self._rank_sharded(users, cands, k)
         out = ops.mf_rank(self.embed_user.weight, self.embed_item.weight,
                           torch.from_numpy(users).to(self.device), torch.from_numpy(np.ascontiguousarray(cands)).to(self.device), k)
+        return out.cpu().numpy()
+
+    def _rank_sharded(self, users, cands, k):
+        """Each rank scores the test users it owns; one all-gather assembles [n_users, k] in loader order."""
+        from ..parallel import allgather_rows, owner_of
+        if self._bounds is None:
+            self._shard(self._default_bounds())
+        mine = np.flatnonzero(owner_of(users, self._bounds) == self.rank_id)
+        lo = int(self._bounds[self.rank_id])
+        if len(mine):
+            loc = ops.mf_rank(self.embed_user.weight, self.embed_item.weight,
+                              torch.from_numpy(users[mine] - lo).to(self.device),
+                              torch.from_numpy(np.ascontiguousarray(cands[mine])).to(self.device), k)
+        else:
+            loc = torch.zeros((0, k), dtype=torch.float32, device=self.device)
+        out = allgather_rows(loc, torch.from_numpy(mine).to(self.device), len(users))
         return out.cpu().numpy()
 
     def full_rank(self, u):

@@ -1,0 +1,270 @@
+"""User-sharded multi-GPU BPR-MF (one process per GPU).
+
+The reference has no multi-device path at all (single process, `AbstractRecommender.py:99-100`), so the
+single-GPU run of this framework is the oracle for N > 1:
+
+* the USER table is row-sharded by contiguous user ranges balanced by interaction count; rank r owns the
+  rows and every training triple of its users -- user-row reads and updates are always local;
+* the ITEM table (<= 9 MB at every BASELINE shape) is replicated;
+* every rank walks the same global epoch permutation and keeps the triples of its users
+  (`drb_shard_gather_triples`), so the union of the local batches of step s IS the single-GPU batch s;
+* per step: phase 1 on the local triples -> NCCL all-reduce (sum) of the item-gradient accumulator, the item
+  counters and the 8 loss/norm scalars -> phase 2 (local user rows + the full item table, bit-identically on
+  every rank because the reduced inputs are identical);
+* at rank time each GPU scores its own users and ONE all-gather assembles the per-user top-K in loader order.
+
+torch.distributed (NCCL on GPUs, gloo in the CPU tests of the host logic) is plumbing; all compute is in
+libdaisyrec_b200.so.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+# --------------------------------------------------------------------------------------- host logic
+def partition_users(weights, world):
+    """Contiguous user ranges with ~equal total weight (interaction / triple counts).
+
+    weights: int array [U] (non-negative).  Returns int64 bounds[world+1], bounds[0]=0, bounds[-1]=U;
+    rank r owns users [bounds[r], bounds[r+1])."""
+    w = np.asarray(weights, dtype=np.int64)
+    U = len(w)
+    csum = np.concatenate([[0], np.cumsum(w)])
+    total = int(csum[-1])
+    bounds = np.zeros(world + 1, np.int64)
+    for r in range(1, world):
+        target = (total * r + world - 1) // world
+        bounds[r] = int(np.searchsorted(csum, target, side="left"))
+    bounds[world] = U
+    return np.maximum.accumulate(np.minimum(bounds, U))
+
+
+def owner_of(users, bounds):
+    """Rank owning each user id."""
+    return np.searchsorted(np.asarray(bounds)[1:], np.asarray(users), side="right")
+
+
+def allreduce_step_buffers(gq, cnt_i, acc, group=None):
+    """The per-step exchange: item-gradient accumulator (fp32), item counters (int64 view of the packed
+    u64 pos|neg<<32 pairs: the halves never carry into each other below 2^32 occurrences), and the 8 fp64
+    loss / norm partial sums."""
+    dist.all_reduce(gq, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(cnt_i, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+
+
+def allgather_rows(local_rows, local_pos, total_rows, group=None):
+    """Assemble a [total_rows, K] matrix from per-rank row blocks with ONE all-gather.
+
+    local_rows: [n_local, K] tensor; local_pos: int64 [n_local] destination row of each local row.
+    Variable counts are padded to the maximum (all_gather needs equal shapes); position -1 marks padding."""
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    n_max = max(int(c.item()) for c in counts)
+    K = local_rows.shape[1]
+    # pack positions next to the payload so a single collective moves both
+    payload = torch.full((n_max, K + 1), -1, dtype=torch.float64, device=local_rows.device)
+    payload[:local_rows.shape[0], :K] = local_rows.to(torch.float64)
+    payload[:local_rows.shape[0], K] = local_pos.to(torch.float64)
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    out = torch.zeros((total_rows, K), dtype=local_rows.dtype, device=local_rows.device)
+    for g in gathered:
+        pos = g[:, K].to(torch.int64)
+        keep = pos >= 0
+        out[pos[keep]] = g[keep, :K].to(local_rows.dtype)
+    return out
+
+
+# --------------------------------------------------------------------------------------- device side
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class ShardedTrainer:
+    """Rank-local state of user-sharded BPR-MF training."""
+
+    def __init__(self, P_local, Q, bounds, rank, world, hp, opt="sgd", group=None):
+        from . import ops
+        self.ops = ops
+        self.P, self.Q = P_local, Q
+        self.bounds, self.rank, self.world, self.group = np.asarray(bounds, np.int64), rank, world, group
+        self.lo, self.hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        self.U_local, self.I, self.F = P_local.shape[0], Q.shape[0], Q.shape[1]
+        assert self.U_local == self.hi - self.lo
+        self.hp = hp
+        self.dev = Q.device
+        self.ws = ops.MFWorkspace(max(1, self.U_local), self.I, self.F, opt, self.dev)
+        lay = (C.c_int64 * 8)()
+        L.check(L.lib().drb_mf_workspace_layout(max(1, self.U_local), self.I, self.F, self.ws.opt, lay))
+        buf = self.ws.buf
+        self.acc = buf[lay[0]:lay[0] + lay[1]].view(torch.float64)
+        self.gq = buf[lay[2]:lay[2] + lay[3]].view(torch.float32)
+        self.cnt_i = buf[lay[4]:lay[4] + lay[5]].view(torch.int64)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.opt_steps = 0
+        self.offsets_host = None
+
+    # ---- train feed
+    def prepare_epoch(self, d_triples, d_perm, batch_global):
+        """Local SoA planes + per-step offsets from the global permutation."""
+        n = d_triples.shape[0] if d_perm is None else d_perm.numel()
+        m = (n + batch_global - 1) // batch_global
+        # upper bound of local triples: count once (cheap) via the counting pass inside the library
+        self.scratch = torch.empty(max(1, m), dtype=torch.int64, device=self.dev)
+        self.step_offsets = torch.empty(m + 1, dtype=torch.int64, device=self.dev)
+        cap = n                                                   # worst case; planes are views of one buffer
+        if getattr(self, "_planes", None) is None or self._planes.shape[1] < cap:
+            self._planes = torch.empty((3, (cap + 3) // 4 * 4), dtype=torch.int32, device=self.dev)
+        L.check(L.lib().drb_shard_gather_triples(_ptr(d_triples), None if d_perm is None else _ptr(d_perm), n, self.lo,
+                                                 self.hi, batch_global, _ptr(self.scratch), _ptr(self.step_offsets),
+                                                 _ptr(self._planes[0]), _ptr(self._planes[1]), _ptr(self._planes[2]),
+                                                 _stream()))
+        self.offsets_host = self.step_offsets.cpu().numpy()
+        self.bu, self.bi, self.bj = self._planes[0], self._planes[1], self._planes[2]
+        return m
+
+    # ---- one synchronous global step
+    def _phase(self, phase, bu, bi, bj, begin, count):
+        L.check(L.lib().drb_mf_bpr_phase(_ptr(self.P), _ptr(self.Q), _ptr(self.ws.buf), max(1, self.U_local), self.I, self.F,
+                                         _ptr(bu), _ptr(bi), _ptr(bj), begin, count, phase, C.byref(self.hp),
+                                         self.opt_steps, _ptr(self.loss), _stream()))
+
+    def step_device(self, bu, bi, bj, begin, count):
+        self._phase(1, bu, bi, bj, begin, count)
+        allreduce_step_buffers(self.gq, self.cnt_i, self.acc, self.group)
+        self._phase(2, bu, bi, bj, begin, count)
+        self.opt_steps += 1
+
+    def step(self, s):
+        b, e = int(self.offsets_host[s]), int(self.offsets_host[s + 1])
+        self.step_device(self.bu, self.bi, self.bj, b, e - b)
+
+    def step_host(self, h_bu, h_bi, h_bj, stage):
+        """End-to-end step from pinned HOST arrays holding this rank's share of the global batch."""
+        n = len(h_bu)
+        stride = (n + 3) // 4 * 4
+        for k, h in enumerate((h_bu, h_bi, h_bj)):
+            stage[k * stride:k * stride + n].copy_(h if isinstance(h, torch.Tensor) else torch.from_numpy(h), non_blocking=True)
+        self.step_device(stage[0:], stage[stride:], stage[2 * stride:], 0, n)
+        return float(self.loss.item())                           # D2H of the global loss
+
+    def check_nan(self):
+        hdr = self.ws.buf[:256].cpu().numpy()
+        status = int(np.frombuffer(hdr[144:148].tobytes(), np.int32)[0])   # WsHeader: barrier 8 + acc 128 + nan_step 8
+        if status == L.DRB_ERR_NAN_LOSS:
+            raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+
+
+# --------------------------------------------------------------------------------------- bench (N > 1)
+def run_sharded_bench(args, rank, local, world, dev):
+    """Weak-scaling arm of bench.py: per-GPU batch fixed (args.batch), global batch = world * batch."""
+    import json
+    import logging
+    from . import ops
+    from .utils.synthetic import init_tables
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    if sys_path_root not in sys.path:
+        sys.path.insert(0, sys_path_root)
+    import bench as B
+
+    d, triples = B.build_workload(args.shape, dev, args.num_ng, args.seed, "cuda")     # identical on every rank
+    U, I, F = d["user_num"], d["item_num"], args.factors
+    T = triples.shape[0]
+    Bg = args.batch * world
+    deg = (d["row_ptr"][1:] - d["row_ptr"][:-1]).cpu().numpy()
+    bounds = partition_users(deg, world)
+    g = torch.Generator(device=dev); g.manual_seed(args.seed)
+    perm = torch.randperm(T, generator=g, device=dev)
+    P0, Q0 = init_tables(U, I, F, args.seed, dev)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.contiguous(), bounds, rank, world, ops.hyper(0.01, 0.001, 0.001))
+    spe = tr.prepare_epoch(triples, perm, Bg)
+    del perm
+    local_counts = np.diff(tr.offsets_host)
+
+    def run(first, k):
+        n_loc = 0
+        for s in range(first, first + k):
+            tr.step(s % spe)
+            n_loc += int(local_counts[s % spe])
+        return n_loc
+
+    clocks = B.ClockSampler(local) if rank == 0 else None
+    run(0, args.warmup)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    n_loc = run(args.warmup, args.steps)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([n_loc], dtype=torch.float64, device=dev)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    tr.check_nan()
+    value = float(tot.item()) / float(ms.item()) * 1e3
+
+    # e2e: pinned host share of each global batch -> H2D + step + D2H loss
+    ke = max(1, min(args.steps, args.e2e_steps))
+    host = []
+    for s in range(ke + 2):
+        b, e = int(tr.offsets_host[(args.warmup + s) % spe]), int(tr.offsets_host[(args.warmup + s) % spe + 1])
+        host.append([t[b:e].cpu().pin_memory() for t in (tr.bu, tr.bi, tr.bj)])
+    stage = torch.empty(3 * (max(len(h[0]) for h in host) + 4) + 4, dtype=torch.int32, device=dev)
+    for s in range(2):
+        tr.step_host(*host[s], stage)
+    torch.cuda.synchronize(); dist.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    n_e = 0
+    for s in range(2, ke + 2):
+        tr.step_host(*host[s], stage)
+        n_e += len(host[s][0])
+    f1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    t2 = time.time()
+    ems = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    etot = torch.tensor([n_e], dtype=torch.float64, device=dev)
+    dist.all_reduce(etot, op=dist.ReduceOp.SUM)
+    h2d = torch.tensor([12.0 * n_e / ke], dtype=torch.float64, device=dev)
+    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        clk = clocks.stop(t0, t2)
+        peak, peak_src = B.measured_peaks()
+        bpt = 24 * F + 12
+        achieved = value / world * bpt / 1e9                      # per-GPU algorithmic GB/s of the fused step
+        line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": B.workload_config(args, d, T, args.batch, {
+                    "parallelism": f"user-row-sharded P x{world}, replicated Q, per-step NCCL all-reduce of gQ/counters/norms",
+                    "global_batch": Bg, "per_gpu_batch": args.batch, "steps_per_epoch": spe}),
+                "clocks": clk,
+                "e2e": {"value": float(etot.item()) / float(ems.item()) * 1e3, "unit": B.UNIT,
+                        "h2d_bytes_per_step": float(h2d.item()), "d2h_bytes_per_step": 8 * world, "steps": ke,
+                        "api": "ShardedTrainer.step_host(rank-local host batch): H2D + phase1 + all-reduce + phase2 + D2H loss"},
+                "gpu_launches": 2 * args.steps,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_triple": bpt,
+                             "kernel": "mf_bpr_steps_kernel (phase 1 + phase 2 launches, per GPU)"}}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -126,6 +126,24 @@ int drb_mf_bpr_train_step_host(float *d_P, float *d_Q, void *d_ws, int32_t user_
                                int64_t batch, const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage,
                                double *h_loss, void *stream);
 
+/* ---- multi-GPU (one process per GPU; user-sharded P, replicated Q) ---------------
+ * There is no multi-device path in the reference (single process, AbstractRecommender.py:99-100);
+ * these entry points split the synchronous step where the exchange has to happen:
+ *   phase 1 (accumulate on local triples) -> host all-reduces gQ / cntI / acc over NCCL ->
+ *   phase 2 (apply: local P rows + the full replicated Q, identically on every rank).
+ * drb_mf_workspace_layout: byte offset/size pairs inside the workspace of
+ *   [0,1] acc (8 doubles)  [2,3] gQ (fp32 I*F)  [4,5] cntI (u64 I)  [6] gP offset  [7] cntU offset. */
+int drb_mf_workspace_layout(int32_t user_num, int32_t item_num, int32_t factors, int32_t opt, int64_t *out8);
+int drb_mf_bpr_phase(float *d_P, float *d_Q, void *d_ws, int32_t user_num, int32_t item_num, int32_t factors,
+                     const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t begin, int64_t count,
+                     int32_t phase, const drb_hyper *hyper, int64_t adam_step0, double *d_loss, void *stream);
+/* Sharded train feed: keep the triples of users [user_lo, user_hi) from the GLOBAL epoch permutation,
+ * renumber users locally, and report where each global step's local batch starts
+ * (d_step_offsets[ceil(n/batch)+1]); d_scratch_counts needs ceil(n/batch) u64. */
+int drb_shard_gather_triples(const int32_t *d_triples, const int64_t *d_perm, int64_t n, int32_t user_lo,
+                             int32_t user_hi, int64_t batch, unsigned long long *d_scratch_counts,
+                             int64_t *d_step_offsets, int32_t *d_bu, int32_t *d_bi, int32_t *d_bj, void *stream);
+
 /* ---- inference ------------------------------------------------------------------------
  * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,
  *   descending sort, first topk ids as float32 (the reference's dtype quirk, :107).
