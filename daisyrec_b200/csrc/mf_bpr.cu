@@ -541,7 +541,7 @@ static StepKernel pick_kernel(int F)
     return pick_kernel_v<1>(g.width, g.nch);
 }
 
-static int launch_steps(StepParams &p, cudaStream_t st)
+static int launch_steps(StepParams &p, cudaStream_t st, bool keep_status = false)
 {
     StepKernel k = pick_kernel(p.F);
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
@@ -561,7 +561,8 @@ static int launch_steps(StepParams &p, cudaStream_t st)
                                    : ((p.opt == DRB_OPT_ADAM) || (3 * p.batch >= ((long long)p.U + p.I) / 4));
     long long want_grid = (dense && p.apply) ? (tiles > rows_work ? tiles : rows_work) : tiles;
     int grid = (int)(want_grid < 1 ? 1 : (want_grid > max_grid ? max_grid : want_grid));
-    if (p.phases & 1) DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, p.phases == 3 ? sizeof(WsHeader) : kHdrResetBytes, st));
+    if (p.phases & 1)
+        DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, (p.phases == 3 && !keep_status) ? sizeof(WsHeader) : kHdrResetBytes, st));
     void *args[] = {&p};
     DRB_CUDA(cudaLaunchCooperativeKernel((void *)k, dim3(grid), dim3(kThreads), args, 0, st));
     return DRB_OK;
@@ -673,6 +674,62 @@ extern "C" int drb_mf_bpr_train_step_host(float *d_P, float *d_Q, void *d_ws, in
     DRB_CUDA(cudaMemcpyAsync(h_loss, d_loss, sizeof(double), cudaMemcpyDeviceToHost, st));
     int64_t nan_step = -1;
     return check_nan(d_ws, st, &nan_step);
+}
+
+// Pipelined end-to-end steps from HOST index planes: the H2D copy of step s+1 (copy stream) overlaps the
+// kernel of step s (compute stream); every step's loss is read back to the host asynchronously.
+extern "C" int drb_mf_bpr_train_steps_host(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
+                                           const int32_t *h_bu, const int32_t *h_bi, const int32_t *h_bj, int64_t n,
+                                           int64_t batch, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                                           int32_t *d_stage, double *d_loss, double *h_loss, int64_t *nan_step,
+                                           void *stream)
+{
+    DRB_REQUIRE(h_bu && h_bi && h_bj && d_stage && d_loss && h_loss && batch > 0 && n_steps >= 0 && n >= 0,
+                "train_steps_host: bad arguments");
+    DRB_REQUIRE(n_steps == 0 || (n_steps - 1) * batch < n, "train_steps_host: %lld steps exceed %lld triples",
+                (long long)n_steps, (long long)n);
+    if (n_steps == 0) return DRB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local cudaStream_t copy_st = nullptr;
+    if (!copy_st) DRB_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    cudaEvent_t ready[2], freed[2], start;
+    for (int k = 0; k < 2; ++k) {
+        DRB_CUDA(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+        DRB_CUDA(cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming));
+    }
+    DRB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    const size_t stride = (size_t)((batch + 3) / 4 * 4);
+    DRB_CUDA(cudaMemsetAsync(d_ws, 0, sizeof(WsHeader), st));   // clear a stale NaN flag once; sticky afterwards
+    DRB_CUDA(cudaEventRecord(start, st));
+    DRB_CUDA(cudaStreamWaitEvent(copy_st, start, 0));            // staging slots may still be in use upstream
+    int rc = DRB_OK;
+    for (int64_t s = 0; s < n_steps && rc == DRB_OK; ++s) {
+        const int slot = (int)(s & 1);
+        int32_t *sb = d_stage + (size_t)slot * 3 * stride;
+        const int64_t base = s * batch, nb = (n - base < batch) ? n - base : batch;
+        const size_t bytes = sizeof(int32_t) * (size_t)nb;
+        if (s >= 2) DRB_CUDA(cudaStreamWaitEvent(copy_st, freed[slot], 0));
+        DRB_CUDA(cudaMemcpyAsync(sb, h_bu + base, bytes, cudaMemcpyHostToDevice, copy_st));
+        DRB_CUDA(cudaMemcpyAsync(sb + stride, h_bi + base, bytes, cudaMemcpyHostToDevice, copy_st));
+        DRB_CUDA(cudaMemcpyAsync(sb + 2 * stride, h_bj + base, bytes, cudaMemcpyHostToDevice, copy_st));
+        DRB_CUDA(cudaEventRecord(ready[slot], copy_st));
+        DRB_CUDA(cudaStreamWaitEvent(st, ready[slot], 0));
+        StepParams p;
+        rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, sb, sb + stride, sb + 2 * stride, nb, nb, 0, 1, hyper, adam_step0 + s,
+                         d_loss + s, 1);
+        if (rc == DRB_OK) rc = launch_steps(p, st, /*keep_status=*/true);
+        if (rc != DRB_OK) break;
+        DRB_CUDA(cudaEventRecord(freed[slot], st));
+        DRB_CUDA(cudaMemcpyAsync(h_loss + s, d_loss + s, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    int rc2 = (rc == DRB_OK) ? check_nan(d_ws, st, nan_step) : rc;
+    cudaStreamSynchronize(copy_st);
+    for (int k = 0; k < 2; ++k) {
+        cudaEventDestroy(ready[k]);
+        cudaEventDestroy(freed[k]);
+    }
+    cudaEventDestroy(start);
+    return rc2;
 }
 
 extern "C" int drb_gather_triples(const int32_t *d_triples, const int64_t *d_perm, int64_t n, int32_t *d_bu,

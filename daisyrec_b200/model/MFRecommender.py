@@ -160,6 +160,21 @@ class MF(GeneralRecommender):
         self._opt_steps += 1
         return loss
 
+    def fit_host_batches(self, h_bu, h_bi, h_bj, batch_size, n_steps=None):
+        """Train on pre-collated HOST index planes (pinned CPU int32 tensors holding consecutive batches of
+        ``batch_size`` triples): the step loop of AbstractRecommender.py:116-128 with the per-step
+        ``.to(device)`` copies and ``loss.item()`` reads kept, but pipelined (copy of batch s+1 under the
+        kernel of batch s).  Returns the per-step losses (CPU float64 tensor)."""
+        self._check_loss_type()
+        self._ensure_ws()
+        n = h_bu.numel()
+        if n_steps is None:
+            n_steps = (n + batch_size - 1) // batch_size
+        losses = ops.mf_bpr_train_steps_host(self.embed_user.weight, self.embed_item.weight, self._ws, h_bu, h_bi, h_bj,
+                                             batch_size, n_steps, self._hp, adam_step0=self._opt_steps)
+        self._opt_steps += n_steps
+        return losses
+
     def predict(self, u, i):
         """MFRecommender.py:99-104 -> python float."""
         return float(self.forward([u], [i]).item())

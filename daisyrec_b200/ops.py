@@ -212,6 +212,26 @@ def mf_bpr_train_step_host(P, Q, ws, h_bu, h_bi, h_bj, hp, stage, adam_step0=0):
     return loss.value
 
 
+def mf_bpr_train_steps_host(P, Q, ws, h_bu, h_bi, h_bj, batch, n_steps, hp, adam_step0=0):
+    """Pipelined end-to-end steps from pinned HOST planes (CPU int32 tensors).  Returns float64 losses [n_steps]."""
+    for t in (h_bu, h_bi, h_bj):
+        if not (isinstance(t, torch.Tensor) and not t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+            raise TypeError("host planes must be contiguous CPU int32 tensors (pin them for overlap)")
+    n = h_bu.numel()
+    stride = (batch + 3) // 4 * 4
+    stage = torch.empty(2 * 3 * stride, dtype=torch.int32, device=P.device)
+    d_loss = torch.empty(max(1, n_steps), dtype=torch.float64, device=P.device)
+    h_loss = torch.empty(max(1, n_steps), dtype=torch.float64).pin_memory()
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_mf_bpr_train_steps_host(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, h_bu.data_ptr(),
+                                             h_bi.data_ptr(), h_bj.data_ptr(), n, batch, n_steps, C.byref(hp), adam_step0,
+                                             _ptr(stage), _ptr(d_loss), h_loss.data_ptr(), C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return h_loss[:n_steps]
+
+
 # ------------------------------------------------------------------ inference
 def mf_rank(P, Q, users, cands, topk):
     _dev(users, torch.int64, "users"); _dev(cands, torch.int64, "cands")

@@ -126,6 +126,14 @@ int drb_mf_bpr_train_step_host(float *d_P, float *d_Q, void *d_ws, int32_t user_
                                int64_t batch, const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage,
                                double *h_loss, void *stream);
 
+/* Pipelined end-to-end steps from HOST index planes (pinned): n_steps steps of `batch` triples; the
+ * H2D copy of step s+1 overlaps the kernel of step s, every step's loss is read back asynchronously into
+ * h_loss[s].  d_stage: 2 * 3 * round_up(batch, 4) int32 (double-buffered staging), d_loss: [n_steps]. */
+int drb_mf_bpr_train_steps_host(float *d_P, float *d_Q, void *d_ws, int32_t user_num, int32_t item_num,
+                                int32_t factors, const int32_t *h_bu, const int32_t *h_bi, const int32_t *h_bj,
+                                int64_t n, int64_t batch, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                                int32_t *d_stage, double *d_loss, double *h_loss, int64_t *nan_step, void *stream);
+
 /* ---- multi-GPU (one process per GPU; user-sharded P, replicated Q) ---------------
  * There is no multi-device path in the reference (single process, AbstractRecommender.py:99-100);
  * these entry points split the synchronous step where the exchange has to happen:

@@ -209,6 +209,26 @@ def test_host_step_entry_matches_device_entry(ops):
     np.testing.assert_allclose(Pa.cpu().numpy(), Pb.cpu().numpy(), atol=2e-6)
 
 
+def test_pipelined_host_steps_match_device_steps(ops):
+    rng = np.random.default_rng(12)
+    U, I, F, B, n = 900, 700, 64, 2048, 2048 * 5 + 77
+    P0 = (rng.standard_normal((U, F)) * 0.1).astype(np.float32)
+    Q0 = (rng.standard_normal((I, F)) * 0.1).astype(np.float32)
+    hb = [torch.from_numpy(rng.integers(m, size=n).astype(np.int32)).pin_memory() for m in (U, I, I)]
+    hp = ops.hyper(0.01, 0.001, 0.001)
+    Pa, Qa, Pb, Qb = dev(P0), dev(Q0), dev(P0), dev(Q0)
+    wa, wb = ops.MFWorkspace(U, I, F, "sgd", "cuda"), ops.MFWorkspace(U, I, F, "sgd", "cuda")
+    la = ops.mf_bpr_train_steps_host(Pa, Qa, wa, *hb, B, 6, hp).numpy()
+    lb = ops.mf_bpr_train_steps(Pb, Qb, wb, *[t.cuda() for t in hb], B, 0, 6, hp).cpu().numpy()
+    np.testing.assert_allclose(la, lb, rtol=1e-6)
+    np.testing.assert_allclose(Pa.cpu().numpy(), Pb.cpu().numpy(), atol=2e-6)
+    np.testing.assert_allclose(Qa.cpu().numpy(), Qb.cpu().numpy(), atol=2e-6)
+    # NaN is sticky across the pipelined steps and surfaces as the reference's ValueError
+    Pa[3, 3] = float("nan")
+    with pytest.raises(ValueError):
+        ops.mf_bpr_train_steps_host(Pa, Qa, wa, *hb, B, 6, hp)
+
+
 # ------------------------------------------------------------------ rank / full_rank / predict
 def test_mf_rank_golden(ops):
     g = golden("mf_rank")
