@@ -26,7 +26,7 @@
 // A NaN loss (ValueError in the reference, :122-123) stops the loop before the update of that step.
 #include <math.h>
 
-#include "common.cuh"
+#include "step.cuh"
 
 namespace drb {
 
@@ -38,68 +38,6 @@ constexpr int kTileMax = 512;  // triples per staged index tile
 #ifndef DRB_UNR
 #define DRB_UNR 2              // triples in flight per lane group (memory-level parallelism)
 #endif
-
-struct WsHeader {
-    unsigned long long barrier;  // grid barrier ticket counter          } reset before every phase-1 launch
-    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, -]  }
-    long long nan_step;          // step whose loss was NaN               } sticky in split (multi-GPU) mode
-    int status;
-    int pad[13];
-};
-constexpr size_t kHdrResetBytes = sizeof(unsigned long long) + sizeof(double) * 16;
-static_assert(sizeof(WsHeader) <= 256, "header must fit its slot");
-
-struct Workspace {
-    WsHeader *hdr;
-    float *gP, *gQ;
-    unsigned *cntU;
-    unsigned long long *cntI;
-    float *mP, *vP, *mQ, *vQ;
-};
-
-static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-static size_t carve(void *base, int U, int I, int F, int opt, Workspace *w)
-{
-    size_t off = 0;
-    char *b = (char *)base;
-    auto take = [&](size_t bytes) {
-        char *p = b ? b + off : nullptr;
-        off += align256(bytes);
-        return p;
-    };
-    Workspace t;
-    t.hdr = (WsHeader *)take(256);
-    t.gP = (float *)take(sizeof(float) * (size_t)U * F);
-    t.gQ = (float *)take(sizeof(float) * (size_t)I * F);
-    t.cntU = (unsigned *)take(sizeof(unsigned) * (size_t)U);
-    t.cntI = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)I);
-    t.mP = t.vP = t.mQ = t.vQ = nullptr;
-    if (opt == DRB_OPT_ADAM) {
-        t.mP = (float *)take(sizeof(float) * (size_t)U * F);
-        t.vP = (float *)take(sizeof(float) * (size_t)U * F);
-        t.mQ = (float *)take(sizeof(float) * (size_t)I * F);
-        t.vQ = (float *)take(sizeof(float) * (size_t)I * F);
-    }
-    if (w) *w = t;
-    return off;
-}
-
-struct StepParams {
-    float *P, *Q;
-    Workspace ws;
-    const int32_t *bu, *bi, *bj;
-    long long n, batch, first_step, n_steps;
-    int U, I, F, tile;
-    float lr, reg1, reg2;
-    int opt;
-    float beta1, beta2, eps;
-    long long adam_step0;
-    double *step_loss;
-    int apply;
-    int phases;      // bit 0: phase 1 (accumulate), bit 1: phase 2 (apply); 3 = fused persistent steps
-    int dense_hint;  // -1 auto, 0 claim, 1 dense sweep (multi-GPU: always dense, counters are global)
-};
 
 // ------------------------------------------------------------------ device pieces
 __device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
@@ -206,7 +144,7 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const bool touched = cnt[k] != 0;
-            if (!act[k] || (OPT == DRB_OPT_SGD && !touched)) continue;
+            if (!act[k] || (OPT == DRB_OPT_SGD && !touched && !p.dense_grad)) continue;
             const float ca = (float)(unsigned)(cnt[k] & 0xffffffffull), cb = (float)(unsigned)(cnt[k] >> 32);
             const float ia = is_user[k] ? nm.inv_u : nm.inv_i, ib = nm.inv_j;
 #pragma unroll
@@ -216,7 +154,7 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
                 Vec<VEC> &t = th[k].c[ch];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    float x = t.v[e], gg = g[k].c[ch].v[e];
+                    float x = t.v[e], gg = p.gscale * g[k].c[ch].v[e];
                     if (touched) {
                         float sg = p.reg1 * sgnf(x);
                         gg += ca * (sg + p.reg2 * x * ia) + cb * (sg + p.reg2 * x * ib);
@@ -354,11 +292,17 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                     float c = -(sg * (1.f - sg)) / (1e-10f + sg);
                     if (has_reg) {
                         float l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
+                        Row<VEC, W, NCH> nu_ = rp[r], ni_ = rqi[r], nj_ = rqj[r];
+                        if (p.Pn != nullptr) {   // regulariser on the ego rows (LightGCNRecommender.py:145-146,159)
+                            nu_ = load_row<VEC, W, NCH>(p.Pn + (size_t)iu[r] * F, gl, chunks, true);
+                            ni_ = load_row<VEC, W, NCH>(p.Qn + (size_t)ii[r] * F, gl, chunks, true);
+                            nj_ = load_row<VEC, W, NCH>(p.Qn + (size_t)ij[r] * F, gl, chunks, true);
+                        }
 #pragma unroll
                         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) {
-                                float a = rp[r].c[ch].v[e], b = rqi[r].c[ch].v[e], d = rqj[r].c[ch].v[e];
+                                float a = nu_.c[ch].v[e], b = ni_.c[ch].v[e], d = nj_.c[ch].v[e];
                                 l1u += fabsf(a); s2u = fmaf(a, a, s2u);
                                 l1i += fabsf(b); s2i = fmaf(b, b, s2i);
                                 l1j += fabsf(d); s2j = fmaf(d, d, s2j);
@@ -541,7 +485,7 @@ static StepKernel pick_kernel(int F)
     return pick_kernel_v<1>(g.width, g.nch);
 }
 
-static int launch_steps(StepParams &p, cudaStream_t st, bool keep_status = false)
+int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
     StepKernel k = pick_kernel(p.F);
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
@@ -565,6 +509,20 @@ static int launch_steps(StepParams &p, cudaStream_t st, bool keep_status = false
         DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, (p.phases == 3 && !keep_status) ? sizeof(WsHeader) : kHdrResetBytes, st));
     void *args[] = {&p};
     DRB_CUDA(cudaLaunchCooperativeKernel((void *)k, dim3(grid), dim3(kThreads), args, 0, st));
+    return DRB_OK;
+}
+
+int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step)
+{
+    WsHeader h;
+    DRB_CUDA(cudaMemcpyAsync(&h, d_ws, sizeof(WsHeader), cudaMemcpyDeviceToHost, st));
+    DRB_CUDA(cudaStreamSynchronize(st));
+    if (h.status == DRB_ERR_NAN_LOSS) {
+        if (nan_step) *nan_step = h.nan_step;
+        set_error("Loss=Nan or Infinity at step %lld: current settings does not fit the recommender", h.nan_step);
+        return DRB_ERR_NAN_LOSS;
+    }
+    if (nan_step) *nan_step = -1;
     return DRB_OK;
 }
 
@@ -606,20 +564,10 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.apply = apply;
     p.phases = 3;
     p.dense_hint = -1;
-    return DRB_OK;
-}
-
-static int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step)
-{
-    WsHeader h;
-    DRB_CUDA(cudaMemcpyAsync(&h, d_ws, sizeof(WsHeader), cudaMemcpyDeviceToHost, st));
-    DRB_CUDA(cudaStreamSynchronize(st));
-    if (h.status == DRB_ERR_NAN_LOSS) {
-        if (nan_step) *nan_step = h.nan_step;
-        set_error("Loss=Nan or Infinity at step %lld: current settings does not fit the recommender", h.nan_step);
-        return DRB_ERR_NAN_LOSS;
-    }
-    if (nan_step) *nan_step = -1;
+    p.Pn = nullptr;
+    p.Qn = nullptr;
+    p.gscale = 1.f;
+    p.dense_grad = 0;
     return DRB_OK;
 }
 

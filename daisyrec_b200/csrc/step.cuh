@@ -1,0 +1,77 @@
+// step.cuh -- shared declarations of the BPR step kernel (mf_bpr.cu), reused by lightgcn.cu.
+#pragma once
+#include "common.cuh"
+
+namespace drb {
+
+struct WsHeader {
+    unsigned long long barrier;  // grid barrier ticket counter          } reset before every phase-1 launch
+    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, -]  }
+    long long nan_step;          // step whose loss was NaN               } sticky in split (multi-GPU) mode
+    int status;
+    int pad[13];
+};
+constexpr size_t kHdrResetBytes = sizeof(unsigned long long) + sizeof(double) * 16;
+static_assert(sizeof(WsHeader) <= 256, "header must fit its slot");
+
+struct Workspace {
+    WsHeader *hdr;
+    float *gP, *gQ;
+    unsigned *cntU;
+    unsigned long long *cntI;
+    float *mP, *vP, *mQ, *vQ;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) {
+        char *p = b ? b + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    Workspace t;
+    t.hdr = (WsHeader *)take(256);
+    t.gP = (float *)take(sizeof(float) * (size_t)U * F);
+    t.gQ = (float *)take(sizeof(float) * (size_t)I * F);
+    t.cntU = (unsigned *)take(sizeof(unsigned) * (size_t)U);
+    t.cntI = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)I);
+    t.mP = t.vP = t.mQ = t.vQ = nullptr;
+    if (opt == DRB_OPT_ADAM) {
+        t.mP = (float *)take(sizeof(float) * (size_t)U * F);
+        t.vP = (float *)take(sizeof(float) * (size_t)U * F);
+        t.mQ = (float *)take(sizeof(float) * (size_t)I * F);
+        t.vQ = (float *)take(sizeof(float) * (size_t)I * F);
+    }
+    if (w) *w = t;
+    return off;
+}
+
+struct StepParams {
+    float *P, *Q;
+    Workspace ws;
+    const int32_t *bu, *bi, *bj;
+    long long n, batch, first_step, n_steps;
+    int U, I, F, tile;
+    float lr, reg1, reg2;
+    int opt;
+    float beta1, beta2, eps;
+    long long adam_step0;
+    double *step_loss;
+    int apply;
+    int phases;      // bit 0: phase 1 (accumulate), bit 1: phase 2 (apply); 3 = fused persistent steps
+    int dense_hint;  // -1 auto, 0 claim, 1 dense sweep (multi-GPU: always dense, counters are global)
+    // LightGCN: scores come from the propagated tables P,Q while the regulariser norms use the ego tables
+    const float *Pn, *Qn;  // ego (norm) tables; nullptr = same as P,Q
+    float gscale;          // factor applied to the accumulated gradient in phase 2 (1/(L+1) for LightGCN)
+    int dense_grad;        // 1: every row has a gradient (propagated), not only the rows a triple touched
+};
+
+
+int launch_steps(StepParams &p, cudaStream_t st, bool keep_status = false);
+int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step);
+
+}  // namespace drb

@@ -264,3 +264,75 @@ def mf_rank_host(P, Q, users, cands, topk):
     L.check(L.lib().drb_mf_rank_host(_ptr(P), _ptr(Q), P.shape[1], users.ctypes.data, len(users), cands.ctypes.data,
                                      cands.shape[1], topk, out.ctypes.data))
     return out
+
+
+# ------------------------------------------------------------------ LightGCN
+def lgcn_norm_adj(coo_u, coo_i, user_num, item_num):
+    """get_norm_adj_mat (LightGCNRecommender.py:73-107) as CSR over the U+I nodes, values bit-identical to the
+    reference: float64 (deg + 1e-7) ** -0.5, (D*A)*D in float64, cast to fp32.  One-off host build (numpy)."""
+    n = user_num + item_num
+    u = np.asarray(coo_u, np.int64)
+    i = np.asarray(coo_i, np.int64) + user_num
+    key = np.unique(np.concatenate([u * n + i, i * n + u]))
+    row, col = key // n, key % n
+    cnt = np.bincount(row, minlength=n)
+    dinv = np.power(cnt.astype(np.float64) + 1e-7, -0.5)
+    val = ((dinv[row] * 1.0) * dinv[col]).astype(np.float32)
+    row_ptr = np.zeros(n + 1, np.int64)
+    np.cumsum(cnt, out=row_ptr[1:])
+    return row_ptr, col.astype(np.int32), val
+
+
+class LgcnGraph:
+    """Device copy of the normalised adjacency + its segment list."""
+
+    def __init__(self, row_ptr, col, val, device):
+        n = len(row_ptr) - 1
+        row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        nseg = int(L.lib().drb_lgcn_segment_count(row_ptr.ctypes.data, n))
+        seg_row = np.empty(max(1, nseg), np.int32)
+        seg_ptr = np.empty(nseg + 1, np.int64)
+        L.check(L.lib().drb_lgcn_segments(row_ptr.ctypes.data, n, seg_row.ctypes.data, seg_ptr.ctypes.data))
+        self.n, self.nseg = n, nseg
+        self.row_ptr = torch.from_numpy(row_ptr).to(device)
+        self.col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).to(device)
+        self.val = torch.from_numpy(np.ascontiguousarray(val, np.float32)).to(device)
+        self.seg_row = torch.from_numpy(seg_row).to(device)
+        self.seg_ptr = torch.from_numpy(seg_ptr).to(device)
+
+    def args(self):
+        return (_ptr(self.row_ptr), _ptr(self.col), _ptr(self.val), _ptr(self.seg_row), _ptr(self.seg_ptr), self.nseg)
+
+
+class LgcnWorkspace:
+    def __init__(self, user_num, item_num, factors, opt, device):
+        self.U, self.I, self.F = user_num, item_num, factors
+        self.opt = L.OPT_SGD if opt == "sgd" else L.OPT_ADAM
+        self.buf = torch.empty(L.lib().drb_lgcn_workspace_bytes(user_num, item_num, factors, self.opt), dtype=torch.uint8,
+                               device=device)
+        L.check(L.lib().drb_lgcn_workspace_init(_ptr(self.buf), user_num, item_num, factors, self.opt, _stream()))
+
+
+def lgcn_propagate(E0, ws, graph, num_layers, out=None):
+    _dev(E0, torch.float32, "E0")
+    Em = out if out is not None else torch.empty_like(E0)
+    L.check(L.lib().drb_lgcn_propagate(_ptr(E0), _ptr(ws.buf), ws.U, ws.I, ws.F, num_layers, *graph.args(), _ptr(Em),
+                                       _stream()))
+    return Em
+
+
+def lgcn_bpr_train_steps(E0, ws, graph, num_layers, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True,
+                         check=True):
+    _dev(E0, torch.float32, "E0")
+    for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
+        _dev(t, torch.int32, nm)
+    losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=E0.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_lgcn_bpr_train_steps(_ptr(E0), _ptr(ws.buf), ws.U, ws.I, ws.F, num_layers, *graph.args(), _ptr(bu),
+                                          _ptr(bi), _ptr(bj), bu.numel(), batch, first_step, n_steps, C.byref(hp),
+                                          adam_step0, 1 if apply else 0, _ptr(losses), 1 if check else 0,
+                                          C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]

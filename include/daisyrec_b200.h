@@ -152,6 +152,29 @@ int drb_shard_gather_triples(const int32_t *d_triples, const int64_t *d_perm, in
                              int32_t user_hi, int64_t batch, unsigned long long *d_scratch_counts,
                              int64_t *d_step_offsets, int32_t *d_bu, int32_t *d_bi, int32_t *d_bj, void *stream);
 
+/* ---- LightGCN + BPR (daisy/model/LightGCNRecommender.py) --------------------------------------
+ * E0 = cat(embed_user.weight, embed_item.weight): ONE contiguous fp32 [(U+I), F] table.
+ * Adjacency: the symmetric normalised A_hat of get_norm_adj_mat (:73-107) as CSR over the U+I nodes
+ * (row_ptr i64, col i32 ascending, val f32), plus its segment list (rows cut into <=256-edge pieces;
+ * drb_lgcn_segment_count / drb_lgcn_segments, host).
+ * drb_lgcn_propagate       forward() :117-129 -> E_mean (what rank / full_rank / predict score with, :171-211;
+ *                          feed its halves to drb_mf_rank / drb_mf_full_rank / drb_mf_predict).
+ * drb_lgcn_bpr_train_steps calc_loss :131-169 + backward + optimizer.step for n_steps batches
+ *                          (apply = 0: calc_loss of one batch only).  2L sparse products per step. */
+int64_t drb_lgcn_segment_count(const int64_t *h_row_ptr, int64_t n_nodes);
+int drb_lgcn_segments(const int64_t *h_row_ptr, int64_t n_nodes, int32_t *h_seg_row, int64_t *h_seg_ptr);
+size_t drb_lgcn_workspace_bytes(int32_t user_num, int32_t item_num, int32_t factors, int32_t opt);
+int drb_lgcn_workspace_init(void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t opt, void *stream);
+int drb_lgcn_propagate(const float *d_E0, void *d_ws, int32_t user_num, int32_t item_num, int32_t factors,
+                       int32_t num_layers, const int64_t *d_row_ptr, const int32_t *d_col, const float *d_val,
+                       const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg, float *d_Em, void *stream);
+int drb_lgcn_bpr_train_steps(float *d_E0, void *d_ws, int32_t user_num, int32_t item_num, int32_t factors,
+                             int32_t num_layers, const int64_t *d_row_ptr, const int32_t *d_col, const float *d_val,
+                             const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg, const int32_t *d_bu,
+                             const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch, int64_t first_step,
+                             int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0, int32_t apply,
+                             double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+
 /* ---- inference ------------------------------------------------------------------------
  * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,
  *   descending sort, first topk ids as float32 (the reference's dtype quirk, :107).

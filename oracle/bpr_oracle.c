@@ -446,3 +446,123 @@ void orc_mf_full_rank(const float *P, const float *Q, int32_t F, int32_t item_nu
     }
     free(sc);
 }
+
+/* ====================================================================================
+ * LightGCN (daisy/model/LightGCNRecommender.py)
+ * ------------------------------------------------------------------------------------
+ * orc_lgcn_propagate: forward() :117-129 -- E_0 = cat(P, Q); E_l = A_hat E_{l-1} (torch.sparse.mm, :122);
+ *   output = mean over the L+1 layers (:125-126).  A_hat is given as CSR over the U+I nodes
+ *   (row_ptr int64, col int32 ascending, val fp32) -- the symmetric normalised adjacency of
+ *   get_norm_adj_mat :73-107 (built by oracle.lgcn_norm_adj in Python, pinned against the reference).
+ *   fp32 products, fp64 row accumulation rounded once (the "exact sum of fp32 terms" convention).
+ * ================================================================================== */
+static void spmm_csr(const int64_t *row_ptr, const int32_t *col, const float *val, int64_t n, int32_t F, const float *X,
+                     float *Y)
+{
+    double *acc = (double *)malloc(sizeof(double) * (size_t)F);
+    for (int64_t r = 0; r < n; r++) {
+        for (int f = 0; f < F; f++) acc[f] = 0.0;
+        for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+            const float *x = X + (int64_t)col[e] * F;
+            float v = val[e];
+            for (int f = 0; f < F; f++) acc[f] += (double)(v * x[f]);
+        }
+        for (int f = 0; f < F; f++) Y[r * F + f] = (float)acc[f];
+    }
+    free(acc);
+}
+
+/* out[n*F] = mean_{l=0..L} A^l X0 */
+void orc_lgcn_propagate(const int64_t *row_ptr, const int32_t *col, const float *val, int64_t n, int32_t F, int32_t L,
+                        const float *X0, float *out)
+{
+    size_t sz = (size_t)n * F;
+    float *a = (float *)malloc(sizeof(float) * sz), *b = (float *)malloc(sizeof(float) * sz);
+    double *sum = (double *)malloc(sizeof(double) * sz);
+    memcpy(a, X0, sizeof(float) * sz);
+    for (size_t k = 0; k < sz; k++) sum[k] = (double)X0[k];
+    for (int l = 0; l < L; l++) {
+        spmm_csr(row_ptr, col, val, n, F, a, b);
+        for (size_t k = 0; k < sz; k++) sum[k] += (double)b[k];
+        float *t = a; a = b; b = t;
+    }
+    for (size_t k = 0; k < sz; k++) out[k] = (float)(sum[k] / (double)(L + 1));
+    free(a); free(b); free(sum);
+}
+
+/* One LightGCN BPR step == calc_loss :131-169 + backward + optimizer.step.
+ *   scores on the PROPAGATED rows (:141-143,:157-158), BPR loss (daisy/utils/loss.py:11),
+ *   regulariser on the EGO (layer-0) rows (:145-146,:159,:163-164), un-squared L1 / Frobenius norms.
+ *   backward: dL/dE_mean is non-zero on the batch rows only; since E_mean = 1/(L+1) sum_l A^l E_0 and A is
+ *   symmetric, dL/dE_0 = 1/(L+1) sum_l A^l (dL/dE_mean)  -> the same propagation applied to the gradient;
+ *   plus the ego-row regulariser gradient.  E0 = cat(P,Q) [(U+I),F] updated in place; opt as in orc_mf_bpr_step.
+ */
+double orc_lgcn_bpr_step(float *E0, int32_t U, int32_t I, int32_t F, int32_t L, const int64_t *row_ptr, const int32_t *col,
+                         const float *val, const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B,
+                         const orc_hyper *h, int32_t apply, float *m, float *v, int64_t step_count)
+{
+    const float gamma = 1e-10f;
+    int64_t n = (int64_t)U + I;
+    size_t sz = (size_t)n * F;
+    float *Em = (float *)malloc(sizeof(float) * sz);
+    orc_lgcn_propagate(row_ptr, col, val, n, F, L, E0, Em);
+    const float *Pm = Em, *Qm = Em + (size_t)U * F, *P = E0, *Q = E0 + (size_t)U * F;
+    float *coef = (float *)malloc(sizeof(float) * (size_t)(B > 0 ? B : 1));
+    double bpr = 0, l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
+    for (int64_t t = 0; t < B; t++) {
+        const float *p = Pm + (int64_t)bu[t] * F, *qi = Qm + (int64_t)bi[t] * F, *qj = Qm + (int64_t)bj[t] * F;
+        float x = orc_dot(p, qi, F) - orc_dot(p, qj, F);
+        float s = 1.f / (1.f + expf(-x));
+        bpr += (double)(-logf(gamma + s));
+        coef[t] = -(s * (1.f - s)) / (gamma + s);
+        const float *pe = P + (int64_t)bu[t] * F, *qie = Q + (int64_t)bi[t] * F, *qje = Q + (int64_t)bj[t] * F;
+        for (int f = 0; f < F; f++) {
+            l1u += fabsf(pe[f]); s2u += (double)(pe[f] * pe[f]);
+            l1i += fabsf(qie[f]); s2i += (double)(qie[f] * qie[f]);
+            l1j += fabsf(qje[f]); s2j += (double)(qje[f] * qje[f]);
+        }
+    }
+    double nu = sqrt(s2u), ni = sqrt(s2i), nj = sqrt(s2j);
+    float loss = (float)bpr;
+    loss += h->reg_1 * ((float)l1u + (float)l1i + (float)l1j);      /* :163 */
+    loss += h->reg_2 * ((float)nu + (float)ni + (float)nj);         /* :164 */
+    if (!apply || isnan(loss)) {
+        free(Em); free(coef);
+        return (double)loss;
+    }
+    /* dL/dE_mean (dense buffer, non-zero on batch rows) */
+    double *Gd = (double *)calloc(sz, sizeof(double));
+    for (int64_t t = 0; t < B; t++) {
+        const float *p = Pm + (int64_t)bu[t] * F, *qi = Qm + (int64_t)bi[t] * F, *qj = Qm + (int64_t)bj[t] * F;
+        double *gu = Gd + (int64_t)bu[t] * F, *gi = Gd + ((int64_t)U + bi[t]) * F, *gj = Gd + ((int64_t)U + bj[t]) * F;
+        float c = coef[t];
+        for (int f = 0; f < F; f++) {
+            gu[f] += (double)(c * (qi[f] - qj[f]));
+            gi[f] += (double)(c * p[f]);
+            gj[f] += (double)(-c * p[f]);
+        }
+    }
+    float *G = (float *)malloc(sizeof(float) * sz), *Gp = (float *)malloc(sizeof(float) * sz);
+    for (size_t k = 0; k < sz; k++) G[k] = (float)Gd[k];
+    orc_lgcn_propagate(row_ptr, col, val, n, F, L, G, Gp);          /* 1/(L+1) sum_l A^l G */
+    /* ego regulariser gradient */
+    float inu = nu > 0 ? (float)(1.0 / nu) : 0.f, ini = ni > 0 ? (float)(1.0 / ni) : 0.f, inj = nj > 0 ? (float)(1.0 / nj) : 0.f;
+    for (size_t k = 0; k < sz; k++) Gd[k] = (double)Gp[k];
+    for (int64_t t = 0; t < B; t++) {
+        const float *pe = P + (int64_t)bu[t] * F, *qie = Q + (int64_t)bi[t] * F, *qje = Q + (int64_t)bj[t] * F;
+        double *gu = Gd + (int64_t)bu[t] * F, *gi = Gd + ((int64_t)U + bi[t]) * F, *gj = Gd + ((int64_t)U + bj[t]) * F;
+        for (int f = 0; f < F; f++) {
+            float sp = (pe[f] > 0) - (pe[f] < 0), si = (qie[f] > 0) - (qie[f] < 0), sj = (qje[f] > 0) - (qje[f] < 0);
+            gu[f] += (double)(h->reg_1 * sp) + (double)(h->reg_2 * pe[f] * inu);
+            gi[f] += (double)(h->reg_1 * si) + (double)(h->reg_2 * qie[f] * ini);
+            gj[f] += (double)(h->reg_1 * sj) + (double)(h->reg_2 * qje[f] * inj);
+        }
+    }
+    if (h->opt == 0) {
+        for (size_t k = 0; k < sz; k++) E0[k] = E0[k] - h->lr * (float)Gd[k];
+    } else {
+        adam_dense(E0, m, v, Gd, (int64_t)sz, h, step_count);
+    }
+    free(Em); free(coef); free(Gd); free(G); free(Gp);
+    return (double)loss;
+}

@@ -238,7 +238,70 @@ def gen_mf_rank():
     _save("mf_rank", **out)
 
 
-ALL = {"sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+# --------------------------------------------------------------------------- LightGCN
+def gen_lightgcn():
+    """LightGCN (LightGCNRecommender.py:73-211): normalised adjacency, forward propagation, 3 training steps
+    (Adam default and SGD, reg on/off, L=2/3), rank / full_rank / predict on the propagated tables."""
+    import pandas as pd
+    import torch
+    from daisy.model.LightGCNRecommender import LightGCN
+    from daisy.utils.utils import get_inter_matrix
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [  # U, I, nnz, F, L, B, lr, reg1, reg2, opt, seed
+        (60, 90, 700, 16, 2, 128, 0.01, 0.0, 0.0, "default", 21),
+        (40, 50, 400, 64, 3, 256, 0.01, 0.001, 0.002, "default", 22),
+        (30, 45, 300, 8, 3, 64, 0.05, 0.001, 0.001, "sgd", 23),
+        (25, 30, 200, 6, 1, 50, 0.01, 0.0, 0.0, "sgd", 24),
+    ]
+    rng0 = np.random.default_rng(99)
+    for k, (U, I, nnz, F, L, B, lr, r1, r2, opt, seed) in enumerate(cases):
+        cu, ci = _synthetic_inter(rng0, U, I, nnz)
+        df = pd.DataFrame({"user": cu, "item": ci, "rating": 1.0, "timestamp": np.arange(len(cu))})
+        cfg = rh.make_config("lightgcn", user_num=U, item_num=I, factors=F, num_layers=L, lr=lr, reg_1=r1, reg_2=r2,
+                             optimizer=opt, epochs=1, topk=10, cand_num=40)
+        cfg["inter_matrix"] = get_inter_matrix(df, cfg)
+        torch.manual_seed(seed)
+        model = LightGCN(cfg)
+        adj = model.norm_adj_matrix.coalesce()
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        E = [torch.cat([model.embed_user.weight, model.embed_item.weight]).detach().numpy().copy()]
+        with torch.no_grad():
+            eu, ei = model.forward()
+        Em0 = torch.cat([eu, ei]).numpy().copy()
+        batches, losses = [], []
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            E.append(torch.cat([model.embed_user.weight, model.embed_item.weight]).detach().numpy().copy())
+        users = rng.permutation(U)[:9].astype(np.int64)
+        cands = rng.integers(I, size=(9, 40)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), c] for u, c in zip(users, cands)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        with torch.no_grad():
+            preds = model.rank(loader)
+            full = np.stack([model.full_rank(int(u)) for u in users[:4]])
+            pp = np.array([model.predict(int(users[0]), int(cands[0][0]))], np.float32)
+            Em_final = torch.cat([model.restore_user_e, model.restore_item_e]).numpy().copy()
+        out.update({f"c{k}_coo_u": cu, f"c{k}_coo_i": ci, f"c{k}_adj_idx": adj.indices().numpy().astype(np.int32),
+                    f"c{k}_adj_val": adj.values().numpy(), f"c{k}_E": np.stack(E), f"c{k}_Em0": Em0,
+                    f"c{k}_batches": np.stack(batches), f"c{k}_loss": np.array(losses, np.float64),
+                    f"c{k}_hyper": np.array([U, I, F, L, lr, r1, r2, 0 if opt == "sgd" else 1], np.float64),
+                    f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32), f"c{k}_preds": preds, f"c{k}_full": full,
+                    f"c{k}_pred_pair": pp, f"c{k}_Em_final": Em_final})
+        print(f"lightgcn case {k}: losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("lightgcn", **out)
+
+
+ALL = {"lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

@@ -184,3 +184,41 @@ def mf_full_rank(P, Q, users, topk):
     lib().orc_mf_full_rank(_f32(P), _f32(Q), P.shape[1], Q.shape[0], _i64(users), C.c_int64(len(users)), topk,
                            _i64(out))
     return out
+
+
+# ---------------------------------------------------------------- LightGCN
+def lgcn_norm_adj(coo_u, coo_i, user_num, item_num):
+    """daisy/model/LightGCNRecommender.py:73-107 (get_norm_adj_mat) as CSR over the U+I nodes.
+
+    A = binary bipartite adjacency (duplicate interactions collapse, as the dok dict does, :87-89);
+    diag = (A>0).sum(1) + 1e-7 in float64, ** -0.5 (:92-96); L = D A D in float64 ((D*A)*D, :98), cast to
+    float32 (:104).  Returns (row_ptr int64[n+1], col int32 ascending per row, val float32)."""
+    n = user_num + item_num
+    u = np.asarray(coo_u, np.int64)
+    i = np.asarray(coo_i, np.int64) + user_num
+    key = np.unique(np.concatenate([u * n + i, i * n + u]))
+    row, col = key // n, key % n
+    deg = np.bincount(row, minlength=n).astype(np.float64)
+    dinv = np.power(deg + 1e-7, -0.5)
+    val = ((dinv[row] * 1.0) * dinv[col]).astype(np.float32)
+    row_ptr = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(row, minlength=n), out=row_ptr[1:])
+    return row_ptr, col.astype(np.int32), val
+
+
+def lgcn_propagate(row_ptr, col, val, E0, L):
+    n, F = E0.shape
+    out = np.empty_like(E0)
+    lib().orc_lgcn_propagate(_i64(row_ptr), _i32(col), _f32(val), C.c_int64(n), F, L, _f32(E0), _f32(out))
+    return out
+
+
+def lgcn_bpr_step(E0, U, I, L, row_ptr, col, val, bu, bi, bj, hp, apply=True, adam_state=None, step_count=1):
+    """In-place step on E0 = cat(P, Q) float32 [(U+I), F].  Returns the loss."""
+    m = v = None
+    if adam_state is not None:
+        m, v = adam_state
+    lib().orc_lgcn_bpr_step.restype = C.c_double
+    return lib().orc_lgcn_bpr_step(_f32(E0), U, I, E0.shape[1], L, _i64(row_ptr), _i32(col), _f32(val), _i32(bu), _i32(bi),
+                                   _i32(bj), C.c_int64(len(bu)), C.byref(hp), int(apply),
+                                   None if m is None else _f32(m), None if v is None else _f32(v), C.c_int64(step_count))
