@@ -566,3 +566,219 @@ double orc_lgcn_bpr_step(float *E0, int32_t U, int32_t I, int32_t F, int32_t L, 
     free(Em); free(coef); free(Gd); free(G); free(Gp);
     return (double)loss;
 }
+
+/* ====================================================================================
+ * NeuMF (daisy/model/NeuMFRecommender.py), model_name == 'NeuMF', dropout == 0.
+ * ------------------------------------------------------------------------------------
+ * forward :118-137   GMF = UG[u] * IG[i];  x0 = cat(UM[u], IM[i]);  for each layer: x = relu(W x + b) (:58-64, the
+ *                    Dropout in front of every Linear is the identity at p = 0);  pred = wp . cat(GMF, x) + bp (:66-71).
+ * calc_loss :139-169 BPR (loss.py:11) + the regulariser EXACTLY as written, including the reference's quirk that
+ *                    lines :158 and :160 use embed_item_GMF(neg_item) where the MLP table was meant:
+ *                      reg_1*(|IG_i|_1+|IG_j|_1) + reg_1*(|IM_i|_1+|IG_j|_1) + reg_2*(|IG_i|+|IG_j|) + reg_2*(|IM_i|+|IG_j|)
+ *                      + reg_1*|UG_u|_1 + reg_1*|UM_u|_1 + reg_2*|UG_u| + reg_2*|UM_u|
+ * backward + optimizer.step: closed form below; dense Adam (torch defaults) or SGD on every parameter.
+ *
+ * Parameter block layout (one flat fp32 buffer `W`, same order as module registration):
+ *   layer l = 0..L-1: weight [out_l, in_l] row-major, then bias [out_l], with in_l = 2D/2^l, out_l = in_l/2;
+ *   then predict weight [2F], predict bias [1].         D = F * 2^(L-1).
+ * ================================================================================== */
+static int64_t neumf_param_count(int F, int L)
+{
+    int64_t D = (int64_t)F << (L - 1), n = 0, in = 2 * D;
+    for (int l = 0; l < L; l++) { n += in * (in / 2) + in / 2; in /= 2; }
+    return n + 2 * F + 1;
+}
+
+int64_t orc_neumf_param_count(int32_t F, int32_t L) { return neumf_param_count(F, L); }
+
+/* forward of one (u, item) pair; acts[] receives the activations of every layer (concatenated), returns pred */
+static float neumf_forward_one(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int F,
+                               int L, int u, int it, float *x0, float *acts, float *gmf)
+{
+    int D = F << (L - 1);
+    for (int f = 0; f < F; f++) gmf[f] = UG[(int64_t)u * F + f] * IG[(int64_t)it * F + f];
+    for (int d = 0; d < D; d++) { x0[d] = UM[(int64_t)u * D + d]; x0[D + d] = IM[(int64_t)it * D + d]; }
+    const float *in = x0;
+    int n_in = 2 * D;
+    const float *w = W;
+    float *out = acts;
+    for (int l = 0; l < L; l++) {
+        int n_out = n_in / 2;
+        const float *b = w + (int64_t)n_in * n_out;
+        for (int o = 0; o < n_out; o++) {
+            double acc = 0.0;
+            for (int k = 0; k < n_in; k++) acc += (double)(w[(int64_t)o * n_in + k] * in[k]);
+            float z = (float)acc + b[o];
+            out[o] = z > 0.f ? z : 0.f;
+        }
+        w = b + n_out;
+        in = out;
+        out += n_out;
+        n_in = n_out;
+    }
+    /* predict layer: weight [2F] over cat(GMF, MLP out), bias */
+    double acc = 0.0;
+    for (int f = 0; f < F; f++) acc += (double)(w[f] * gmf[f]);
+    for (int f = 0; f < F; f++) acc += (double)(w[F + f] * in[f]);
+    return (float)acc + w[2 * F];
+}
+
+void orc_neumf_predict(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int32_t F,
+                       int32_t L, const int32_t *u, const int32_t *it, int64_t n, float *out)
+{
+    int D = F << (L - 1);
+    float *x0 = (float *)malloc(sizeof(float) * (size_t)(2 * D + 2 * D + F));
+    for (int64_t t = 0; t < n; t++) out[t] = neumf_forward_one(UG, IG, UM, IM, W, F, L, u[t], it[t], x0, x0 + 2 * D, x0 + 4 * D);
+    free(x0);
+}
+
+/* Adam / SGD on a flat block given fp64 gradients */
+static void update_block(float *theta, float *m, float *v, const double *g, int64_t n, const orc_hyper *h, int64_t step_count)
+{
+    if (h->opt == 0) {
+        for (int64_t k = 0; k < n; k++) theta[k] = theta[k] - h->lr * (float)g[k];
+    } else {
+        adam_dense(theta, m, v, g, n, h, step_count);
+    }
+}
+
+/* One NeuMF BPR step.  tables: UG[U,F] IG[I,F] UM[U,D] IM[I,D]; W flat tower block.  state (Adam): m,v blocks in the
+ * order UG, IG, UM, IM, W (each table-sized), may be NULL for SGD.  Returns the loss. */
+double orc_neumf_bpr_step(float *UG, float *IG, float *UM, float *IM, float *W, int32_t U, int32_t I, int32_t F, int32_t L,
+                          const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B, const orc_hyper *h,
+                          int32_t apply, float **m, float **v, int64_t step_count)
+{
+    const float gamma = 1e-10f;
+    const int D = F << (L - 1);
+    int n_act = 0;
+    { int in = 2 * D; for (int l = 0; l < L; l++) { n_act += in / 2; in /= 2; } }
+    const int64_t nW = neumf_param_count(F, L);
+    /* per-row storage of x0 / activations / gmf for pos and neg */
+    size_t per = (size_t)(2 * D + n_act + F);
+    float *buf = (float *)malloc(sizeof(float) * per * 2 * (size_t)(B > 0 ? B : 1));
+    float *coef = (float *)malloc(sizeof(float) * (size_t)(B > 0 ? B : 1));
+    double bpr = 0, l1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   /* UG_u, UM_u, IG_i, IM_i, IG_j */
+    for (int64_t t = 0; t < B; t++) {
+        float *rp = buf + per * (size_t)(2 * t), *rn = rp + per;
+        float pos = neumf_forward_one(UG, IG, UM, IM, W, F, L, bu[t], bi[t], rp, rp + 2 * D, rp + 2 * D + n_act);
+        float neg = neumf_forward_one(UG, IG, UM, IM, W, F, L, bu[t], bj[t], rn, rn + 2 * D, rn + 2 * D + n_act);
+        float x = pos - neg;
+        float s = 1.f / (1.f + expf(-x));
+        bpr += (double)(-logf(gamma + s));
+        coef[t] = -(s * (1.f - s)) / (gamma + s);
+        const float *rows[5] = {UG + (int64_t)bu[t] * F, UM + (int64_t)bu[t] * D, IG + (int64_t)bi[t] * F,
+                                IM + (int64_t)bi[t] * D, IG + (int64_t)bj[t] * F};
+        const int len[5] = {F, D, F, D, F};
+        for (int q = 0; q < 5; q++)
+            for (int f = 0; f < len[q]; f++) { l1[q] += fabsf(rows[q][f]); s2[q] += (double)(rows[q][f] * rows[q][f]); }
+    }
+    double nr[5];
+    for (int q = 0; q < 5; q++) nr[q] = sqrt(s2[q]);
+    float loss = (float)bpr;                                             /* :154-167, fp32 scalar adds in order */
+    loss += h->reg_1 * ((float)l1[2] + (float)l1[4]);
+    loss += h->reg_1 * ((float)l1[3] + (float)l1[4]);
+    loss += h->reg_2 * ((float)nr[2] + (float)nr[4]);
+    loss += h->reg_2 * ((float)nr[3] + (float)nr[4]);
+    loss += h->reg_1 * (float)l1[0];
+    loss += h->reg_1 * (float)l1[1];
+    loss += h->reg_2 * (float)nr[0];
+    loss += h->reg_2 * (float)nr[1];
+    if (!apply || isnan(loss)) { free(buf); free(coef); return (double)loss; }
+
+    double *gUG = (double *)calloc((size_t)U * F, sizeof(double)), *gIG = (double *)calloc((size_t)I * F, sizeof(double));
+    double *gUM = (double *)calloc((size_t)U * D, sizeof(double)), *gIM = (double *)calloc((size_t)I * D, sizeof(double));
+    double *gW = (double *)calloc((size_t)nW, sizeof(double));
+    float *dcur = (float *)malloc(sizeof(float) * (size_t)(2 * D)), *dprev = (float *)malloc(sizeof(float) * (size_t)(2 * D));
+    float inv[5];
+    for (int q = 0; q < 5; q++) inv[q] = nr[q] > 0 ? (float)(1.0 / nr[q]) : 0.f;
+    /* offsets of each layer's weight inside W */
+    int64_t woff[16]; int nin[16];
+    { int64_t o = 0; int in = 2 * D; for (int l = 0; l < L; l++) { woff[l] = o; nin[l] = in; o += (int64_t)in * (in / 2) + in / 2; in /= 2; } woff[L] = o; }
+    const float *wp = W + woff[L];
+    for (int64_t t = 0; t < B; t++) {
+        for (int side = 0; side < 2; side++) {
+            const float *r = buf + per * (size_t)(2 * t + side);
+            const float *x0 = r, *acts = r + 2 * D, *gmf = r + 2 * D + n_act;
+            int u = bu[t], it = side == 0 ? bi[t] : bj[t];
+            float dp = side == 0 ? coef[t] : -coef[t];                     /* dL/dpred */
+            /* predict layer */
+            const float *hL = acts + (n_act - F);
+            for (int f = 0; f < F; f++) {
+                gW[woff[L] + f] += (double)(dp * gmf[f]);
+                gW[woff[L] + F + f] += (double)(dp * hL[f]);
+                gUG[(int64_t)u * F + f] += (double)(dp * wp[f] * IG[(int64_t)it * F + f]);
+                gIG[(int64_t)it * F + f] += (double)(dp * wp[f] * UG[(int64_t)u * F + f]);
+            }
+            gW[woff[L] + 2 * F] += (double)dp;
+            /* tower backward */
+            for (int f = 0; f < F; f++) dcur[f] = dp * wp[F + f];
+            int a_off = n_act;                                            /* end of layer l's activations */
+            for (int l = L - 1; l >= 0; l--) {
+                int n_in = nin[l], n_out = n_in / 2;
+                a_off -= n_out;
+                const float *out = acts + a_off;
+                const float *in = (l == 0) ? x0 : acts + (a_off - n_in);
+                const float *w = W + woff[l];
+                for (int o = 0; o < n_out; o++) if (!(out[o] > 0.f)) dcur[o] = 0.f;   /* relu' */
+                for (int k = 0; k < n_in; k++) dprev[k] = 0.f;
+                for (int o = 0; o < n_out; o++) {
+                    float dz = dcur[o];
+                    gW[woff[l] + (int64_t)n_in * n_out + o] += (double)dz;
+                    for (int k = 0; k < n_in; k++) {
+                        gW[woff[l] + (int64_t)o * n_in + k] += (double)(dz * in[k]);
+                        dprev[k] += dz * w[(int64_t)o * n_in + k];
+                    }
+                }
+                float *tmp = dcur; dcur = dprev; dprev = tmp;
+            }
+            for (int d = 0; d < D; d++) {
+                gUM[(int64_t)u * D + d] += (double)dcur[d];
+                gIM[(int64_t)it * D + d] += (double)dcur[D + d];
+            }
+        }
+        /* regulariser gradients (per occurrence), with the :158/:160 quirk: IG_j twice, IM_j never */
+        int u = bu[t], i = bi[t], j = bj[t];
+        for (int f = 0; f < F; f++) {
+            float a = UG[(int64_t)u * F + f], b = IG[(int64_t)i * F + f], c = IG[(int64_t)j * F + f];
+            gUG[(int64_t)u * F + f] += (double)(h->reg_1 * ((a > 0) - (a < 0))) + (double)(h->reg_2 * a * inv[0]);
+            gIG[(int64_t)i * F + f] += (double)(h->reg_1 * ((b > 0) - (b < 0))) + (double)(h->reg_2 * b * inv[2]);
+            gIG[(int64_t)j * F + f] += 2.0 * ((double)(h->reg_1 * ((c > 0) - (c < 0))) + (double)(h->reg_2 * c * inv[4]));
+        }
+        for (int d = 0; d < D; d++) {
+            float a = UM[(int64_t)u * D + d], b = IM[(int64_t)i * D + d];
+            gUM[(int64_t)u * D + d] += (double)(h->reg_1 * ((a > 0) - (a < 0))) + (double)(h->reg_2 * a * inv[1]);
+            gIM[(int64_t)i * D + d] += (double)(h->reg_1 * ((b > 0) - (b < 0))) + (double)(h->reg_2 * b * inv[3]);
+        }
+    }
+    update_block(UG, m ? m[0] : NULL, v ? v[0] : NULL, gUG, (int64_t)U * F, h, step_count);
+    update_block(IG, m ? m[1] : NULL, v ? v[1] : NULL, gIG, (int64_t)I * F, h, step_count);
+    update_block(UM, m ? m[2] : NULL, v ? v[2] : NULL, gUM, (int64_t)U * D, h, step_count);
+    update_block(IM, m ? m[3] : NULL, v ? v[3] : NULL, gIM, (int64_t)I * D, h, step_count);
+    update_block(W, m ? m[4] : NULL, v ? v[4] : NULL, gW, nW, h, step_count);
+    free(buf); free(coef); free(gUG); free(gIG); free(gUM); free(gIM); free(gW); free(dcur); free(dprev);
+    return (double)loss;
+}
+
+/* NeuMF.rank :178-209 / full_rank :211-232: scores through the full tower; ties by lower position / item id */
+void orc_neumf_rank(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int32_t F, int32_t L,
+                    const int64_t *users, int64_t n_users, const int64_t *cands, int32_t cand_num, int32_t item_num,
+                    int32_t topk, float *out_f, int64_t *out_i)
+{
+    int D = F << (L - 1);
+    int cnt = cands ? cand_num : item_num;
+    orc_sc *sc = (orc_sc *)malloc(sizeof(orc_sc) * (size_t)cnt);
+    float *x0 = (float *)malloc(sizeof(float) * (size_t)(4 * D + F));
+    for (int64_t r = 0; r < n_users; r++) {
+        for (int k = 0; k < cnt; k++) {
+            int it = cands ? (int)cands[r * cand_num + k] : k;
+            sc[k].s = neumf_forward_one(UG, IG, UM, IM, W, F, L, (int)users[r], it, x0, x0 + 2 * D, x0 + 4 * D);
+            sc[k].pos = k;
+        }
+        qsort(sc, (size_t)cnt, sizeof(orc_sc), sc_desc);
+        for (int k = 0; k < topk && k < cnt; k++) {
+            if (cands) out_f[r * topk + k] = (float)cands[r * cand_num + sc[k].pos];
+            else out_i[r * topk + k] = sc[k].pos;
+        }
+    }
+    free(sc); free(x0);
+}

@@ -301,7 +301,81 @@ def gen_lightgcn():
     _save("lightgcn", **out)
 
 
-ALL = {"lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+# --------------------------------------------------------------------------- NeuMF
+def _neumf_flat(model):
+    """4 tables + the flat tower block in module-registration order (layer weight, bias, ..., predict weight, bias)."""
+    import torch.nn as nn
+    tabs = [t.weight.detach().numpy().copy() for t in (model.embed_user_GMF, model.embed_item_GMF,
+                                                        model.embed_user_MLP, model.embed_item_MLP)]
+    parts = []
+    for mod in model.MLP_layers:
+        if isinstance(mod, nn.Linear):
+            parts += [mod.weight.detach().numpy().ravel(), mod.bias.detach().numpy().ravel()]
+    parts += [model.predict_layer.weight.detach().numpy().ravel(), model.predict_layer.bias.detach().numpy().ravel()]
+    return tabs, np.concatenate(parts).astype(np.float32)
+
+
+def gen_neumf():
+    """NeuMF (NeuMFRecommender.py:16-232), model_name='NeuMF', dropout=0 (dropout>0 draws torch-RNG masks that no
+    other implementation can reproduce): init stream, 3 training steps (Adam default / SGD, reg with the :158/:160
+    quirk), rank / full_rank / predict."""
+    import torch
+    from daisy.model.NeuMFRecommender import NeuMF
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [  # U, I, F, L, B, lr, reg1, reg2, opt, seed
+        (40, 60, 8, 2, 64, 0.001, 0.001, 0.001, "default", 31),
+        (30, 50, 32, 2, 128, 0.001, 0.0, 0.0, "default", 32),          # BASELINE config 3 tower 128->64->32
+        (25, 35, 24, 2, 100, 0.01, 0.002, 0.003, "sgd", 33),           # reference default factors=24
+        (20, 30, 16, 3, 96, 0.001, 0.001, 0.001, "default", 34),
+        (15, 20, 6, 1, 40, 0.01, 0.001, 0.0, "sgd", 35),
+    ]
+    for k, (U, I, F, L, B, lr, r1, r2, opt, seed) in enumerate(cases):
+        cfg = rh.make_config("neumf", user_num=U, item_num=I, factors=F, num_layers=L, lr=lr, reg_1=r1, reg_2=r2,
+                             optimizer=opt, dropout=0.0, epochs=1, topk=10, cand_num=40)
+        torch.manual_seed(seed)
+        model = NeuMF(cfg)
+        with torch.no_grad():                                        # spread the scores so ranking is well separated
+            for t in (model.embed_user_GMF, model.embed_item_GMF, model.embed_user_MLP, model.embed_item_MLP):
+                t.weight.mul_(3.0)
+        tabs0_init, _ = _neumf_flat(model)
+        model.train()
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        snaps = [_neumf_flat(model)]
+        batches, losses = [], []
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]).long(), torch.from_numpy(b[1]).long(), torch.from_numpy(b[2]).long()])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            snaps.append(_neumf_flat(model))
+        model.eval()
+        users = rng.permutation(U)[:7].astype(np.int64)
+        cands = rng.integers(I, size=(7, 40)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), c] for u, c in zip(users, cands)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        with torch.no_grad():
+            preds = model.rank(loader)
+            full = np.stack([model.full_rank(int(u)) for u in users[:3]])
+            pp = np.array([model.predict(int(users[q]), int(cands[q][0])) for q in range(4)], np.float32)
+        for q, name in enumerate(("UG", "IG", "UM", "IM")):
+            out[f"c{k}_{name}"] = np.stack([s_[0][q] for s_ in snaps])
+        out.update({f"c{k}_W": np.stack([s_[1] for s_ in snaps]), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64),
+                    f"c{k}_hyper": np.array([U, I, F, L, lr, r1, r2, 0 if opt == "sgd" else 1, seed], np.float64),
+                    f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32), f"c{k}_preds": preds, f"c{k}_full": full,
+                    f"c{k}_pred_pairs": pp})
+        print(f"neumf case {k}: losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("neumf", **out)
+
+
+ALL = {"neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

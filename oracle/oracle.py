@@ -222,3 +222,50 @@ def lgcn_bpr_step(E0, U, I, L, row_ptr, col, val, bu, bi, bj, hp, apply=True, ad
     return lib().orc_lgcn_bpr_step(_f32(E0), U, I, E0.shape[1], L, _i64(row_ptr), _i32(col), _f32(val), _i32(bu), _i32(bi),
                                    _i32(bj), C.c_int64(len(bu)), C.byref(hp), int(apply),
                                    None if m is None else _f32(m), None if v is None else _f32(v), C.c_int64(step_count))
+
+
+# ---------------------------------------------------------------- NeuMF
+def neumf_param_count(F, L):
+    lib().orc_neumf_param_count.restype = C.c_int64
+    return int(lib().orc_neumf_param_count(F, L))
+
+
+def neumf_predict(tabs, W, F, L, u, it):
+    UG, IG, UM, IM = tabs
+    out = np.empty(len(u), np.float32)
+    lib().orc_neumf_predict(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i32(u), _i32(it), C.c_int64(len(u)),
+                            _f32(out))
+    return out
+
+
+def neumf_bpr_step(tabs, W, F, L, bu, bi, bj, hp, apply=True, adam_state=None, step_count=1):
+    """In-place step on the 4 tables (UG, IG, UM, IM) and the flat tower block W.  adam_state = (m[5], v[5])."""
+    UG, IG, UM, IM = tabs
+    PF = C.POINTER(C.c_float)
+    m = v = None
+    if adam_state is not None:
+        m = (PF * 5)(*[_f32(a) for a in adam_state[0]])
+        v = (PF * 5)(*[_f32(a) for a in adam_state[1]])
+    lib().orc_neumf_bpr_step.restype = C.c_double
+    return lib().orc_neumf_bpr_step(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), UG.shape[0], IG.shape[0], F, L,
+                                    _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), int(apply), m, v,
+                                    C.c_int64(step_count))
+
+
+def neumf_rank(tabs, W, F, L, users, cands, topk):
+    UG, IG, UM, IM = tabs
+    users = np.ascontiguousarray(users, np.int64)
+    cands = np.ascontiguousarray(cands, np.int64)
+    out = np.empty((len(users), topk), np.float32)
+    lib().orc_neumf_rank(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i64(users), C.c_int64(len(users)),
+                         _i64(cands), cands.shape[1], IG.shape[0], topk, _f32(out), None)
+    return out
+
+
+def neumf_full_rank(tabs, W, F, L, users, topk):
+    UG, IG, UM, IM = tabs
+    users = np.ascontiguousarray(users, np.int64)
+    out = np.empty((len(users), topk), np.int64)
+    lib().orc_neumf_rank(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i64(users), C.c_int64(len(users)),
+                         None, 0, IG.shape[0], topk, None, _i64(out))
+    return out
