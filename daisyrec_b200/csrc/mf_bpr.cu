@@ -145,7 +145,7 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
         for (int k = 0; k < R; ++k) {
             const bool touched = cnt[k] != 0;
             if (!act[k] || (OPT == DRB_OPT_SGD && !touched && !p.dense_grad)) continue;
-            const float ca = (float)(unsigned)(cnt[k] & 0xffffffffull), cb = (float)(unsigned)(cnt[k] >> 32);
+            const float ca = (float)(unsigned)(cnt[k] & 0xffffffffull), cb = p.neg_mult * (float)(unsigned)(cnt[k] >> 32);
             const float ia = is_user[k] ? nm.inv_u : nm.inv_i, ib = nm.inv_j;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
                     st_row<VEC>(g_p[k] + c * VEC, z);
                 }
             }
-            if (touched && gl == 0) {
+            if (touched && gl == 0 && !p.keep_counts) {
                 long long r = r0 + (long long)k * tg;
                 if (is_user[k]) p.ws.cntU[r] = 0u; else p.ws.cntI[r - p.U] = 0ull;
             }
@@ -568,6 +568,8 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.Qn = nullptr;
     p.gscale = 1.f;
     p.dense_grad = 0;
+    p.neg_mult = 1.f;
+    p.keep_counts = 0;
     return DRB_OK;
 }
 

@@ -1,0 +1,611 @@
+// neumf.cu -- NeuMF + BPR on the B200 path, fp32 tower on CUDA cores.
+//
+// Stands behind daisy/model/NeuMFRecommender.py (model_name == 'NeuMF'):
+//   forward   :118-137  GMF = UG[u]*IG[i];  x0 = cat(UM[u], IM[i]);  L x (Dropout -> Linear -> ReLU);  Linear(2F, 1)
+//   calc_loss :139-169  BPR + the regulariser as written, quirk included (:158,:160 use the GMF table for the MLP-neg term)
+//   backward + optimizer.step (AbstractRecommender.py:125-126; dense Adam by default, NeuMFRecommender.py:74)
+//   rank / full_rank / predict :171-232 (scores through the whole tower)
+//
+// One training step on a batch of B triples (R = 2B rows: pos rows [0,B), neg rows [B,2B)):
+//   gather      A_0[R, 2D]  = cat(UM[u], IM[item])                      (lane group per row, 128-bit loads)
+//   tower fwd   A_l = relu(A_{l-1} W_l^T + b_l)                         (tiled fp32 GEMM, fused bias + ReLU)
+//   head        pred, BPR coefficient, loss + regulariser norms, GMF gradients (RED.ADD.F32x4), dZ_L, row counters
+//   tower bwd   gW_l += dZ_l^T A_{l-1} (split-K, atomics);  dZ_{l-1} = (dZ_l W_l) * [A_{l-1} > 0]
+//   scatter     gUM[u] += dA_0[:, :D] (pos + neg rows), gIM[item] += dA_0[:, D:]
+//   apply       the MF dense sweep (mf_bpr.cu) on the table pairs (UG,IG) and (UM,IM) with per-table norms and the
+//               2x / 0x negative-count multipliers of the quirk; a small dense Adam/SGD kernel on the tower block.
+// Parameter block W (flat fp32, module-registration order): per layer weight [out,in] + bias [out]; predict weight [2F] + bias.
+//
+// Rooflines: the tower is ~124 KFLOP per triple at F=32, L=2 (fwd+bwd, both items) against ~2.3 KB of embedding traffic:
+// compute-bound on CUDA cores in this fp32 path; the bf16 tcgen05 tower of BASELINE config 3 replaces the three GEMM
+// call sites only.
+#include "step.cuh"
+
+namespace drb {
+
+constexpr int kMaxLayers = 8;
+
+struct NeumfDims {
+    int U, I, F, L, D;
+    int n[kMaxLayers + 1];              // n[0] = 2D, n[l] = n[l-1]/2, n[L] = F
+    long long w_off[kMaxLayers], b_off[kMaxLayers], wp_off, bp_off, nW;
+    long long act_off[kMaxLayers + 1];  // offset of A_l inside the activation buffer, in units of R floats
+    long long act_cols;                 // sum_l n[l]
+};
+
+static bool make_dims(NeumfDims &d, int U, int I, int F, int L)
+{
+    if (U <= 0 || I <= 0 || F <= 0 || L < 1 || L > kMaxLayers || (F % 4) != 0) return false;
+    d.U = U; d.I = I; d.F = F; d.L = L; d.D = F << (L - 1);
+    d.n[0] = 2 * d.D;
+    long long o = 0, a = 0;
+    for (int l = 0; l < L; ++l) {
+        d.n[l + 1] = d.n[l] / 2;
+        d.w_off[l] = o; o += (long long)d.n[l] * d.n[l + 1];
+        d.b_off[l] = o; o += d.n[l + 1];
+    }
+    d.wp_off = o; o += 2 * F;
+    d.bp_off = o; o += 1;
+    d.nW = o;
+    for (int l = 0; l <= L; ++l) { d.act_off[l] = a; a += d.n[l]; }
+    d.act_cols = a;
+    return true;
+}
+
+struct NeumfWs {
+    WsHeader *hdrG, *hdrM;       // phase-2 headers of the (UG,IG) and (UM,IM) table pairs
+    double *red;                 // [16] batch reductions: bpr, l1[5], s2[5]  (UG_u, UM_u, IG_i, IM_i, IG_j)
+    float *gUG, *gIG, *gUM, *gIM, *gW;
+    unsigned *cntU;
+    unsigned long long *cntI;
+    float *mUG, *vUG, *mIG, *vIG, *mUM, *vUM, *mIM, *vIM, *mW, *vW;
+    float *acts, *dA, *dB;       // activations [act_cols * R], two gradient ping-pong buffers [2D * R]
+};
+
+static size_t carve_neumf(void *base, const NeumfDims &d, int opt, long long max_rows, NeumfWs *w)
+{
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) {
+        char *p = b ? b + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    NeumfWs t;
+    t.hdrG = (WsHeader *)take(256);
+    t.hdrM = (WsHeader *)take(256);
+    t.red = (double *)take(16 * sizeof(double));
+    const size_t uf = sizeof(float) * (size_t)d.U * d.F, itf = sizeof(float) * (size_t)d.I * d.F;
+    const size_t ud = sizeof(float) * (size_t)d.U * d.D, itd = sizeof(float) * (size_t)d.I * d.D;
+    const size_t wb = sizeof(float) * (size_t)d.nW;
+    t.gUG = (float *)take(uf); t.gIG = (float *)take(itf); t.gUM = (float *)take(ud); t.gIM = (float *)take(itd);
+    t.gW = (float *)take(wb);
+    t.cntU = (unsigned *)take(sizeof(unsigned) * (size_t)d.U);
+    t.cntI = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)d.I);
+    t.mUG = t.vUG = t.mIG = t.vIG = t.mUM = t.vUM = t.mIM = t.vIM = t.mW = t.vW = nullptr;
+    if (opt == DRB_OPT_ADAM) {
+        t.mUG = (float *)take(uf); t.vUG = (float *)take(uf); t.mIG = (float *)take(itf); t.vIG = (float *)take(itf);
+        t.mUM = (float *)take(ud); t.vUM = (float *)take(ud); t.mIM = (float *)take(itd); t.vIM = (float *)take(itd);
+        t.mW = (float *)take(wb); t.vW = (float *)take(wb);
+    }
+    t.acts = (float *)take(sizeof(float) * (size_t)d.act_cols * (size_t)max_rows);
+    t.dA = (float *)take(sizeof(float) * (size_t)d.n[0] * (size_t)max_rows);
+    t.dB = (float *)take(sizeof(float) * (size_t)d.n[0] * (size_t)max_rows);
+    if (w) *w = t;
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------ generic fp32 GEMM
+// C[M,N] (op)= opA(A)[M,K] * opB(B)[K,N];  64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+//   TA = false: A(m,k) = A[m*lda + k]      TA = true: A(m,k) = A[k*lda + m]
+//   TB = false: B(k,n) = B[k*ldb + n]      TB = true: B(k,n) = B[n*ldb + k]
+//   EPI 0: C = acc   1: C = relu(acc + bias[n])   2: C = acc * (ref(m,n) > 0)   3: atomicAdd(C, acc) (split-K over grid.z)
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float *__restrict__ A, long long lda,
+                                                    const float *__restrict__ B, long long ldb, float *__restrict__ C,
+                                                    long long ldc, const float *__restrict__ bias,
+                                                    const float *__restrict__ ref, long long ldref, int k_chunk)
+{
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    const int kb = (EPI == 3) ? blockIdx.z * k_chunk : 0;
+    const int ke = (EPI == 3) ? min(K, kb + k_chunk) : K;
+    float acc[4][4] = {};
+    for (int k0 = kb; k0 < ke; k0 += 16) {
+        // load tiles: 16x64 each = 1024 elements, 4 per thread
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int e = tid + q * 256;
+            int kk, mm;
+            if (TA) { kk = e >> 6; mm = e & 63; } else { mm = e >> 4; kk = e & 15; }
+            long long m = m0 + mm;
+            int k = k0 + kk;
+            float v = 0.f;
+            if (m < M && k < ke) v = TA ? __ldg(A + (long long)k * lda + m) : __ldg(A + m * lda + k);
+            As[kk][mm] = v;
+            int nn;
+            if (TB) { nn = e >> 4; kk = e & 15; } else { kk = e >> 6; nn = e & 63; }
+            int n = n0 + nn;
+            k = k0 + kk;
+            v = 0.f;
+            if (n < N && k < ke) v = TB ? __ldg(B + (long long)n * ldb + k) : __ldg(B + (long long)k * ldb + n);
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (EPI == 1) { v += bias[n]; v = v > 0.f ? v : 0.f; }
+            if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v : 0.f; }
+            if (EPI == 3) atomicAdd(C + m * ldc + n, v); else C[m * ldc + n] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB, int EPI>
+static int launch_sgemm(long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb, float *C,
+                        long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st)
+{
+    if (M <= 0 || N <= 0 || K <= 0) return DRB_OK;
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), 1);
+    int k_chunk = K;
+    if (EPI == 3) {   // split-K so that the tiny [out x in] result still fills the machine
+        long long tiles = (long long)grid.x * grid.y;
+        long long want = ((long long)sm_count() * 4 + tiles - 1) / tiles;          // chunks wanted for occupancy
+        long long max_chunks = (K + 2047) / 2048;                                   // >= 2048 rows per chunk
+        long long chunks = want < max_chunks ? want : max_chunks;
+        if (chunks < 1) chunks = 1;
+        k_chunk = (int)(((K + chunks - 1) / chunks + 15) / 16 * 16);
+        grid.z = (unsigned)((K + k_chunk - 1) / k_chunk);
+    }
+    sgemm_kernel<TA, TB, EPI><<<grid, 256, 0, st>>>((int)M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, k_chunk);
+    DRB_CUDA(cudaGetLastError());
+    return DRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ gather / head / scatter
+// A_0[r, :] = cat(UM[u_r], IM[item_r]);  rows [0,B) use bi, rows [B,2B) use bj.   One thread per float4.
+__global__ void neumf_gather_kernel(const float *__restrict__ UM, const float *__restrict__ IM, const int32_t *__restrict__ bu,
+                                    const int32_t *__restrict__ bi, const int32_t *__restrict__ bj, long long B, int D,
+                                    float *__restrict__ A0)
+{
+    const int d4 = D / 4;
+    const long long total = 2 * B * 2 * d4;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        long long r = k / (2 * d4);
+        int c = (int)(k - r * 2 * d4);
+        long long t = r < B ? r : r - B;
+        const float4 *src;
+        if (c < d4) src = reinterpret_cast<const float4 *>(UM + (size_t)bu[t] * D) + c;
+        else src = reinterpret_cast<const float4 *>(IM + (size_t)(r < B ? bi[t] : bj[t]) * D) + (c - d4);
+        reinterpret_cast<float4 *>(A0 + (size_t)r * 2 * D)[c] = __ldcg(src);
+    }
+}
+
+// inference variant: row r scores (users[r / per_user], item) with item = cands[r] or r % per_user
+__global__ void neumf_gather_pairs_kernel(const float *__restrict__ UM, const float *__restrict__ IM,
+                                          const int64_t *__restrict__ users, const int64_t *__restrict__ items,
+                                          long long row0, long long rows, int per_user, int D, float *__restrict__ A0)
+{
+    const int d4 = D / 4;
+    const long long total = rows * 2 * d4;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        long long r = k / (2 * d4);
+        int c = (int)(k - r * 2 * d4);
+        long long g = row0 + r;
+        long long u = users[g / per_user];
+        long long it = items ? items[g] : (g % per_user);
+        const float4 *src = c < d4 ? reinterpret_cast<const float4 *>(UM + (size_t)u * D) + c
+                                   : reinterpret_cast<const float4 *>(IM + (size_t)it * D) + (c - d4);
+        reinterpret_cast<float4 *>(A0 + (size_t)r * 2 * D)[c] = __ldcg(src);
+    }
+}
+
+// One warp per triple.  red[0] bpr, red[1..5] l1 of (UG_u, UM_u, IG_i, IM_i, IG_j), red[6..10] their squared sums.
+__global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict__ UG, const float *__restrict__ IG,
+                                                         const float *__restrict__ UM, const float *__restrict__ IM,
+                                                         const float *__restrict__ wp, const float *__restrict__ AL,
+                                                         const int32_t *__restrict__ bu, const int32_t *__restrict__ bi,
+                                                         const int32_t *__restrict__ bj, long long B, int F, int D, int has_reg,
+                                                         int apply, float *__restrict__ gUG, float *__restrict__ gIG,
+                                                         float *__restrict__ gWp, float *__restrict__ dZL,
+                                                         unsigned *__restrict__ cntU, unsigned long long *__restrict__ cntI,
+                                                         double *__restrict__ red)
+{
+    extern __shared__ float s_gw[];                 // [2F + 1] CTA partial of the predict-layer gradient
+    __shared__ double s_red[11];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int k = threadIdx.x; k < 2 * F + 1; k += blockDim.x) s_gw[k] = 0.f;
+    if (threadIdx.x < 11) s_red[threadIdx.x] = 0.0;
+    __syncthreads();
+    float acc[11] = {};
+    float gwa[4] = {}, gwb[4] = {};                 // predict-layer gradient partials of this lane (F <= 128)
+    const bool reg_gw = F <= 128;
+    const float bp = wp[2 * F];
+    for (long long t = (long long)blockIdx.x * nwarp + warp; t < B; t += (long long)gridDim.x * nwarp) {
+        const int u = bu[t], i = bi[t], j = bj[t];
+        const float *ug = UG + (size_t)u * F, *igi = IG + (size_t)i * F, *igj = IG + (size_t)j * F;
+        const float *hp = AL + (size_t)t * F, *hn = AL + (size_t)(B + t) * F;
+        float sp = 0.f, sn = 0.f;
+        for (int f = lane; f < F; f += 32) {
+            float a = __ldcg(ug + f), b = __ldcg(igi + f), c = __ldcg(igj + f);
+            float w0 = wp[f], w1 = wp[F + f];
+            sp = fmaf(w0, a * b, sp); sp = fmaf(w1, hp[f], sp);
+            sn = fmaf(w0, a * c, sn); sn = fmaf(w1, hn[f], sn);
+            if (has_reg) {
+                acc[1] += fabsf(a); acc[6] = fmaf(a, a, acc[6]);
+                acc[3] += fabsf(b); acc[8] = fmaf(b, b, acc[8]);
+                acc[5] += fabsf(c); acc[10] = fmaf(c, c, acc[10]);
+            }
+        }
+        if (has_reg) {
+            const float *um = UM + (size_t)u * D, *imi = IM + (size_t)i * D;
+            for (int d = lane; d < D; d += 32) {
+                float a = __ldcg(um + d), b = __ldcg(imi + d);
+                acc[2] += fabsf(a); acc[7] = fmaf(a, a, acc[7]);
+                acc[4] += fabsf(b); acc[9] = fmaf(b, b, acc[9]);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            sp += __shfl_xor_sync(0xffffffffu, sp, off);
+            sn += __shfl_xor_sync(0xffffffffu, sn, off);
+        }
+        const float x = (sp + bp) - (sn + bp);
+        const float sg = 1.f / (1.f + expf(-x));
+        if (lane == 0) acc[0] += -logf(1e-10f + sg);
+        const float c = -(sg * (1.f - sg)) / (1e-10f + sg);
+        if (!apply) continue;
+        for (int f = lane, q = 0; f < F; f += 32, ++q) {
+            float a = __ldcg(ug + f), b = __ldcg(igi + f), cc = __ldcg(igj + f);
+            float w0 = wp[f], w1 = wp[F + f];
+            // predict-layer weight gradient: dp * cat(GMF, h) summed over pos (+c) and neg (-c)
+            float ga = c * (a * b) - c * (a * cc), gb = c * hp[f] - c * hn[f];
+            if (reg_gw) { gwa[q & 3] += ga; gwb[q & 3] += gb; }
+            else { atomicAdd(&s_gw[f], ga); atomicAdd(&s_gw[F + f], gb); }
+            // GMF table gradients
+            atomicAdd(gUG + (size_t)u * F + f, c * w0 * b - c * w0 * cc);
+            atomicAdd(gIG + (size_t)i * F + f, c * w0 * a);
+            atomicAdd(gIG + (size_t)j * F + f, -c * w0 * a);
+            // dZ_L = dp * w1 * relu'(h)
+            dZL[(size_t)t * F + f] = hp[f] > 0.f ? c * w1 : 0.f;
+            dZL[(size_t)(B + t) * F + f] = hn[f] > 0.f ? -c * w1 : 0.f;
+        }
+        if (lane == 0) {
+            red_add_u32(cntU + u, 1u);
+            red_add_u64(cntI + i, 1ull);
+            red_add_u64(cntI + j, 1ull << 32);
+        }
+    }
+    if (apply && reg_gw)
+        for (int f = lane, q = 0; f < F; f += 32, ++q) {
+            atomicAdd(&s_gw[f], gwa[q & 3]);
+            atomicAdd(&s_gw[F + f], gwb[q & 3]);
+        }
+    // block reduction of the scalars
+    const int nv = has_reg ? 11 : 1;
+    for (int k = 0; k < nv; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) atomicAdd(&s_red[k], (double)v);
+    }
+    __syncthreads();
+    if (threadIdx.x < nv && s_red[threadIdx.x] != 0.0) atomicAdd(red + threadIdx.x, s_red[threadIdx.x]);
+    if (apply)
+        for (int k = threadIdx.x; k < 2 * F; k += blockDim.x)
+            if (s_gw[k] != 0.f) atomicAdd(gWp + k, s_gw[k]);
+    // the bias gradient of the predict layer is sum(+c) + sum(-c) == 0 exactly for a pairwise loss
+}
+
+// gb[n] += sum_m dZ[m, n]
+__global__ void colsum_kernel(const float *__restrict__ dZ, long long M, int N, float *__restrict__ gb)
+{
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    long long rows_per = (M + gridDim.x - 1) / gridDim.x;
+    long long lo = (long long)blockIdx.x * rows_per, hi = min(M, lo + rows_per);
+    float s = 0.f;
+    for (long long m = lo; m < hi; ++m) s += dZ[m * N + n];
+    if (s != 0.f) atomicAdd(gb + n, s);
+}
+
+// gUM[u] += dA0[t,:D] + dA0[B+t,:D];  gIM[i] += dA0[t,D:];  gIM[j] += dA0[B+t,D:]      (RED.ADD.F32x4)
+__global__ void neumf_scatter_kernel(const float *__restrict__ dA0, const int32_t *__restrict__ bu,
+                                     const int32_t *__restrict__ bi, const int32_t *__restrict__ bj, long long B, int D,
+                                     float *__restrict__ gUM, float *__restrict__ gIM)
+{
+    const int d4 = D / 4;
+    const long long total = B * d4;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        long long t = k / d4;
+        int c = (int)(k - t * d4);
+        const float4 *rp = reinterpret_cast<const float4 *>(dA0 + (size_t)t * 2 * D);
+        const float4 *rn = reinterpret_cast<const float4 *>(dA0 + (size_t)(B + t) * 2 * D);
+        float4 up = rp[c], un = rn[c], ip = rp[d4 + c], in_ = rn[d4 + c];
+        Vec<4> v;
+        v.v[0] = up.x + un.x; v.v[1] = up.y + un.y; v.v[2] = up.z + un.z; v.v[3] = up.w + un.w;
+        red_row<4>(gUM + (size_t)bu[t] * D + c * 4, v);
+        v.v[0] = ip.x; v.v[1] = ip.y; v.v[2] = ip.z; v.v[3] = ip.w;
+        red_row<4>(gIM + (size_t)bi[t] * D + c * 4, v);
+        v.v[0] = in_.x; v.v[1] = in_.y; v.v[2] = in_.z; v.v[3] = in_.w;
+        red_row<4>(gIM + (size_t)bj[t] * D + c * 4, v);
+    }
+}
+
+// Assemble the fp32 loss in the reference's order (NeuMFRecommender.py:154-167), publish it, and prime the two
+// phase-2 headers (norms per table pair; NaN -> sticky status so that nothing is applied).
+__global__ void neumf_finalize_kernel(const double *__restrict__ red, float reg1, float reg2, WsHeader *hG, WsHeader *hM,
+                                      double *__restrict__ loss_out, long long step)
+{
+    const double bpr = red[0];
+    const double *l1 = red + 1, *s2 = red + 6;     // 0 UG_u, 1 UM_u, 2 IG_i, 3 IM_i, 4 IG_j
+    double nr[5];
+    for (int q = 0; q < 5; ++q) nr[q] = sqrt(s2[q]);
+    float loss = (float)bpr;
+    loss += reg1 * ((float)l1[2] + (float)l1[4]);
+    loss += reg1 * ((float)l1[3] + (float)l1[4]);
+    loss += reg2 * ((float)nr[2] + (float)nr[4]);
+    loss += reg2 * ((float)nr[3] + (float)nr[4]);
+    loss += reg1 * (float)l1[0];
+    loss += reg1 * (float)l1[1];
+    loss += reg2 * (float)nr[0];
+    loss += reg2 * (float)nr[1];
+    *loss_out = (double)loss;
+    const bool bad = isnan(loss);
+    // phase 2 reads acc[0] = {bpr, l1u, l1i, l1j, s2u, s2i, s2j}; only the squared sums matter for the update
+    double *g = hG->acc[0], *m = hM->acc[0];
+    g[0] = bad ? (double)loss : 0.0; g[1] = g[2] = g[3] = 0.0; g[4] = s2[0]; g[5] = s2[2]; g[6] = s2[4];
+    m[0] = bad ? (double)loss : 0.0; m[1] = m[2] = m[3] = 0.0; m[4] = s2[1]; m[5] = s2[3]; m[6] = 0.0;
+    if (bad) {
+        hG->status = DRB_ERR_NAN_LOSS; hG->nan_step = step;
+        hM->status = DRB_ERR_NAN_LOSS; hM->nan_step = step;
+    }
+}
+
+// dense optimiser step on the tower block (SGD, or torch.optim.Adam's single-tensor rule)
+__global__ void neumf_update_w_kernel(float *__restrict__ W, float *__restrict__ g, float *__restrict__ m,
+                                      float *__restrict__ v, long long n, float lr, int opt, float beta1, float beta2,
+                                      float eps, float step_size, float bc2_sqrt, const WsHeader *hdr)
+{
+    if (hdr->status != 0) return;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        float gk = g[k];
+        g[k] = 0.f;
+        if (opt == DRB_OPT_SGD) {
+            W[k] = W[k] - lr * gk;
+        } else {
+            float mm = m[k], vv = v[k];
+            mm = mm + (gk - mm) * (1.f - beta1);
+            vv = vv * beta2 + (1.f - beta2) * gk * gk;
+            float denom = sqrtf(vv) / bc2_sqrt + eps;
+            W[k] = W[k] - step_size * (mm / denom);
+            m[k] = mm; v[k] = vv;
+        }
+    }
+}
+
+// scores[r] = wp . cat(UG[u]*IG[item], A_L[r]) + bp      (inference head)
+__global__ void neumf_score_kernel(const float *__restrict__ UG, const float *__restrict__ IG, const float *__restrict__ wp,
+                                   const float *__restrict__ AL, const int64_t *__restrict__ users,
+                                   const int64_t *__restrict__ items, long long row0, long long rows, int per_user, int F,
+                                   float *__restrict__ scores)
+{
+    const int lane = threadIdx.x & 31;
+    long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < rows; r += nw) {
+        long long g = row0 + r;
+        long long u = users[g / per_user];
+        long long it = items ? items[g] : (g % per_user);
+        float s = 0.f;
+        for (int f = lane; f < F; f += 32) {
+            s = fmaf(wp[f], __ldcg(UG + (size_t)u * F + f) * __ldcg(IG + (size_t)it * F + f), s);
+            s = fmaf(wp[F + f], AL[(size_t)r * F + f], s);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) scores[g] = s + wp[2 * F];
+    }
+}
+
+static int grid1d(long long n, int block, int per_sm = 16)
+{
+    long long b = (n + block - 1) / block, cap = (long long)sm_count() * per_sm;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// tower forward on `rows` rows already gathered into acts' A_0 block
+static int tower_forward(const NeumfDims &d, const float *W, float *acts, long long R, long long rows, cudaStream_t st)
+{
+    for (int l = 0; l < d.L; ++l) {
+        const float *in = acts + d.act_off[l] * R;
+        float *out = acts + d.act_off[l + 1] * R;
+        int rc = launch_sgemm<false, true, 1>(rows, d.n[l + 1], d.n[l], in, d.n[l], W + d.w_off[l], d.n[l], out, d.n[l + 1],
+                                              W + d.b_off[l], nullptr, 0, st);
+        if (rc != DRB_OK) return rc;
+    }
+    return DRB_OK;
+}
+
+}  // namespace drb
+
+using namespace drb;
+
+extern "C" int64_t drb_neumf_param_count(int32_t F, int32_t L)
+{
+    NeumfDims d;
+    if (!make_dims(d, 1, 1, F, L)) return -1;
+    return d.nW;
+}
+
+extern "C" size_t drb_neumf_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_t L, int32_t opt, int64_t max_rows)
+{
+    NeumfDims d;
+    if (!make_dims(d, U, I, F, L)) return 0;
+    return carve_neumf(nullptr, d, opt, max_rows, nullptr);
+}
+
+extern "C" int drb_neumf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F, int32_t L, int32_t opt,
+                                        int64_t max_rows, void *stream)
+{
+    NeumfDims d;
+    DRB_REQUIRE(d_ws && make_dims(d, U, I, F, L), "neumf_workspace_init: bad arguments (factors must be a multiple of 4)");
+    NeumfWs w;
+    carve_neumf(d_ws, d, opt, max_rows, &w);
+    // zero everything except the (large) activation scratch
+    size_t head = (size_t)((char *)w.acts - (char *)d_ws);
+    DRB_CUDA(cudaMemsetAsync(d_ws, 0, head, (cudaStream_t)stream));
+    return DRB_OK;
+}
+
+// n_steps synchronous NeuMF+BPR steps (apply != 0) or the loss of one batch (apply == 0).
+extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, float *d_IM, float *d_W, void *d_ws,
+                                         int32_t U, int32_t I, int32_t F, int32_t L, int64_t max_rows,
+                                         const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
+                                         int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *h,
+                                         int64_t adam_step0, int32_t apply, double *d_step_loss, int32_t sync_and_check,
+                                         int64_t *nan_step, void *stream)
+{
+    NeumfDims d;
+    DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf: bad dims (factors must be a positive multiple of 4, 1 <= num_layers <= 8)");
+    DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_bu && d_bi && d_bj && h && d_step_loss, "neumf: null argument");
+    DRB_REQUIRE(batch > 0 && 2 * batch <= max_rows, "neumf: batch %lld needs 2*batch <= max_rows=%lld", (long long)batch,
+                (long long)max_rows);
+    DRB_REQUIRE(n_steps == 0 || (first_step + n_steps - 1) * batch < n, "neumf: steps exceed %lld triples", (long long)n);
+    DRB_REQUIRE(h->opt == DRB_OPT_SGD || h->opt == DRB_OPT_ADAM, "unknown optimizer id %d", h->opt);
+    if (n_steps == 0) return DRB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    NeumfWs w;
+    carve_neumf(d_ws, d, h->opt, max_rows, &w);
+    const int has_reg = (h->reg_1 != 0.f) || (h->reg_2 != 0.f);
+    DRB_CUDA(cudaMemsetAsync(w.hdrG, 0, 512, st));            // both headers: clear a stale NaN flag
+    for (int64_t s = 0; s < n_steps; ++s) {
+        const int64_t base = (first_step + s) * batch, B = (n - base < batch) ? n - base : batch;
+        const long long R = 2 * B;
+        const int32_t *bu = d_bu + base, *bi = d_bi + base, *bj = d_bj + base;
+        DRB_CUDA(cudaMemsetAsync(w.red, 0, 16 * sizeof(double), st));
+        // forward
+        neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts);
+        DRB_CUDA(cudaGetLastError());
+        int rc = tower_forward(d, d_W, w.acts, R, R, st);
+        if (rc != DRB_OK) return rc;
+        const float *AL = w.acts + d.act_off[d.L] * R;
+        float *dZ = w.dA;                                        // dZ_L [R, F]
+        neumf_head_kernel<<<grid1d(B, 8, 8), 256, sizeof(float) * (2 * F + 1), st>>>(
+            d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, w.gUG, w.gIG,
+            w.gW + d.wp_off, dZ, w.cntU, w.cntI, w.red);
+        DRB_CUDA(cudaGetLastError());
+        neumf_finalize_kernel<<<1, 1, 0, st>>>(w.red, h->reg_1, h->reg_2, w.hdrG, w.hdrM, d_step_loss + s, first_step + s);
+        DRB_CUDA(cudaGetLastError());
+        if (!apply) break;
+        // tower backward
+        float *cur = w.dA, *nxt = w.dB;
+        for (int l = d.L - 1; l >= 0; --l) {
+            const float *Aprev = w.acts + d.act_off[l] * R;
+            // gW_l[out,in] += dZ^T A_{l-1}     (split-K over the R rows)
+            rc = launch_sgemm<true, false, 3>(d.n[l + 1], d.n[l], (int)R, cur, d.n[l + 1], Aprev, d.n[l], w.gW + d.w_off[l],
+                                              d.n[l], nullptr, nullptr, 0, st);
+            if (rc != DRB_OK) return rc;
+            colsum_kernel<<<dim3(64, (d.n[l + 1] + 63) / 64), 64, 0, st>>>(cur, R, d.n[l + 1], w.gW + d.b_off[l]);
+            DRB_CUDA(cudaGetLastError());
+            // dA_{l-1} = dZ W_l, masked by relu'(A_{l-1}) for hidden layers
+            if (l > 0)
+                rc = launch_sgemm<false, false, 2>(R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
+                                                   d.n[l], nullptr, Aprev, d.n[l], st);
+            else
+                rc = launch_sgemm<false, false, 0>(R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
+                                                   d.n[l], nullptr, nullptr, 0, st);
+            if (rc != DRB_OK) return rc;
+            float *t = cur; cur = nxt; nxt = t;
+        }
+        neumf_scatter_kernel<<<grid1d(B * (d.D / 4), 256), 256, 0, st>>>(cur, bu, bi, bj, B, d.D, w.gUM, w.gIM);
+        DRB_CUDA(cudaGetLastError());
+        // apply: table pairs through the MF dense sweep, tower block through the small dense kernel
+        StepParams p;
+        p.bu = bu; p.bi = bi; p.bj = bj; p.n = B; p.batch = B; p.first_step = 0; p.n_steps = 1;
+        p.U = U; p.I = I; p.tile = 512;
+        p.lr = h->lr; p.reg1 = h->reg_1; p.reg2 = h->reg_2; p.opt = h->opt;
+        p.beta1 = h->beta1; p.beta2 = h->beta2; p.eps = h->eps; p.adam_step0 = adam_step0 + s;
+        p.step_loss = w.red + 12;                                // scratch: the real loss was written by finalize
+        p.apply = 1; p.phases = 2; p.dense_hint = 1; p.Pn = nullptr; p.Qn = nullptr; p.gscale = 1.f; p.dense_grad = 0;
+        p.ws.cntU = w.cntU; p.ws.cntI = w.cntI;
+        // (UG, IG): negative occurrences weigh 2x (lines :157 and :158 both add |IG_j|)
+        p.P = d_UG; p.Q = d_IG; p.F = F; p.ws.hdr = w.hdrG; p.ws.gP = w.gUG; p.ws.gQ = w.gIG;
+        p.ws.mP = w.mUG; p.ws.vP = w.vUG; p.ws.mQ = w.mIG; p.ws.vQ = w.vIG; p.neg_mult = 2.f; p.keep_counts = 1;
+        rc = launch_steps(p, st, true);
+        if (rc != DRB_OK) return rc;
+        // (UM, IM): the MLP item table is never regularised on the negative side
+        p.P = d_UM; p.Q = d_IM; p.F = d.D; p.ws.hdr = w.hdrM; p.ws.gP = w.gUM; p.ws.gQ = w.gIM;
+        p.ws.mP = w.mUM; p.ws.vP = w.vUM; p.ws.mQ = w.mIM; p.ws.vQ = w.vIM; p.neg_mult = 0.f; p.keep_counts = 0;
+        rc = launch_steps(p, st, true);
+        if (rc != DRB_OK) return rc;
+        double tt = (double)(adam_step0 + s + 1);
+        float step_size = (float)((double)h->lr / (1.0 - pow((double)h->beta1, tt)));
+        float bc2_sqrt = (float)sqrt(1.0 - pow((double)h->beta2, tt));
+        neumf_update_w_kernel<<<grid1d(d.nW, 256), 256, 0, st>>>(d_W, w.gW, w.mW, w.vW, d.nW, h->lr, h->opt, h->beta1, h->beta2,
+                                                                 h->eps, step_size, bc2_sqrt, w.hdrG);
+        DRB_CUDA(cudaGetLastError());
+    }
+    if (sync_and_check) return check_nan(w.hdrG, st, nan_step);
+    return DRB_OK;
+}
+
+// scores[n_users * per_user] for (users[r / per_user], items[r]) pairs (items == NULL: every item id 0..per_user-1)
+extern "C" int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
+                                void *d_ws, int32_t U, int32_t I, int32_t F, int32_t L, int32_t opt, int64_t max_rows,
+                                const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,
+                                float *d_scores, void *stream)
+{
+    NeumfDims d;
+    DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf_scores: bad dims");
+    DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_users && d_scores && per_user > 0 && max_rows > 0,
+                "neumf_scores: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    NeumfWs w;
+    carve_neumf(d_ws, d, opt, max_rows, &w);   // same layout as training: only the dA/dB scratch is touched here
+    const long long total = (long long)n_users * per_user;
+    for (long long row0 = 0; row0 < total; row0 += max_rows) {
+        long long rows = total - row0 < max_rows ? total - row0 : max_rows;
+        neumf_gather_pairs_kernel<<<grid1d(rows * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, d_users, d_items, row0, rows,
+                                                                                   per_user, d.D, w.dA);
+        DRB_CUDA(cudaGetLastError());
+        // use dA as A_0 and dB as ping-pong for the hidden layers (independent of the optimiser layout)
+        const float *in = w.dA;
+        float *bufs[2] = {w.dB, w.dA};
+        for (int l = 0; l < d.L; ++l) {
+            float *out = bufs[l & 1];
+            int rc = launch_sgemm<false, true, 1>(rows, d.n[l + 1], d.n[l], in, d.n[l], d_W + d.w_off[l], d.n[l], out,
+                                                  d.n[l + 1], d_W + d.b_off[l], nullptr, 0, st);
+            if (rc != DRB_OK) return rc;
+            in = out;
+        }
+        neumf_score_kernel<<<grid1d(rows * 32, 256), 256, 0, st>>>(d_UG, d_IG, d_W + d.wp_off, in, d_users, d_items, row0, rows,
+                                                                  per_user, F, d_scores);
+        DRB_CUDA(cudaGetLastError());
+    }
+    return DRB_OK;
+}

@@ -91,6 +91,39 @@ __global__ void __launch_bounds__(kRankThreads) rank_kernel(const float *__restr
     }
 }
 
+// top-K of PRE-COMPUTED scores (NeuMF: the scores come out of the tower).  MODE as in rank_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(kRankThreads) topk_scores_kernel(const float *__restrict__ scores,
+                                                                   const int64_t *__restrict__ cands, int count, int K,
+                                                                   int nkeys, float *__restrict__ out_f,
+                                                                   int64_t *__restrict__ out_i)
+{
+    extern __shared__ unsigned long long keys[];
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.x;
+    const float *srow = scores + row * count;
+    const int64_t *crow = (MODE == 0) ? cands + row * count : nullptr;
+    int done = 0;
+    bool first = true;
+    while (done < count) {
+        const int lo = first ? 0 : K;
+        const int take = min(count - done, nkeys - lo);
+        for (int i = tid + lo + take; i < nkeys; i += kRankThreads) keys[i] = ~0ull;
+        for (int c = tid; c < take; c += kRankThreads) keys[lo + c] = make_key(srow[done + c], (unsigned)(done + c));
+        __syncthreads();
+        bitonic_sort(keys, nkeys, tid);
+        done += take;
+        first = false;
+    }
+    for (int k = tid; k < K; k += kRankThreads) {
+        unsigned pos = (unsigned)(keys[k] & 0xffffffffull);
+        if (MODE == 0)
+            out_f[row * K + k] = (float)crow[pos];
+        else
+            out_i[row * K + k] = (int64_t)pos;
+    }
+}
+
 template <int VEC, int W, int NCH>
 __global__ void predict_kernel(const float *__restrict__ P, const float *__restrict__ Q, int F, const int32_t *__restrict__ u,
                                const int32_t *__restrict__ it, long long n, float *__restrict__ out)
@@ -180,6 +213,27 @@ extern "C" int drb_mf_full_rank(const float *d_P, const float *d_Q, int32_t F, i
 {
     DRB_REQUIRE(d_out, "mf_full_rank: null argument");
     return launch_rank(1, d_P, d_Q, F, d_users, n_users, nullptr, item_num, topk, nullptr, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int drb_topk_from_scores(const float *d_scores, const int64_t *d_cands, int64_t n_rows, int32_t count, int32_t topk,
+                                    float *d_out_f, int64_t *d_out_i, void *stream)
+{
+    DRB_REQUIRE(d_scores && count > 0 && topk > 0 && topk <= count && n_rows >= 0 && 2 * topk <= kRankMaxKeys &&
+                    ((d_cands && d_out_f) || (!d_cands && d_out_i)),
+                "topk_from_scores: bad arguments");
+    if (n_rows == 0) return DRB_OK;
+    int nkeys = 64;
+    while (nkeys < count && nkeys < kRankMaxKeys) nkeys <<= 1;
+    while (nkeys < 2 * topk) nkeys <<= 1;
+    size_t smem = sizeof(unsigned long long) * (size_t)nkeys;
+    if (d_cands)
+        topk_scores_kernel<0><<<(unsigned)n_rows, kRankThreads, smem, (cudaStream_t)stream>>>(d_scores, d_cands, count, topk, nkeys,
+                                                                                             d_out_f, nullptr);
+    else
+        topk_scores_kernel<1><<<(unsigned)n_rows, kRankThreads, smem, (cudaStream_t)stream>>>(d_scores, nullptr, count, topk,
+                                                                                             nkeys, nullptr, d_out_i);
+    DRB_CUDA(cudaGetLastError());
+    return DRB_OK;
 }
 
 extern "C" int drb_mf_predict(const float *d_P, const float *d_Q, int32_t F, const int32_t *d_u, const int32_t *d_i,

@@ -68,6 +68,9 @@ struct StepParams {
     const float *Pn, *Qn;  // ego (norm) tables; nullptr = same as P,Q
     float gscale;          // factor applied to the accumulated gradient in phase 2 (1/(L+1) for LightGCN)
     int dense_grad;        // 1: every row has a gradient (propagated), not only the rows a triple touched
+    // NeuMF: the item-side regulariser counts the negative occurrences 2x (GMF table) or 0x (MLP table)
+    float neg_mult;        // multiplier of the negative-occurrence count in the regulariser gradient
+    int keep_counts;       // 1: leave the row counters untouched (another table pair still needs them)
 };
 
 

@@ -336,3 +336,62 @@ def lgcn_bpr_train_steps(E0, ws, graph, num_layers, bu, bi, bj, batch, first_ste
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
     L.check(rc)
     return losses[:n_steps]
+
+
+# ------------------------------------------------------------------ NeuMF
+def neumf_param_count(factors, num_layers):
+    return int(L.lib().drb_neumf_param_count(factors, num_layers))
+
+
+class NeumfWorkspace:
+    def __init__(self, user_num, item_num, factors, num_layers, opt, max_rows, device):
+        self.U, self.I, self.F, self.Ln, self.max_rows = user_num, item_num, factors, num_layers, int(max_rows)
+        self.opt = L.OPT_SGD if opt == "sgd" else L.OPT_ADAM
+        nbytes = L.lib().drb_neumf_workspace_bytes(user_num, item_num, factors, num_layers, self.opt, self.max_rows)
+        if nbytes == 0:
+            raise ValueError("NeuMF: factors must be a positive multiple of 4 and 1 <= num_layers <= 8")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        L.check(L.lib().drb_neumf_workspace_init(_ptr(self.buf), user_num, item_num, factors, num_layers, self.opt,
+                                                 self.max_rows, _stream()))
+
+
+def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True):
+    for t in list(tabs) + [W]:
+        _dev(t, torch.float32, "table")
+    for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
+        _dev(t, torch.int32, nm)
+    losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=W.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_neumf_bpr_train_steps(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf),
+                                           ws.U, ws.I, ws.F, ws.Ln, ws.max_rows, _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(),
+                                           batch, first_step, n_steps, C.byref(hp), adam_step0, 1 if apply else 0,
+                                           _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]
+
+
+def neumf_scores(tabs, W, ws, users, items, per_user):
+    """scores [n_users, per_user]: items = int64 [n_users, per_user] candidate ids, or None for all item ids."""
+    _dev(users, torch.int64, "users")
+    if items is not None:
+        _dev(items, torch.int64, "items")
+    out = torch.empty((users.numel(), per_user), dtype=torch.float32, device=W.device)
+    L.check(L.lib().drb_neumf_scores(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf), ws.U,
+                                     ws.I, ws.F, ws.Ln, ws.opt, ws.max_rows, _ptr(users), users.numel(),
+                                     None if items is None else _ptr(items), per_user, _ptr(out), _stream()))
+    return out
+
+
+def topk_from_scores(scores, cands, topk):
+    _dev(scores, torch.float32, "scores")
+    n, cnt = scores.shape
+    if cands is not None:
+        _dev(cands, torch.int64, "cands")
+        out = torch.empty((n, topk), dtype=torch.float32, device=scores.device)
+        L.check(L.lib().drb_topk_from_scores(_ptr(scores), _ptr(cands), n, cnt, topk, _ptr(out), None, _stream()))
+    else:
+        out = torch.empty((n, topk), dtype=torch.int64, device=scores.device)
+        L.check(L.lib().drb_topk_from_scores(_ptr(scores), None, n, cnt, topk, None, _ptr(out), _stream()))
+    return out

@@ -175,6 +175,34 @@ int drb_lgcn_bpr_train_steps(float *d_E0, void *d_ws, int32_t user_num, int32_t 
                              int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0, int32_t apply,
                              double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 
+/* ---- NeuMF + BPR (daisy/model/NeuMFRecommender.py, model_name 'NeuMF') -----------------------------
+ * Tables: UG [U,F], IG [I,F] (embed_*_GMF), UM [U,D], IM [I,D] (embed_*_MLP), D = F * 2^(L-1);
+ * W: the tower as ONE flat fp32 block in module-registration order -- per layer weight [out,in] then bias [out]
+ * (in = 2D / 2^l), then predict_layer weight [2F] and bias [1]  (NeuMFRecommender.py:58-71).
+ * max_rows: rows of activation scratch (>= 2 * batch for training; any size for scoring).
+ * drb_neumf_bpr_train_steps  calc_loss :139-169 (regulariser quirk of :158/:160 included) + backward +
+ *                            optimizer.step for n_steps batches; apply = 0: calc_loss of one batch.  dropout = 0.
+ * drb_neumf_scores           forward :118-137 for (users[r / per_user], items[r]) pairs (items NULL: all item ids):
+ *                            what rank / full_rank / predict score with (:171-232); feed to drb_topk_from_scores. */
+int64_t drb_neumf_param_count(int32_t factors, int32_t num_layers);
+size_t drb_neumf_workspace_bytes(int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t opt,
+                                 int64_t max_rows);
+int drb_neumf_workspace_init(void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers,
+                             int32_t opt, int64_t max_rows, void *stream);
+int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, float *d_IM, float *d_W, void *d_ws,
+                              int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int64_t max_rows,
+                              const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
+                              int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                              int32_t apply, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
+                     void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t opt,
+                     int64_t max_rows, const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,
+                     float *d_scores, void *stream);
+/* top-K of pre-computed scores [n_rows, count]: ids from d_cands (float32 out, rank) or positions (int64 out, full_rank);
+ * descending score, ties by lower position. */
+int drb_topk_from_scores(const float *d_scores, const int64_t *d_cands, int64_t n_rows, int32_t count, int32_t topk,
+                         float *d_out_f, int64_t *d_out_i, void *stream);
+
 /* ---- inference ------------------------------------------------------------------------
  * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,
  *   descending sort, first topk ids as float32 (the reference's dtype quirk, :107).

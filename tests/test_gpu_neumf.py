@@ -1,0 +1,121 @@
+"""GPU parity for NeuMF: golden fixtures from the reference + oracle on random inputs."""
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+NAMES = ("UG", "IG", "UM", "IM")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from daisyrec_b200 import ops as o
+    o.require_cuda()
+    return o
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_neumf_golden(ops):
+    g = golden("neumf")
+    for c in range(int(g["ncases"])):
+        U, I, F, L, lr, r1, r2, opt, seed = g[f"c{c}_hyper"]
+        U, I, F, L = int(U), int(I), int(F), int(L)
+        if F % 4:
+            continue                                                  # 128-bit rows: factors multiple of 4
+        optn = "sgd" if opt == 0 else "adam"
+        hp = ops.hyper(lr, r1, r2, optn)
+        bs, losses = g[f"c{c}_batches"], g[f"c{c}_loss"]
+        tabs = [dev(g[f"c{c}_{n}"][0]) for n in NAMES]
+        W = dev(g[f"c{c}_W"][0])
+        ws = ops.NeumfWorkspace(U, I, F, L, optn, 4096, "cuda")
+        for s in range(bs.shape[0]):
+            b = [dev(bs[s][k]) for k in range(3)]
+            l0 = ops.neumf_bpr_train_steps(tabs, W, ws, *b, b[0].numel(), 0, 1, hp, apply=False).item()
+            loss = ops.neumf_bpr_train_steps(tabs, W, ws, *b, b[0].numel(), 0, 1, hp, adam_step0=s).item()
+            assert abs(l0 - losses[s]) <= 3e-5 * abs(losses[s]) and abs(loss - losses[s]) <= 3e-5 * abs(losses[s]), (c, s)
+            tol = (5e-6 if opt == 0 else 1e-4) * (s + 1)
+            for q, n in enumerate(NAMES):
+                want = g[f"c{c}_{n}"][s + 1]
+                np.testing.assert_allclose(tabs[q].cpu().numpy(), want, rtol=0, atol=tol * max(1.0, np.abs(want).max()),
+                                           err_msg=f"case {c} step {s} table {n}")
+            np.testing.assert_allclose(W.cpu().numpy(), g[f"c{c}_W"][s + 1], rtol=0, atol=tol * max(1.0, np.abs(g[f"c{c}_W"][s + 1]).max()))
+        # inference on the reference's final parameters: ids bit-exact, scores to fp32 rounding
+        tabs = [dev(g[f"c{c}_{n}"][-1]) for n in NAMES]
+        W = dev(g[f"c{c}_W"][-1])
+        users, cands = g[f"c{c}_users"], g[f"c{c}_cands"].astype(np.int64)
+        sc = ops.neumf_scores(tabs, W, ws, dev(users), dev(cands), cands.shape[1])
+        assert np.array_equal(ops.topk_from_scores(sc, dev(cands), 10).cpu().numpy(), g[f"c{c}_preds"])
+        scf = ops.neumf_scores(tabs, W, ws, dev(users[:3]), None, I)
+        assert np.array_equal(ops.topk_from_scores(scf, None, 10).cpu().numpy(), g[f"c{c}_full"])
+        np.testing.assert_allclose(sc[:4, 0].cpu().numpy(), g[f"c{c}_pred_pairs"], rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("F,L,opt,reg,B", [(32, 2, "adam", 0.001, 3000), (64, 1, "sgd", 0.0, 1000), (8, 3, "adam", 0.002, 777),
+                                           (24, 2, "sgd", 0.001, 2049)])
+def test_neumf_vs_oracle_random(ops, orc, F, L, opt, reg, B):
+    rng = np.random.default_rng(F * 7 + L)
+    U, I = 400, 300
+    D = F * 2 ** (L - 1)
+    shapes = [(U, F), (I, F), (U, D), (I, D)]
+    tabs_h = [(rng.standard_normal(s) * 0.3).astype(np.float32) for s in shapes]
+    nW = orc.neumf_param_count(F, L)
+    W_h = (rng.standard_normal(nW) * 0.2).astype(np.float32)
+    tabs_o, W_o = [t.copy() for t in tabs_h], W_h.copy()
+    tabs, W = [dev(t) for t in tabs_h], dev(W_h)
+    hp_d, hp_o = ops.hyper(0.01, reg, reg, opt), orc.hyper(0.01, reg, reg, opt)
+    ws = ops.NeumfWorkspace(U, I, F, L, opt, 2 * B, "cuda")
+    adam = None if opt == "sgd" else ([np.zeros_like(a) for a in tabs_o + [W_o]], [np.zeros_like(a) for a in tabs_o + [W_o]])
+    for s in range(2):
+        b = [rng.integers(U, size=B).astype(np.int32), np.minimum(I - 1, rng.zipf(1.3, size=B) - 1).astype(np.int32),
+             rng.integers(I, size=B).astype(np.int32)]
+        lo = orc.neumf_bpr_step(tabs_o, W_o, F, L, *b, hp_o, True, adam, s + 1)
+        ld = ops.neumf_bpr_train_steps(tabs, W, ws, *[dev(x) for x in b], B, 0, 1, hp_d, adam_step0=s).item()
+        assert abs(ld - lo) <= 1e-5 * abs(lo), (ld, lo)
+        tol = 2e-5 if opt == "sgd" else 3e-4
+        for q in range(4):
+            np.testing.assert_allclose(tabs[q].cpu().numpy(), tabs_o[q], rtol=0, atol=tol, err_msg=f"step {s} table {q}")
+        np.testing.assert_allclose(W.cpu().numpy(), W_o, rtol=0, atol=tol * 5)
+    # scores vs oracle
+    users = rng.integers(U, size=20).astype(np.int64)
+    cands = rng.integers(I, size=(20, 50)).astype(np.int64)
+    sc = ops.neumf_scores(tabs, W, ws, dev(users), dev(cands), 50).cpu().numpy()
+    want = orc.neumf_predict(tabs_o, W_o, F, L, np.repeat(users, 50).astype(np.int32), cands.reshape(-1).astype(np.int32))
+    np.testing.assert_allclose(sc.reshape(-1), want, rtol=0, atol=2e-3)
+
+
+def test_neumf_dropin_class(ops):
+    from daisyrec_b200.model.NeuMFRecommender import NeuMF
+    from daisyrec_b200.utils.dataset import BasicDataset, CandidatesDataset, get_dataloader
+    g = golden("neumf")
+    c = 1
+    U, I, F, L, lr, r1, r2, opt, seed = g[f"c{c}_hyper"]
+    U, I, F, L = int(U), int(I), int(F), int(L)
+    cfg = dict(gpu='', logger=logging.getLogger('t'), lr=lr, epochs=1, reg_1=r1, reg_2=r2, dropout=0.0, model_name='NeuMF',
+               GMF_model=None, MLP_model=None, user_num=U, item_num=I, factors=F, num_layers=L, loss_type='BPR',
+               optimizer='default', init_method='default', early_stop=False, topk=10, progress=False)
+    torch.manual_seed(int(seed))
+    model = NeuMF(cfg)
+    # same constructor RNG stream as the reference (the fixture multiplied the embeddings by 3 afterwards)
+    np.testing.assert_array_equal(model.tower.cpu().numpy(), g[f"c{c}_W"][0])
+    np.testing.assert_allclose(model.embed_user_GMF.weight.cpu().numpy() * 3.0, g[f"c{c}_UG"][0], rtol=1e-6)
+    model.load_state_dict({'embed_user_GMF.weight': dev(g[f"c{c}_UG"][0]), 'embed_item_GMF.weight': dev(g[f"c{c}_IG"][0]),
+                           'embed_user_MLP.weight': dev(g[f"c{c}_UM"][0]), 'embed_item_MLP.weight': dev(g[f"c{c}_IM"][0]),
+                           'tower': dev(g[f"c{c}_W"][0])})
+    bs = g[f"c{c}_batches"]
+    data = np.ascontiguousarray(np.concatenate([bs[s].T for s in range(3)]))
+    model.fit(get_dataloader(BasicDataset(data), batch_size=bs.shape[2], shuffle=False))
+    np.testing.assert_allclose(model.embed_item_MLP.weight.cpu().numpy(), g[f"c{c}_IM"][3], rtol=0, atol=5e-4)
+    users, cands = g[f"c{c}_users"], g[f"c{c}_cands"].astype(np.int64)
+    loader = get_dataloader(CandidatesDataset([[int(u), cc] for u, cc in zip(users, cands)]), batch_size=128, shuffle=False)
+    preds = model.rank(loader)
+    assert preds.dtype == np.float32 and preds.shape == (7, 10)
+    assert model.full_rank(int(users[0])).dtype == np.int64
+    with pytest.raises(NotImplementedError):
+        NeuMF(dict(cfg, dropout=0.5))
