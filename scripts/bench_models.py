@@ -1,0 +1,117 @@
+"""Secondary measurements (not the driver's bench): BASELINE configs 3, 4, 5 on one GPU.
+
+    python scripts/bench_models.py lightgcn|neumf|mf-netflix [--batch B] [--steps K]
+Prints one JSON line per run: triples/s with CUDA events around K steps after warm-up.
+"""
+import argparse
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from daisyrec_b200 import ops  # noqa: E402
+from daisyrec_b200.utils.synthetic import SHAPES, make_interactions  # noqa: E402
+
+
+def timed(fn, warm, steps):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def batches(U, I, n, dev, d=None):
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    if d is not None:                                       # real (u,i) pairs + uniform negatives
+        idx = torch.randint(0, d["coo_u"].numel(), (n,), device=dev, generator=g)
+        bu, bi = d["coo_u"][idx].contiguous(), d["coo_i"][idx].contiguous()
+    else:
+        bu = torch.randint(0, U, (n,), device=dev, dtype=torch.int32, generator=g)
+        bi = torch.randint(0, I, (n,), device=dev, dtype=torch.int32, generator=g)
+    bj = torch.randint(0, I, (n,), device=dev, dtype=torch.int32, generator=g)
+    return bu, bi, bj
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["lightgcn", "neumf", "mf-netflix"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=10)
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    if a.what == "lightgcn":
+        U, I, nnz = SHAPES["amazon-book"]
+        F, L = 64, 3
+        B = a.batch or 65536
+        d = make_interactions(U, I, nnz, device=dev)
+        row_ptr, col, val = ops.lgcn_norm_adj(d["coo_u"].cpu().numpy(), d["coo_i"].cpu().numpy(), U, I)
+        graph = ops.LgcnGraph(row_ptr, col, val, dev)
+        E0 = (torch.randn(U + I, F, device=dev) * 0.05).contiguous()
+        ws = ops.LgcnWorkspace(U, I, F, "adam", dev)
+        hp = ops.hyper(0.01, 0.0, 0.0, "adam")
+        bu, bi, bj = batches(U, I, B * 4, dev, d)
+        step = [0]
+
+        def fn():
+            ops.lgcn_bpr_train_steps(E0, ws, graph, L, bu, bi, bj, B, step[0] % 4, 1, hp, adam_step0=step[0], check=False)
+            step[0] += 1
+        ms = timed(fn, 3, a.steps)
+        nnzA = int(row_ptr[-1])
+        alg = 2 * L * (nnzA * (8 + 4 * F) + (U + I) * 4 * F) + B * (24 * F + 12)
+        print(json.dumps(dict(model="LightGCN", shape="amazon-book", U=U, I=I, nnzA=nnzA, F=F, L=L, batch=B, ms_per_step=ms,
+                              triples_per_s=B / ms * 1e3, alg_bytes_per_step=alg, alg_GBps=alg / ms / 1e6,
+                              spmm_segments=graph.nseg)))
+    elif a.what == "neumf":
+        U, I, _ = SHAPES["ml-20m"]
+        F, L = 32, 2
+        B = a.batch or 262144
+        D = F * 2 ** (L - 1)
+        tabs = [(torch.randn(s, device=dev) * 0.05).contiguous() for s in ((U, F), (I, F), (U, D), (I, D))]
+        W = (torch.randn(ops.neumf_param_count(F, L), device=dev) * 0.1).contiguous()
+        ws = ops.NeumfWorkspace(U, I, F, L, "adam", 2 * B, dev)
+        hp = ops.hyper(0.001, 0.001, 0.001, "adam")
+        bu, bi, bj = batches(U, I, B * 4, dev)
+        step = [0]
+
+        def fn():
+            ops.neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, B, step[0] % 4, 1, hp, adam_step0=step[0], check=False)
+            step[0] += 1
+        ms = timed(fn, 3, a.steps)
+        flop = 0
+        n_in = 2 * D
+        for _ in range(L):
+            flop += 2 * n_in * (n_in // 2)
+            n_in //= 2
+        flop_triple = 2 * 3 * flop                          # 2 items x (fwd + 2 bwd GEMMs)
+        print(json.dumps(dict(model="NeuMF", shape="ml-20m", F=F, L=L, batch=B, ms_per_step=ms, triples_per_s=B / ms * 1e3,
+                              tower_TFLOPs=B * flop_triple / ms / 1e9, tower="fp32 CUDA cores")))
+    else:
+        U, I, nnz = SHAPES["netflix"]
+        F = 128
+        B = a.batch or (1 << 20)
+        P = (torch.randn(U, F, device=dev) * 0.01).contiguous()
+        Q = (torch.randn(I, F, device=dev) * 0.01).contiguous()
+        ws = ops.MFWorkspace(U, I, F, "sgd", dev)
+        hp = ops.hyper(0.01, 0.001, 0.001)
+        K = 16
+        bu, bi, bj = batches(U, I, B * K, dev)
+        bi = (I * torch.rand(B * K, device=dev).pow(2.0)).to(torch.int32).clamp_(0, I - 1)
+
+        def fn():
+            ops.mf_bpr_train_steps(P, Q, ws, bu, bi, bj, B, 0, K, hp, check=False)
+        ms = timed(fn, 1, max(1, a.steps // 4)) / K
+        print(json.dumps(dict(model="MF", shape="netflix", U=U, I=I, F=F, batch=B, ms_per_step=ms, triples_per_s=B / ms * 1e3,
+                              alg_GBps=B * (24 * F + 12) / ms / 1e6)))
+
+
+if __name__ == "__main__":
+    main()
