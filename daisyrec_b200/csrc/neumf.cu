@@ -20,6 +20,7 @@
 // compute-bound on CUDA cores in this fp32 path; the bf16 tcgen05 tower of BASELINE config 3 replaces the three GEMM
 // call sites only.
 #include "step.cuh"
+#include "umma_gemm.cuh"
 
 namespace drb {
 
@@ -184,6 +185,15 @@ static int launch_sgemm(long long M, int N, int K, const float *A, long long lda
     sgemm_kernel<TA, TB, EPI><<<grid, 256, 0, st>>>((int)M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, k_chunk);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
+}
+
+// dtype 0: fp32 CUDA cores (sgemm_kernel)   dtype 1: bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM
+template <bool TA, bool TB, int EPI>
+static int launch_gemm(int dtype, long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb,
+                       float *C, long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st)
+{
+    if (dtype == 1 && N <= kUmmaMaxN) return launch_umma_gemm<TA, TB, EPI>(M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, st);
+    return launch_sgemm<TA, TB, EPI>(M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, st);
 }
 
 // ------------------------------------------------------------------------------------------ gather / head / scatter
@@ -439,13 +449,14 @@ static int grid1d(long long n, int block, int per_sm = 16)
 }
 
 // tower forward on `rows` rows already gathered into acts' A_0 block
-static int tower_forward(const NeumfDims &d, const float *W, float *acts, long long R, long long rows, cudaStream_t st)
+static int tower_forward(const NeumfDims &d, const float *W, float *acts, long long R, long long rows, int dtype,
+                         cudaStream_t st)
 {
     for (int l = 0; l < d.L; ++l) {
         const float *in = acts + d.act_off[l] * R;
         float *out = acts + d.act_off[l + 1] * R;
-        int rc = launch_sgemm<false, true, 1>(rows, d.n[l + 1], d.n[l], in, d.n[l], W + d.w_off[l], d.n[l], out, d.n[l + 1],
-                                              W + d.b_off[l], nullptr, 0, st);
+        int rc = launch_gemm<false, true, 1>(dtype, rows, d.n[l + 1], d.n[l], in, d.n[l], W + d.w_off[l], d.n[l], out,
+                                             d.n[l + 1], W + d.b_off[l], nullptr, 0, st);
         if (rc != DRB_OK) return rc;
     }
     return DRB_OK;
@@ -487,10 +498,11 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
                                          int32_t U, int32_t I, int32_t F, int32_t L, int64_t max_rows,
                                          const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
                                          int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *h,
-                                         int64_t adam_step0, int32_t apply, double *d_step_loss, int32_t sync_and_check,
-                                         int64_t *nan_step, void *stream)
+                                         int64_t adam_step0, int32_t apply, int32_t tower_dtype, double *d_step_loss,
+                                         int32_t sync_and_check, int64_t *nan_step, void *stream)
 {
     NeumfDims d;
+    DRB_REQUIRE(tower_dtype == 0 || tower_dtype == 1, "neumf: tower_dtype must be 0 (fp32) or 1 (bf16 tcgen05)");
     DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf: bad dims (factors must be a positive multiple of 4, 1 <= num_layers <= 8)");
     DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_bu && d_bi && d_bj && h && d_step_loss, "neumf: null argument");
     DRB_REQUIRE(batch > 0 && 2 * batch <= max_rows, "neumf: batch %lld needs 2*batch <= max_rows=%lld", (long long)batch,
@@ -511,7 +523,7 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         // forward
         neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts);
         DRB_CUDA(cudaGetLastError());
-        int rc = tower_forward(d, d_W, w.acts, R, R, st);
+        int rc = tower_forward(d, d_W, w.acts, R, R, tower_dtype, st);
         if (rc != DRB_OK) return rc;
         const float *AL = w.acts + d.act_off[d.L] * R;
         float *dZ = w.dA;                                        // dZ_L [R, F]
@@ -527,17 +539,17 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         for (int l = d.L - 1; l >= 0; --l) {
             const float *Aprev = w.acts + d.act_off[l] * R;
             // gW_l[out,in] += dZ^T A_{l-1}     (split-K over the R rows)
-            rc = launch_sgemm<true, false, 3>(d.n[l + 1], d.n[l], (int)R, cur, d.n[l + 1], Aprev, d.n[l], w.gW + d.w_off[l],
+            rc = launch_gemm<true, false, 3>(tower_dtype, d.n[l + 1], d.n[l], (int)R, cur, d.n[l + 1], Aprev, d.n[l], w.gW + d.w_off[l],
                                               d.n[l], nullptr, nullptr, 0, st);
             if (rc != DRB_OK) return rc;
             colsum_kernel<<<dim3(64, (d.n[l + 1] + 63) / 64), 64, 0, st>>>(cur, R, d.n[l + 1], w.gW + d.b_off[l]);
             DRB_CUDA(cudaGetLastError());
             // dA_{l-1} = dZ W_l, masked by relu'(A_{l-1}) for hidden layers
             if (l > 0)
-                rc = launch_sgemm<false, false, 2>(R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
+                rc = launch_gemm<false, false, 2>(tower_dtype, R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
                                                    d.n[l], nullptr, Aprev, d.n[l], st);
             else
-                rc = launch_sgemm<false, false, 0>(R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
+                rc = launch_gemm<false, false, 0>(tower_dtype, R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
                                                    d.n[l], nullptr, nullptr, 0, st);
             if (rc != DRB_OK) return rc;
             float *t = cur; cur = nxt; nxt = t;
@@ -578,7 +590,7 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
 extern "C" int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
                                 void *d_ws, int32_t U, int32_t I, int32_t F, int32_t L, int32_t opt, int64_t max_rows,
                                 const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,
-                                float *d_scores, void *stream)
+                                int32_t tower_dtype, float *d_scores, void *stream)
 {
     NeumfDims d;
     DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf_scores: bad dims");
@@ -598,8 +610,8 @@ extern "C" int drb_neumf_scores(const float *d_UG, const float *d_IG, const floa
         float *bufs[2] = {w.dB, w.dA};
         for (int l = 0; l < d.L; ++l) {
             float *out = bufs[l & 1];
-            int rc = launch_sgemm<false, true, 1>(rows, d.n[l + 1], d.n[l], in, d.n[l], d_W + d.w_off[l], d.n[l], out,
-                                                  d.n[l + 1], d_W + d.b_off[l], nullptr, 0, st);
+            int rc = launch_gemm<false, true, 1>(tower_dtype, rows, d.n[l + 1], d.n[l], in, d.n[l], d_W + d.w_off[l], d.n[l],
+                                                 out, d.n[l + 1], d_W + d.b_off[l], nullptr, 0, st);
             if (rc != DRB_OK) return rc;
             in = out;
         }
@@ -608,4 +620,20 @@ extern "C" int drb_neumf_scores(const float *d_UG, const float *d_IG, const floa
         DRB_CUDA(cudaGetLastError());
     }
     return DRB_OK;
+}
+
+// Test hook: C (op)= opA(A) opB(B) through the tower's GEMM dispatcher.  variant 0: NT + bias + ReLU (forward),
+// 1: NN + ReLU mask (input gradient), 2: NN plain, 3: TN split-K accumulate (weight gradient).  dtype as tower_dtype.
+extern "C" int drb_gemm_test(int32_t variant, int32_t dtype, int64_t M, int32_t N, int32_t K, const float *d_A, int64_t lda,
+                             const float *d_B, int64_t ldb, float *d_C, int64_t ldc, const float *d_bias, const float *d_ref,
+                             int64_t ldref, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (variant) {
+    case 0: return launch_gemm<false, true, 1>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, d_bias, nullptr, 0, st);
+    case 1: return launch_gemm<false, false, 2>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, d_ref, ldref, st);
+    case 2: return launch_gemm<false, false, 0>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, nullptr, 0, st);
+    case 3: return launch_gemm<true, false, 3>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, nullptr, 0, st);
+    }
+    DRB_REQUIRE(false, "gemm_test: unknown variant %d", variant);
 }

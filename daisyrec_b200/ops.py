@@ -355,7 +355,8 @@ class NeumfWorkspace:
                                                  self.max_rows, _stream()))
 
 
-def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True):
+def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True,
+                          tower_dtype=0):
     for t in list(tabs) + [W]:
         _dev(t, torch.float32, "table")
     for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
@@ -365,14 +366,14 @@ def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, h
     rc = L.lib().drb_neumf_bpr_train_steps(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf),
                                            ws.U, ws.I, ws.F, ws.Ln, ws.max_rows, _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(),
                                            batch, first_step, n_steps, C.byref(hp), adam_step0, 1 if apply else 0,
-                                           _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
+                                           tower_dtype, _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
     if rc == L.DRB_ERR_NAN_LOSS:
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
     L.check(rc)
     return losses[:n_steps]
 
 
-def neumf_scores(tabs, W, ws, users, items, per_user):
+def neumf_scores(tabs, W, ws, users, items, per_user, tower_dtype=0):
     """scores [n_users, per_user]: items = int64 [n_users, per_user] candidate ids, or None for all item ids."""
     _dev(users, torch.int64, "users")
     if items is not None:
@@ -380,7 +381,7 @@ def neumf_scores(tabs, W, ws, users, items, per_user):
     out = torch.empty((users.numel(), per_user), dtype=torch.float32, device=W.device)
     L.check(L.lib().drb_neumf_scores(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf), ws.U,
                                      ws.I, ws.F, ws.Ln, ws.opt, ws.max_rows, _ptr(users), users.numel(),
-                                     None if items is None else _ptr(items), per_user, _ptr(out), _stream()))
+                                     None if items is None else _ptr(items), per_user, tower_dtype, _ptr(out), _stream()))
     return out
 
 
@@ -395,3 +396,11 @@ def topk_from_scores(scores, cands, topk):
         out = torch.empty((n, topk), dtype=torch.int64, device=scores.device)
         L.check(L.lib().drb_topk_from_scores(_ptr(scores), None, n, cnt, topk, None, _ptr(out), _stream()))
     return out
+
+
+def gemm_test(variant, dtype, A, B, C_out, M, N, K, bias=None, ref=None):
+    """Tower GEMM dispatcher (tests): variant 0 NT+bias+ReLU, 1 NN+mask, 2 NN, 3 TN split-K accumulate."""
+    L.check(L.lib().drb_gemm_test(variant, dtype, M, N, K, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C_out),
+                                  C_out.stride(0), None if bias is None else _ptr(bias), None if ref is None else _ptr(ref),
+                                  0 if ref is None else ref.stride(0), _stream()))
+    return C_out

@@ -193,11 +193,18 @@ int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, float *d_IM
                               int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int64_t max_rows,
                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
                               int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
-                              int32_t apply, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+                              int32_t apply, int32_t tower_dtype, double *d_step_loss, int32_t sync_and_check,
+                              int64_t *nan_step, void *stream);
 int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
                      void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t opt,
                      int64_t max_rows, const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,
-                     float *d_scores, void *stream);
+                     int32_t tower_dtype, float *d_scores, void *stream);
+/* tower_dtype: 0 = fp32 on CUDA cores (parity path), 1 = bf16 operands on tcgen05 tensor cores with the fp32
+ * accumulator in tensor memory (BASELINE config 3).  drb_gemm_test exposes the tower's GEMM dispatcher to the tests:
+ * variant 0 NT+bias+ReLU (forward), 1 NN+ReLU-mask (input gradient), 2 NN, 3 TN split-K accumulate (weight gradient). */
+int drb_gemm_test(int32_t variant, int32_t dtype, int64_t M, int32_t N, int32_t K, const float *d_A, int64_t lda,
+                  const float *d_B, int64_t ldb, float *d_C, int64_t ldc, const float *d_bias, const float *d_ref,
+                  int64_t ldref, void *stream);
 /* top-K of pre-computed scores [n_rows, count]: ids from d_cands (float32 out, rank) or positions (int64 out, full_rank);
  * descending score, ties by lower position. */
 int drb_topk_from_scores(const float *d_scores, const int64_t *d_cands, int64_t n_rows, int32_t count, int32_t topk,

@@ -1,0 +1,83 @@
+"""tcgen05 (bf16 operands, fp32 TMEM accumulator) GEMM of the NeuMF tower vs a float64 product of the bf16-rounded
+operands, and the bf16-tower training step vs the fp32 tower (BASELINE config 3 tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from daisyrec_b200 import ops as o
+    o.require_cuda()
+    return o
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float64)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 128), (4096, 32, 64), (300, 24, 48), (129, 128, 32), (77, 16, 200), (2048, 256, 96)])
+def test_umma_forward_nt_bias_relu(ops, M, N, K):
+    g = torch.Generator(device="cuda"); g.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.2
+    b = torch.randn(N, device="cuda", generator=g)
+    want = torch.relu(bf(A) @ bf(W).T + b.double()).float()
+    for dtype in (0, 1):
+        C = torch.full((M, N), -7.0, device="cuda")
+        ops.gemm_test(0, dtype, A, W, C, M, N, K, bias=b)
+        torch.cuda.synchronize()
+        ref = want if dtype == 1 else torch.relu(A.double() @ W.double().T + b.double()).float()
+        tol = 1e-4 * max(1.0, float(ref.abs().max()))
+        assert float((C - ref).abs().max()) <= tol, (dtype, float((C - ref).abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K", [(777, 128, 64), (1024, 64, 32), (500, 96, 48)])
+def test_umma_input_gradient_nn_mask(ops, M, N, K):
+    g = torch.Generator(device="cuda"); g.manual_seed(M * 3 + N)
+    dZ = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(K, N, device="cuda", generator=g) * 0.3          # [out, in] row-major
+    ref_act = torch.randn(M, N, device="cuda", generator=g)
+    want = ((bf(dZ) @ bf(W)) * (ref_act > 0)).float()
+    C = torch.zeros(M, N, device="cuda")
+    ops.gemm_test(1, 1, dZ, W, C, M, N, K, ref=ref_act)
+    assert float((C - want).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+    C2 = torch.zeros(M, N, device="cuda")
+    ops.gemm_test(2, 1, dZ, W, C2, M, N, K)
+    assert float((C2 - (bf(dZ) @ bf(W)).float()).abs().max()) <= 1e-4 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("Mo,Ni,R", [(64, 128, 5000), (32, 64, 70000), (24, 48, 999), (128, 256, 4096)])
+def test_umma_weight_gradient_tn_splitk(ops, Mo, Ni, R):
+    g = torch.Generator(device="cuda"); g.manual_seed(Mo + Ni + R)
+    dZ = torch.randn(R, Mo, device="cuda", generator=g) * 0.1
+    X = torch.randn(R, Ni, device="cuda", generator=g)
+    want = (bf(dZ).T @ bf(X)).float()
+    C = torch.zeros(Mo, Ni, device="cuda")
+    ops.gemm_test(3, 1, dZ, X, C, Mo, Ni, R)
+    assert float((C - want).abs().max()) <= 2e-4 * max(1.0, float(want.abs().max()))
+
+
+def test_neumf_bf16_tower_step_close_to_fp32(ops):
+    """One NeuMF step with the tcgen05 bf16 tower vs the fp32 tower: loss within 2e-3 relative, tables within bf16 noise."""
+    rng = np.random.default_rng(0)
+    U, I, F, L, B = 500, 400, 32, 2, 4096
+    D = F * 2 ** (L - 1)
+    tabs_h = [(rng.standard_normal(s) * 0.2).astype(np.float32) for s in ((U, F), (I, F), (U, D), (I, D))]
+    W_h = (rng.standard_normal(ops.neumf_param_count(F, L)) * 0.15).astype(np.float32)
+    b = [torch.from_numpy(rng.integers(m, size=B).astype(np.int32)).cuda() for m in (U, I, I)]
+    hp = ops.hyper(0.01, 0.001, 0.001, "sgd")
+    res = []
+    for dtype in (0, 1):
+        tabs = [torch.from_numpy(t).cuda() for t in tabs_h]
+        W = torch.from_numpy(W_h).cuda()
+        ws = ops.NeumfWorkspace(U, I, F, L, "sgd", 2 * B, "cuda")
+        loss = ops.neumf_bpr_train_steps(tabs, W, ws, *b, B, 0, 1, hp, tower_dtype=dtype).item()
+        res.append((loss, [t.cpu().numpy() for t in tabs], W.cpu().numpy()))
+    (l0, t0, w0), (l1, t1, w1) = res
+    assert abs(l1 - l0) <= 2e-3 * abs(l0), (l0, l1)
+    for a, c in zip(t0 + [w0], t1 + [w1]):
+        upd = np.abs(a - c).max()
+        assert upd <= 5e-4, upd                                     # lr * (bf16 relative error ~ 4e-3) * |grad|
