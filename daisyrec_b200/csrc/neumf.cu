@@ -331,16 +331,23 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
     // the bias gradient of the predict layer is sum(+c) + sum(-c) == 0 exactly for a pairwise loss
 }
 
-// gb[n] += sum_m dZ[m, n]
-__global__ void colsum_kernel(const float *__restrict__ dZ, long long M, int N, float *__restrict__ gb)
+// gb[n] += sum_m dZ[m, n]      (coalesced: consecutive threads read consecutive columns of one row)
+__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ dZ, long long M, int N, float *__restrict__ gb)
 {
-    const int n = blockIdx.y * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    long long rows_per = (M + gridDim.x - 1) / gridDim.x;
-    long long lo = (long long)blockIdx.x * rows_per, hi = min(M, lo + rows_per);
+    __shared__ float s_part[256];
+    const int rows_per_pass = 256 / N > 0 ? 256 / N : 1;       // N <= 256
+    const int tr = threadIdx.x / N, tn = threadIdx.x % N;
     float s = 0.f;
-    for (long long m = lo; m < hi; ++m) s += dZ[m * N + n];
-    if (s != 0.f) atomicAdd(gb + n, s);
+    if (tr < rows_per_pass)
+        for (long long m = (long long)blockIdx.x * rows_per_pass + tr; m < M; m += (long long)gridDim.x * rows_per_pass)
+            s += dZ[m * N + tn];
+    s_part[threadIdx.x] = (tr < rows_per_pass) ? s : 0.f;
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float t = 0.f;
+        for (int q = 0; q < rows_per_pass; ++q) t += s_part[q * N + threadIdx.x];
+        if (t != 0.f) atomicAdd(gb + threadIdx.x, t);
+    }
 }
 
 // gUM[u] += dA0[t,:D] + dA0[B+t,:D];  gIM[i] += dA0[t,D:];  gIM[j] += dA0[B+t,D:]      (RED.ADD.F32x4)
@@ -542,7 +549,7 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
             rc = launch_gemm<true, false, 3>(tower_dtype, d.n[l + 1], d.n[l], (int)R, cur, d.n[l + 1], Aprev, d.n[l], w.gW + d.w_off[l],
                                               d.n[l], nullptr, nullptr, 0, st);
             if (rc != DRB_OK) return rc;
-            colsum_kernel<<<dim3(64, (d.n[l + 1] + 63) / 64), 64, 0, st>>>(cur, R, d.n[l + 1], w.gW + d.b_off[l]);
+            colsum_kernel<<<sm_count() * 4, 256, 0, st>>>(cur, R, d.n[l + 1], w.gW + d.b_off[l]);
             DRB_CUDA(cudaGetLastError());
             // dA_{l-1} = dZ W_l, masked by relu'(A_{l-1}) for hidden layers
             if (l > 0)

@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
                                                         const float *__restrict__ ref, long long ldref, int k_chunk, int Npad,
                                                         int tmem_cols)
 {
-    __shared__ __align__(128) unsigned char sA[128 * kUmmaBK * 2];
-    __shared__ __align__(128) unsigned char sB[kUmmaMaxN * kUmmaBK * 2];
+    __shared__ __align__(128) unsigned char s_all[(128 + kUmmaMaxN) * kUmmaBK * 2];   // A tile | B tile; reused by the epilogue
+    unsigned char *sA = s_all, *sB = s_all + 128 * kUmmaBK * 2;
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -168,27 +168,50 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
         phase ^= 1;
         tc_fence_after();
     }
-    // epilogue: lane == output row inside this warp's 32-lane quarter of TMEM
-    const long long m = m0 + warp * 32 + lane;
+    // epilogue: lane == output row inside this warp's 32-lane quarter of TMEM.  32 columns at a time are pulled out with
+    // one tcgen05.ld.32x32b.x32, transposed through a padded shared-memory tile (the operand buffers are free now) and
+    // written / accumulated with row-contiguous, fully coalesced accesses (lane == column).
+    float *tile = reinterpret_cast<float *>(s_all) + warp * (32 * 33);
+    const long long mrow0 = m0 + warp * 32;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
     const bool any = kb < ke;
-    for (int c = 0; c < Npad; c += 8) {
-        uint32_t r[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(taddr + (uint32_t)c));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < M && any) {
+    for (int c = 0; c < Npad; c += 32) {
+        uint32_t r[32];
+        if (c + 32 <= Npad) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr + (uint32_t)c));
+        } else {   // Npad is a multiple of 16: a trailing half chunk
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr + (uint32_t)c));
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                int n = c + e;
-                if (n >= N) continue;
-                float v = __uint_as_float(r[e]);
-                if (EPI == 1) { v += bias[n]; v = v > 0.f ? v : 0.f; }
+            for (int e = 16; e < 32; ++e) r[e] = 0u;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 32; ++e) tile[lane * 33 + e] = __uint_as_float(r[e]);
+        __syncwarp();
+        const int n = c + lane;
+        if (any && n < N) {
+            const float bn = (EPI == 1) ? bias[n] : 0.f;
+            for (int rr = 0; rr < 32; ++rr) {
+                const long long m = mrow0 + rr;
+                if (m >= M) break;
+                float v = tile[rr * 33 + lane];
+                if (EPI == 1) { v += bn; v = v > 0.f ? v : 0.f; }
                 if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v : 0.f; }
                 if (EPI == 3) atomicAdd(C + m * ldc + n, v); else C[m * ldc + n] = v;
             }
         }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();

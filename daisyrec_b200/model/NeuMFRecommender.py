@@ -73,6 +73,11 @@ class NeuMF(GeneralRecommender):
         self._ws = None
         self._opt_steps = 0
         self._rows = int(config.get('neumf_scratch_rows', 1 << 16))
+        # optional B200 key: 'fp32' (CUDA cores, parity path, default) | 'bf16' (tcgen05 tensor cores, BASELINE config 3)
+        td = str(config.get('tower_dtype', 'fp32')).lower()
+        if td not in ('fp32', 'bf16'):
+            raise ValueError(f"tower_dtype must be 'fp32' or 'bf16', got {td!r}")
+        self._tower_dtype = 1 if td == 'bf16' else 0
 
     # ------------------------------------------------------------------ plumbing
     def _tabs(self):
@@ -115,7 +120,7 @@ class NeuMF(GeneralRecommender):
         if self._ws is None:
             self._workspace(2 * batch, self._fit_opt, fresh=True)
         losses = ops.neumf_bpr_train_steps(self._tabs(), self.tower, self._ws, bu, bi, bj, batch, first, n_steps, self._hp,
-                                           adam_step0=self._opt_steps)
+                                           adam_step0=self._opt_steps, tower_dtype=self._tower_dtype)
         self._opt_steps += n_steps
         return losses
 
@@ -131,7 +136,7 @@ class NeuMF(GeneralRecommender):
         u = torch.as_tensor(user).to(self.device, torch.int64).reshape(-1).contiguous()
         i = torch.as_tensor(item).to(self.device, torch.int64).reshape(-1, 1).contiguous()
         self._ensure(1)
-        return ops.neumf_scores(self._tabs(), self.tower, self._ws, u, i, 1).reshape(-1)
+        return ops.neumf_scores(self._tabs(), self.tower, self._ws, u, i, 1, self._tower_dtype).reshape(-1)
 
     __call__ = forward
 
@@ -140,7 +145,7 @@ class NeuMF(GeneralRecommender):
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         self._ensure(2 * bu.numel())
         loss = ops.neumf_bpr_train_steps(self._tabs(), self.tower, self._ws, bu, bi, bj, bu.numel(), 0, 1, self._hp,
-                                         apply=False)
+                                         apply=False, tower_dtype=self._tower_dtype)
         return loss.to(torch.float32).reshape(())
 
     def train_step(self, batch):
@@ -168,12 +173,12 @@ class NeuMF(GeneralRecommender):
         self._ensure(1)
         d_users = torch.from_numpy(users).to(self.device)
         d_cands = torch.from_numpy(np.ascontiguousarray(cands)).to(self.device)
-        scores = ops.neumf_scores(self._tabs(), self.tower, self._ws, d_users, d_cands, cands.shape[1])
+        scores = ops.neumf_scores(self._tabs(), self.tower, self._ws, d_users, d_cands, cands.shape[1], self._tower_dtype)
         k = min(self.topk, cands.shape[1])
         return ops.topk_from_scores(scores, d_cands, k).cpu().numpy()
 
     def full_rank(self, u):
         self._ensure(1)
         users = torch.tensor([int(u)], dtype=torch.int64, device=self.device)
-        scores = ops.neumf_scores(self._tabs(), self.tower, self._ws, users, None, self.item_num)
+        scores = ops.neumf_scores(self._tabs(), self.tower, self._ws, users, None, self.item_num, self._tower_dtype)
         return ops.topk_from_scores(scores, None, min(self.topk, self.item_num))[0].cpu().numpy()

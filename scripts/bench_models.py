@@ -46,6 +46,7 @@ def main():
     ap.add_argument("what", choices=["lightgcn", "neumf", "mf-netflix"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--tower", default="fp32", choices=["fp32", "bf16"])
     a = ap.parse_args()
     dev = torch.device("cuda")
     if a.what == "lightgcn":
@@ -83,7 +84,8 @@ def main():
         step = [0]
 
         def fn():
-            ops.neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, B, step[0] % 4, 1, hp, adam_step0=step[0], check=False)
+            ops.neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, B, step[0] % 4, 1, hp, adam_step0=step[0], check=False,
+                                      tower_dtype=1 if a.tower == 'bf16' else 0)
             step[0] += 1
         ms = timed(fn, 3, a.steps)
         flop = 0
@@ -93,7 +95,7 @@ def main():
             n_in //= 2
         flop_triple = 2 * 3 * flop                          # 2 items x (fwd + 2 bwd GEMMs)
         print(json.dumps(dict(model="NeuMF", shape="ml-20m", F=F, L=L, batch=B, ms_per_step=ms, triples_per_s=B / ms * 1e3,
-                              tower_TFLOPs=B * flop_triple / ms / 1e9, tower="fp32 CUDA cores")))
+                              tower_TFLOPs=B * flop_triple / ms / 1e9, tower="fp32 CUDA cores" if a.tower == "fp32" else "bf16 tcgen05 (TMEM accumulator)")))
     else:
         U, I, nnz = SHAPES["netflix"]
         F = 128
