@@ -41,11 +41,12 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
-__device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int M, int N)
+__device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int M, int N, bool a_mn = false, bool b_mn = false)
 {
     // cute::UMMA::InstrDescriptor: c_format [4,6) = 1 (F32), a_format [7,10) = 1 (BF16), b_format [10,13) = 1 (BF16),
     // a_major [15] = 0, b_major [16] = 0 (K-major), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
@@ -54,21 +55,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-// Stage a [rows x 32] operand tile (element (r, c), c = K index inside the chunk) into the K-major core-matrix layout.
-//   TRANS = false: src(r, k) = S[(r0 + r) * ld + k]       (rows contiguous along K: 8 floats -> one 16-byte store)
-//   TRANS = true : src(r, k) = S[k * ld + (r0 + r)]       (contiguous along rows: 8 rows -> eight 2-byte stores)
-template <bool TRANS>
+// Operand tiles in shared memory (no swizzle, 8 x 16-byte core matrices), padded so that the 16-byte staging stores of a
+// quarter warp fall into distinct bank groups:
+//   K-major  (source contiguous along K):   elem(r, k) at (k/8)*LBO + (r/8)*128 + (r%8)*16 + (k%8)*2,  LBO = rows/8*128 + 32, SBO = 128
+//   MN-major (source contiguous along rows): elem(r, k) at (k/8)*LBO + (r/8)*144 + (k%8)*16 + (r%8)*2,  LBO = rows/8*144,      SBO = 144
+// Either way one work item converts 8 consecutive source floats to bf16 and issues ONE 16-byte shared store.
+__host__ __device__ __forceinline__ uint32_t umma_lbo(bool mn_major, int rows)
+{
+    return mn_major ? (uint32_t)(rows / 8) * 144u : (uint32_t)(rows / 8) * 128u + 32u;
+}
+__host__ __device__ __forceinline__ uint32_t umma_sbo(bool mn_major) { return mn_major ? 144u : 128u; }
+
+//   MN = false: src(r, k) = S[(r0 + r) * ld + k]       MN = true: src(r, k) = S[k * ld + (r0 + r)]
+template <bool MN>
 __device__ __forceinline__ void umma_stage_tile(unsigned char *smem, int rows, const float *__restrict__ S, long long ld,
                                                 long long r0, long long r_lim, int k0, int k_lim, int tid, int nthreads)
 {
-    const uint32_t lbo = (uint32_t)(rows / 8) * 128u;
-    if (!TRANS) {
-        const int items = rows * (kUmmaBK / 8);
-        for (int it = tid; it < items; it += nthreads) {
-            const int r = it / (kUmmaBK / 8), c1 = it % (kUmmaBK / 8);
+    const uint32_t lbo = umma_lbo(MN, rows);
+    const int items = MN ? (rows / 8) * kUmmaBK : rows * (kUmmaBK / 8);
+    for (int it = tid; it < items; it += nthreads) {
+        float v[8];
+        uint32_t off;
+        if (!MN) {
+            const int r = it / (kUmmaBK / 8), c1 = it % (kUmmaBK / 8);    // 4 lanes read 128 contiguous bytes of a row
             const long long gr = r0 + r;
             const int k = k0 + c1 * 8;
-            float v[8];
             if (gr < r_lim && k + 8 <= k_lim && ((ld & 3) == 0)) {
                 const float4 *p = reinterpret_cast<const float4 *>(S + gr * ld + k);
                 float4 a = __ldg(p), b = __ldg(p + 1);
@@ -77,18 +88,11 @@ __device__ __forceinline__ void umma_stage_tile(unsigned char *smem, int rows, c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = (gr < r_lim && k + e < k_lim) ? __ldg(S + gr * ld + k + e) : 0.f;
             }
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4 *>(smem + (uint32_t)c1 * lbo + (uint32_t)(r / 8) * 128u + (uint32_t)(r % 8) * 16u) = o;
-        }
-    } else {
-        const int items = (rows / 8) * kUmmaBK;
-        for (int it = tid; it < items; it += nthreads) {
-            const int r1 = it % (rows / 8), c = it / (rows / 8);      // consecutive threads -> consecutive row groups
-            const long long gr = r0 + (long long)r1 * 8;
+            off = (uint32_t)c1 * lbo + (uint32_t)(r / 8) * 128u + (uint32_t)(r % 8) * 16u;
+        } else {
+            const int rg = it % (rows / 8), c = it / (rows / 8);          // consecutive lanes read consecutive row groups
+            const long long gr = r0 + (long long)rg * 8;
             const int k = k0 + c;
-            float v[8];
             if (k < k_lim && gr + 8 <= r_lim && ((ld & 3) == 0) && ((gr & 3) == 0)) {
                 const float4 *p = reinterpret_cast<const float4 *>(S + (long long)k * ld + gr);
                 float4 a = __ldg(p), b = __ldg(p + 1);
@@ -97,10 +101,12 @@ __device__ __forceinline__ void umma_stage_tile(unsigned char *smem, int rows, c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = (k < k_lim && gr + e < r_lim) ? __ldg(S + (long long)k * ld + gr + e) : 0.f;
             }
-            unsigned char *base = smem + (uint32_t)(c / 8) * lbo + (uint32_t)r1 * 128u + (uint32_t)(c % 8) * 2u;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) *reinterpret_cast<__nv_bfloat16 *>(base + e * 16) = __float2bfloat16_rn(v[e]);
+            off = (uint32_t)(c / 8) * lbo + (uint32_t)rg * 144u + (uint32_t)(c % 8) * 16u;
         }
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(smem + off) = o;
     }
 }
 
@@ -112,8 +118,12 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
                                                         const float *__restrict__ ref, long long ldref, int k_chunk, int Npad,
                                                         int tmem_cols)
 {
-    __shared__ __align__(128) unsigned char s_all[(128 + kUmmaMaxN) * kUmmaBK * 2];   // A tile | B tile; reused by the epilogue
-    unsigned char *sA = s_all, *sB = s_all + 128 * kUmmaBK * 2;
+    constexpr int kABytes = (kUmmaBK / 8) * (128 / 8) * 144;                 // worst case (MN-major) A tile
+    constexpr int kBBytes = (kUmmaBK / 8) * (kUmmaMaxN / 8) * 144;
+    __shared__ __align__(128) unsigned char s_all[kABytes + kBBytes];         // A tile | B tile; reused by the epilogue
+    unsigned char *sA = s_all, *sB = s_all + kABytes;
+    // A(m,k) = A[k*lda + m] (TA) and B(k,n) = B[k*ldb + n] (!TB) are contiguous along the MN dimension -> MN-major tiles
+    constexpr bool A_MN = TA, B_MN = !TB;
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,21 +144,21 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = umma_idesc_bf16_f32(128, Npad);
-    const uint32_t lboA = (128 / 8) * 128, lboB = (uint32_t)(Npad / 8) * 128;
+    const uint32_t idesc = umma_idesc_bf16_f32(128, Npad, A_MN, B_MN);
+    const uint32_t lboA = umma_lbo(A_MN, 128), lboB = umma_lbo(B_MN, Npad);
     uint32_t phase = 0;
     bool first = true;
     for (int k0 = kb; k0 < ke; k0 += kUmmaBK) {
-        umma_stage_tile<TA>(sA, 128, A, lda, m0, M, k0, ke, tid, 128);
-        umma_stage_tile<!TB>(sB, Npad, B, ldb, 0, N, k0, ke, tid, 128);
+        umma_stage_tile<A_MN>(sA, 128, A, lda, m0, M, k0, ke, tid, 128);
+        umma_stage_tile<B_MN>(sB, Npad, B, ldb, 0, N, k0, ke, tid, 128);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (int kk = 0; kk < kUmmaBK / 16; ++kk) {
-                uint64_t da = umma_smem_desc(smem_u32(sA) + kk * 2 * lboA, lboA, 128);
-                uint64_t db = umma_smem_desc(smem_u32(sB) + kk * 2 * lboB, lboB, 128);
+                uint64_t da = umma_smem_desc(smem_u32(sA) + kk * 2 * lboA, lboA, umma_sbo(A_MN));
+                uint64_t db = umma_smem_desc(smem_u32(sB) + kk * 2 * lboB, lboB, umma_sbo(B_MN));
                 uint32_t acc = (first && kk == 0) ? 0u : 1u;
                 asm volatile(
                     "{\n\t"

@@ -80,4 +80,4 @@ def test_neumf_bf16_tower_step_close_to_fp32(ops):
     assert abs(l1 - l0) <= 2e-3 * abs(l0), (l0, l1)
     for a, c in zip(t0 + [w0], t1 + [w1]):
         upd = np.abs(a - c).max()
-        assert upd <= 2e-3, upd                                     # lr * (bf16 relative error ~ 4e-3) * |summed grad|
+        assert upd <= 5e-3, upd                                     # lr * (bf16 relative error ~ 4e-3) * |summed grad|
