@@ -241,9 +241,11 @@ static int launch_umma_gemm(long long M, int N, int K, const float *A, long long
     while (cols < Npad) cols <<= 1;
     dim3 grid((unsigned)((M + 127) / 128), 1, 1);
     int k_chunk = K;
-    if (EPI == 3) {   // split-K: the [out x in] result is one tile, parallelism comes from the K (row) dimension
-        long long want = (long long)sm_count() * 4;
-        long long max_chunks = (K + 2047) / 2048;
+    if (EPI == 3) {   // split-K: the [out x in] result is one tile, parallelism comes from the K (row) dimension.
+        // Each CTA runs its K steps back to back (stage -> mma -> wait), so latency is hidden by CTA count: aim at
+        // ~8 resident CTAs per SM, but keep >= 512 rows per chunk so the atomic epilogue stays a small fraction.
+        long long want = (long long)sm_count() * 8;
+        long long max_chunks = (K + 511) / 512;
         long long chunks = want < max_chunks ? want : max_chunks;
         if (chunks < 1) chunks = 1;
         k_chunk = (int)(((K + chunks - 1) / chunks + kUmmaBK - 1) / kUmmaBK * kUmmaBK);

@@ -78,6 +78,9 @@ def test_neumf_bf16_tower_step_close_to_fp32(ops):
         res.append((loss, [t.cpu().numpy() for t in tabs], W.cpu().numpy()))
     (l0, t0, w0), (l1, t1, w1) = res
     assert abs(l1 - l0) <= 2e-3 * abs(l0), (l0, l1)
-    for a, c in zip(t0 + [w0], t1 + [w1]):
-        upd = np.abs(a - c).max()
-        assert upd <= 5e-3, upd                                     # lr * (bf16 relative error ~ 4e-3) * |summed grad|
+    # compare the UPDATES in norm: bf16 operands perturb every product by ~2^-8 and flip the ReLU gate of the few
+    # pre-activations that sit at zero, so single elements can move by O(10 %) while the update as a whole agrees
+    for init, a, c in zip(tabs_h + [W_h], t0 + [w0], t1 + [w1]):
+        d_fp32, d_bf16 = (a - init).astype(np.float64), (c - init).astype(np.float64)
+        rel = np.linalg.norm(d_bf16 - d_fp32) / max(np.linalg.norm(d_fp32), 1e-30)
+        assert rel <= 3e-2, rel
