@@ -105,7 +105,8 @@ template <bool TA, bool TB, int EPI>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float *__restrict__ A, long long lda,
                                                     const float *__restrict__ B, long long ldb, float *__restrict__ C,
                                                     long long ldc, const float *__restrict__ bias,
-                                                    const float *__restrict__ ref, long long ldref, int k_chunk)
+                                                    const float *__restrict__ ref, long long ldref, int k_chunk,
+                                                    float alpha)
 {
     __shared__ float As[16][64 + 4];
     __shared__ float Bs[16][64 + 4];
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             if (n >= N) continue;
             float v = acc[i][j];
             if (EPI == 1) { v += bias[n]; v = v > 0.f ? v : 0.f; }
-            if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v : 0.f; }
+            if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v * alpha : 0.f; }
             if (EPI == 3) atomicAdd(C + m * ldc + n, v); else C[m * ldc + n] = v;
         }
     }
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
 
 template <bool TA, bool TB, int EPI>
 static int launch_sgemm(long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb, float *C,
-                        long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st)
+                        long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st, float alpha = 1.f)
 {
     if (M <= 0 || N <= 0 || K <= 0) return DRB_OK;
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), 1);
@@ -182,7 +183,7 @@ static int launch_sgemm(long long M, int N, int K, const float *A, long long lda
         k_chunk = (int)(((K + chunks - 1) / chunks + 15) / 16 * 16);
         grid.z = (unsigned)((K + k_chunk - 1) / k_chunk);
     }
-    sgemm_kernel<TA, TB, EPI><<<grid, 256, 0, st>>>((int)M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, k_chunk);
+    sgemm_kernel<TA, TB, EPI><<<grid, 256, 0, st>>>((int)M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, k_chunk, alpha);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }
@@ -190,17 +191,47 @@ static int launch_sgemm(long long M, int N, int K, const float *A, long long lda
 // dtype 0: fp32 CUDA cores (sgemm_kernel)   dtype 1: bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM
 template <bool TA, bool TB, int EPI>
 static int launch_gemm(int dtype, long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb,
-                       float *C, long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st)
+                       float *C, long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st,
+                       float alpha = 1.f)
 {
-    if (dtype == 1 && N <= kUmmaMaxN) return launch_umma_gemm<TA, TB, EPI>(M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, st);
-    return launch_sgemm<TA, TB, EPI>(M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, st);
+    if (dtype == 1 && N <= kUmmaMaxN)
+        return launch_umma_gemm<TA, TB, EPI>(M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, st, alpha);
+    return launch_sgemm<TA, TB, EPI>(M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, st, alpha);
 }
 
 // ------------------------------------------------------------------------------------------ gather / head / scatter
+// Dropout (NeuMFRecommender.py:61: nn.Dropout in front of every Linear, active in train mode).  The reference draws its
+// masks from torch's global RNG; here they are counter-based: keep(layer, step, element) = Philox4x32-10(seed;
+// element/4, layer, step) word (element%4) >= p * 2^32.  Counter-based masks can be regenerated in the backward pass
+// (layer 0) instead of being stored.  Kept values are scaled by 1/(1-p) like torch.
+struct Drop {
+    float p, inv_keep;
+    uint32_t k0, k1, step, thresh;
+};
+
+__device__ __forceinline__ float4 drop4(float4 v, const Drop &d, unsigned long long chunk, uint32_t layer)
+{
+    uint32_t c[4] = {(uint32_t)chunk, (uint32_t)(chunk >> 32), layer, d.step};
+    philox4x32(c, d.k0, d.k1);
+    v.x = c[0] >= d.thresh ? v.x * d.inv_keep : 0.f;
+    v.y = c[1] >= d.thresh ? v.y * d.inv_keep : 0.f;
+    v.z = c[2] >= d.thresh ? v.z * d.inv_keep : 0.f;
+    v.w = c[3] >= d.thresh ? v.w * d.inv_keep : 0.f;
+    return v;
+}
+
+// in-place dropout of a hidden activation block (n4 float4 chunks)
+__global__ void neumf_dropout_kernel(float *__restrict__ A, long long n4, Drop d, uint32_t layer)
+{
+    float4 *p = reinterpret_cast<float4 *>(A);
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x)
+        p[k] = drop4(p[k], d, (unsigned long long)k, layer);
+}
+
 // A_0[r, :] = cat(UM[u_r], IM[item_r]);  rows [0,B) use bi, rows [B,2B) use bj.   One thread per float4.
 __global__ void neumf_gather_kernel(const float *__restrict__ UM, const float *__restrict__ IM, const int32_t *__restrict__ bu,
                                     const int32_t *__restrict__ bi, const int32_t *__restrict__ bj, long long B, int D,
-                                    float *__restrict__ A0)
+                                    float *__restrict__ A0, Drop drop)
 {
     const int d4 = D / 4;
     const long long total = 2 * B * 2 * d4;
@@ -211,7 +242,9 @@ __global__ void neumf_gather_kernel(const float *__restrict__ UM, const float *_
         const float4 *src;
         if (c < d4) src = reinterpret_cast<const float4 *>(UM + (size_t)bu[t] * D) + c;
         else src = reinterpret_cast<const float4 *>(IM + (size_t)(r < B ? bi[t] : bj[t]) * D) + (c - d4);
-        reinterpret_cast<float4 *>(A0 + (size_t)r * 2 * D)[c] = __ldcg(src);
+        float4 v = __ldcg(src);
+        if (drop.p > 0.f) v = drop4(v, drop, (unsigned long long)k, 0u);
+        reinterpret_cast<float4 *>(A0 + (size_t)r * 2 * D)[c] = v;
     }
 }
 
@@ -353,7 +386,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ d
 // gUM[u] += dA0[t,:D] + dA0[B+t,:D];  gIM[i] += dA0[t,D:];  gIM[j] += dA0[B+t,D:]      (RED.ADD.F32x4)
 __global__ void neumf_scatter_kernel(const float *__restrict__ dA0, const int32_t *__restrict__ bu,
                                      const int32_t *__restrict__ bi, const int32_t *__restrict__ bj, long long B, int D,
-                                     float *__restrict__ gUM, float *__restrict__ gIM)
+                                     float *__restrict__ gUM, float *__restrict__ gIM, Drop drop)
 {
     const int d4 = D / 4;
     const long long total = B * d4;
@@ -363,6 +396,11 @@ __global__ void neumf_scatter_kernel(const float *__restrict__ dA0, const int32_
         const float4 *rp = reinterpret_cast<const float4 *>(dA0 + (size_t)t * 2 * D);
         const float4 *rn = reinterpret_cast<const float4 *>(dA0 + (size_t)(B + t) * 2 * D);
         float4 up = rp[c], un = rn[c], ip = rp[d4 + c], in_ = rn[d4 + c];
+        if (drop.p > 0.f) {   // d(A_0) = d(A_0') * mask_0 / (1-p): same counters as the gather (chunk = row * 2*d4 + col)
+            const unsigned long long cp = (unsigned long long)t * 2 * d4, cn = (unsigned long long)(B + t) * 2 * d4;
+            up = drop4(up, drop, cp + c, 0u); un = drop4(un, drop, cn + c, 0u);
+            ip = drop4(ip, drop, cp + d4 + c, 0u); in_ = drop4(in_, drop, cn + d4 + c, 0u);
+        }
         Vec<4> v;
         v.v[0] = up.x + un.x; v.v[1] = up.y + un.y; v.v[2] = up.z + un.z; v.v[3] = up.w + un.w;
         red_row<4>(gUM + (size_t)bu[t] * D + c * 4, v);
@@ -457,7 +495,7 @@ static int grid1d(long long n, int block, int per_sm = 16)
 
 // tower forward on `rows` rows already gathered into acts' A_0 block
 static int tower_forward(const NeumfDims &d, const float *W, float *acts, long long R, long long rows, int dtype,
-                         cudaStream_t st)
+                         const Drop &drop, cudaStream_t st)
 {
     for (int l = 0; l < d.L; ++l) {
         const float *in = acts + d.act_off[l] * R;
@@ -465,6 +503,11 @@ static int tower_forward(const NeumfDims &d, const float *W, float *acts, long l
         int rc = launch_gemm<false, true, 1>(dtype, rows, d.n[l + 1], d.n[l], in, d.n[l], W + d.w_off[l], d.n[l], out,
                                              d.n[l + 1], W + d.b_off[l], nullptr, 0, st);
         if (rc != DRB_OK) return rc;
+        if (drop.p > 0.f && l + 1 < d.L) {   // the next Linear sees dropout(relu(z_l)); the tower output is not dropped
+            long long n4 = rows * d.n[l + 1] / 4;
+            neumf_dropout_kernel<<<grid1d(n4, 256), 256, 0, st>>>(out, n4, drop, (uint32_t)(l + 1));
+            DRB_CUDA(cudaGetLastError());
+        }
     }
     return DRB_OK;
 }
@@ -505,11 +548,13 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
                                          int32_t U, int32_t I, int32_t F, int32_t L, int64_t max_rows,
                                          const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
                                          int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *h,
-                                         int64_t adam_step0, int32_t apply, int32_t tower_dtype, double *d_step_loss,
-                                         int32_t sync_and_check, int64_t *nan_step, void *stream)
+                                         int64_t adam_step0, int32_t apply, int32_t tower_dtype, float dropout,
+                                         uint64_t dropout_seed, double *d_step_loss, int32_t sync_and_check,
+                                         int64_t *nan_step, void *stream)
 {
     NeumfDims d;
     DRB_REQUIRE(tower_dtype == 0 || tower_dtype == 1, "neumf: tower_dtype must be 0 (fp32) or 1 (bf16 tcgen05)");
+    DRB_REQUIRE(dropout >= 0.f && dropout < 1.f, "neumf: dropout must be in [0, 1)");
     DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf: bad dims (factors must be a positive multiple of 4, 1 <= num_layers <= 8)");
     DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_bu && d_bi && d_bj && h && d_step_loss, "neumf: null argument");
     DRB_REQUIRE(batch > 0 && 2 * batch <= max_rows, "neumf: batch %lld needs 2*batch <= max_rows=%lld", (long long)batch,
@@ -527,10 +572,15 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         const long long R = 2 * B;
         const int32_t *bu = d_bu + base, *bi = d_bi + base, *bj = d_bj + base;
         DRB_CUDA(cudaMemsetAsync(w.red, 0, 16 * sizeof(double), st));
+        Drop drop;
+        drop.p = dropout; drop.inv_keep = 1.f / (1.f - dropout);
+        drop.k0 = (uint32_t)dropout_seed; drop.k1 = (uint32_t)(dropout_seed >> 32);
+        drop.step = (uint32_t)(adam_step0 + s);
+        drop.thresh = (uint32_t)fmin(4294967295.0, (double)dropout * 4294967296.0);
         // forward
-        neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts);
+        neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts, drop);
         DRB_CUDA(cudaGetLastError());
-        int rc = tower_forward(d, d_W, w.acts, R, R, tower_dtype, st);
+        int rc = tower_forward(d, d_W, w.acts, R, R, tower_dtype, drop, st);
         if (rc != DRB_OK) return rc;
         const float *AL = w.acts + d.act_off[d.L] * R;
         float *dZ = w.dA;                                        // dZ_L [R, F]
@@ -554,14 +604,14 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
             // dA_{l-1} = dZ W_l, masked by relu'(A_{l-1}) for hidden layers
             if (l > 0)
                 rc = launch_gemm<false, false, 2>(tower_dtype, R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
-                                                   d.n[l], nullptr, Aprev, d.n[l], st);
+                                                   d.n[l], nullptr, Aprev, d.n[l], st, drop.inv_keep);
             else
                 rc = launch_gemm<false, false, 0>(tower_dtype, R, d.n[l], d.n[l + 1], cur, d.n[l + 1], d_W + d.w_off[l], d.n[l], nxt,
                                                    d.n[l], nullptr, nullptr, 0, st);
             if (rc != DRB_OK) return rc;
             float *t = cur; cur = nxt; nxt = t;
         }
-        neumf_scatter_kernel<<<grid1d(B * (d.D / 4), 256), 256, 0, st>>>(cur, bu, bi, bj, B, d.D, w.gUM, w.gIM);
+        neumf_scatter_kernel<<<grid1d(B * (d.D / 4), 256), 256, 0, st>>>(cur, bu, bi, bj, B, d.D, w.gUM, w.gIM, drop);
         DRB_CUDA(cudaGetLastError());
         // apply: table pairs through the MF dense sweep, tower block through the small dense kernel
         StepParams p;

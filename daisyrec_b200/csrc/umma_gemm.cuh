@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
                                                         const float *__restrict__ B, long long ldb, float *__restrict__ C,
                                                         long long ldc, const float *__restrict__ bias,
                                                         const float *__restrict__ ref, long long ldref, int k_chunk, int Npad,
-                                                        int tmem_cols)
+                                                        int tmem_cols, float alpha)
 {
     constexpr int kABytes = (kUmmaBK / 8) * (128 / 8) * 144;                 // worst case (MN-major) A tile
     constexpr int kBBytes = (kUmmaBK / 8) * (kUmmaMaxN / 8) * 144;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
                 if (m >= M) break;
                 float v = tile[rr * 33 + lane];
                 if (EPI == 1) { v += bn; v = v > 0.f ? v : 0.f; }
-                if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v : 0.f; }
+                if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v * alpha : 0.f; }
                 if (EPI == 3) atomicAdd(C + m * ldc + n, v); else C[m * ldc + n] = v;
             }
         }
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
 
 template <bool TA, bool TB, int EPI>
 static int launch_umma_gemm(long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb, float *C,
-                            long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st)
+                            long long ldc, const float *bias, const float *ref, long long ldref, cudaStream_t st,
+                            float alpha = 1.f)
 {
     if (M <= 0 || N <= 0 || K <= 0) return DRB_OK;
     DRB_REQUIRE(N <= kUmmaMaxN, "umma_gemm: N=%d exceeds %d", N, kUmmaMaxN);
@@ -251,7 +252,8 @@ static int launch_umma_gemm(long long M, int N, int K, const float *A, long long
         k_chunk = (int)(((K + chunks - 1) / chunks + kUmmaBK - 1) / kUmmaBK * kUmmaBK);
         grid.z = (unsigned)((K + k_chunk - 1) / k_chunk);
     }
-    umma_gemm_kernel<TA, TB, EPI><<<grid, 128, 0, st>>>((int)M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, k_chunk, Npad, cols);
+    umma_gemm_kernel<TA, TB, EPI><<<grid, 128, 0, st>>>((int)M, N, K, A, lda, B, ldb, C, ldc, bias, ref, ldref, k_chunk, Npad, cols,
+                                                        alpha);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }

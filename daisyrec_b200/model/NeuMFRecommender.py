@@ -35,9 +35,9 @@ class NeuMF(GeneralRecommender):
         if self.model != 'NeuMF':
             raise NotImplementedError(f"model_name={self.model!r}: the B200 hot path covers 'NeuMF' (GMF / MLP / NeuMF-pre "
                                       "are outside BASELINE.json's configs)")
-        if self.dropout and float(self.dropout) > 0:
-            raise NotImplementedError('dropout > 0 draws torch-RNG masks inside the tower (NeuMFRecommender.py:61); the B200 '
-                                      'path implements dropout=0 only -- pass --dropout 0')
+        self.dropout = float(self.dropout or 0.0)
+        if not (0.0 <= self.dropout < 1.0):
+            raise ValueError(f'dropout must be in [0, 1), got {self.dropout}')
         if self.factors % 4 != 0:
             raise NotImplementedError('NeuMF on the B200 path needs factors to be a multiple of 4 (128-bit rows)')
         F, Ln = self.factors, self.num_layers
@@ -111,6 +111,9 @@ class NeuMF(GeneralRecommender):
         return self._ws
 
     def _begin_fit(self, opt):
+        # dropout masks are counter-based (Philox) on the device; the key is drawn from torch's global RNG so that
+        # torch.manual_seed makes runs reproducible (the masks themselves are NOT torch's: parity holds at dropout=0)
+        self._drop_seed = int(torch.empty((), dtype=torch.int64).random_().item()) if self.dropout > 0 else 0
         self._hp = self._hyper(opt)
         self._opt_steps = 0
         self._fit_opt = opt
@@ -120,7 +123,8 @@ class NeuMF(GeneralRecommender):
         if self._ws is None:
             self._workspace(2 * batch, self._fit_opt, fresh=True)
         losses = ops.neumf_bpr_train_steps(self._tabs(), self.tower, self._ws, bu, bi, bj, batch, first, n_steps, self._hp,
-                                           adam_step0=self._opt_steps, tower_dtype=self._tower_dtype)
+                                           adam_step0=self._opt_steps, tower_dtype=self._tower_dtype,
+                                           dropout=self.dropout if self.training else 0.0, dropout_seed=self._drop_seed)
         self._opt_steps += n_steps
         return losses
 
@@ -145,14 +149,20 @@ class NeuMF(GeneralRecommender):
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         self._ensure(2 * bu.numel())
         loss = ops.neumf_bpr_train_steps(self._tabs(), self.tower, self._ws, bu, bi, bj, bu.numel(), 0, 1, self._hp,
-                                         apply=False, tower_dtype=self._tower_dtype)
+                                         apply=False, tower_dtype=self._tower_dtype, adam_step0=self._opt_steps,
+                                         dropout=self.dropout if self.training else 0.0, dropout_seed=self._drop_seed)
         return loss.to(torch.float32).reshape(())
 
     def train_step(self, batch):
         self._check_loss_type()
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         self._ensure(2 * bu.numel())
-        return float(self._train_steps(bu, bi, bj, bu.numel(), 0, 1).item())
+        was = self.training
+        self.train()                                                 # a training step runs in train mode (dropout on)
+        try:
+            return float(self._train_steps(bu, bi, bj, bu.numel(), 0, 1).item())
+        finally:
+            self.train(was)
 
     def predict(self, u, i):
         return float(self.forward([int(u)], [int(i)]).item())

@@ -356,7 +356,7 @@ class NeumfWorkspace:
 
 
 def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True,
-                          tower_dtype=0):
+                          tower_dtype=0, dropout=0.0, dropout_seed=0):
     for t in list(tabs) + [W]:
         _dev(t, torch.float32, "table")
     for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
@@ -366,7 +366,8 @@ def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, h
     rc = L.lib().drb_neumf_bpr_train_steps(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf),
                                            ws.U, ws.I, ws.F, ws.Ln, ws.max_rows, _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(),
                                            batch, first_step, n_steps, C.byref(hp), adam_step0, 1 if apply else 0,
-                                           tower_dtype, _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
+                                           tower_dtype, C.c_float(dropout), C.c_uint64(dropout_seed), _ptr(losses),
+                                           1 if check else 0, C.byref(nan_step), _stream())
     if rc == L.DRB_ERR_NAN_LOSS:
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
     L.check(rc)

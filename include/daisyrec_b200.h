@@ -181,7 +181,9 @@ int drb_lgcn_bpr_train_steps(float *d_E0, void *d_ws, int32_t user_num, int32_t 
  * (in = 2D / 2^l), then predict_layer weight [2F] and bias [1]  (NeuMFRecommender.py:58-71).
  * max_rows: rows of activation scratch (>= 2 * batch for training; any size for scoring).
  * drb_neumf_bpr_train_steps  calc_loss :139-169 (regulariser quirk of :158/:160 included) + backward +
- *                            optimizer.step for n_steps batches; apply = 0: calc_loss of one batch.  dropout = 0.
+ *                            optimizer.step for n_steps batches; apply = 0: calc_loss of one batch.
+ *                            dropout (config['dropout'], :61): counter-based Philox masks keyed by dropout_seed and the
+ *                            global step -- same distribution as nn.Dropout, not torch's RNG stream (parity at dropout = 0).
  * drb_neumf_scores           forward :118-137 for (users[r / per_user], items[r]) pairs (items NULL: all item ids):
  *                            what rank / full_rank / predict score with (:171-232); feed to drb_topk_from_scores. */
 int64_t drb_neumf_param_count(int32_t factors, int32_t num_layers);
@@ -193,8 +195,8 @@ int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, float *d_IM
                               int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int64_t max_rows,
                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
                               int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
-                              int32_t apply, int32_t tower_dtype, double *d_step_loss, int32_t sync_and_check,
-                              int64_t *nan_step, void *stream);
+                              int32_t apply, int32_t tower_dtype, float dropout, uint64_t dropout_seed,
+                              double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
                      void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t opt,
                      int64_t max_rows, const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,

@@ -126,5 +126,49 @@ def test_neumf_dropin_class(ops):
     preds = model.rank(loader)
     assert preds.dtype == np.float32 and preds.shape == (7, 10)
     assert model.full_rank(int(users[0])).dtype == np.int64
+    # the reference's default dropout=0.5 trains (device masks), and eval-mode inference ignores dropout
+    torch.manual_seed(3)
+    m2 = NeuMF(dict(cfg, dropout=0.5))
+    m2.fit(get_dataloader(BasicDataset(data), batch_size=bs.shape[2], shuffle=False))
+    assert np.isfinite(m2.tower.cpu().numpy()).all() and m2.rank(loader).shape == (7, 10)
     with pytest.raises(NotImplementedError):
-        NeuMF(dict(cfg, dropout=0.5))
+        NeuMF(dict(cfg, model_name='GMF'))
+
+
+@pytest.mark.parametrize("tower_dtype", [0])
+def test_neumf_dropout_gradient_consistency(ops, tower_dtype):
+    """Dropout forward/backward consistency without access to torch's masks: with counter-based masks the loss at fixed
+    (seed, step) is a deterministic function of the parameters, so the SGD update must equal -lr * its numerical gradient."""
+    rng = np.random.default_rng(1)
+    U, I, F, L, B, p, seed = 60, 50, 8, 2, 512, 0.3, 12345
+    D = F * 2 ** (L - 1)
+    tabs_h = [(rng.standard_normal(s) * 0.5).astype(np.float32) for s in ((U, F), (I, F), (U, D), (I, D))]
+    W_h = (rng.standard_normal(ops.neumf_param_count(F, L)) * 0.4).astype(np.float32)
+    b = [dev(rng.integers(m, size=B).astype(np.int32)) for m in (U, I, I)]
+    lr = 1e-3
+    hp = ops.hyper(lr, 0.0, 0.0, "sgd")
+    ws = ops.NeumfWorkspace(U, I, F, L, "sgd", 2 * B, "cuda")
+
+    def loss_at(W_np, tabs_np):
+        return ops.neumf_bpr_train_steps([dev(t) for t in tabs_np], dev(W_np), ws, *b, B, 0, 1, hp, adam_step0=5, apply=False,
+                                         tower_dtype=tower_dtype, dropout=p, dropout_seed=seed).item()
+    l_drop, l_nodrop = loss_at(W_h, tabs_h), ops.neumf_bpr_train_steps([dev(t) for t in tabs_h], dev(W_h), ws, *b, B, 0, 1, hp,
+                                                                       apply=False).item()
+    assert l_drop != l_nodrop and loss_at(W_h, tabs_h) == l_drop          # masks active and deterministic
+    tabs, W = [dev(t) for t in tabs_h], dev(W_h)
+    ops.neumf_bpr_train_steps(tabs, W, ws, *b, B, 0, 1, hp, adam_step0=5, tower_dtype=tower_dtype, dropout=p, dropout_seed=seed)
+    gW = (W_h - W.cpu().numpy()) / lr
+    gUM = (tabs_h[2] - tabs[2].cpu().numpy()) / lr
+    eps = 2e-2
+    # numerical gradient on the largest-gradient coordinates of the tower block and of the user MLP table
+    for k in np.argsort(-np.abs(gW))[:6]:
+        Wp, Wm = W_h.copy(), W_h.copy()
+        Wp[k] += eps; Wm[k] -= eps
+        num = (loss_at(Wp, tabs_h) - loss_at(Wm, tabs_h)) / (2 * eps)
+        assert abs(num - gW[k]) <= 0.03 * abs(gW[k]) + 0.05, (k, num, gW[k])
+    for flat in np.argsort(-np.abs(gUM).ravel())[:4]:
+        r, c = divmod(int(flat), D)
+        tp, tm = [t.copy() for t in tabs_h], [t.copy() for t in tabs_h]
+        tp[2][r, c] += eps; tm[2][r, c] -= eps
+        num = (loss_at(W_h, tp) - loss_at(W_h, tm)) / (2 * eps)
+        assert abs(num - gUM[r, c]) <= 0.03 * abs(gUM[r, c]) + 0.05, (r, c, num, gUM[r, c])
