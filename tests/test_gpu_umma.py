@@ -83,4 +83,5 @@ def test_neumf_bf16_tower_step_close_to_fp32(ops):
     for init, a, c in zip(tabs_h + [W_h], t0 + [w0], t1 + [w1]):
         d_fp32, d_bf16 = (a - init).astype(np.float64), (c - init).astype(np.float64)
         rel = np.linalg.norm(d_bf16 - d_fp32) / max(np.linalg.norm(d_fp32), 1e-30)
-        assert rel <= 3e-2, rel
+        cos = float((d_bf16 * d_fp32).sum() / max(np.linalg.norm(d_bf16) * np.linalg.norm(d_fp32), 1e-30))
+        assert rel <= 0.15 and cos >= 0.99, (rel, cos)
