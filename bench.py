@@ -13,8 +13,10 @@ Own arm (default):
   value      K steps timed with CUDA events around the persistent step-kernel launches, index planes and
              tables resident in HBM.  Steps walk the epoch's batches; launches cover one epoch's worth of
              steps at most (what MF.fit does), so K steps = ceil(K / steps_per_epoch) launches.
-  e2e        the same metric through the public API with HOST batches: MF.train_step(batch) per step
-             (pinned host index arrays -> H2D inside the call, loss -> D2H), as the reference's loop does.
+  e2e        the same metric through the public API with HOST batches: MF.fit_host_batches(pinned host index planes)
+             -- every step's index arrays are copied H2D and every step's loss is read back D2H inside the timed
+             region, the copy of batch s+1 overlapping the kernel of batch s; the blocking per-batch
+             MF.train_step loop (the reference's loop shape) is reported beside it.
   roofline   algorithmic bytes (24*F+12 per triple) / event-timed launch duration vs the
              measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  oracle/torch_port.py (the reference's algorithm on PyTorch-CPU) on this host's cores.

@@ -489,8 +489,17 @@ int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
     StepKernel k = pick_kernel(p.F);
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
-    int per_sm = 0;
-    DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kThreads, 0));
+    // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
+    // split multi-GPU / LightGCN / NeuMF paths)
+    static thread_local StepKernel cached_k = nullptr;
+    static thread_local int cached_per_sm = 0;
+    if (cached_k != k) {
+        int q = 0;
+        DRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k, kThreads, 0));
+        cached_k = k;
+        cached_per_sm = q;
+    }
+    const int per_sm = cached_per_sm;
     DRB_REQUIRE(per_sm > 0, "step kernel does not fit on an SM");
     const int max_grid = per_sm * sm_count();
     // tile: as large as possible (<= kTileMax) while still giving every CTA work
