@@ -305,7 +305,8 @@ def run_own(args):
     #      e2e_sync = MF.train_step per batch with a blocking loss read, exactly the reference's loop shape
     ke = max(1, min(args.steps, args.e2e_steps, spe - 1))
     planes = [t[:ke * B].cpu().pin_memory() for t in (bu, bi, bj)]
-    model.fit_host_batches(*[p_[:3 * B] for p_ in planes], B, 3)     # warm-up
+    wk = min(3, ke)
+    model.fit_host_batches(*[p_[:wk * B] for p_ in planes], B, wk)   # warm-up
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -281,15 +281,37 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                     rqi[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ii[r] * F, gl, chunks, ok[r]);
                     rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r]);
                 }
+                // scores of the UNR triples of this group (every lane of the group ends up with the same x)
+                float xs[UNR], cs[UNR];
+#pragma unroll
+                for (int r = 0; r < UNR; ++r)
+                    xs[r] = dot_rows<VEC, W, NCH>(rp[r], rqi[r]) - dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
+                // The scalar chain sigmoid -> log -> coefficient costs ~40 instructions and would be replayed by all W
+                // lanes for each of the UNR triples; instead lane gl evaluates it ONCE, for triple (gl % UNR) of its
+                // group, and the coefficients are handed round with one shuffle per triple.
+                if constexpr (W >= UNR) {
+                    float x_own = xs[0];
+                    bool ok_own = ok[0];
+#pragma unroll
+                    for (int r = 1; r < UNR; ++r)
+                        if ((gl % UNR) == r) { x_own = xs[r]; ok_own = ok[r]; }
+                    const float sg = 1.f / (1.f + expf(-x_own));
+                    if (gl < UNR && ok_own) t_loss += -logf(1e-10f + sg);
+                    const float c_own = -(sg * (1.f - sg)) / (1e-10f + sg);
+#pragma unroll
+                    for (int r = 0; r < UNR; ++r) cs[r] = __shfl_sync(0xffffffffu, c_own, (lane - gl) + r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < UNR; ++r) {
+                        const float sg = 1.f / (1.f + expf(-xs[r]));
+                        if (gl == 0 && ok[r]) t_loss += -logf(1e-10f + sg);
+                        cs[r] = -(sg * (1.f - sg)) / (1e-10f + sg);
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < UNR; ++r) {
-                    float pos = dot_rows<VEC, W, NCH>(rp[r], rqi[r]);
-                    float neg = dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
                     if (!ok[r]) continue;
-                    float x = pos - neg;
-                    float sg = 1.f / (1.f + expf(-x));
-                    if (gl == 0) t_loss += -logf(1e-10f + sg);
-                    float c = -(sg * (1.f - sg)) / (1e-10f + sg);
+                    const float c = cs[r];
                     if (has_reg) {
                         float l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
                         Row<VEC, W, NCH> nu_ = rp[r], ni_ = rqi[r], nj_ = rqj[r];

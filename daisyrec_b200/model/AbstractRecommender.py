@@ -128,6 +128,9 @@ class GeneralRecommender(AbstractRecommender):
         self.logger = config['logger']
         self.steps_per_launch = int(config.get('steps_per_launch', 0))   # 0 = whole epoch in one launch
         self.show_progress = bool(config.get('progress', True))
+        # 'torch' (default): the DataLoader's own CPU permutation -> the reference's batches bit for bit;
+        # 'device': torch.randperm on the GPU seeded from the global RNG (same distribution, no 8-byte/triple H2D)
+        self.shuffle_engine = str(config.get('shuffle_engine', 'torch'))
         # one process per GPU (torchrun): user-sharded training / ranking, see daisyrec_b200/parallel.py
         import torch.distributed as dist
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -185,8 +188,14 @@ class GeneralRecommender(AbstractRecommender):
                 self._triples_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.int32)).to(self.device)
                 self._triples_key = (id(data), T)
             d_triples = self._triples_dev
-        perm = epoch_permutation(T, shuffle, gen)
-        d_perm = None if perm is None else perm.to(self.device, non_blocking=False)
+        if shuffle and self.shuffle_engine == 'device':
+            torch.empty((), dtype=torch.int64).random_(generator=gen)                 # _base_seed, as the DataLoader draws it
+            g = torch.Generator(device=self.device)
+            g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            d_perm = torch.randperm(T, generator=g, device=self.device)
+        else:
+            perm = epoch_permutation(T, shuffle, gen)
+            d_perm = None if perm is None else perm.to(self.device, non_blocking=False)
         bu, bi, bj = ops.gather_triples(d_triples, d_perm)
         n_use = (T // bs) * bs if drop_last else T
         nsteps = (n_use + bs - 1) // bs
