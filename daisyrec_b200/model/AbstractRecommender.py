@@ -237,10 +237,7 @@ class GeneralRecommender(AbstractRecommender):
             nsteps -= 1
         pbar = tqdm(total=nsteps, disable=not self.show_progress or self.rank_id != 0)
         pbar.set_description(f'[Epoch {epoch:03d}]')
-        losses = torch.empty(nsteps, dtype=torch.float64, device=self.device)
-        for s in range(nsteps):
-            trainer.step(s)
-            losses[s] = trainer.loss[0]
+        losses = trainer.train_steps(0, nsteps)
         trainer.check_nan()
         current_loss = float(losses.sum().item())
         pbar.update(nsteps)

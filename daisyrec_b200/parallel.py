@@ -85,6 +85,25 @@ def allgather_rows(local_rows, local_pos, total_rows, group=None):
 
 
 # --------------------------------------------------------------------------------------- device side
+_NATIVE_COMM = {"ready": False}
+
+
+def init_native_comm(group=None):
+    """Create the library's own NCCL communicator (rank 0's ncclUniqueId is broadcast with torch.distributed)."""
+    if _NATIVE_COMM["ready"]:
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        L.check(L.lib().drb_comm_unique_id(buf))
+        ident.copy_(torch.tensor(list(buf), dtype=torch.uint8))
+    dist.broadcast(ident, 0, group=group)
+    host = ident.cpu().numpy()
+    L.check(L.lib().drb_comm_init(host.ctypes.data, rank, world))
+    _NATIVE_COMM["ready"] = True
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -96,8 +115,13 @@ def _ptr(t):
 class ShardedTrainer:
     """Rank-local state of user-sharded BPR-MF training."""
 
-    def __init__(self, P_local, Q, bounds, rank, world, hp, opt="sgd", group=None):
+    def __init__(self, P_local, Q, bounds, rank, world, hp, opt="sgd", group=None, comm="nccl"):
         from . import ops
+        # comm = "nccl": the library enqueues kernels + one grouped NCCL all-reduce per step itself (no host round trip);
+        # comm = "torch": per-step torch.distributed collectives (also what the gloo CPU tests of the host logic exercise)
+        self.comm = comm if (comm == "torch" or dist.get_backend(group) == "nccl") else "torch"
+        if self.comm == "nccl":
+            init_native_comm(group)
         self.ops = ops
         self.P, self.Q = P_local, Q
         self.bounds, self.rank, self.world, self.group = np.asarray(bounds, np.int64), rank, world, group
@@ -152,6 +176,23 @@ class ShardedTrainer:
         b, e = int(self.offsets_host[s]), int(self.offsets_host[s + 1])
         self.step_device(self.bu, self.bi, self.bj, b, e - b)
 
+    def train_steps(self, first, n_steps, losses=None):
+        """Global steps first .. first+n_steps-1 of the prepared epoch; returns the per-step global losses (device)."""
+        if losses is None:
+            losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
+        if self.comm == "nccl":
+            offs = np.ascontiguousarray(self.offsets_host, np.int64)
+            L.check(L.lib().drb_mf_bpr_train_steps_sharded(_ptr(self.P), _ptr(self.Q), _ptr(self.ws.buf), max(1, self.U_local),
+                                                           self.I, self.F, _ptr(self.bu), _ptr(self.bi), _ptr(self.bj),
+                                                           offs.ctypes.data, first, n_steps, C.byref(self.hp), self.opt_steps,
+                                                           _ptr(losses), _stream()))
+            self.opt_steps += n_steps
+        else:
+            for k in range(n_steps):
+                self.step(first + k)
+                losses[k] = self.loss[0]
+        return losses[:n_steps]
+
     def step_host(self, h_bu, h_bi, h_bj, stage):
         """End-to-end step from pinned HOST arrays holding this rank's share of the global batch."""
         n = len(h_bu)
@@ -196,11 +237,18 @@ def run_sharded_bench(args, rank, local, world, dev):
     del perm
     local_counts = np.diff(tr.offsets_host)
 
+    scratch_losses = torch.empty(spe + 1, dtype=torch.float64, device=dev)
+
     def run(first, k):
-        n_loc = 0
-        for s in range(first, first + k):
-            tr.step(s % spe)
-            n_loc += int(local_counts[s % spe])
+        """k global steps starting at `first`, walking the epoch cyclically; one native call per epoch segment."""
+        n_loc, s = 0, first
+        while k > 0:
+            pos = s % spe
+            seg = min(k, spe - pos)
+            tr.train_steps(pos, seg, scratch_losses)
+            n_loc += int(local_counts[pos:pos + seg].sum())
+            s += seg
+            k -= seg
         return n_loc
 
     clocks = B.ClockSampler(local) if rank == 0 else None
@@ -254,7 +302,8 @@ def run_sharded_bench(args, rank, local, world, dev):
                 "warmup": args.warmup, "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": B.workload_config(args, d, T, args.batch, {
-                    "parallelism": f"user-row-sharded P x{world}, replicated Q, per-step NCCL all-reduce of gQ/counters/norms",
+                    "parallelism": f"user-row-sharded P x{world}, replicated Q, per step ONE grouped NCCL all-reduce of "
+                                   "gQ/counters/norms enqueued by the library between the phase-1 and phase-2 kernels",
                     "global_batch": Bg, "per_gpu_batch": args.batch, "steps_per_epoch": spe}),
                 "clocks": clk,
                 "e2e": {"value": float(etot.item()) / float(ems.item()) * 1e3, "unit": B.UNIT,

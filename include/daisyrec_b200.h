@@ -212,6 +212,17 @@ int drb_gemm_test(int32_t variant, int32_t dtype, int64_t M, int32_t N, int32_t 
 int drb_topk_from_scores(const float *d_scores, const int64_t *d_cands, int64_t n_rows, int32_t count, int32_t topk,
                          float *d_out_f, int64_t *d_out_i, void *stream);
 
+/* Native NCCL path of the sharded step: the library enqueues phase 1 -> ONE grouped all-reduce of {gQ, cntI, acc} ->
+ * phase 2 for n_steps global steps on `stream` with no host round trip per step.  The communicator is created from a
+ * 128-byte ncclUniqueId that rank 0 obtains (drb_comm_unique_id) and the host broadcasts to every rank. */
+int drb_comm_unique_id(uint8_t *h_out128);
+int drb_comm_init(const uint8_t *h_id128, int32_t rank, int32_t world);
+int drb_comm_destroy(void);
+int drb_mf_bpr_train_steps_sharded(float *d_P_local, float *d_Q, void *d_ws, int32_t user_num_local, int32_t item_num,
+                                   int32_t factors, const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj,
+                                   const int64_t *h_step_offsets, int64_t first_step, int64_t n_steps,
+                                   const drb_hyper *hyper, int64_t adam_step0, double *d_step_loss, void *stream);
+
 /* ---- inference ------------------------------------------------------------------------
  * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,
  *   descending sort, first topk ids as float32 (the reference's dtype quirk, :107).
