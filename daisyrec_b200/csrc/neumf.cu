@@ -101,6 +101,7 @@ static size_t carve_neumf(void *base, const NeumfDims &d, int opt, long long max
 //   TA = false: A(m,k) = A[m*lda + k]      TA = true: A(m,k) = A[k*lda + m]
 //   TB = false: B(k,n) = B[k*ldb + n]      TB = true: B(k,n) = B[n*ldb + k]
 //   EPI 0: C = acc   1: C = relu(acc + bias[n])   2: C = acc * (ref(m,n) > 0)   3: atomicAdd(C, acc) (split-K over grid.z)
+//   EPI 4: atomicAdd(C^T, acc): the product is accumulated into the transposed matrix C[n*ldc + m] (split-K)
 template <bool TA, bool TB, int EPI>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float *__restrict__ A, long long lda,
                                                     const float *__restrict__ B, long long ldb, float *__restrict__ C,
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long m0 = (long long)blockIdx.x * 64;
     const int n0 = blockIdx.y * 64;
-    const int kb = (EPI == 3) ? blockIdx.z * k_chunk : 0;
-    const int ke = (EPI == 3) ? min(K, kb + k_chunk) : K;
+    const int kb = (EPI >= 3) ? blockIdx.z * k_chunk : 0;
+    const int ke = (EPI >= 3) ? min(K, kb + k_chunk) : K;
     float acc[4][4] = {};
     for (int k0 = kb; k0 < ke; k0 += 16) {
         // load tiles: 16x64 each = 1024 elements, 4 per thread
@@ -162,7 +163,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             float v = acc[i][j];
             if (EPI == 1) { v += bias[n]; v = v > 0.f ? v : 0.f; }
             if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v * alpha : 0.f; }
-            if (EPI == 3) atomicAdd(C + m * ldc + n, v); else C[m * ldc + n] = v;
+            if (EPI == 3) atomicAdd(C + m * ldc + n, v);
+            else if (EPI == 4) atomicAdd(C + (long long)n * ldc + m, v);   // transposed accumulate: C^T += acc
+            else C[m * ldc + n] = v;
         }
     }
 }
@@ -174,7 +177,7 @@ static int launch_sgemm(long long M, int N, int K, const float *A, long long lda
     if (M <= 0 || N <= 0 || K <= 0) return DRB_OK;
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), 1);
     int k_chunk = K;
-    if (EPI == 3) {   // split-K so that the tiny [out x in] result still fills the machine
+    if (EPI >= 3) {   // split-K so that the tiny [out x in] result still fills the machine
         long long tiles = (long long)grid.x * grid.y;
         long long want = ((long long)sm_count() * 4 + tiles - 1) / tiles;          // chunks wanted for occupancy
         long long max_chunks = (K + 2047) / 2048;                                   // >= 2048 rows per chunk
@@ -267,13 +270,19 @@ __global__ void neumf_gather_pairs_kernel(const float *__restrict__ UM, const fl
     }
 }
 
-// One warp per triple.  red[0] bpr, red[1..5] l1 of (UG_u, UM_u, IG_i, IM_i, IG_j), red[6..10] their squared sums.
+// A group of W = min(32, next_pow2(F/4)) lanes per triple (4 triples per warp at F=32); float4 everywhere:
+// 128-bit row loads, RED.ADD.F32x4 for the GMF-table gradients, 128-bit dZ_L stores.
+// red[0] bpr, red[1..5] l1 of (UG_u, UM_u, IG_i, IM_i, IG_j), red[6..10] their squared sums.
+__device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float abs4(float4 v) { return fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w); }
+__device__ __forceinline__ float sq4(float4 v, float s) { return fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s)))); }
+
 __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict__ UG, const float *__restrict__ IG,
                                                          const float *__restrict__ UM, const float *__restrict__ IM,
                                                          const float *__restrict__ wp, const float *__restrict__ AL,
                                                          const int32_t *__restrict__ bu, const int32_t *__restrict__ bi,
                                                          const int32_t *__restrict__ bj, long long B, int F, int D, int has_reg,
-                                                         int apply, float *__restrict__ gUG, float *__restrict__ gIG,
+                                                         int apply, int W, float *__restrict__ gUG, float *__restrict__ gIG,
                                                          float *__restrict__ gWp, float *__restrict__ dZL,
                                                          unsigned *__restrict__ cntU, unsigned long long *__restrict__ cntI,
                                                          double *__restrict__ red)
@@ -281,73 +290,96 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
     extern __shared__ float s_gw[];                 // [2F + 1] CTA partial of the predict-layer gradient
     __shared__ double s_red[11];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int gpw = 32 / W, gl = lane % W, gw = lane / W;
+    const int chunks = F / 4, dchunks = D / 4;
     for (int k = threadIdx.x; k < 2 * F + 1; k += blockDim.x) s_gw[k] = 0.f;
     if (threadIdx.x < 11) s_red[threadIdx.x] = 0.0;
     __syncthreads();
     float acc[11] = {};
-    float gwa[4] = {}, gwb[4] = {};                 // predict-layer gradient partials of this lane (F <= 128)
-    const bool reg_gw = F <= 128;
+    float4 gwa = make_float4(0.f, 0.f, 0.f, 0.f), gwb = gwa;   // predict-layer gradient partials of this lane's chunk
+    const bool one_chunk = chunks <= W;                        // F <= 128: each lane owns at most one chunk
     const float bp = wp[2 * F];
-    for (long long t = (long long)blockIdx.x * nwarp + warp; t < B; t += (long long)gridDim.x * nwarp) {
-        const int u = bu[t], i = bi[t], j = bj[t];
+    const long long groups = (long long)gridDim.x * nwarp * gpw;
+    const long long g0 = ((long long)blockIdx.x * nwarp + warp) * gpw + gw;
+    const long long rounds = (B + groups - 1) / groups;
+    for (long long rd = 0; rd < rounds; ++rd) {
+        const long long t = rd * groups + g0;
+        const bool ok = t < B;
+        const int u = ok ? bu[t] : 0, i = ok ? bi[t] : 0, j = ok ? bj[t] : 0;
         const float *ug = UG + (size_t)u * F, *igi = IG + (size_t)i * F, *igj = IG + (size_t)j * F;
-        const float *hp = AL + (size_t)t * F, *hn = AL + (size_t)(B + t) * F;
+        const float *hp = AL + (size_t)(ok ? t : 0) * F, *hn = AL + (size_t)(ok ? B + t : 0) * F;
         float sp = 0.f, sn = 0.f;
-        for (int f = lane; f < F; f += 32) {
-            float a = __ldcg(ug + f), b = __ldcg(igi + f), c = __ldcg(igj + f);
-            float w0 = wp[f], w1 = wp[F + f];
-            sp = fmaf(w0, a * b, sp); sp = fmaf(w1, hp[f], sp);
-            sn = fmaf(w0, a * c, sn); sn = fmaf(w1, hn[f], sn);
-            if (has_reg) {
-                acc[1] += fabsf(a); acc[6] = fmaf(a, a, acc[6]);
-                acc[3] += fabsf(b); acc[8] = fmaf(b, b, acc[8]);
-                acc[5] += fabsf(c); acc[10] = fmaf(c, c, acc[10]);
+        for (int c = gl; c < chunks; c += W) {
+            float4 a = ldcg4(ug + 4 * c), b = ldcg4(igi + 4 * c), d = ldcg4(igj + 4 * c);
+            float4 w0 = *reinterpret_cast<const float4 *>(wp + 4 * c), w1 = *reinterpret_cast<const float4 *>(wp + F + 4 * c);
+            float4 h0 = *reinterpret_cast<const float4 *>(hp + 4 * c), h1 = *reinterpret_cast<const float4 *>(hn + 4 * c);
+            sp = fmaf(w0.x, a.x * b.x, sp); sp = fmaf(w1.x, h0.x, sp); sn = fmaf(w0.x, a.x * d.x, sn); sn = fmaf(w1.x, h1.x, sn);
+            sp = fmaf(w0.y, a.y * b.y, sp); sp = fmaf(w1.y, h0.y, sp); sn = fmaf(w0.y, a.y * d.y, sn); sn = fmaf(w1.y, h1.y, sn);
+            sp = fmaf(w0.z, a.z * b.z, sp); sp = fmaf(w1.z, h0.z, sp); sn = fmaf(w0.z, a.z * d.z, sn); sn = fmaf(w1.z, h1.z, sn);
+            sp = fmaf(w0.w, a.w * b.w, sp); sp = fmaf(w1.w, h0.w, sp); sn = fmaf(w0.w, a.w * d.w, sn); sn = fmaf(w1.w, h1.w, sn);
+            if (has_reg && ok) {
+                acc[1] += abs4(a); acc[6] = sq4(a, acc[6]);
+                acc[3] += abs4(b); acc[8] = sq4(b, acc[8]);
+                acc[5] += abs4(d); acc[10] = sq4(d, acc[10]);
             }
         }
-        if (has_reg) {
+        if (has_reg && ok) {
             const float *um = UM + (size_t)u * D, *imi = IM + (size_t)i * D;
-            for (int d = lane; d < D; d += 32) {
-                float a = __ldcg(um + d), b = __ldcg(imi + d);
-                acc[2] += fabsf(a); acc[7] = fmaf(a, a, acc[7]);
-                acc[4] += fabsf(b); acc[9] = fmaf(b, b, acc[9]);
+            for (int c = gl; c < dchunks; c += W) {
+                float4 a = ldcg4(um + 4 * c), b = ldcg4(imi + 4 * c);
+                acc[2] += abs4(a); acc[7] = sq4(a, acc[7]);
+                acc[4] += abs4(b); acc[9] = sq4(b, acc[9]);
             }
         }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
+        for (int off = W >> 1; off >= 1; off >>= 1) {
             sp += __shfl_xor_sync(0xffffffffu, sp, off);
             sn += __shfl_xor_sync(0xffffffffu, sn, off);
         }
         const float x = (sp + bp) - (sn + bp);
         const float sg = 1.f / (1.f + expf(-x));
-        if (lane == 0) acc[0] += -logf(1e-10f + sg);
+        if (gl == 0 && ok) acc[0] += -logf(1e-10f + sg);
         const float c = -(sg * (1.f - sg)) / (1e-10f + sg);
-        if (!apply) continue;
-        for (int f = lane, q = 0; f < F; f += 32, ++q) {
-            float a = __ldcg(ug + f), b = __ldcg(igi + f), cc = __ldcg(igj + f);
-            float w0 = wp[f], w1 = wp[F + f];
+        if (!apply || !ok) continue;
+        for (int cc = gl; cc < chunks; cc += W) {
+            float4 a = ldcg4(ug + 4 * cc), b = ldcg4(igi + 4 * cc), d = ldcg4(igj + 4 * cc);
+            float4 w0 = *reinterpret_cast<const float4 *>(wp + 4 * cc), w1 = *reinterpret_cast<const float4 *>(wp + F + 4 * cc);
+            float4 h0 = *reinterpret_cast<const float4 *>(hp + 4 * cc), h1 = *reinterpret_cast<const float4 *>(hn + 4 * cc);
             // predict-layer weight gradient: dp * cat(GMF, h) summed over pos (+c) and neg (-c)
-            float ga = c * (a * b) - c * (a * cc), gb = c * hp[f] - c * hn[f];
-            if (reg_gw) { gwa[q & 3] += ga; gwb[q & 3] += gb; }
-            else { atomicAdd(&s_gw[f], ga); atomicAdd(&s_gw[F + f], gb); }
-            // GMF table gradients
-            atomicAdd(gUG + (size_t)u * F + f, c * w0 * b - c * w0 * cc);
-            atomicAdd(gIG + (size_t)i * F + f, c * w0 * a);
-            atomicAdd(gIG + (size_t)j * F + f, -c * w0 * a);
+            float4 ga = make_float4(c * (a.x * b.x) - c * (a.x * d.x), c * (a.y * b.y) - c * (a.y * d.y),
+                                    c * (a.z * b.z) - c * (a.z * d.z), c * (a.w * b.w) - c * (a.w * d.w));
+            float4 gb = make_float4(c * h0.x - c * h1.x, c * h0.y - c * h1.y, c * h0.z - c * h1.z, c * h0.w - c * h1.w);
+            if (one_chunk) {
+                gwa.x += ga.x; gwa.y += ga.y; gwa.z += ga.z; gwa.w += ga.w;
+                gwb.x += gb.x; gwb.y += gb.y; gwb.z += gb.z; gwb.w += gb.w;
+            } else {
+                atomicAdd(&s_gw[4 * cc], ga.x); atomicAdd(&s_gw[4 * cc + 1], ga.y); atomicAdd(&s_gw[4 * cc + 2], ga.z); atomicAdd(&s_gw[4 * cc + 3], ga.w);
+                atomicAdd(&s_gw[F + 4 * cc], gb.x); atomicAdd(&s_gw[F + 4 * cc + 1], gb.y); atomicAdd(&s_gw[F + 4 * cc + 2], gb.z); atomicAdd(&s_gw[F + 4 * cc + 3], gb.w);
+            }
+            // GMF table gradients (one RED.ADD.F32x4 per row chunk)
+            Vec<4> v;
+            v.v[0] = c * w0.x * b.x - c * w0.x * d.x; v.v[1] = c * w0.y * b.y - c * w0.y * d.y;
+            v.v[2] = c * w0.z * b.z - c * w0.z * d.z; v.v[3] = c * w0.w * b.w - c * w0.w * d.w;
+            red_row<4>(gUG + (size_t)u * F + 4 * cc, v);
+            v.v[0] = c * w0.x * a.x; v.v[1] = c * w0.y * a.y; v.v[2] = c * w0.z * a.z; v.v[3] = c * w0.w * a.w;
+            red_row<4>(gIG + (size_t)i * F + 4 * cc, v);
+            v.v[0] = -v.v[0]; v.v[1] = -v.v[1]; v.v[2] = -v.v[2]; v.v[3] = -v.v[3];
+            red_row<4>(gIG + (size_t)j * F + 4 * cc, v);
             // dZ_L = dp * w1 * relu'(h)
-            dZL[(size_t)t * F + f] = hp[f] > 0.f ? c * w1 : 0.f;
-            dZL[(size_t)(B + t) * F + f] = hn[f] > 0.f ? -c * w1 : 0.f;
+            *reinterpret_cast<float4 *>(dZL + (size_t)t * F + 4 * cc) =
+                make_float4(h0.x > 0.f ? c * w1.x : 0.f, h0.y > 0.f ? c * w1.y : 0.f, h0.z > 0.f ? c * w1.z : 0.f, h0.w > 0.f ? c * w1.w : 0.f);
+            *reinterpret_cast<float4 *>(dZL + (size_t)(B + t) * F + 4 * cc) =
+                make_float4(h1.x > 0.f ? -c * w1.x : 0.f, h1.y > 0.f ? -c * w1.y : 0.f, h1.z > 0.f ? -c * w1.z : 0.f, h1.w > 0.f ? -c * w1.w : 0.f);
         }
-        if (lane == 0) {
+        if (gl == 0) {
             red_add_u32(cntU + u, 1u);
             red_add_u64(cntI + i, 1ull);
             red_add_u64(cntI + j, 1ull << 32);
         }
     }
-    if (apply && reg_gw)
-        for (int f = lane, q = 0; f < F; f += 32, ++q) {
-            atomicAdd(&s_gw[f], gwa[q & 3]);
-            atomicAdd(&s_gw[F + f], gwb[q & 3]);
-        }
+    if (apply && one_chunk && gl < chunks) {
+        atomicAdd(&s_gw[4 * gl], gwa.x); atomicAdd(&s_gw[4 * gl + 1], gwa.y); atomicAdd(&s_gw[4 * gl + 2], gwa.z); atomicAdd(&s_gw[4 * gl + 3], gwa.w);
+        atomicAdd(&s_gw[F + 4 * gl], gwb.x); atomicAdd(&s_gw[F + 4 * gl + 1], gwb.y); atomicAdd(&s_gw[F + 4 * gl + 2], gwb.z); atomicAdd(&s_gw[F + 4 * gl + 3], gwb.w);
+    }
     // block reduction of the scalars
     const int nv = has_reg ? 11 : 1;
     for (int k = 0; k < nv; ++k) {
@@ -584,8 +616,10 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         if (rc != DRB_OK) return rc;
         const float *AL = w.acts + d.act_off[d.L] * R;
         float *dZ = w.dA;                                        // dZ_L [R, F]
-        neumf_head_kernel<<<grid1d(B, 8, 8), 256, sizeof(float) * (2 * F + 1), st>>>(
-            d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, w.gUG, w.gIG,
+        int hw = 1;
+        while (hw < F / 4 && hw < 32) hw <<= 1;                  // lanes per triple in the head kernel
+        neumf_head_kernel<<<grid1d(B, 8 * (32 / hw), 8), 256, sizeof(float) * (2 * F + 1), st>>>(
+            d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, hw, w.gUG, w.gIG,
             w.gW + d.wp_off, dZ, w.cntU, w.cntI, w.red);
         DRB_CUDA(cudaGetLastError());
         neumf_finalize_kernel<<<1, 1, 0, st>>>(w.red, h->reg_1, h->reg_2, w.hdrG, w.hdrM, d_step_loss + s, first_step + s);
@@ -595,8 +629,10 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         float *cur = w.dA, *nxt = w.dB;
         for (int l = d.L - 1; l >= 0; --l) {
             const float *Aprev = w.acts + d.act_off[l] * R;
-            // gW_l[out,in] += dZ^T A_{l-1}     (split-K over the R rows)
-            rc = launch_gemm<true, false, 3>(tower_dtype, d.n[l + 1], d.n[l], (int)R, cur, d.n[l + 1], Aprev, d.n[l], w.gW + d.w_off[l],
+            // gW_l[out,in] += dZ^T A_{l-1}, computed as (A_{l-1}^T dZ)^T: the wide dimension (in) fills the 128-row MMA tile
+            // and the narrow one (out) becomes N, so the TMEM footprint per CTA is small and more CTAs overlap
+            // (split-K over the R rows; transposed atomic accumulate into gW_l)
+            rc = launch_gemm<true, false, 4>(tower_dtype, d.n[l], d.n[l + 1], (int)R, Aprev, d.n[l], cur, d.n[l + 1], w.gW + d.w_off[l],
                                               d.n[l], nullptr, nullptr, 0, st);
             if (rc != DRB_OK) return rc;
             colsum_kernel<<<sm_count() * 4, 256, 0, st>>>(cur, R, d.n[l + 1], w.gW + d.b_off[l]);
@@ -691,6 +727,7 @@ extern "C" int drb_gemm_test(int32_t variant, int32_t dtype, int64_t M, int32_t 
     case 1: return launch_gemm<false, false, 2>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, d_ref, ldref, st);
     case 2: return launch_gemm<false, false, 0>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, nullptr, 0, st);
     case 3: return launch_gemm<true, false, 3>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, nullptr, 0, st);
+    case 4: return launch_gemm<true, false, 4>(dtype, M, N, K, d_A, lda, d_B, ldb, d_C, ldc, nullptr, nullptr, 0, st);
     }
     DRB_REQUIRE(false, "gemm_test: unknown variant %d", variant);
 }

@@ -111,6 +111,7 @@ __device__ __forceinline__ void umma_stage_tile(unsigned char *smem, int rows, c
 }
 
 // EPI 0: C = acc   1: C = relu(acc + bias[n])   2: C = acc * (ref(m,n) > 0)   3: atomicAdd(C, acc) (split-K over grid.z)
+// EPI 4: atomicAdd(C^T, acc) -- transposed accumulate C[n*ldc + m] (split-K)
 template <bool TA, bool TB, int EPI>
 __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, const float *__restrict__ A, long long lda,
                                                         const float *__restrict__ B, long long ldb, float *__restrict__ C,
@@ -128,8 +129,8 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long m0 = (long long)blockIdx.x * 128;
-    const int kb = (EPI == 3) ? blockIdx.z * k_chunk : 0;
-    const int ke = (EPI == 3) ? min(K, kb + k_chunk) : K;
+    const int kb = (EPI >= 3) ? blockIdx.z * k_chunk : 0;
+    const int ke = (EPI >= 3) ? min(K, kb + k_chunk) : K;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols)
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(128) umma_gemm_kernel(int M, int N, int K, con
                 float v = tile[rr * 33 + lane];
                 if (EPI == 1) { v += bn; v = v > 0.f ? v : 0.f; }
                 if (EPI == 2) { v = (ref[m * ldref + n] > 0.f) ? v * alpha : 0.f; }
-                if (EPI == 3) atomicAdd(C + m * ldc + n, v); else C[m * ldc + n] = v;
+                if (EPI == 3) atomicAdd(C + m * ldc + n, v);
+                else if (EPI == 4) atomicAdd(C + (long long)n * ldc + m, v);
+                else C[m * ldc + n] = v;
             }
         }
         __syncwarp();
@@ -242,7 +245,7 @@ static int launch_umma_gemm(long long M, int N, int K, const float *A, long long
     while (cols < Npad) cols <<= 1;
     dim3 grid((unsigned)((M + 127) / 128), 1, 1);
     int k_chunk = K;
-    if (EPI == 3) {   // split-K: the [out x in] result is one tile, parallelism comes from the K (row) dimension.
+    if (EPI >= 3) {   // split-K: the [out x in] result is one tile, parallelism comes from the K (row) dimension.
         // Each CTA runs its K steps back to back (stage -> mma -> wait), so latency is hidden by CTA count: aim at
         // ~8 resident CTAs per SM, but keep >= 512 rows per chunk so the atomic epilogue stays a small fraction.
         long long want = (long long)sm_count() * 8;

@@ -60,6 +60,20 @@ def test_umma_weight_gradient_tn_splitk(ops, Mo, Ni, R):
     assert float((C - want).abs().max()) <= 2e-4 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("Mi,No,R", [(128, 64, 5000), (64, 32, 70000), (48, 24, 999), (256, 128, 4096)])
+def test_umma_weight_gradient_transposed_accumulate(ops, Mi, No, R):
+    """variant 4 (what the tower uses): gW[out, in] += (X^T dZ)^T with the wide dimension on the MMA rows."""
+    g = torch.Generator(device="cuda"); g.manual_seed(Mi + No + R)
+    X = torch.randn(R, Mi, device="cuda", generator=g)
+    dZ = torch.randn(R, No, device="cuda", generator=g) * 0.1
+    want = (bf(dZ).T @ bf(X)).float()                                   # [out, in]
+    for dtype in (0, 1):
+        C = torch.zeros(No, Mi, device="cuda")
+        ops.gemm_test(4, dtype, X, dZ, C, Mi, No, R)
+        ref = want if dtype == 1 else (dZ.double().T @ X.double()).float()
+        assert float((C - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), dtype
+
+
 def test_neumf_bf16_tower_step_close_to_fp32(ops):
     """One NeuMF step with the tcgen05 bf16 tower vs the fp32 tower: loss within 2e-3 relative, tables within bf16 noise."""
     rng = np.random.default_rng(0)
