@@ -1,1 +1,3 @@
 from .MFRecommender import MF  # noqa: F401
+from .NeuMFRecommender import NeuMF  # noqa: F401
+from .LightGCNRecommender import LightGCN  # noqa: F401
