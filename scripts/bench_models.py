@@ -43,7 +43,7 @@ def batches(U, I, n, dev, d=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["lightgcn", "neumf", "mf-netflix"])
+    ap.add_argument("what", choices=["lightgcn", "neumf", "mf-netflix", "mf-fit"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tower", default="fp32", choices=["fp32", "bf16"])
@@ -96,6 +96,28 @@ def main():
         flop_triple = 2 * 3 * flop                          # 2 items x (fwd + 2 bwd GEMMs)
         print(json.dumps(dict(model="NeuMF", shape="ml-20m", F=F, L=L, batch=B, ms_per_step=ms, triples_per_s=B / ms * 1e3,
                               tower_TFLOPs=B * flop_triple / ms / 1e9, tower="fp32 CUDA cores" if a.tower == "fp32" else "bf16 tcgen05 (TMEM accumulator)")))
+    elif a.what == "mf-fit":
+        # wall-clock of the drop-in API at config-2 scale: MF(config).fit(DataLoader over the 80 M sampler triples)
+        import logging, time as _t
+        sys.path.insert(0, ".")
+        import bench as Bn
+        from daisyrec_b200.model.MFRecommender import MF
+        from daisyrec_b200.utils.dataset import BasicDataset, get_dataloader
+        from daisyrec_b200.utils.sampler import TripleArray
+        d, triples = Bn.build_workload("ml-20m", dev, 4, 2022, "cuda")
+        host = triples.cpu().numpy().view(TripleArray)
+        host._drb_device = triples
+        for engine in ("torch", "device"):
+            cfg = dict(gpu="", logger=logging.getLogger("b"), lr=0.01, reg_1=0.001, reg_2=0.001, epochs=2, topk=50,
+                       user_num=d["user_num"], item_num=d["item_num"], factors=64, loss_type="BPR", optimizer="default",
+                       init_method="default", early_stop=False, progress=False, shuffle_engine=engine)
+            model = MF(cfg)
+            loader = get_dataloader(BasicDataset(host), batch_size=a.batch or (1 << 20), shuffle=True)
+            torch.cuda.synchronize(); t0 = _t.time()
+            model.fit(loader)
+            torch.cuda.synchronize(); dt = _t.time() - t0
+            print(json.dumps(dict(model="MF.fit drop-in", shuffle_engine=engine, epochs=2, triples=int(host.shape[0]),
+                                  wall_s=dt, triples_per_s_wall=2 * host.shape[0] / dt)))
     else:
         U, I, nnz = SHAPES["netflix"]
         F = 128

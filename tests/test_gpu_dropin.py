@@ -94,3 +94,29 @@ def test_unsupported_options_fail_loudly():
         m.fit([])
     with pytest.raises(NotImplementedError):
         MF(_config(user_num=10, item_num=10, loss_type='nope')).fit([])
+
+
+def test_edge_cases_small_inputs():
+    """Inputs the reference mishandles or never sees: one test user (the reference's .squeeze() breaks, MFRecommender.py:115),
+    fewer triples than one batch, topk larger than the candidate list, a user without any train interaction."""
+    from daisyrec_b200.model.MFRecommender import MF
+    from daisyrec_b200.utils.sampler import BasicNegtiveSampler
+    from daisyrec_b200.utils.dataset import BasicDataset, CandidatesDataset, get_dataloader
+    U, I = 12, 20
+    cfg = _config(user_num=U, item_num=I, factors=8, topk=50, cand_num=7)
+    torch.manual_seed(0); np.random.seed(0)
+    model = MF(cfg)
+    loader1 = get_dataloader(CandidatesDataset([[3, np.array([1, 5, 5, 9, 0, 2, 19])]]), batch_size=128, shuffle=False)
+    out = model.rank(loader1)
+    assert out.shape == (1, 7) and sorted(out[0].tolist()) == [0, 1, 2, 5, 5, 9, 19]      # topk clipped to cand_num
+    df = pd.DataFrame({"user": [0, 0, 1, 3, 3, 3], "item": [1, 2, 3, 4, 5, 6], "rating": 1.0, "timestamp": range(6)})
+    ur = {0: {1, 2}, 1: {3}, 3: {4, 5, 6}}
+    from collections import defaultdict
+    cfg['train_ur'] = defaultdict(set, ur)                              # users 2, 4..11 have no interactions
+    tri = BasicNegtiveSampler(df, cfg).sampling()
+    assert tri.shape == (24, 3)
+    for u, i, j in tri:
+        assert j not in ur[int(u)] and 0 <= j < I
+    model.fit(get_dataloader(BasicDataset(tri), batch_size=256, shuffle=True))          # 24 triples < one batch
+    assert np.isfinite(model.embed_user.weight.cpu().numpy()).all()
+    assert model.rank(get_dataloader(CandidatesDataset([]), batch_size=128, shuffle=False)).shape[0] == 0
