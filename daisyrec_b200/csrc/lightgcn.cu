@@ -89,36 +89,23 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_seg_kernel(Adj a, const flo
         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc.c[ch].v[q] = 0.f;
-        // Edge metadata is fetched cooperatively: lane gl of the group loads (col, val) of edge eb + gl ONCE for a batch
-        // of W edges, and the batch is then walked E edges at a time with shuffles handing the pair round -- two loads
-        // per W edges per lane instead of two per edge (the kernel is issue-bound, ncu r01e: 67 % issue slots busy).
-        const int gbase = lane - gl;
-        // groups of one warp own segments of different lengths: shuffles must name only this group's lanes
-        const unsigned gmask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << gbase);
-        for (long long eb = b; eb < e; eb += W) {
-            const long long mine = eb + gl;
-            const int my_c = mine < e ? __ldg(a.col + mine) : 0;
-            const float my_v = mine < e ? __ldg(a.val + mine) : 0.f;
-            const int nb_e = (int)min((long long)W, e - eb);
-            for (int q0 = 0; q0 < nb_e; q0 += E) {
-                float vv[E];
-                Row<VEC, W, NCH> x[E];
+        for (long long e0 = b; e0 < e; e0 += E) {
+            int cc[E];
+            float vv[E];
+            Row<VEC, W, NCH> x[E];
 #pragma unroll
-                for (int q = 0; q < E; ++q) {
-                    const int src = gbase + ((q0 + q) & (W - 1));
-                    const int cq = __shfl_sync(gmask, my_c, src);
-                    vv[q] = __shfl_sync(gmask, my_v, src);
-                    const bool ok = q0 + q < nb_e;
-                    if (!ok) vv[q] = 0.f;
-                    x[q] = load_row<VEC, W, NCH>(X + (size_t)cq * F, gl, chunks, ok);
-                }
-#pragma unroll
-                for (int q = 0; q < E; ++q)
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch)
-#pragma unroll
-                        for (int z = 0; z < VEC; ++z) acc.c[ch].v[z] = fmaf(vv[q], x[q].c[ch].v[z], acc.c[ch].v[z]);
+            for (int q = 0; q < E; ++q) {
+                bool ok = e0 + q < e;
+                cc[q] = ok ? __ldg(a.col + e0 + q) : 0;
+                vv[q] = ok ? __ldg(a.val + e0 + q) : 0.f;
+                x[q] = load_row<VEC, W, NCH>(X + (size_t)cc[q] * F, gl, chunks, ok);
             }
+#pragma unroll
+            for (int q = 0; q < E; ++q)
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                    for (int z = 0; z < VEC; ++z) acc.c[ch].v[z] = fmaf(vv[q], x[q].c[ch].v[z], acc.c[ch].v[z]);
         }
         const bool multi = (a.row_ptr[r + 1] - a.row_ptr[r]) != (e - b);
 #pragma unroll
