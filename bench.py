@@ -108,13 +108,14 @@ def measured_peaks():
 
 
 def profiled_traffic(factors, batch):
-    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), else None."""
+    """dram bytes per STEP from the committed ncu capture (profiles/traffic.json), else None; the caller scales it to
+    the steps of its average launch."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
             t = json.load(open(p))
             if t.get("factors") == factors and t.get("batch") == batch:
-                return t.get("dram_bytes_per_launch")
+                return t.get("dram_bytes_per_step")
         except Exception:  # noqa: BLE001
             pass
     return None
@@ -357,7 +358,9 @@ def run_own(args):
             "gpu_launches": launches,
             "gpu_launches_note": "persistent cooperative kernel: one launch runs up to steps_per_epoch synchronous steps",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(F, B), "peak_source": peak_src,
+                         "traffic": (lambda t_: None if t_ is None else t_ * (args.steps / len(evs)))(profiled_traffic(F, B)),
+                         "traffic_note": "dram__bytes_read+write per step from profiles/r01b (ncu --set full) x steps per launch",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_triple": bytes_per_triple,
                          "kernel": "mf_bpr_steps_kernel", "avg_launch_ms": avg_launch_ms},
             "cpu_baseline": {"value": cpu_tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
