@@ -191,6 +191,24 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
     }
 }
 
+// Fresh uniform negative for (user u, global triple index gt, step): a Philox word scaled to [0, n_comp) by multiply-high,
+// then the k-th item missing from the user's sorted row: item = k + #{s : col[s] - s <= k} (one binary search).
+__device__ __forceinline__ int draw_negative(const StepParams &p, int u, unsigned long long gt, unsigned long long step)
+{
+    const long long rb = p.neg_row_ptr[u], re = p.neg_row_ptr[u + 1];
+    const unsigned n_comp = (unsigned)((long long)p.I - (re - rb));
+    uint32_t c[4] = {(uint32_t)gt, (uint32_t)(gt >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+    philox4x32(c, (uint32_t)p.neg_seed, (uint32_t)(p.neg_seed >> 32));
+    const int k = (int)__umulhi(c[0], n_comp);
+    long long lo = 0, hi = re - rb;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if ((long long)__ldg(p.neg_col + rb + mid) - mid <= (long long)k) lo = mid + 1; else hi = mid;
+    }
+    const int item = k + (int)lo;
+    return item < p.I ? item : p.I - 1;   // only reachable for a user who interacted with every item (rejected by the host)
+}
+
 template <int VEC, int W, int NCH>
 __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepParams p)
 {
@@ -277,6 +295,11 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                     iu[r] = ok[r] ? xu[t] : 0;
                     ii[r] = ok[r] ? xi[t] : 0;
                     ij[r] = ok[r] ? xj[t] : 0;
+                    if (p.neg_row_ptr != nullptr && ok[r]) {
+                        const long long gt = base + t_i * tile + t;            // position of the triple in the planes
+                        ij[r] = draw_negative(p, iu[r], (unsigned long long)gt, (unsigned long long)step);
+                        if (p.neg_out != nullptr && gl == 0) p.neg_out[gt] = ij[r];
+                    }
                     rp[r] = load_row<VEC, W, NCH>(p.P + (size_t)iu[r] * F, gl, chunks, ok[r]);
                     rqi[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ii[r] * F, gl, chunks, ok[r]);
                     rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r]);
@@ -601,6 +624,10 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.dense_grad = 0;
     p.neg_mult = 1.f;
     p.keep_counts = 0;
+    p.neg_row_ptr = nullptr;
+    p.neg_col = nullptr;
+    p.neg_out = nullptr;
+    p.neg_seed = 0ull;
     return DRB_OK;
 }
 
@@ -615,6 +642,32 @@ extern "C" int drb_mf_bpr_train_steps(float *d_P, float *d_Q, void *d_ws, int32_
                          d_step_loss, 1);
     if (rc != DRB_OK) return rc;
     if (n_steps == 0) return DRB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_steps(p, st);
+    if (rc != DRB_OK) return rc;
+    if (sync_and_check) return check_nan(d_ws, st, nan_step);
+    return DRB_OK;
+}
+
+extern "C" int drb_mf_bpr_train_steps_fused_neg(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
+                                                const int32_t *d_bu, const int32_t *d_bi, const int64_t *d_row_ptr,
+                                                const int32_t *d_col, uint64_t seed, int32_t *d_neg_out, int64_t n,
+                                                int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *hyper,
+                                                int64_t adam_step0, double *d_step_loss, int32_t sync_and_check,
+                                                int64_t *nan_step, void *stream)
+{
+    DRB_REQUIRE(d_row_ptr && d_col, "train_steps_fused_neg: the user->item CSR is required");
+    StepParams p;
+    // the negative plane is unused in this mode (bi stands in so that the TMA staging code stays uniform)
+    int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu, d_bi, d_bi, n, batch, first_step, n_steps, hyper, adam_step0,
+                         d_step_loss, 1);
+    if (rc != DRB_OK) return rc;
+    if (n_steps == 0) return DRB_OK;
+    p.neg_row_ptr = d_row_ptr;
+    p.neg_col = d_col;
+    p.neg_out = d_neg_out;
+    p.neg_seed = seed;
+    p.dense_hint = 1;   // phase 2 must not re-derive negatives: dense sweep only
     cudaStream_t st = (cudaStream_t)stream;
     rc = launch_steps(p, st);
     if (rc != DRB_OK) return rc;

@@ -71,6 +71,13 @@ struct StepParams {
     // NeuMF: the item-side regulariser counts the negative occurrences 2x (GMF table) or 0x (MLP table)
     float neg_mult;        // multiplier of the negative-occurrence count in the regulariser gradient
     int keep_counts;       // 1: leave the row counters untouched (another table pair still needs them)
+    // Fused negative sampling (throughput mode, NOT the reference's per-user-once table): when neg_row_ptr != nullptr the
+    // negative of triple t of step s is drawn inside phase 1: k = Philox(seed; t, step) scaled to [0, I - deg(u)), then
+    // the k-th item outside the user's sorted CSR row (same complement distribution as sampler.py:86, fresh every step).
+    const int64_t *neg_row_ptr;
+    const int32_t *neg_col;
+    int32_t *neg_out;      // optional: the drawn negatives are written here (aligned with bu/bi) for inspection
+    unsigned long long neg_seed;
 };
 
 

@@ -49,6 +49,19 @@ class MF(GeneralRecommender):
         self._ws = None
         self._opt_steps = 0
         self._stage = None
+        # optional B200 key: 'table' (default; the reference's per-user-once negatives, taken from the loader's triples) |
+        # 'fused' (throughput mode: a fresh negative per triple and step is drawn inside the step kernel from the
+        # complement of the user's train row; the loader's third column is ignored)
+        self.neg_sampling = str(config.get('neg_sampling', 'table'))
+        self._csr_dev = None
+        if self.neg_sampling == 'fused':
+            from ..utils.sampler import csr_from_ur
+            row_ptr, col = config['train_csr'] if config.get('train_csr') is not None else csr_from_ur(config['train_ur'], self.user_num)
+            if int(np.max(np.diff(row_ptr))) >= self.item_num:
+                raise ValueError("'a' cannot be empty unless no samples are taken")
+            self._csr_dev = (torch.from_numpy(np.ascontiguousarray(row_ptr, np.int64)).to(self.device),
+                             torch.from_numpy(np.ascontiguousarray(col, np.int32)).to(self.device))
+            self._neg_seed = int(torch.empty((), dtype=torch.int64).random_().item()) & ((1 << 63) - 1)
 
     # ------------------------------------------------------------------ plumbing
     def parameters(self):
@@ -118,6 +131,12 @@ class MF(GeneralRecommender):
             self._begin_fit(self._optimizer_name())
 
     def _train_steps(self, bu, bi, bj, batch, first, n_steps):
+        if self.neg_sampling == 'fused':
+            losses = ops.mf_bpr_train_steps_fused_neg(self.embed_user.weight, self.embed_item.weight, self._ws, bu, bi,
+                                                      self._csr_dev[0], self._csr_dev[1], self._neg_seed + self._opt_steps,
+                                                      batch, first, n_steps, self._hp, adam_step0=self._opt_steps)
+            self._opt_steps += n_steps
+            return losses
         losses = ops.mf_bpr_train_steps(self.embed_user.weight, self.embed_item.weight, self._ws, bu, bi, bj, batch,
                                         first, n_steps, self._hp, adam_step0=self._opt_steps)
         self._opt_steps += n_steps

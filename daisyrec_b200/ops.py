@@ -185,6 +185,25 @@ def mf_bpr_train_steps(P, Q, ws, bu, bi, bj, batch, first_step, n_steps, hp, ada
     return losses[:n_steps]
 
 
+def mf_bpr_train_steps_fused_neg(P, Q, ws, bu, bi, d_row_ptr, d_col, seed, batch, first_step, n_steps, hp, adam_step0=0,
+                                 neg_out=None, check=True):
+    """Throughput mode: negatives are drawn inside the step kernel (fresh per triple and step) from the complement of the
+    user's CSR row.  neg_out (optional int32 [n]) receives them."""
+    _dev(P, torch.float32, "P"); _dev(Q, torch.float32, "Q"); _dev(bu, torch.int32, "bu"); _dev(bi, torch.int32, "bi")
+    _dev(d_row_ptr, torch.int64, "row_ptr"); _dev(d_col, torch.int32, "col")
+    losses = torch.empty(max(n_steps, 1), dtype=torch.float64, device=P.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_mf_bpr_train_steps_fused_neg(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, _ptr(bu), _ptr(bi),
+                                                  _ptr(d_row_ptr), _ptr(d_col), C.c_uint64(seed),
+                                                  None if neg_out is None else _ptr(neg_out), bu.numel(), batch, first_step,
+                                                  n_steps, C.byref(hp), adam_step0, _ptr(losses), 1 if check else 0,
+                                                  C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]
+
+
 def mf_bpr_loss(P, Q, ws, bu, bi, bj, hp):
     _dev(P, torch.float32, "P"); _dev(Q, torch.float32, "Q")
     loss = torch.empty(1, dtype=torch.float64, device=P.device)

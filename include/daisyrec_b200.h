@@ -115,6 +115,15 @@ int drb_mf_bpr_train_steps(float *d_P, float *d_Q, void *d_ws, int32_t user_num,
                            const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
                            int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
                            double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+/* Throughput mode with the sampler FUSED into the step (north_star): no negative plane; the negative of every triple is
+ * drawn inside phase 1 -- Philox word -> rank k in [0, item_num - deg(u)) -> k-th item missing from the user's sorted CSR
+ * row -- i.e. the reference's complement distribution (sampler.py:86) but fresh for every triple and step instead of
+ * once per user.  NOT reference semantics (opt-in).  d_neg_out (optional, n int32) receives the drawn negatives. */
+int drb_mf_bpr_train_steps_fused_neg(float *d_P, float *d_Q, void *d_ws, int32_t user_num, int32_t item_num,
+                                     int32_t factors, const int32_t *d_bu, const int32_t *d_bi, const int64_t *d_row_ptr,
+                                     const int32_t *d_col, uint64_t seed, int32_t *d_neg_out, int64_t n, int64_t batch,
+                                     int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                                     double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 /* MF.calc_loss(batch) only (no update): MFRecommender.py:70-97 */
 int drb_mf_bpr_loss(const float *d_P, const float *d_Q, void *d_ws, int32_t user_num, int32_t item_num,
                     int32_t factors, const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t batch,

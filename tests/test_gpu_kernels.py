@@ -209,6 +209,43 @@ def test_host_step_entry_matches_device_entry(ops):
     np.testing.assert_allclose(Pa.cpu().numpy(), Pb.cpu().numpy(), atol=2e-6)
 
 
+def test_fused_negative_sampling_mode(ops):
+    """Throughput mode (sampler fused into the step): the drawn negatives lie in the complement of the user's row, are
+    uniform over it, change per step, and a table-mode step on the SAME negatives reproduces the fused step."""
+    rng = np.random.default_rng(21)
+    U, I, F, B, nnz = 1200, 900, 64, 4096, 40_000
+    cu = rng.integers(U, size=nnz).astype(np.int32)
+    ci = np.minimum(I - 1, rng.zipf(1.2, size=nnz) - 1).astype(np.int32)
+    row_ptr, col = csr_from_coo(cu, ci, U)
+    P0 = (rng.standard_normal((U, F)) * 0.1).astype(np.float32)
+    Q0 = (rng.standard_normal((I, F)) * 0.1).astype(np.float32)
+    n = 3 * B
+    sel = rng.integers(nnz, size=n)
+    bu, bi = dev(cu[sel]), dev(ci[sel])
+    neg = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    hp = ops.hyper(0.01, 0.001, 0.001)
+    Pa, Qa = dev(P0), dev(Q0)
+    wa = ops.MFWorkspace(U, I, F, "sgd", "cuda")
+    la = ops.mf_bpr_train_steps_fused_neg(Pa, Qa, wa, bu, bi, dev(row_ptr), dev(col), 99, B, 0, 3, hp, neg_out=neg).cpu().numpy()
+    j = neg.cpu().numpy()
+    assert (j >= 0).all() and (j < I).all()
+    pos = set(zip(cu.tolist(), ci.tolist()))
+    assert not any((int(u), int(x)) in pos for u, x in zip(cu[sel], j))          # complement membership
+    assert len(np.unique(j)) > 0.5 * min(I, n) and abs(j.mean() / I - 0.5) < 0.05   # spread over the item range
+    # same (u, i) pair drawn in different steps gets different negatives (fresh per triple and step)
+    neg2 = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    ops.mf_bpr_train_steps_fused_neg(dev(P0), dev(Q0), ops.MFWorkspace(U, I, F, "sgd", "cuda"), bu, bi, dev(row_ptr), dev(col), 100,
+                                     B, 0, 3, hp, neg_out=neg2)
+    assert (neg2 != neg).float().mean() > 0.9
+    # equivalence: table mode on the recorded negatives
+    Pb, Qb = dev(P0), dev(Q0)
+    wb = ops.MFWorkspace(U, I, F, "sgd", "cuda")
+    lb = ops.mf_bpr_train_steps(Pb, Qb, wb, bu, bi, neg, B, 0, 3, hp).cpu().numpy()
+    np.testing.assert_allclose(la, lb, rtol=1e-6)
+    np.testing.assert_allclose(Pa.cpu().numpy(), Pb.cpu().numpy(), atol=2e-6)
+    np.testing.assert_allclose(Qa.cpu().numpy(), Qb.cpu().numpy(), atol=2e-6)
+
+
 def test_pipelined_host_steps_match_device_steps(ops):
     rng = np.random.default_rng(12)
     U, I, F, B, n = 900, 700, 64, 2048, 2048 * 5 + 77
