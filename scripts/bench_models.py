@@ -43,7 +43,7 @@ def batches(U, I, n, dev, d=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["lightgcn", "neumf", "mf-netflix", "mf-fit"])
+    ap.add_argument("what", choices=["lightgcn", "neumf", "mf-netflix", "mf-fit", "mf-fused"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--tower", default="fp32", choices=["fp32", "bf16"])
@@ -96,6 +96,23 @@ def main():
         flop_triple = 2 * 3 * flop                          # 2 items x (fwd + 2 bwd GEMMs)
         print(json.dumps(dict(model="NeuMF", shape="ml-20m", F=F, L=L, batch=B, ms_per_step=ms, triples_per_s=B / ms * 1e3,
                               tower_TFLOPs=B * flop_triple / ms / 1e9, tower="fp32 CUDA cores" if a.tower == "fp32" else "bf16 tcgen05 (TMEM accumulator)")))
+    elif a.what == "mf-fused":
+        # throughput mode: negatives drawn inside the step kernel (Philox + k-th complement over the CSR row)
+        U, I, nnz = SHAPES["ml-20m"]
+        F, B, K = 64, a.batch or (1 << 20), 16
+        d = make_interactions(U, I, nnz, device=dev)
+        P = (torch.randn(U, F, device=dev) * 0.01).contiguous(); Q = (torch.randn(I, F, device=dev) * 0.01).contiguous()
+        ws = ops.MFWorkspace(U, I, F, "sgd", dev)
+        hp = ops.hyper(0.01, 0.001, 0.001)
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        idx = torch.randint(0, d["coo_u"].numel(), (B * K,), device=dev, generator=g)
+        bu, bi = d["coo_u"][idx].contiguous(), d["coo_i"][idx].contiguous()
+        bj = torch.randint(0, I, (B * K,), device=dev, dtype=torch.int32, generator=g)
+        ms_f = timed(lambda: ops.mf_bpr_train_steps_fused_neg(P, Q, ws, bu, bi, d["row_ptr"], d["col"], 1, B, 0, K, hp, check=False), 1, 3) / K
+        ms_t = timed(lambda: ops.mf_bpr_train_steps(P, Q, ws, bu, bi, bj, B, 0, K, hp, check=False), 1, 3) / K
+        print(json.dumps(dict(model="MF", shape="ml-20m", F=F, batch=B, fused_sampler_ms_per_step=ms_f,
+                              fused_sampler_triples_per_s=B / ms_f * 1e3, table_mode_ms_per_step=ms_t,
+                              table_mode_triples_per_s=B / ms_t * 1e3)))
     elif a.what == "mf-fit":
         # wall-clock of the drop-in API at config-2 scale: MF(config).fit(DataLoader over the 80 M sampler triples)
         import logging, time as _t

@@ -121,7 +121,7 @@ def test_mf_steps_golden(ops):
 
 
 @pytest.mark.parametrize("F,B,opt", [(64, 4096, "sgd"), (32, 1000, "sgd"), (128, 777, "sgd"), (100, 513, "sgd"),
-                                     (24, 300, "adam"), (7, 129, "sgd"), (256, 600, "sgd")])
+                                     (24, 300, "adam"), (7, 129, "sgd"), (256, 600, "sgd"), (1024, 300, "sgd"), (2, 64, "sgd")])
 def test_mf_step_vs_oracle_random(ops, orc, F, B, opt):
     rng = np.random.default_rng(F * 1000 + B)
     U, I = 500, 300
@@ -291,7 +291,7 @@ def test_ml100k_rank_golden(ops):
 
 
 @pytest.mark.parametrize("F,I,C,K", [(64, 5000, 1000, 50), (32, 9000, 1000, 50), (100, 700, 333, 20),
-                                     (128, 12000, 4097, 100), (6, 100, 64, 64), (64, 30000, 1000, 50)])
+                                     (128, 12000, 4097, 100), (6, 100, 64, 64), (64, 30000, 1000, 50), (512, 3000, 700, 50), (1, 50, 20, 5)])
 def test_rank_vs_oracle_bit_exact(ops, orc, F, I, C, K):
     rng = np.random.default_rng(F + I + C)
     U, n = 200, 37
