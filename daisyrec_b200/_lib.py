@@ -19,12 +19,13 @@ vp = C.c_void_p
 
 DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_NAN_LOSS, DRB_ERR_EMPTY_SET, DRB_ERR_NO_DEVICE = range(6)
 OPT_SGD, OPT_ADAM = 0, 1
+LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2}
 
 
 class Hyper(C.Structure):
     """struct drb_hyper"""
     _fields_ = [("lr", C.c_float), ("reg_1", C.c_float), ("reg_2", C.c_float), ("opt", C.c_int32),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("loss", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol of include/daisyrec_b200.h

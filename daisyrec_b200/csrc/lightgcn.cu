@@ -302,7 +302,7 @@ extern "C" int drb_lgcn_bpr_train_steps(float *d_E0, void *d_ws, int32_t U, int3
         p.dense_hint = 1;
         p.Pn = d_E0; p.Qn = d_E0 + (size_t)U * F;
         p.gscale = 1.f; p.dense_grad = 1; p.neg_mult = 1.f; p.keep_counts = 0;
-        p.neg_row_ptr = nullptr; p.neg_col = nullptr; p.neg_out = nullptr; p.neg_seed = 0ull;
+        p.neg_row_ptr = nullptr; p.neg_col = nullptr; p.neg_out = nullptr; p.neg_seed = 0ull; p.loss = DRB_LOSS_BPR;
         if (!apply) {
             p.phases = 3;                                        // loss only: both phases in one launch, no update
             return launch_steps(p, st, /*keep_status=*/true);

@@ -304,31 +304,54 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                     rqi[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ii[r] * F, gl, chunks, ok[r]);
                     rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r]);
                 }
-                // scores of the UNR triples of this group (every lane of the group ends up with the same x)
-                float xs[UNR], cs[UNR];
+                // scores of the UNR triples of this group (every lane of the group ends up with the same values)
+                float ps[UNR], ns[UNR], cs[UNR], cn[UNR];
 #pragma unroll
-                for (int r = 0; r < UNR; ++r)
-                    xs[r] = dot_rows<VEC, W, NCH>(rp[r], rqi[r]) - dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
-                // The scalar chain sigmoid -> log -> coefficient costs ~40 instructions and would be replayed by all W
-                // lanes for each of the UNR triples; instead lane gl evaluates it ONCE, for triple (gl % UNR) of its
-                // group, and the coefficients are handed round with one shuffle per triple.
+                for (int r = 0; r < UNR; ++r) {
+                    ps[r] = dot_rows<VEC, W, NCH>(rp[r], rqi[r]);
+                    ns[r] = dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
+                }
+                // The scalar chain (sigmoid -> log -> coefficient, ~40 instructions) would be replayed by all W lanes for
+                // each of the UNR triples; instead lane gl evaluates it ONCE, for triple (gl % UNR) of its group, and the
+                // coefficients d(loss)/d(pos), d(loss)/d(neg) are handed round with shuffles.
+                auto pair_loss = [&](float pos, float neg, float &c_pos, float &c_neg) -> float {
+                    if (p.loss == DRB_LOSS_HL) {            // clamp(1 - (pos - neg), min=0); clamp's backward passes at equality
+                        const float m = 1.f - (pos - neg);
+                        c_pos = (m >= 0.f) ? -1.f : 0.f;
+                        c_neg = -c_pos;
+                        return m > 0.f ? m : 0.f;
+                    }
+                    if (p.loss == DRB_LOSS_TL) {            // sigmoid(neg - pos) + sigmoid(neg^2)
+                        const float s1 = 1.f / (1.f + expf(-(neg - pos))), s2 = 1.f / (1.f + expf(-(neg * neg)));
+                        c_pos = -(s1 * (1.f - s1));
+                        c_neg = s1 * (1.f - s1) + s2 * (1.f - s2) * 2.f * neg;
+                        return s1 + s2;
+                    }
+                    const float x = pos - neg;
+                    const float sg = 1.f / (1.f + expf(-x));
+                    c_pos = -(sg * (1.f - sg)) / (1e-10f + sg);
+                    c_neg = -c_pos;
+                    return -logf(1e-10f + sg);
+                };
                 if constexpr (W >= UNR) {
-                    float x_own = xs[0];
+                    float p_own = ps[0], n_own = ns[0];
                     bool ok_own = ok[0];
 #pragma unroll
                     for (int r = 1; r < UNR; ++r)
-                        if ((gl % UNR) == r) { x_own = xs[r]; ok_own = ok[r]; }
-                    const float sg = 1.f / (1.f + expf(-x_own));
-                    if (gl < UNR && ok_own) t_loss += -logf(1e-10f + sg);
-                    const float c_own = -(sg * (1.f - sg)) / (1e-10f + sg);
+                        if ((gl % UNR) == r) { p_own = ps[r]; n_own = ns[r]; ok_own = ok[r]; }
+                    float cp_own, cn_own;
+                    const float l_own = pair_loss(p_own, n_own, cp_own, cn_own);
+                    if (gl < UNR && ok_own) t_loss += l_own;
 #pragma unroll
-                    for (int r = 0; r < UNR; ++r) cs[r] = __shfl_sync(0xffffffffu, c_own, (lane - gl) + r);
+                    for (int r = 0; r < UNR; ++r) {
+                        cs[r] = __shfl_sync(0xffffffffu, cp_own, (lane - gl) + r);
+                        cn[r] = __shfl_sync(0xffffffffu, cn_own, (lane - gl) + r);
+                    }
                 } else {
 #pragma unroll
                     for (int r = 0; r < UNR; ++r) {
-                        const float sg = 1.f / (1.f + expf(-xs[r]));
-                        if (gl == 0 && ok[r]) t_loss += -logf(1e-10f + sg);
-                        cs[r] = -(sg * (1.f - sg)) / (1e-10f + sg);
+                        const float l = pair_loss(ps[r], ns[r], cs[r], cn[r]);
+                        if (gl == 0 && ok[r]) t_loss += l;
                     }
                 }
 #pragma unroll
@@ -363,9 +386,15 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                             Vec<VEC> gu, gi, gj;
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) {
-                                gu.v[e] = c * (rqi[r].c[ch].v[e] - rqj[r].c[ch].v[e]);
-                                gi.v[e] = c * rp[r].c[ch].v[e];
-                                gj.v[e] = -gi.v[e];
+                                if (p.loss == DRB_LOSS_BPR) {     // c_neg == -c_pos: the reference's BPR arithmetic, unchanged
+                                    gu.v[e] = c * (rqi[r].c[ch].v[e] - rqj[r].c[ch].v[e]);
+                                    gi.v[e] = c * rp[r].c[ch].v[e];
+                                    gj.v[e] = -gi.v[e];
+                                } else {
+                                    gu.v[e] = c * rqi[r].c[ch].v[e] + cn[r] * rqj[r].c[ch].v[e];
+                                    gi.v[e] = c * rp[r].c[ch].v[e];
+                                    gj.v[e] = cn[r] * rp[r].c[ch].v[e];
+                                }
                             }
                             red_row<VEC>(p.ws.gP + (size_t)iu[r] * F + cc * VEC, gu);
                             red_row<VEC>(p.ws.gQ + (size_t)ii[r] * F + cc * VEC, gi);
@@ -604,6 +633,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
     DRB_REQUIRE(h->opt == DRB_OPT_SGD || h->opt == DRB_OPT_ADAM, "unknown optimizer id %d", h->opt);
+    DRB_REQUIRE(h->loss >= DRB_LOSS_BPR && h->loss <= DRB_LOSS_TL, "unknown loss id %d", h->loss);
     DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0 || n == 0, "steps [%lld,%lld) exceed %lld triples", first,
                 first + nsteps, n);
     p.P = P; p.Q = Q;
@@ -628,6 +658,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.neg_col = nullptr;
     p.neg_out = nullptr;
     p.neg_seed = 0ull;
+    p.loss = h->loss;
     return DRB_OK;
 }
 

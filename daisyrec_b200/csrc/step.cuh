@@ -78,6 +78,7 @@ struct StepParams {
     const int32_t *neg_col;
     int32_t *neg_out;      // optional: the drawn negatives are written here (aligned with bu/bi) for inspection
     unsigned long long neg_seed;
+    int loss;              // DRB_LOSS_BPR / _HL / _TL (pair-wise criterion, AbstractRecommender.py:79-93)
 };
 
 

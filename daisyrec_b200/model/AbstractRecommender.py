@@ -106,12 +106,15 @@ class AbstractRecommender(object):
             self.logger.info('Received unrecognized optimizer, set default Adam optimizer')
         return 'adam'
 
+    SUPPORTED_LOSSES = ('BPR',)
+
     def _check_loss_type(self):
         lt = str(self.loss_type).upper()
-        if lt == 'BPR':
+        if lt in self.SUPPORTED_LOSSES:
             return
-        if lt in ('CL', 'SL', 'HL', 'TL'):
-            raise NotImplementedError(f"loss_type '{lt}' is outside the B200 hot path (BPR is native)")
+        if lt in ('CL', 'SL', 'HL', 'TL', 'BPR'):
+            raise NotImplementedError(f"loss_type '{lt}' is outside the B200 hot path of {type(self).__name__} "
+                                      f"(native: {', '.join(self.SUPPORTED_LOSSES)})")
         raise NotImplementedError(f'Invalid loss type: {self.loss_type}...')
 
 

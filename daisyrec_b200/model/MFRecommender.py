@@ -18,6 +18,8 @@ from .AbstractRecommender import GeneralRecommender, _Table, _init_table, _INIT
 
 
 class MF(GeneralRecommender):
+    SUPPORTED_LOSSES = ('BPR', 'HL', 'TL')      # the pair-wise criteria of AbstractRecommender.py:84-89
+
     def __init__(self, config):
         """Same keys as the reference (MFRecommender.py:46-59): lr, reg_1, reg_2, epochs, topk,
         user_num, item_num, factors, loss_type, optimizer, init_method, early_stop (+ gpu, logger)."""
@@ -115,7 +117,7 @@ class MF(GeneralRecommender):
         return allgather_rows(self.embed_user.weight, pos, self.user_num)
 
     def _hyper(self, opt=None):
-        return ops.hyper(self.lr, self.reg_1, self.reg_2, opt or self._optimizer_name())
+        return ops.hyper(self.lr, self.reg_1, self.reg_2, opt or self._optimizer_name(), loss=str(self.loss_type).upper())
 
     def _begin_fit(self, opt):
         """fit() builds a fresh optimizer (AbstractRecommender.py:105): fresh Adam moments / step count."""

@@ -30,8 +30,8 @@ def require_cuda():
         raise RuntimeError("daisyrec_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
 
 
-def hyper(lr, reg_1, reg_2, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8):
-    return L.Hyper(lr, reg_1, reg_2, L.OPT_SGD if opt == "sgd" else L.OPT_ADAM, beta1, beta2, eps)
+def hyper(lr, reg_1, reg_2, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8, loss="BPR"):
+    return L.Hyper(lr, reg_1, reg_2, L.OPT_SGD if opt == "sgd" else L.OPT_ADAM, beta1, beta2, eps, L.LOSS_KIND[loss.upper()])
 
 
 def device_query():

@@ -41,12 +41,17 @@ extern "C" {
 #define DRB_OPT_SGD 0         /* optim.SGD(lr)   AbstractRecommender.py:55-56                     */
 #define DRB_OPT_ADAM 1        /* optim.Adam(lr)  AbstractRecommender.py:53-54 (dense, torch defaults) */
 
+#define DRB_LOSS_BPR 0        /* BPRLoss   daisy/utils/loss.py:5-13   -log(1e-10 + sigmoid(pos - neg))           */
+#define DRB_LOSS_HL 1         /* HingeLoss daisy/utils/loss.py:16-23  clamp(1 - (pos - neg), min=0)    (MF only)  */
+#define DRB_LOSS_TL 2         /* TOP1Loss  daisy/utils/loss.py:26-33  sigmoid(neg - pos) + sigmoid(neg^2) (MF only) */
+
 typedef struct drb_hyper {
     float lr;                 /* config['lr']                                                      */
     float reg_1;              /* config['reg_1']  L1 coefficient  (MFRecommender.py:88,94)        */
     float reg_2;              /* config['reg_2']  Frobenius coefficient (MFRecommender.py:89,95)  */
     int32_t opt;              /* DRB_OPT_*                                                         */
     float beta1, beta2, eps;  /* Adam (torch defaults 0.9, 0.999, 1e-8)                           */
+    int32_t loss;             /* DRB_LOSS_*: config['loss_type'] of the pair-wise family              */
 } drb_hyper;
 
 /* ---- library / device ----------------------------------------------------------- */

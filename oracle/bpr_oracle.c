@@ -269,7 +269,31 @@ typedef struct {
     float lr, reg_1, reg_2;
     int32_t opt;
     float beta1, beta2, eps;
+    int32_t loss; /* 0 BPR (loss.py:5-13), 1 HL = HingeLoss (loss.py:16-23), 2 TL = TOP1Loss (loss.py:26-33) */
 } orc_hyper;
+
+/* pairwise loss term and its derivatives w.r.t. the positive / negative score */
+static float pair_loss(int kind, float pos, float neg, float *cp, float *cn)
+{
+    const float gamma = 1e-10f;
+    if (kind == 1) {                       /* clamp(1 - (pos - neg), min=0); clamp's backward passes at equality */
+        float m = 1.f - (pos - neg);
+        *cp = (m >= 0.f) ? -1.f : 0.f;
+        *cn = -*cp;
+        return m > 0.f ? m : 0.f;
+    }
+    if (kind == 2) {                       /* sigmoid(neg - pos) + sigmoid(neg^2) */
+        float s1 = 1.f / (1.f + expf(-(neg - pos))), s2 = 1.f / (1.f + expf(-(neg * neg)));
+        *cp = -(s1 * (1.f - s1));
+        *cn = s1 * (1.f - s1) + s2 * (1.f - s2) * 2.f * neg;
+        return s1 + s2;
+    }
+    float x = pos - neg;
+    float s = 1.f / (1.f + expf(-x));
+    *cp = -(s * (1.f - s)) / (gamma + s);
+    *cn = -*cp;
+    return -logf(gamma + s);
+}
 
 static void adam_dense(float *theta, float *m, float *v, const double *g, int64_t n, const orc_hyper *h,
                        int64_t step_count)
@@ -293,16 +317,12 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
                        const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP,
                        float *mQ, float *vQ, int64_t step_count, double *parts)
 {
-    const float gamma = 1e-10f;
-    float *coef = (float *)malloc(sizeof(float) * (size_t)(B > 0 ? B : 1));
+    float *coef = (float *)malloc(sizeof(float) * 2 * (size_t)(B > 0 ? B : 1));
     double bpr = 0.0, l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
     for (int64_t t = 0; t < B; t++) {
         const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = Q + (int64_t)bj[t] * F;
         float pos = orc_dot(p, qi, F), neg = orc_dot(p, qj, F);
-        float x = pos - neg;
-        float s = 1.f / (1.f + expf(-x));
-        bpr += (double)(-logf(gamma + s));
-        coef[t] = -(s * (1.f - s)) / (gamma + s);
+        bpr += (double)pair_loss(h->loss, pos, neg, &coef[2 * t], &coef[2 * t + 1]);
         for (int f = 0; f < F; f++) {
             l1u += fabsf(p[f]);
             s2u += (double)(p[f] * p[f]);
@@ -334,12 +354,13 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
     for (int64_t t = 0; t < B; t++) {
         const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = Q + (int64_t)bj[t] * F;
         double *gu = gP + (int64_t)bu[t] * F, *gi = gQ + (int64_t)bi[t] * F, *gj = gQ + (int64_t)bj[t] * F;
-        float c = coef[t];
+        float cp = coef[2 * t], cn = coef[2 * t + 1];
         for (int f = 0; f < F; f++) {
             float sp = (p[f] > 0) - (p[f] < 0), si = (qi[f] > 0) - (qi[f] < 0), sj = (qj[f] > 0) - (qj[f] < 0);
-            gu[f] += (double)(c * (qi[f] - qj[f])) + (double)(h->reg_1 * sp) + (double)(h->reg_2 * p[f] * inu);
-            gi[f] += (double)(c * p[f]) + (double)(h->reg_1 * si) + (double)(h->reg_2 * qi[f] * ini);
-            gj[f] += (double)(-c * p[f]) + (double)(h->reg_1 * sj) + (double)(h->reg_2 * qj[f] * inj);
+            double du = (h->loss == 0) ? (double)(cp * (qi[f] - qj[f])) : (double)(cp * qi[f]) + (double)(cn * qj[f]);
+            gu[f] += du + (double)(h->reg_1 * sp) + (double)(h->reg_2 * p[f] * inu);
+            gi[f] += (double)(cp * p[f]) + (double)(h->reg_1 * si) + (double)(h->reg_2 * qi[f] * ini);
+            gj[f] += (double)(cn * p[f]) + (double)(h->reg_1 * sj) + (double)(h->reg_2 * qj[f] * inj);
         }
     }
     if (h->opt == 0) {

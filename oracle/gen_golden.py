@@ -168,10 +168,15 @@ def gen_mf_steps():
         (13, 9, 6, 50, 0.01, 0.001, 0.001, "sgd", 4),       # F%4 != 0, heavy duplicates
         (40, 60, 64, 128, 0.001, 0.001, 0.001, "adam", 5),
         (20, 20, 7, 33, 0.01, 0.0, 0.001, "adam", 6),       # odd F
+        (40, 60, 32, 128, 0.01, 0.001, 0.001, "sgd", 7, "HL"),   # HingeLoss (loss.py:16-23)
+        (40, 60, 64, 128, 0.01, 0.001, 0.001, "sgd", 8, "TL"),   # TOP1Loss (loss.py:26-33)
+        (30, 30, 16, 96, 0.001, 0.0, 0.0, "adam", 9, "TL"),
     ]
-    for k, (U, I, F, B, lr, r1, r2, opt, seed) in enumerate(cases):
+    for k, case in enumerate(cases):
+        U, I, F, B, lr, r1, r2, opt, seed = case[:9]
+        loss_type = case[9] if len(case) > 9 else "BPR"
         cfg = rh.make_config("mf", user_num=U, item_num=I, factors=F, lr=lr, reg_1=r1, reg_2=r2, optimizer=opt,
-                             epochs=1)
+                             epochs=1, loss_type=loss_type)
         torch.manual_seed(seed)
         model = MF(cfg)
         with torch.no_grad():                                 # larger weights so the loss is not ~log 2 everywhere
@@ -195,7 +200,8 @@ def gen_mf_steps():
             Q.append(model.embed_item.weight.detach().numpy().copy())
         out.update({f"c{k}_P": np.stack(P), f"c{k}_Q": np.stack(Q), f"c{k}_batches": np.stack(batches),
                     f"c{k}_loss": np.array(losses, np.float64),
-                    f"c{k}_hyper": np.array([lr, r1, r2, 0 if opt == "sgd" else 1], np.float64)})
+                    f"c{k}_hyper": np.array([lr, r1, r2, 0 if opt == "sgd" else 1,
+                                             {"BPR": 0, "HL": 1, "TL": 2}[loss_type]], np.float64)})
     out["ncases"] = np.array(len(cases))
     _save("mf_steps", **out)
 

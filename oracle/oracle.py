@@ -22,11 +22,14 @@ def build(force=False):
 
 class Hyper(C.Structure):
     _fields_ = [("lr", C.c_float), ("reg_1", C.c_float), ("reg_2", C.c_float), ("opt", C.c_int32),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("loss", C.c_int32)]
 
 
-def hyper(lr=0.01, reg_1=0.001, reg_2=0.001, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8):
-    return Hyper(lr, reg_1, reg_2, 0 if opt == "sgd" else 1, beta1, beta2, eps)
+LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2}
+
+
+def hyper(lr=0.01, reg_1=0.001, reg_2=0.001, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8, loss="BPR"):
+    return Hyper(lr, reg_1, reg_2, 0 if opt == "sgd" else 1, beta1, beta2, eps, LOSS_KIND[loss.upper()])
 
 
 _lib = None

@@ -101,12 +101,12 @@ def test_sampler_empty_complement(ops):
 def test_mf_steps_golden(ops):
     g = golden("mf_steps")
     for c in range(int(g["ncases"])):
-        lr, r1, r2, opt = g[f"c{c}_hyper"]
+        lr, r1, r2, opt, lk = g[f"c{c}_hyper"]
         optn = "sgd" if opt == 0 else "adam"
         Ps, Qs, bs, losses = g[f"c{c}_P"], g[f"c{c}_Q"], g[f"c{c}_batches"], g[f"c{c}_loss"]
         U, F = Ps[0].shape
         I = Qs[0].shape[0]
-        hp = ops.hyper(lr, r1, r2, optn)
+        hp = ops.hyper(lr, r1, r2, optn, loss=("BPR", "HL", "TL")[int(lk)])
         P, Q = dev(Ps[0]), dev(Qs[0])
         ws = ops.MFWorkspace(U, I, F, optn, "cuda")
         for s in range(bs.shape[0]):
