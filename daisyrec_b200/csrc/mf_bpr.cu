@@ -209,7 +209,7 @@ __device__ __forceinline__ int draw_negative(const StepParams &p, int u, unsigne
     return item < p.I ? item : p.I - 1;   // only reachable for a user who interacted with every item (rejected by the host)
 }
 
-template <int VEC, int W, int NCH>
+template <int VEC, int W, int NCH, bool GEN>
 __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepParams p)
 {
     constexpr int GPW = 32 / W;                  // lane groups per warp
@@ -315,13 +315,13 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                 // each of the UNR triples; instead lane gl evaluates it ONCE, for triple (gl % UNR) of its group, and the
                 // coefficients d(loss)/d(pos), d(loss)/d(neg) are handed round with shuffles.
                 auto pair_loss = [&](float pos, float neg, float &c_pos, float &c_neg) -> float {
-                    if (p.loss == DRB_LOSS_HL) {            // clamp(1 - (pos - neg), min=0); clamp's backward passes at equality
+                    if (GEN && p.loss == DRB_LOSS_HL) {     // clamp(1 - (pos - neg), min=0); clamp's backward passes at equality
                         const float m = 1.f - (pos - neg);
                         c_pos = (m >= 0.f) ? -1.f : 0.f;
                         c_neg = -c_pos;
                         return m > 0.f ? m : 0.f;
                     }
-                    if (p.loss == DRB_LOSS_TL) {            // sigmoid(neg - pos) + sigmoid(neg^2)
+                    if (GEN && p.loss == DRB_LOSS_TL) {     // sigmoid(neg - pos) + sigmoid(neg^2)
                         const float s1 = 1.f / (1.f + expf(-(neg - pos))), s2 = 1.f / (1.f + expf(-(neg * neg)));
                         c_pos = -(s1 * (1.f - s1));
                         c_neg = s1 * (1.f - s1) + s2 * (1.f - s2) * 2.f * neg;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
 #pragma unroll
                     for (int r = 0; r < UNR; ++r) {
                         cs[r] = __shfl_sync(0xffffffffu, cp_own, (lane - gl) + r);
-                        cn[r] = __shfl_sync(0xffffffffu, cn_own, (lane - gl) + r);
+                        cn[r] = GEN ? __shfl_sync(0xffffffffu, cn_own, (lane - gl) + r) : -cs[r];
                     }
                 } else {
 #pragma unroll
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                             Vec<VEC> gu, gi, gj;
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) {
-                                if (p.loss == DRB_LOSS_BPR) {     // c_neg == -c_pos: the reference's BPR arithmetic, unchanged
+                                if (!GEN || p.loss == DRB_LOSS_BPR) {   // c_neg == -c_pos: the reference's BPR arithmetic
                                     gu.v[e] = c * (rqi[r].c[ch].v[e] - rqj[r].c[ch].v[e]);
                                     gi.v[e] = c * rp[r].c[ch].v[e];
                                     gj.v[e] = -gi.v[e];
@@ -539,29 +539,35 @@ __global__ void gather_triples_kernel(const int32_t *__restrict__ triples, const
 // ------------------------------------------------------------------ host dispatch
 typedef void (*StepKernel)(StepParams);
 
-template <int VEC>
+template <int VEC, bool GEN>
 static StepKernel pick_kernel_v(int W, int NCH)
 {
 #define DRB_CASE(w, n) \
-    if (W == w && NCH == n) return mf_bpr_steps_kernel<VEC, w, n>;
+    if (W == w && NCH == n) return mf_bpr_steps_kernel<VEC, w, n, GEN>;
     DRB_CASE(1, 1) DRB_CASE(2, 1) DRB_CASE(4, 1) DRB_CASE(8, 1) DRB_CASE(16, 1) DRB_CASE(32, 1)
     DRB_CASE(32, 2) DRB_CASE(32, 4) DRB_CASE(32, 8)
 #undef DRB_CASE
     return nullptr;
 }
 
-static StepKernel pick_kernel(int F)
+// GEN = false: BPR only (the hot instantiation, no loss-kind branches); GEN = true: HL / TL selected at run time
+static StepKernel pick_kernel(int F, bool gen)
 {
     if (F <= 0) return nullptr;
     RowGeom g = row_geom(F);
-    if (g.vec == 4) return pick_kernel_v<4>(g.width, g.nch);
-    if (g.vec == 2) return pick_kernel_v<2>(g.width, g.nch);
-    return pick_kernel_v<1>(g.width, g.nch);
+    if (gen) {
+        if (g.vec == 4) return pick_kernel_v<4, true>(g.width, g.nch);
+        if (g.vec == 2) return pick_kernel_v<2, true>(g.width, g.nch);
+        return pick_kernel_v<1, true>(g.width, g.nch);
+    }
+    if (g.vec == 4) return pick_kernel_v<4, false>(g.width, g.nch);
+    if (g.vec == 2) return pick_kernel_v<2, false>(g.width, g.nch);
+    return pick_kernel_v<1, false>(g.width, g.nch);
 }
 
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
-    StepKernel k = pick_kernel(p.F);
+    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR);
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
     // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
     // split multi-GPU / LightGCN / NeuMF paths)
