@@ -24,6 +24,10 @@
 //   -- grid barrier --           next step.
 //
 // A NaN loss (ValueError in the reference, :122-123) stops the loop before the update of that step.
+//
+// Variants of the same kernel: GEN = false is the BPR-only hot instantiation, GEN = true selects HingeLoss / TOP1Loss
+// (daisy/utils/loss.py:16-33) at run time; `phases` splits it into phase-1 / phase-2 launches (multi-GPU exchange,
+// LightGCN, NeuMF); `neg_row_ptr` switches on the fused sampler (a fresh negative per triple drawn inside phase 1).
 #include <math.h>
 
 #include "step.cuh"

@@ -10,15 +10,15 @@
 //   gather      A_0[R, 2D]  = cat(UM[u], IM[item])                      (lane group per row, 128-bit loads)
 //   tower fwd   A_l = relu(A_{l-1} W_l^T + b_l)                         (tiled fp32 GEMM, fused bias + ReLU)
 //   head        pred, BPR coefficient, loss + regulariser norms, GMF gradients (RED.ADD.F32x4), dZ_L, row counters
-//   tower bwd   gW_l += dZ_l^T A_{l-1} (split-K, atomics);  dZ_{l-1} = (dZ_l W_l) * [A_{l-1} > 0]
+//   tower bwd   gW_l += (A_{l-1}^T dZ_l)^T (split-K, transposed atomic accumulate);  dZ_{l-1} = (dZ_l W_l) * [A_{l-1} > 0]
 //   scatter     gUM[u] += dA_0[:, :D] (pos + neg rows), gIM[item] += dA_0[:, D:]
 //   apply       the MF dense sweep (mf_bpr.cu) on the table pairs (UG,IG) and (UM,IM) with per-table norms and the
 //               2x / 0x negative-count multipliers of the quirk; a small dense Adam/SGD kernel on the tower block.
 // Parameter block W (flat fp32, module-registration order): per layer weight [out,in] + bias [out]; predict weight [2F] + bias.
 //
 // Rooflines: the tower is ~124 KFLOP per triple at F=32, L=2 (fwd+bwd, both items) against ~2.3 KB of embedding traffic:
-// compute-bound on CUDA cores in this fp32 path; the bf16 tcgen05 tower of BASELINE config 3 replaces the three GEMM
-// call sites only.
+// compute-bound on CUDA cores in the fp32 path (tower_dtype 0); with tower_dtype 1 the three GEMM call sites run on
+// tcgen05 (umma_gemm.cuh) and the step becomes bound by streaming the fp32 activations (profiles/r01c).
 #include "step.cuh"
 #include "umma_gemm.cuh"
 

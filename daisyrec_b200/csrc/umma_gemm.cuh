@@ -9,11 +9,13 @@
 // One CTA (128 threads) owns a 128-row tile of C and the full N (<= 256):
 //   * TMEM: `cols` columns (power of two >= 32) x 128 lanes hold the fp32 accumulator (tcgen05.alloc by warp 0);
 //   * per 32-deep K chunk all threads stage A[128x32] and B[Npad x 32] into shared memory in the canonical
-//     K-major no-swizzle core-matrix layout (8 rows x 16 bytes per core matrix; LBO = distance between the two
-//     K-adjacent core matrices, SBO = distance between 8-row groups), fence.proxy.async, then ONE thread issues
-//     two tcgen05.mma (K = 16 each, M = 128, N = Npad) and tcgen05.commit's an mbarrier that releases the buffers;
-//   * epilogue: warp w reads TMEM lanes [32w, 32w+32) with tcgen05.ld.32x32b.x8 (lane == output row), applies
-//     bias/ReLU/mask, and stores fp32 (or atomically accumulates for split-K).
+//     no-swizzle core-matrix layouts (8 x 16-byte core matrices; K-major for operands that are contiguous along K,
+//     MN-major for the transposed operands of the backward GEMMs; LBO / SBO padded so the 16-byte staging stores are
+//     bank-conflict free), fence.proxy.async, then ONE thread issues two tcgen05.mma (K = 16 each, M = 128,
+//     N = Npad) and tcgen05.commit's an mbarrier that releases the buffers;
+//   * epilogue: warp w reads TMEM lanes [32w, 32w+32) with tcgen05.ld.32x32b.x32 (lane == output row), transposes the
+//     32x32 block through shared memory and writes row-contiguous fp32 with bias / ReLU / mask fused, or atomically
+//     accumulates (optionally transposed) for the split-K weight gradient.
 // The tower GEMMs are skinny (N, K <= 128 against M ~ 10^6): they are bound by streaming A from HBM, not by the
 // tensor pipe, so the kernel relies on several resident CTAs per SM for overlap rather than on an intra-CTA pipeline.
 #pragma once
