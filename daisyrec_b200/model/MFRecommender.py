@@ -67,13 +67,19 @@ class MF(GeneralRecommender):
 
     # ------------------------------------------------------------------ plumbing
     def parameters(self):
-        return [self.embed_user.weight, self.embed_item.weight]
+        return [self._full_user_table(), self.embed_item.weight]
 
     def state_dict(self):
-        return {'embed_user.weight': self.embed_user.weight, 'embed_item.weight': self.embed_item.weight}
+        return {'embed_user.weight': self._full_user_table(), 'embed_item.weight': self.embed_item.weight}
 
     def load_state_dict(self, sd):
-        self.embed_user.weight.copy_(sd['embed_user.weight'])
+        pu = sd['embed_user.weight']
+        if self.world > 1:                                            # keep this rank's rows of the full table
+            if self._bounds is None:
+                self._shard(self._default_bounds())
+            lo, hi = int(self._bounds[self.rank_id]), int(self._bounds[self.rank_id + 1])
+            pu = pu[lo:hi]
+        self.embed_user.weight.copy_(pu)
         self.embed_item.weight.copy_(sd['embed_item.weight'])
 
     def to(self, device):
@@ -151,17 +157,29 @@ class MF(GeneralRecommender):
         return np.ascontiguousarray(x, dtype=np.int32)
 
     # ------------------------------------------------------------------ reference surface
+    def _full_user_table(self):
+        """[user_num, factors] user table: the local tensor on one GPU, an all-gather of the shards under torchrun
+        (a collective: like every driver call in SPMD mode it must be reached by all ranks)."""
+        if self.world == 1:
+            return self.embed_user.weight
+        if self._bounds is None:
+            self._shard(self._default_bounds())
+        return self.gather_user_table()
+
     def forward(self, user, item):
         """MFRecommender.py:63-68: pred = (P[user] * Q[item]).sum(-1) for index tensors."""
         u = torch.as_tensor(user).to(self.device, torch.int32).reshape(-1).contiguous()
         i = torch.as_tensor(item).to(self.device, torch.int32).reshape(-1).contiguous()
-        return ops.mf_predict(self.embed_user.weight, self.embed_item.weight, u, i)
+        return ops.mf_predict(self._full_user_table(), self.embed_item.weight, u, i)
 
     __call__ = forward
 
     def calc_loss(self, batch):
         """MFRecommender.py:70-97 (BPR branch): 0-d fp32 loss of one (user, pos, neg) batch; no update."""
         self._check_loss_type()
+        if self.world > 1:
+            raise NotImplementedError('calc_loss / train_step on single batches are single-GPU entry points; under torchrun '
+                                      'use fit(train_loader) (user-sharded global steps)')
         self._ensure_ws()
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         loss = ops.mf_bpr_loss(self.embed_user.weight, self.embed_item.weight, self._ws, bu, bi, bj, self._hp)
@@ -171,6 +189,8 @@ class MF(GeneralRecommender):
         """zero_grad + calc_loss + backward + optimizer.step on one HOST batch
         (AbstractRecommender.py:119-128); returns loss.item()."""
         self._check_loss_type()
+        if self.world > 1:
+            raise NotImplementedError('train_step is a single-GPU entry point; under torchrun use fit(train_loader)')
         self._ensure_ws()
         hb = [self._host_i32(b) for b in batch[:3]]
         n = len(hb[0])
@@ -244,10 +264,10 @@ class MF(GeneralRecommender):
         """MFRecommender.py:126-133 -> int64 ndarray [topk]; no masking of train items."""
         users = torch.tensor([int(u)], dtype=torch.int64, device=self.device)
         k = min(self.topk, self.item_num)
-        return ops.mf_full_rank(self.embed_user.weight, self.embed_item.weight, users, k)[0].cpu().numpy()
+        return ops.mf_full_rank(self._full_user_table(), self.embed_item.weight, users, k)[0].cpu().numpy()
 
     def full_rank_users(self, users):
         """Batched full_rank (B200 extension): int64 ndarray [len(users), topk]."""
         users = torch.as_tensor(np.asarray(users, dtype=np.int64)).to(self.device)
         k = min(self.topk, self.item_num)
-        return ops.mf_full_rank(self.embed_user.weight, self.embed_item.weight, users, k).cpu().numpy()
+        return ops.mf_full_rank(self._full_user_table(), self.embed_item.weight, users, k).cpu().numpy()
