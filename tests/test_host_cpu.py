@@ -115,3 +115,27 @@ def test_synthetic_generator_shape():
     assert torch.unique(key).numel() == 60000                         # unique pairs
     deg = d["row_ptr"][1:] - d["row_ptr"][:-1]
     assert int(deg.min()) >= 1
+
+
+def test_loader_plan_decoding():
+    """fit() takes the bulk path only for the reference's own loader shape; anything else is iterated batch by batch."""
+    from torch.utils.data import DataLoader, RandomSampler, WeightedRandomSampler
+    from daisyrec_b200.model.AbstractRecommender import loader_plan
+    from daisyrec_b200.utils.dataset import BasicDataset, get_dataloader
+    data = np.arange(30, dtype=np.int32).reshape(10, 3)
+    plan = loader_plan(get_dataloader(BasicDataset(data), batch_size=4, shuffle=True, num_workers=4))
+    assert plan is not None and plan[0] is data and plan[1:4] == (4, True, False)
+    plan = loader_plan(DataLoader(BasicDataset(data), batch_size=3, shuffle=False, drop_last=True))
+    assert plan[1:4] == (3, False, True)
+    g = torch.Generator(); g.manual_seed(1)
+    assert loader_plan(DataLoader(BasicDataset(data), batch_size=4, sampler=RandomSampler(data, generator=g))) is None
+    assert loader_plan(DataLoader(BasicDataset(data), batch_size=4, sampler=WeightedRandomSampler([1.0] * 10, 10))) is None
+    assert loader_plan(DataLoader(BasicDataset(data[:, :2]), batch_size=4)) is None           # not <u,i,j> rows
+    assert loader_plan([[torch.zeros(4), torch.zeros(4), torch.zeros(4)]]) is None            # plain list of batches
+    # the DataLoader and the plan consume the global RNG identically: same first batch
+    from daisyrec_b200.model.AbstractRecommender import epoch_permutation
+    torch.manual_seed(7)
+    first = next(iter(get_dataloader(BasicDataset(data), batch_size=4, shuffle=True)))
+    torch.manual_seed(7)
+    perm = epoch_permutation(10, True)
+    assert [int(x) for x in first[0]] == data[perm[:4].numpy(), 0].tolist()
