@@ -89,16 +89,16 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_seg_kernel(Adj a, const flo
         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
             for (int q = 0; q < VEC; ++q) acc.c[ch].v[q] = 0.f;
-        for (long long e0 = b; e0 < e; e0 += E) {
-            int cc[E];
+        // main loop: whole groups of E edges, no bounds checks (a full segment is 256 edges = 64 iterations)
+        long long e0 = b;
+        for (; e0 + E <= e; e0 += E) {
             float vv[E];
             Row<VEC, W, NCH> x[E];
 #pragma unroll
             for (int q = 0; q < E; ++q) {
-                bool ok = e0 + q < e;
-                cc[q] = ok ? __ldg(a.col + e0 + q) : 0;
-                vv[q] = ok ? __ldg(a.val + e0 + q) : 0.f;
-                x[q] = load_row<VEC, W, NCH>(X + (size_t)cc[q] * F, gl, chunks, ok);
+                const int cq = __ldg(a.col + e0 + q);
+                vv[q] = __ldg(a.val + e0 + q);
+                x[q] = load_row<VEC, W, NCH>(X + (size_t)cq * F, gl, chunks, true);
             }
 #pragma unroll
             for (int q = 0; q < E; ++q)
@@ -106,6 +106,16 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_seg_kernel(Adj a, const flo
                 for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
                     for (int z = 0; z < VEC; ++z) acc.c[ch].v[z] = fmaf(vv[q], x[q].c[ch].v[z], acc.c[ch].v[z]);
+        }
+        // tail: fewer than E edges left, same ascending-column accumulation order
+        for (; e0 < e; ++e0) {
+            const int cq = __ldg(a.col + e0);
+            const float v1 = __ldg(a.val + e0);
+            const Row<VEC, W, NCH> x1 = load_row<VEC, W, NCH>(X + (size_t)cq * F, gl, chunks, true);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                for (int z = 0; z < VEC; ++z) acc.c[ch].v[z] = fmaf(v1, x1.c[ch].v[z], acc.c[ch].v[z]);
         }
         const bool multi = (a.row_ptr[r + 1] - a.row_ptr[r]) != (e - b);
 #pragma unroll
