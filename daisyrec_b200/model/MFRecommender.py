@@ -116,7 +116,6 @@ class MF(GeneralRecommender):
         """Full [user_num, factors] user table on every rank (one all-gather of the shards)."""
         if self.world == 1:
             return self.embed_user.weight
-        import torch.distributed as dist
         from ..parallel import allgather_rows
         lo, hi = int(self._bounds[self.rank_id]), int(self._bounds[self.rank_id + 1])
         pos = torch.arange(lo, hi, device=self.device)

@@ -213,7 +213,6 @@ class ShardedTrainer:
 def run_sharded_bench(args, rank, local, world, dev):
     """Weak-scaling arm of bench.py: per-GPU batch fixed (args.batch), global batch = world * batch."""
     import json
-    import logging
     from . import ops
     from .utils.synthetic import init_tables
     sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -5,7 +5,6 @@ Data generation is setup, not hot path: it uses ordinary torch ops on whatever d
 [10, item_num/4], rescaled to the requested nnz); items follow a Zipf(1.0) popularity over a
 random relabelling; (user, item) pairs are unique; COO rows come in a random "time" order.
 """
-import numpy as np
 import torch
 
 SHAPES = {

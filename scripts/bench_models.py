@@ -6,9 +6,7 @@ Prints one JSON line per run: triples/s with CUDA events around K steps after wa
 import argparse
 import json
 import sys
-import time
 
-import numpy as np
 import torch
 
 sys.path.insert(0, ".")

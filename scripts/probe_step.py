@@ -1,6 +1,6 @@
 """Quick throughput probe of the step kernel at the ML-20M shape (dev tool, not the bench)."""
-import sys, time, json
-import numpy as np, torch
+import sys, json
+import torch
 sys.path.insert(0, ".")
 from daisyrec_b200 import ops
 
