@@ -381,7 +381,93 @@ def gen_neumf():
     _save("neumf", **out)
 
 
-ALL = {"neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+# --------------------------------------------------------------------------- evaluation KPIs
+def gen_metrics():
+    """daisy/utils/metrics.py:18-57,59-96,98-251 (calc_ranking_results / Metric.run) on synthetic rank lists:
+    duplicate ids, users without hits, users whose whole list hits, topk inside and outside common_ks."""
+    import logging
+    import tempfile
+    from daisy.utils.metrics import calc_ranking_results, Metric
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [(200, 500, 50), (64, 90, 7), (33, 40, 20), (1, 30, 10)]
+    for c, (n, I, topk) in enumerate(cases):
+        test_u = rng.permutation(n * 3)[:n].astype(np.int64)             # user ids, arbitrary order
+        test_ur, preds = {}, np.zeros((n, topk), np.float32)
+        for r, u in enumerate(test_u):
+            g = int(rng.integers(1, min(I, 40)))
+            gt = rng.choice(I, size=g, replace=False)
+            test_ur[int(u)] = set(int(x) for x in gt)
+            row = rng.integers(0, I, size=topk)                            # duplicates happen (with replacement)
+            mode = r % 5
+            if mode == 0:                                                  # no hit at all
+                pool = np.setdiff1d(np.arange(I), gt)
+                row = rng.choice(pool, size=topk) if len(pool) else row
+            elif mode == 1:                                                # every position hits (duplicates of gt)
+                row = rng.choice(gt, size=topk)
+            elif mode == 2:                                                # one planted hit, repeated twice
+                pool = np.setdiff1d(np.arange(I), gt)
+                if len(pool):
+                    row = rng.choice(pool, size=topk)
+                pos = int(rng.integers(topk))
+                row[pos] = gt[0]
+                row[min(topk - 1, pos + 2)] = gt[0]
+            preds[r] = row
+        item_pop = rng.integers(0, 1000, size=I).astype(np.float64)
+        names = ["recall", "mrr", "ndcg", "hit", "precision", "coverage"]
+        cfg = {"logger": logging.getLogger("gold"), "res_path": tempfile.mkdtemp() + "/", "metrics": names,
+               "item_num": I, "topk": topk, "item_pop": item_pop}
+        res = calc_ranking_results(test_ur, preds, list(test_u), cfg)
+        ks = np.array([int(k) for k in res.columns[1:]], np.int32)
+        cfg2 = dict(cfg, metrics=names + ["popularity"])                  # Popularity indexes item_pop: integer preds only
+        res2 = calc_ranking_results(test_ur, preds.astype(np.int64), list(test_u), cfg2)
+        # 'map' is accepted by Metric.run (:84) but has no display name (:5-16), so calc_ranking_results raises
+        # KeyError on it; pin it through Metric.run with the same per-cutoff slicing (:49-50)
+        mrun = Metric(dict(cfg, metrics=["map"]))
+        kpi_map = np.array([mrun.run(test_ur, preds[:, :int(k)], list(test_u))[0] for k in ks], np.float64)
+        gt_len = np.array([len(test_ur[int(u)]) for u in test_u], np.int32)
+        gt_flat = np.concatenate([np.array(sorted(test_ur[int(u)]), np.int32) for u in test_u])
+        out.update({f"c{c}_preds": preds, f"c{c}_test_u": test_u, f"c{c}_gt_flat": gt_flat, f"c{c}_gt_len": gt_len,
+                    f"c{c}_ks": ks, f"c{c}_item_pop": item_pop, f"c{c}_meta": np.array([n, I, topk], np.int64),
+                    f"c{c}_kpi": res.values[:, 1:].astype(np.float64),     # [6 metrics, len(ks)], rows = kpi_names
+                    f"c{c}_kpi_pop": res2.values[:, 1:].astype(np.float64),   # [7 metrics, len(ks)] (+ popularity)
+                    f"c{c}_kpi_map": kpi_map})                                 # [len(ks)]
+        print(res2)
+    out["ncases"] = np.array(len(cases))
+    out["kpi_names"] = np.array(["recall", "mrr", "ndcg", "hit", "precision", "coverage", "popularity"])
+    _save("metrics", **out)
+
+
+# --------------------------------------------------------------------------- popularity-mixed / point-wise sampler
+def gen_sampler_pop():
+    """daisy/utils/sampler.py:43-53,64-81 ('low-pop' / 'high-pop' mix) and :93-98 (point-wise explode, CL / SL)."""
+    import pandas as pd
+    from daisy.utils.sampler import BasicNegtiveSampler
+    rng = np.random.default_rng(19)
+    out = {}
+    cases = [(40, 70, 500, 4, 2022, "high-pop", 0.5, "BPR"), (25, 300, 400, 5, 7, "low-pop", 0.3, "BPR"),
+             (30, 64, 350, 3, 99, "high-pop", 1.0, "BPR"), (30, 64, 350, 4, 5, "low-pop", 0.1, "BPR"),
+             (20, 50, 200, 2, 3, "uniform", 0.0, "CL"), (20, 50, 200, 3, 4, "high-pop", 0.4, "SL")]
+    for c, (U, I, nnz, G, seed, method, ratio, loss) in enumerate(cases):
+        cu, ci = _synthetic_inter(rng, U, I, nnz, None)
+        rating = rng.integers(1, 6, size=len(cu)).astype(np.float64) if loss == "SL" else np.ones(len(cu))
+        df = pd.DataFrame({"user": cu, "item": ci, "rating": rating, "timestamp": np.arange(len(cu))})
+        cfg = rh.make_config("mf", user_num=U, item_num=I, num_ng=G, train_ur=_ur_from(cu, ci), sample_method=method,
+                             sample_ratio=ratio, loss_type=loss)
+        np.random.seed(seed)
+        smp = BasicNegtiveSampler(df, cfg)
+        rows = smp.sampling()
+        nxt = np.random.randint(0, 2 ** 31 - 1, size=3)
+        out.update({f"c{c}_coo_u": cu, f"c{c}_coo_i": ci, f"c{c}_rating": rating, f"c{c}_rows": rows, f"c{c}_next": nxt,
+                    f"c{c}_meta": np.array([U, I, G, seed], np.int64), f"c{c}_ratio": np.array(ratio),
+                    f"c{c}_method": np.array(method), f"c{c}_loss": np.array(loss),
+                    f"c{c}_pop_prob": np.zeros(0) if smp.pop_prob is None else np.asarray(smp.pop_prob, np.float64)})
+        print(f"sampler_pop case {c}: rows {rows.shape}, head {rows[:2].tolist()}")
+    out["ncases"] = np.array(len(cases))
+    _save("sampler_pop", **out)
+
+
+ALL = {"metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

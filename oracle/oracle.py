@@ -14,8 +14,8 @@ _SO = os.path.join(_HERE, "_build", "libbpr_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "bpr_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("bpr_oracle.c", "eval_oracle.c", "Makefile"))
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -129,6 +129,47 @@ def build_candidates_user(mt_state, gt, train, item_num, cand_num):
                                          item_num, cand_num, _i64(out))
     if rc != 0:
         raise ValueError("a cannot be empty")
+    return out
+
+
+KPI_NAMES = ("recall", "mrr", "ndcg", "hit", "precision", "map", "coverage", "popularity")
+
+
+def gt_csr(test_ur, test_u):
+    """test_ur (dict user -> set) in test_u order -> (gt_ptr int64[n+1], gt_idx int32 ascending per row)."""
+    lens = np.array([len(test_ur[u]) for u in test_u], np.int64)
+    ptr = np.zeros(len(test_u) + 1, np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    idx = np.concatenate([np.sort(np.fromiter(test_ur[u], np.int32, len(test_ur[u]))) for u in test_u]) \
+        if len(test_u) else np.zeros(0, np.int32)
+    return ptr, np.ascontiguousarray(idx, np.int32)
+
+
+def rank_metrics(preds, gt_ptr, gt_idx, ks, item_num, item_pop=None):
+    """-> float64 [len(ks), 8] in KPI_NAMES order (daisy/utils/metrics.py)."""
+    preds = np.ascontiguousarray(preds, np.float32)
+    ks = np.ascontiguousarray(ks, np.int32)
+    out = np.zeros((len(ks), len(KPI_NAMES)), np.float64)
+    pop = None if item_pop is None else np.ascontiguousarray(item_pop, np.float64)
+    lib().orc_rank_metrics(_f32(preds), C.c_int64(preds.shape[0]), C.c_int32(preds.shape[1]), _i64(gt_ptr), _i32(gt_idx),
+                           _i32(ks), C.c_int32(len(ks)), C.c_int32(item_num), _p(pop, C.c_double), _p(out, C.c_double))
+    return out
+
+
+def sample_negatives_pop(mt_state, row_ptr, col, user_num, item_num, uniform_num, other_num, cdf):
+    js = np.zeros((user_num, uniform_num + other_num), np.int32)
+    cdf = np.ascontiguousarray(cdf, np.float64)
+    rc = lib().orc_sample_negatives_pop(_p(mt_state, C.c_uint32), _i64(row_ptr), _i32(col), user_num, item_num,
+                                        uniform_num, other_num, _p(cdf, C.c_double), _i32(js))
+    if rc != 0:
+        raise ValueError("a cannot be empty (user %d has interacted with every item)" % (-rc - 1))
+    return js
+
+
+def explode_pointwise(coo_u, coo_i, label, js):
+    n, g = len(coo_u), js.shape[1]
+    out = np.empty((n * (1 + g), 3), np.int32)
+    lib().orc_explode_pointwise(_i32(coo_u), _i32(coo_i), _i32(label), C.c_int64(n), _i32(js), g, _i32(out))
     return out
 
 
