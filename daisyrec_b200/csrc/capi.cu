@@ -42,7 +42,7 @@ int sm_count()
 
 }  // namespace drb
 
-extern "C" int drb_version(void) { return 101; }
+extern "C" int drb_version(void) { return 102; }
 
 extern "C" const char *drb_last_error(void) { return drb::g_err; }
 

@@ -26,7 +26,8 @@
 // A NaN loss (ValueError in the reference, :122-123) stops the loop before the update of that step.
 //
 // Variants of the same kernel: GEN = false is the BPR-only hot instantiation, GEN = true selects HingeLoss / TOP1Loss
-// (daisy/utils/loss.py:16-33) at run time; `phases` splits it into phase-1 / phase-2 launches (multi-GPU exchange,
+// (daisy/utils/loss.py:16-33) or the point-wise CL / SL branch (MFRecommender.py:75-81: the third plane holds the label,
+// only P_u and Q_i take part) at run time; `phases` splits it into phase-1 / phase-2 launches (multi-GPU exchange,
 // LightGCN, NeuMF); `neg_row_ptr` switches on the fused sampler (a fresh negative per triple drawn inside phase 1).
 #include <math.h>
 
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
     uint32_t par0 = 0, par1 = 0;
     unsigned long long epoch = 0;
     const int tile = p.tile;
+    const bool pw = GEN && p.loss >= DRB_LOSS_CL;   // point-wise: bj is the label plane, no negative row
 
     // stage one index tile: TMA bulk copy when full and 16-byte aligned, plain loads otherwise
     auto stage = [&](long long tbase, int cnt, int b) {
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
             for (int tb = 0; tb < cnt; tb += GROUPS * UNR) {
                 Row<VEC, W, NCH> rp[UNR], rqi[UNR], rqj[UNR];
                 int iu[UNR], ii[UNR], ij[UNR];
+                float lab[UNR];
                 bool ok[UNR];
 #pragma unroll
                 for (int r = 0; r < UNR; ++r) {
@@ -299,6 +302,11 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                     iu[r] = ok[r] ? xu[t] : 0;
                     ii[r] = ok[r] ? xi[t] : 0;
                     ij[r] = ok[r] ? xj[t] : 0;
+                    lab[r] = 0.f;
+                    if (pw) {                       // label = batch[2].float() (MFRecommender.py:76); the j row stays zero
+                        lab[r] = (float)ij[r];
+                        ij[r] = 0;
+                    }
                     if (p.neg_row_ptr != nullptr && ok[r]) {
                         const long long gt = base + t_i * tile + t;            // position of the triple in the planes
                         ij[r] = draw_negative(p, iu[r], (unsigned long long)gt, (unsigned long long)step);
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                     }
                     rp[r] = load_row<VEC, W, NCH>(p.P + (size_t)iu[r] * F, gl, chunks, ok[r]);
                     rqi[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ii[r] * F, gl, chunks, ok[r]);
-                    rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r]);
+                    rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r] && !pw);
                 }
                 // scores of the UNR triples of this group (every lane of the group ends up with the same values)
                 float ps[UNR], ns[UNR], cs[UNR], cn[UNR];
@@ -314,11 +322,26 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                 for (int r = 0; r < UNR; ++r) {
                     ps[r] = dot_rows<VEC, W, NCH>(rp[r], rqi[r]);
                     ns[r] = dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
+                    if (pw) ns[r] = lab[r];         // pair_loss receives the label in place of the negative score
                 }
                 // The scalar chain (sigmoid -> log -> coefficient, ~40 instructions) would be replayed by all W lanes for
                 // each of the UNR triples; instead lane gl evaluates it ONCE, for triple (gl % UNR) of its group, and the
                 // coefficients d(loss)/d(pos), d(loss)/d(neg) are handed round with shuffles.
                 auto pair_loss = [&](float pos, float neg, float &c_pos, float &c_neg) -> float {
+                    if (GEN && p.loss == DRB_LOSS_CL) {     // BCEWithLogitsLoss(sum): (1-y) x - log_sigmoid(x), neg = y
+                        const float z = expf(-fabsf(pos));
+                        const float logsig = fminf(pos, 0.f) - log1pf(z);
+                        const float dls = pos < 0.f ? 1.f - z / (1.f + z) : z / (1.f + z);
+                        c_pos = (1.f - neg) - dls;
+                        c_neg = 0.f;
+                        return (1.f - neg) * pos - logsig;
+                    }
+                    if (GEN && p.loss == DRB_LOSS_SL) {     // MSELoss(sum): (x - y)^2, neg = y
+                        const float d = pos - neg;
+                        c_pos = 2.f * d;
+                        c_neg = 0.f;
+                        return d * d;
+                    }
                     if (GEN && p.loss == DRB_LOSS_HL) {     // clamp(1 - (pos - neg), min=0); clamp's backward passes at equality
                         const float m = 1.f - (pos - neg);
                         c_pos = (m >= 0.f) ? -1.f : 0.f;
@@ -402,12 +425,12 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                             }
                             red_row<VEC>(p.ws.gP + (size_t)iu[r] * F + cc * VEC, gu);
                             red_row<VEC>(p.ws.gQ + (size_t)ii[r] * F + cc * VEC, gi);
-                            red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
+                            if (!pw) red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
                         }
                         if (gl == 0) {
                             red_add_u32(p.ws.cntU + iu[r], 1u);
                             red_add_u64(p.ws.cntI + ii[r], 1ull);
-                            red_add_u64(p.ws.cntI + ij[r], 1ull << 32);
+                            if (!pw) red_add_u64(p.ws.cntI + ij[r], 1ull << 32);
                         }
                     }
                 }
@@ -490,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                         if (ok) {
                             u = __ldg(p.bu + base + t0 + t);
                             i = __ldg(p.bi + base + t0 + t);
-                            j = __ldg(p.bj + base + t0 + t);
+                            j = pw ? i : __ldg(p.bj + base + t0 + t);   // point-wise: that plane holds labels
                         }
                         unsigned cu = 0;
                         unsigned long long ci = 0, cj = 0;
@@ -643,7 +666,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
     DRB_REQUIRE(h->opt == DRB_OPT_SGD || h->opt == DRB_OPT_ADAM, "unknown optimizer id %d", h->opt);
-    DRB_REQUIRE(h->loss >= DRB_LOSS_BPR && h->loss <= DRB_LOSS_TL, "unknown loss id %d", h->loss);
+    DRB_REQUIRE(h->loss >= DRB_LOSS_BPR && h->loss <= DRB_LOSS_SL, "unknown loss id %d", h->loss);
     DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0 || n == 0, "steps [%lld,%lld) exceed %lld triples", first,
                 first + nsteps, n);
     p.P = P; p.Q = Q;
@@ -698,6 +721,7 @@ extern "C" int drb_mf_bpr_train_steps_fused_neg(float *d_P, float *d_Q, void *d_
                                                 int64_t *nan_step, void *stream)
 {
     DRB_REQUIRE(d_row_ptr && d_col, "train_steps_fused_neg: the user->item CSR is required");
+    DRB_REQUIRE(hyper && hyper->loss < DRB_LOSS_CL, "train_steps_fused_neg: pair-wise losses only");
     StepParams p;
     // the negative plane is unused in this mode (bi stands in so that the TMA staging code stays uniform)
     int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu, d_bi, d_bi, n, batch, first_step, n_steps, hyper, adam_step0,
@@ -839,6 +863,7 @@ extern "C" int drb_mf_bpr_phase(float *d_P, float *d_Q, void *d_ws, int32_t U, i
 {
     DRB_REQUIRE(phase == 1 || phase == 2, "mf_bpr_phase: phase must be 1 or 2");
     DRB_REQUIRE(begin >= 0 && count >= 0, "mf_bpr_phase: bad range");
+    DRB_REQUIRE(hyper && hyper->loss < DRB_LOSS_CL, "mf_bpr_phase: the sharded step covers the pair-wise losses only");
     StepParams p;
     // count may be 0 on a rank (its users have no triple in this global batch): phases still run (loss, sweep)
     int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu + begin, d_bi + begin, d_bj + begin, count, count > 0 ? count : 1,

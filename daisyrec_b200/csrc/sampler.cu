@@ -46,6 +46,12 @@ struct Mt {
         y ^= y >> 18;
         return y;
     }
+    // RandomState.random_sample(): 53-bit double from two words (legacy mt19937_next_double)
+    double uniform01()
+    {
+        uint32_t a = next() >> 5, b = next() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
     // RandomState.randint(0, n): masked rejection on 32-bit words; n == 1 consumes nothing
     uint32_t bounded(uint32_t n)
     {
@@ -148,6 +154,63 @@ __global__ void explode_kernel(const int32_t *__restrict__ coo_u, const int32_t 
     }
 }
 
+// popularity-mixed table (sampler.py:64-81): columns [0, un) = k-th complement of a uniform rank, columns
+// [un, un+on) = searchsorted(cdf, x, side='right') of a uniform double (RandomState.choice(p=...))
+__global__ void assemble_mixed_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                      const int32_t *__restrict__ draws, const double *__restrict__ cdf,
+                                      const double *__restrict__ u01, int U, int I, int un, int on,
+                                      int32_t *__restrict__ js)
+{
+    const int G = un + on;
+    long long total = (long long)U * G;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int u = (int)(idx / G), g = (int)(idx - (long long)u * G);
+        if (g < un) {
+            long long b = row_ptr[u], e = row_ptr[u + 1];
+            int k = draws[(long long)u * un + g];
+            long long lo = 0, hi = e - b;
+            while (lo < hi) {
+                long long mid = (lo + hi) >> 1;
+                if ((long long)__ldg(col + b + mid) - mid <= (long long)k) lo = mid + 1; else hi = mid;
+            }
+            js[idx] = k + (int)lo;
+        } else {
+            double x = u01[(long long)u * on + (g - un)];
+            int lo = 0, hi = I;  // first index with cdf[index] > x
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (__ldg(cdf + mid) <= x) lo = mid + 1; else hi = mid;
+            }
+            js[idx] = lo;
+        }
+    }
+}
+
+// point-wise explode (sampler.py:93-98): nnz positive rows (u, i, label) then nnz*G negative rows (u, js[u,g], 0)
+__global__ void explode_pointwise_kernel(const int32_t *__restrict__ coo_u, const int32_t *__restrict__ coo_i,
+                                         const int32_t *__restrict__ label, long long nnz,
+                                         const int32_t *__restrict__ js, int G, int32_t *__restrict__ rows)
+{
+    long long total = nnz * (1 + G);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int32_t *t = rows + 3 * idx;
+        if (idx < nnz) {
+            t[0] = __ldg(coo_u + idx);
+            t[1] = __ldg(coo_i + idx);
+            t[2] = __ldg(label + idx);
+        } else {
+            long long n = idx - nnz, r = n / G;
+            int g = (int)(n - r * G);
+            int u = __ldg(coo_u + r);
+            t[0] = u;
+            t[1] = __ldg(js + (long long)u * G + g);
+            t[2] = 0;
+        }
+    }
+}
+
 static int grid_for(long long n, int block)
 {
     long long b = (n + block - 1) / block, cap = (long long)sm_count() * 16;
@@ -184,6 +247,52 @@ extern "C" int drb_sampler_draw_mt19937(uint32_t *st, const int64_t *h_row_ptr, 
         }
         for (int32_t g = 0; g < G; ++g) h_draws[(int64_t)u * G + g] = (int32_t)mt.bounded((uint32_t)n);
     }
+    return DRB_OK;
+}
+
+extern "C" int drb_sampler_draw_mt19937_mixed(uint32_t *st, const int64_t *h_row_ptr, int32_t U, int32_t I,
+                                              int32_t uniform_num, int32_t other_num, int32_t *h_draws, double *h_u01,
+                                              int32_t *bad_user)
+{
+    DRB_REQUIRE(st && h_row_ptr && U >= 0 && I > 0 && uniform_num >= 0 && other_num >= 0 && uniform_num + other_num > 0,
+                "sampler_draw_mt19937_mixed: bad arguments");
+    DRB_REQUIRE((uniform_num == 0 || h_draws) && (other_num == 0 || h_u01), "sampler_draw_mt19937_mixed: null output");
+    Mt mt{st, st + 624};
+    for (int32_t u = 0; u < U; ++u) {  // per user: uniform ranks first, then the weighted draws (sampler.py:71-80)
+        int64_t n = (int64_t)I - (h_row_ptr[u + 1] - h_row_ptr[u]);
+        if (n <= 0 && uniform_num > 0) {
+            if (bad_user) *bad_user = u;
+            set_error("'a' cannot be empty: user %d has interacted with every item", u);
+            return DRB_ERR_EMPTY_SET;
+        }
+        for (int32_t g = 0; g < uniform_num; ++g) h_draws[(int64_t)u * uniform_num + g] = (int32_t)mt.bounded((uint32_t)n);
+        for (int32_t g = 0; g < other_num; ++g) h_u01[(int64_t)u * other_num + g] = mt.uniform01();
+    }
+    return DRB_OK;
+}
+
+extern "C" int drb_sampler_assemble_mixed(const int64_t *d_row_ptr, const int32_t *d_col, const int32_t *d_draws,
+                                          const double *d_cdf, const double *d_u01, int32_t U, int32_t I,
+                                          int32_t uniform_num, int32_t other_num, int32_t *d_js, void *stream)
+{
+    DRB_REQUIRE(d_row_ptr && d_js && U > 0 && I > 0 && uniform_num >= 0 && other_num >= 0 && uniform_num + other_num > 0,
+                "sampler_assemble_mixed: bad arguments");
+    DRB_REQUIRE((uniform_num == 0 || d_draws) && (other_num == 0 || (d_cdf && d_u01)), "sampler_assemble_mixed: null input");
+    assemble_mixed_kernel<<<grid_for((long long)U * (uniform_num + other_num), 256), 256, 0, (cudaStream_t)stream>>>(
+        d_row_ptr, d_col, d_draws, d_cdf, d_u01, U, I, uniform_num, other_num, d_js);
+    DRB_CUDA(cudaGetLastError());
+    return DRB_OK;
+}
+
+extern "C" int drb_sampler_explode_pointwise(const int32_t *d_coo_u, const int32_t *d_coo_i, const int32_t *d_label,
+                                             int64_t nnz, const int32_t *d_js, int32_t G, int32_t *d_rows, void *stream)
+{
+    DRB_REQUIRE(d_coo_u && d_coo_i && d_label && d_rows && nnz >= 0 && G >= 0 && (G == 0 || d_js),
+                "sampler_explode_pointwise: bad arguments");
+    if (nnz == 0) return DRB_OK;
+    explode_pointwise_kernel<<<grid_for(nnz * (1 + G), 256), 256, 0, (cudaStream_t)stream>>>(d_coo_u, d_coo_i, d_label,
+                                                                                             nnz, d_js, G, d_rows);
+    DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }
 

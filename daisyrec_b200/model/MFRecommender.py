@@ -18,7 +18,8 @@ from .AbstractRecommender import GeneralRecommender, _Table, _init_table, _INIT
 
 
 class MF(GeneralRecommender):
-    SUPPORTED_LOSSES = ('BPR', 'HL', 'TL')      # the pair-wise criteria of AbstractRecommender.py:84-89
+    # the pair-wise criteria of AbstractRecommender.py:83-88 and the point-wise ones of :79-82 (batch[2] = label)
+    SUPPORTED_LOSSES = ('BPR', 'HL', 'TL', 'CL', 'SL')
 
     def __init__(self, config):
         """Same keys as the reference (MFRecommender.py:46-59): lr, reg_1, reg_2, epochs, topk,
@@ -126,6 +127,9 @@ class MF(GeneralRecommender):
 
     def _begin_fit(self, opt):
         """fit() builds a fresh optimizer (AbstractRecommender.py:105): fresh Adam moments / step count."""
+        if str(self.loss_type).upper() in ('CL', 'SL') and (self.world > 1 or self.neg_sampling == 'fused'):
+            raise NotImplementedError('the point-wise losses (CL / SL) run on one GPU with sampler-made rows; the sharded '
+                                      'step and the fused negative sampler cover the pair-wise losses')
         self._hp = self._hyper(opt)
         self._opt_steps = 0
         if self.world > 1:
@@ -174,7 +178,8 @@ class MF(GeneralRecommender):
     __call__ = forward
 
     def calc_loss(self, batch):
-        """MFRecommender.py:70-97 (BPR branch): 0-d fp32 loss of one (user, pos, neg) batch; no update."""
+        """MFRecommender.py:70-97: 0-d fp32 loss of one (user, pos, neg) -- or, for CL / SL, (user, item, label) --
+        batch; no update."""
         self._check_loss_type()
         if self.world > 1:
             raise NotImplementedError('calc_loss / train_step on single batches are single-GPU entry points; under torchrun '

@@ -141,6 +141,70 @@ def kth_complement_var(d_row_ptr, d_col, d_offsets, d_draws):
     return out
 
 
+def sampler_draw_mt19937_mixed(state, row_ptr, user_num, item_num, uniform_num, other_num):
+    """Host: numpy-stream replay of the popularity-mixed branch (sampler.py:71-80) -> (ranks i32, doubles f64)."""
+    row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+    draws = np.empty((user_num, uniform_num), np.int32)
+    u01 = np.empty((user_num, other_num), np.float64)
+    bad = C.c_int32(-1)
+    rc = L.lib().drb_sampler_draw_mt19937_mixed(state.ctypes.data, row_ptr.ctypes.data, user_num, item_num, uniform_num,
+                                                other_num, draws.ctypes.data, u01.ctypes.data, C.byref(bad))
+    if rc == L.DRB_ERR_EMPTY_SET:
+        raise ValueError("'a' cannot be empty unless no samples are taken")
+    L.check(rc)
+    return draws, u01
+
+
+def sampler_assemble_mixed(d_row_ptr, d_col, d_draws, d_cdf, d_u01, item_num):
+    _dev(d_row_ptr, torch.int64, "row_ptr"); _dev(d_col, torch.int32, "col")
+    _dev(d_draws, torch.int32, "draws"); _dev(d_cdf, torch.float64, "cdf"); _dev(d_u01, torch.float64, "u01")
+    U, un, on = d_row_ptr.numel() - 1, d_draws.shape[1], d_u01.shape[1]
+    js = torch.empty((U, un + on), dtype=torch.int32, device=d_row_ptr.device)
+    L.check(L.lib().drb_sampler_assemble_mixed(_ptr(d_row_ptr), _ptr(d_col), _ptr(d_draws), _ptr(d_cdf), _ptr(d_u01), U,
+                                               item_num, un, on, _ptr(js), _stream()))
+    return js
+
+
+def sampler_explode_pointwise(d_coo_u, d_coo_i, d_label, d_js):
+    _dev(d_coo_u, torch.int32, "coo_u"); _dev(d_coo_i, torch.int32, "coo_i")
+    _dev(d_label, torch.int32, "label"); _dev(d_js, torch.int32, "js")
+    nnz, G = d_coo_u.numel(), d_js.shape[1]
+    rows = torch.empty((nnz * (1 + G), 3), dtype=torch.int32, device=d_coo_u.device)
+    L.check(L.lib().drb_sampler_explode_pointwise(_ptr(d_coo_u), _ptr(d_coo_i), _ptr(d_label), nnz, _ptr(d_js), G,
+                                                  _ptr(rows), _stream()))
+    return rows
+
+
+# ------------------------------------------------------------------ evaluation KPIs
+def rank_metrics(d_preds, d_gt_ptr, d_gt_idx, ks, item_num, d_item_pop=None):
+    """calc_ranking_results' numbers for rank()'s device output: -> float64 CUDA tensor [len(ks), 8] (L.KPI_NAMES)."""
+    _dev(d_preds, torch.float32, "preds"); _dev(d_gt_ptr, torch.int64, "gt_ptr"); _dev(d_gt_idx, torch.int32, "gt_idx")
+    if d_item_pop is not None:
+        _dev(d_item_pop, torch.float64, "item_pop")
+    ks = np.ascontiguousarray(ks, np.int32)
+    n, ld = d_preds.shape
+    ws = torch.empty(L.lib().drb_rank_metrics_workspace_bytes(item_num, len(ks)), dtype=torch.uint8, device=d_preds.device)
+    out = torch.empty((len(ks), len(L.KPI_NAMES)), dtype=torch.float64, device=d_preds.device)
+    L.check(L.lib().drb_rank_metrics(_ptr(d_preds), n, ld, _ptr(d_gt_ptr), _ptr(d_gt_idx), ks.ctypes.data, len(ks),
+                                     item_num, None if d_item_pop is None else _ptr(d_item_pop), _ptr(ws), _ptr(out),
+                                     _stream()))
+    return out
+
+
+def rank_metrics_host(preds, gt_ptr, gt_idx, ks, item_num, item_pop=None):
+    """Same through host buffers (H2D/D2H inside the library) -> float64 numpy [len(ks), 8]."""
+    preds = np.ascontiguousarray(preds, np.float32)
+    gt_ptr = np.ascontiguousarray(gt_ptr, np.int64)
+    gt_idx = np.ascontiguousarray(gt_idx, np.int32)
+    ks = np.ascontiguousarray(ks, np.int32)
+    pop = None if item_pop is None else np.ascontiguousarray(item_pop, np.float64)
+    out = np.empty((len(ks), len(L.KPI_NAMES)), np.float64)
+    L.check(L.lib().drb_rank_metrics_host(preds.ctypes.data, preds.shape[0], preds.shape[1], gt_ptr.ctypes.data,
+                                          gt_idx.ctypes.data, ks.ctypes.data, len(ks), item_num,
+                                          None if pop is None else pop.ctypes.data, out.ctypes.data))
+    return out
+
+
 # ------------------------------------------------------------------ train feed
 def gather_triples(d_triples, d_perm=None):
     _dev(d_triples, torch.int32, "triples")

@@ -1,10 +1,13 @@
-"""Pair-wise negative sampler with the reference's class name and config keys
+"""Negative sampler with the reference's class name and config keys
 (daisy/utils/sampler.py:3-103), computed on the device through the C ABI.
 
-Reference semantics kept bit for bit in the uniform + pair-wise branch: per USER, ``num_ng``
-draws (with replacement) from the sorted complement of the user's train positives, using numpy's
-global legacy RandomState; every positive row is then paired with its user's negatives
-(``explode``).  The global numpy RNG is advanced exactly as the reference would advance it.
+Reference semantics kept bit for bit: per USER, ``num_ng`` draws (with replacement) using numpy's
+global legacy RandomState -- uniform over the sorted complement of the user's train positives
+(:84-89), or, for ``sample_method`` 'low-pop' / 'high-pop', ``num_ng - int(sample_ratio*num_ng)``
+such draws followed by popularity-weighted draws over all items (:43-53, :64-81); every positive
+row is then paired with its user's negatives (``explode``): [T,3] triples for BPR / HL / TL
+(:99-101), or positives-then-negatives labelled rows for CL / SL (:93-98).  The global numpy RNG is
+advanced exactly as the reference would advance it.
 """
 import numpy as np
 import torch
@@ -59,22 +62,56 @@ class BasicNegtiveSampler(AbstractSampler):
         assert self.sample_method in ['uniform', 'low-pop', 'high-pop'], f'Invalid sampling method: {self.sample_method}'
         assert 0 <= self.sample_ratio <= 1, 'Invalid sample ratio value'
         self.df = df
+        self.pop_prob = None
+        if self.sample_method in ['high-pop', 'low-pop']:          # sampler.py:43-53
+            cnt = np.bincount(np.asarray(df[self.iid_name].values, dtype=np.int64), minlength=self.item_num)
+            seen = cnt > 0
+            pop = cnt[seen] / cnt.sum()                            # groupby(item).size() rescaled to [0, 1]
+            if self.sample_method == 'high-pop':
+                norm_pop = np.zeros(self.item_num)
+                norm_pop[seen] = pop
+            else:
+                norm_pop = np.ones(self.item_num)
+                norm_pop[seen] = 1 - pop
+            self.pop_prob = norm_pop / norm_pop.sum()
+
+    def _pointwise(self, d_coo_u, d_coo_i, d_js):
+        """CL / SL rows (sampler.py:58-59, :93-98): positives (u, i, rating) then negatives (u, j, 0), int32."""
+        label = np.ascontiguousarray(self.df[self.inter_name].values).astype(np.int32)
+        d_rows = ops.sampler_explode_pointwise(d_coo_u, d_coo_i, torch.from_numpy(label).cuda(), d_js)
+        out = d_rows.cpu().numpy().view(TripleArray)
+        out._drb_device = d_rows
+        return out
 
     def sampling(self):
+        if self.loss_type not in ('BPR', 'HL', 'TL', 'CL', 'SL'):
+            raise NotImplementedError
+        coo_u = np.ascontiguousarray(self.df[self.uid_name].values, dtype=np.int32)
+        coo_i = np.ascontiguousarray(self.df[self.iid_name].values, dtype=np.int32)
         if self.num_ng == 0:
+            if self.loss_type in ('CL', 'SL'):
+                ops.require_cuda()
+                d_js = torch.zeros((self.user_num, 0), dtype=torch.int32, device='cuda')
+                return self._pointwise(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
             raise NotImplementedError('loss function (BPR, TL, HL) need num_ng > 0')
-        if self.sample_method != 'uniform' or self.loss_type not in ('BPR', 'HL', 'TL'):
-            raise NotImplementedError(
-                'daisyrec_b200 accelerates the uniform pair-wise branch (sampler.py:84-89,99-101); '
-                f'sample_method={self.sample_method!r} / loss_type={self.loss_type!r} is outside the B200 hot path')
         ops.require_cuda()
         U, I, G = self.user_num, self.item_num, self.num_ng
         row_ptr, col = self.csr if self.csr is not None else csr_from_ur(self.ur, U)
-        coo_u = np.ascontiguousarray(self.df[self.uid_name].values, dtype=np.int32)
-        coo_i = np.ascontiguousarray(self.df[self.iid_name].values, dtype=np.int32)
         d_row_ptr = torch.from_numpy(np.ascontiguousarray(row_ptr, np.int64)).cuda()
         d_col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).cuda()
-        if self.rng_engine == 'numpy':
+        if self.pop_prob is not None:
+            if self.rng_engine != 'numpy':
+                raise NotImplementedError("sampler_rng='philox' covers the uniform branch only")
+            other_num = int(self.sample_ratio * G)                 # sampler.py:65-66
+            state = ops.mt19937_from_numpy()
+            draws, u01 = ops.sampler_draw_mt19937_mixed(state, row_ptr, U, I, G - other_num, other_num)
+            ops.mt19937_to_numpy(state)
+            cdf = self.pop_prob.cumsum()                           # RandomState.choice(p=...) ahead of searchsorted
+            cdf /= cdf[-1]
+            d_js = ops.sampler_assemble_mixed(d_row_ptr, d_col, torch.from_numpy(draws).cuda(),
+                                              torch.from_numpy(cdf).cuda(), torch.from_numpy(u01).cuda(), I)
+            d_draws = None
+        elif self.rng_engine == 'numpy':
             state = ops.mt19937_from_numpy()
             draws = ops.sampler_draw_mt19937(state, row_ptr, U, I, G)         # host: sequential MT19937 words
             ops.mt19937_to_numpy(state)                                       # numpy's stream moves on as in the reference
@@ -84,9 +121,12 @@ class BasicNegtiveSampler(AbstractSampler):
             d_draws, bad = ops.sampler_draw_philox(seed, 0, d_row_ptr, U, I, G)
             if int(bad.item()) < U:
                 raise ValueError("'a' cannot be empty unless no samples are taken")
-        d_js = ops.sampler_kth_complement(d_row_ptr, d_col, d_draws, I)
-        d_tr = ops.sampler_explode(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
+        if d_draws is not None:
+            d_js = ops.sampler_kth_complement(d_row_ptr, d_col, d_draws, I)
         self.js = d_js
+        if self.loss_type in ('CL', 'SL'):
+            return self._pointwise(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
+        d_tr = ops.sampler_explode(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
         out = d_tr.cpu().numpy().view(TripleArray)
         out._drb_device = d_tr
         return out

@@ -44,6 +44,10 @@ extern "C" {
 #define DRB_LOSS_BPR 0        /* BPRLoss   daisy/utils/loss.py:5-13   -log(1e-10 + sigmoid(pos - neg))           */
 #define DRB_LOSS_HL 1         /* HingeLoss daisy/utils/loss.py:16-23  clamp(1 - (pos - neg), min=0)    (MF only)  */
 #define DRB_LOSS_TL 2         /* TOP1Loss  daisy/utils/loss.py:26-33  sigmoid(neg - pos) + sigmoid(neg^2) (MF only) */
+/* point-wise branch of MF.calc_loss (MFRecommender.py:75-81): the third index plane (d_bj) holds the int label
+ * (sampler.py:93-98), only P_u and Q_i are scored and regularised; MF only, single GPU, no fused sampler */
+#define DRB_LOSS_CL 3         /* nn.BCEWithLogitsLoss(reduction='sum')  AbstractRecommender.py:79-80 */
+#define DRB_LOSS_SL 4         /* nn.MSELoss(reduction='sum')            AbstractRecommender.py:81-82 */
 
 typedef struct drb_hyper {
     float lr;                 /* config['lr']                                                      */
@@ -84,6 +88,22 @@ int drb_sampler_explode(const int32_t *d_coo_u, const int32_t *d_coo_i, int64_t 
 int drb_sample_triples_host(uint32_t *h_state625, const int64_t *h_row_ptr, const int32_t *h_col,
                             const int32_t *h_coo_u, const int32_t *h_coo_i, int64_t nnz, int32_t user_num,
                             int32_t item_num, int32_t num_ng, int32_t *h_js, int32_t *h_triples, int32_t *bad_user);
+
+/* popularity-mixed branch, sample_method 'low-pop' / 'high-pop' (sampler.py:43-53,64-81): per user first
+ * uniform_num = num_ng - int(sample_ratio*num_ng) uniform ranks as above, then other_num weighted draws
+ * np.random.choice(arange(item_num), p=pop_prob) = searchsorted(cdf, random_sample(), 'right') with
+ * cdf = pop_prob.cumsum() / cdf[-1] (RandomState.choice).  The host call replays the word stream (ranks +
+ * 53-bit doubles, two words each); the device call turns both into the js table [user_num, uniform_num+other_num]. */
+int drb_sampler_draw_mt19937_mixed(uint32_t *h_state625, const int64_t *h_row_ptr, int32_t user_num, int32_t item_num,
+                                   int32_t uniform_num, int32_t other_num, int32_t *h_draws, double *h_u01,
+                                   int32_t *bad_user);
+int drb_sampler_assemble_mixed(const int64_t *d_row_ptr, const int32_t *d_col, const int32_t *d_draws,
+                               const double *d_cdf, const double *d_u01, int32_t user_num, int32_t item_num,
+                               int32_t uniform_num, int32_t other_num, int32_t *d_js, void *stream);
+/* point-wise explode, loss_type CL / SL (sampler.py:93-98): int32 [nnz*(1+G), 3] = the nnz positive rows
+ * (u, i, label) followed by the nnz*G negative rows (u, js[u,g], 0). */
+int drb_sampler_explode_pointwise(const int32_t *d_coo_u, const int32_t *d_coo_i, const int32_t *d_label, int64_t nnz,
+                                  const int32_t *d_js, int32_t num_ng, int32_t *d_rows, void *stream);
 
 /* ---- candidate sets for ranking: build_candidates_set ------------------------------------
  * daisy/utils/utils.py:53-85.  Per test user the reference draws cand_num-|gt| ids from the
@@ -252,6 +272,32 @@ int drb_mf_predict(const float *d_P, const float *d_Q, int32_t factors, const in
                    int64_t n, float *d_out, void *stream);
 int drb_mf_rank_host(const float *d_P, const float *d_Q, int32_t factors, const int64_t *h_users, int64_t n_users,
                      const int64_t *h_cands, int32_t cand_num, int32_t topk, float *h_out);
+
+/* ---- evaluation: calc_ranking_results / Metric.run ------------------------------------------------
+ * daisy/utils/metrics.py:18-57 (cut-off loop), :59-96 (dispatch), :98-251 (the KPIs).
+ * d_preds: rank()'s float32 [n_users, ld] output; ground truth as CSR aligned with its rows
+ * (gt_ptr i64[n_users+1], gt_idx i32 ascending inside a row = sorted(test_ur[test_u[row]])).
+ * h_ks[nk]: the cut-offs (common_ks of :41-43), each in [1, min(ld, 256)], nk <= 8.
+ * d_out: double [nk, DRB_KPI_COUNT], the np.mean over users of each KPI at each cut-off (fp64 like the
+ * reference; in1d semantics: duplicate ids in a list each count).  Coverage counts distinct ids in
+ * [0, item_num); Popularity needs d_item_pop (double [item_num], loader.py:191-194), NULL leaves it 0. */
+#define DRB_KPI_RECALL 0      /* metrics.py:170-180 */
+#define DRB_KPI_MRR 1         /* :182-196 */
+#define DRB_KPI_NDCG 2        /* :215-238 */
+#define DRB_KPI_HIT 3         /* :240-251 */
+#define DRB_KPI_PRECISION 4   /* :158-168 */
+#define DRB_KPI_MAP 5         /* :198-213 */
+#define DRB_KPI_COVERAGE 6    /* :98-102  */
+#define DRB_KPI_POPULARITY 7  /* :104-122 */
+#define DRB_KPI_COUNT 8
+size_t drb_rank_metrics_workspace_bytes(int32_t item_num, int32_t nk);
+int drb_rank_metrics(const float *d_preds, int64_t n_users, int32_t ld, const int64_t *d_gt_ptr,
+                     const int32_t *d_gt_idx, const int32_t *h_ks, int32_t nk, int32_t item_num,
+                     const double *d_item_pop, void *d_ws, double *d_out, void *stream);
+/* host-buffer form (numpy in, numpy out: the signature calc_ranking_results is called with) */
+int drb_rank_metrics_host(const float *h_preds, int64_t n_users, int32_t ld, const int64_t *h_gt_ptr,
+                          const int32_t *h_gt_idx, const int32_t *h_ks, int32_t nk, int32_t item_num,
+                          const double *h_item_pop, double *h_out);
 
 #ifdef __cplusplus
 }

@@ -269,13 +269,32 @@ typedef struct {
     float lr, reg_1, reg_2;
     int32_t opt;
     float beta1, beta2, eps;
-    int32_t loss; /* 0 BPR (loss.py:5-13), 1 HL = HingeLoss (loss.py:16-23), 2 TL = TOP1Loss (loss.py:26-33) */
+    int32_t loss; /* 0 BPR (loss.py:5-13), 1 HL = HingeLoss (loss.py:16-23), 2 TL = TOP1Loss (loss.py:26-33);
+                   * point-wise branch of MF.calc_loss (MFRecommender.py:75-81), batch[2] = label:
+                   * 3 CL = nn.BCEWithLogitsLoss(reduction='sum'), 4 SL = nn.MSELoss(reduction='sum')
+                   * (AbstractRecommender.py:79-82) */
 } orc_hyper;
 
 /* pairwise loss term and its derivatives w.r.t. the positive / negative score */
 static float pair_loss(int kind, float pos, float neg, float *cp, float *cn)
 {
     const float gamma = 1e-10f;
+    if (kind == 3) {                       /* point-wise, neg carries the label y.  ATen binary_cross_entropy_with_logits:
+                                            * (1 - y) x - log_sigmoid(x), log_sigmoid(x) = min(x,0) - log1p(exp(-|x|));
+                                            * log_sigmoid_backward: x < 0 ? 1 - z/(1+z) : z/(1+z), z = exp(-|x|) */
+        float x = pos, y = neg, z = expf(-fabsf(x));
+        float logsig = fminf(x, 0.f) - log1pf(z);
+        float dls = x < 0.f ? 1.f - z / (1.f + z) : z / (1.f + z);
+        *cp = (1.f - y) - dls;
+        *cn = 0.f;
+        return (1.f - y) * x - logsig;
+    }
+    if (kind == 4) {                       /* point-wise MSE: (x - y)^2 */
+        float d = pos - neg;
+        *cp = 2.f * d;
+        *cn = 0.f;
+        return d * d;
+    }
     if (kind == 1) {                       /* clamp(1 - (pos - neg), min=0); clamp's backward passes at equality */
         float m = 1.f - (pos - neg);
         *cp = (m >= 0.f) ? -1.f : 0.f;
@@ -319,17 +338,20 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
 {
     float *coef = (float *)malloc(sizeof(float) * 2 * (size_t)(B > 0 ? B : 1));
     double bpr = 0.0, l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
+    const int pw = h->loss >= 3;           /* point-wise: bj holds labels, only P_u and Q_i are regularised (:79-80,:94-95) */
     for (int64_t t = 0; t < B; t++) {
-        const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = Q + (int64_t)bj[t] * F;
-        float pos = orc_dot(p, qi, F), neg = orc_dot(p, qj, F);
+        const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = pw ? NULL : Q + (int64_t)bj[t] * F;
+        float pos = orc_dot(p, qi, F), neg = pw ? (float)bj[t] : orc_dot(p, qj, F);
         bpr += (double)pair_loss(h->loss, pos, neg, &coef[2 * t], &coef[2 * t + 1]);
         for (int f = 0; f < F; f++) {
             l1u += fabsf(p[f]);
             s2u += (double)(p[f] * p[f]);
             l1i += fabsf(qi[f]);
             s2i += (double)(qi[f] * qi[f]);
-            l1j += fabsf(qj[f]);
-            s2j += (double)(qj[f] * qj[f]);
+            if (!pw) {
+                l1j += fabsf(qj[f]);
+                s2j += (double)(qj[f] * qj[f]);
+            }
         }
     }
     double nu = sqrt(s2u), ni = sqrt(s2i), nj = sqrt(s2j);
@@ -352,9 +374,19 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
     float inu = nu > 0 ? (float)(1.0 / nu) : 0.f, ini = ni > 0 ? (float)(1.0 / ni) : 0.f,
           inj = nj > 0 ? (float)(1.0 / nj) : 0.f;
     for (int64_t t = 0; t < B; t++) {
-        const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = Q + (int64_t)bj[t] * F;
-        double *gu = gP + (int64_t)bu[t] * F, *gi = gQ + (int64_t)bi[t] * F, *gj = gQ + (int64_t)bj[t] * F;
+        const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F;
+        double *gu = gP + (int64_t)bu[t] * F, *gi = gQ + (int64_t)bi[t] * F;
         float cp = coef[2 * t], cn = coef[2 * t + 1];
+        if (pw) {
+            for (int f = 0; f < F; f++) {
+                float sp = (p[f] > 0) - (p[f] < 0), si = (qi[f] > 0) - (qi[f] < 0);
+                gu[f] += (double)(cp * qi[f]) + (double)(h->reg_1 * sp) + (double)(h->reg_2 * p[f] * inu);
+                gi[f] += (double)(cp * p[f]) + (double)(h->reg_1 * si) + (double)(h->reg_2 * qi[f] * ini);
+            }
+            continue;
+        }
+        const float *qj = Q + (int64_t)bj[t] * F;
+        double *gj = gQ + (int64_t)bj[t] * F;
         for (int f = 0; f < F; f++) {
             float sp = (p[f] > 0) - (p[f] < 0), si = (qi[f] > 0) - (qi[f] < 0), sj = (qj[f] > 0) - (qj[f] < 0);
             double du = (h->loss == 0) ? (double)(cp * (qi[f] - qj[f])) : (double)(cp * qi[f]) + (double)(cn * qj[f]);

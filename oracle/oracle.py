@@ -25,7 +25,7 @@ class Hyper(C.Structure):
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("loss", C.c_int32)]
 
 
-LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2}
+LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2, "CL": 3, "SL": 4}
 
 
 def hyper(lr=0.01, reg_1=0.001, reg_2=0.001, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8, loss="BPR"):

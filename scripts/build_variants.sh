@@ -12,7 +12,7 @@ done
 wait
 for cfg in "$@"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o daisyrec_b200/lib/variants/lib_${cfg}.so \
-       daisyrec_b200/lib/variants/mf_bpr_${cfg}.o daisyrec_b200/lib/capi.o daisyrec_b200/lib/sampler.o daisyrec_b200/lib/rank.o daisyrec_b200/lib/shard.o daisyrec_b200/lib/lightgcn.o daisyrec_b200/lib/neumf.o
+       daisyrec_b200/lib/variants/mf_bpr_${cfg}.o daisyrec_b200/lib/capi.o daisyrec_b200/lib/sampler.o daisyrec_b200/lib/rank.o daisyrec_b200/lib/shard.o daisyrec_b200/lib/lightgcn.o daisyrec_b200/lib/neumf.o daisyrec_b200/lib/comm.o daisyrec_b200/lib/metrics.o -ldl
   rm daisyrec_b200/lib/variants/mf_bpr_${cfg}.o
 done
 ls daisyrec_b200/lib/variants

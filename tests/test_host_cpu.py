@@ -139,3 +139,55 @@ def test_loader_plan_decoding():
     torch.manual_seed(7)
     perm = epoch_permutation(10, True)
     assert [int(x) for x in first[0]] == data[perm[:4].numpy(), 0].tolist()
+
+
+def test_host_mixed_draws_replay_reference_fixture():
+    """drb_sampler_draw_mt19937_mixed (host part of the 'low-pop' / 'high-pop' branch, sampler.py:64-81): ranks and
+    doubles off numpy's stream; the device lookups are restated with numpy here (setdiff1d / searchsorted)."""
+    import pandas as pd
+    from daisyrec_b200 import ops
+    from daisyrec_b200.utils.sampler import BasicNegtiveSampler, csr_from_ur
+    from daisyrec_b200.utils.utils import get_ur
+    g = golden("sampler_pop")
+    for c in range(int(g["ncases"])):
+        method, loss = str(g[f"c{c}_method"]), str(g[f"c{c}_loss"])
+        if method == "uniform" or loss != "BPR":
+            continue
+        U, I, G, seed = (int(v) for v in g[f"c{c}_meta"])
+        df = pd.DataFrame({"user": g[f"c{c}_coo_u"], "item": g[f"c{c}_coo_i"], "rating": g[f"c{c}_rating"]})
+        ur = get_ur(df)
+        cfg = dict(UID_NAME='user', IID_NAME='item', INTER_NAME='rating', user_num=U, item_num=I, num_ng=G,
+                   sample_method=method, sample_ratio=float(g[f"c{c}_ratio"]), loss_type=loss, train_ur=ur)
+        smp = BasicNegtiveSampler(df, cfg)
+        assert np.array_equal(smp.pop_prob, g[f"c{c}_pop_prob"])
+        other = int(float(g[f"c{c}_ratio"]) * G)
+        row_ptr, col = csr_from_ur(ur, U)
+        st = ops.mt19937_seed(seed)
+        draws, u01 = ops.sampler_draw_mt19937_mixed(st, row_ptr, U, I, G - other, other)
+        cdf = smp.pop_prob.cumsum()
+        cdf /= cdf[-1]
+        js = np.zeros((U, G), np.int32)
+        for u in range(U):
+            comp = np.setdiff1d(np.arange(I), col[row_ptr[u]:row_ptr[u + 1]])
+            js[u, :G - other] = comp[draws[u]]
+            js[u, G - other:] = cdf.searchsorted(u01[u], side='right')
+        rows = g[f"c{c}_rows"]
+        assert np.array_equal(js[rows[:, 0], np.tile(np.arange(G), len(rows) // G)], rows[:, 2])
+        ops.mt19937_to_numpy(st)
+        assert np.array_equal(np.random.randint(0, 2 ** 31 - 1, size=3), g[f"c{c}_next"])
+
+
+def test_metrics_mirror_host_logic():
+    from daisyrec_b200.utils.metrics import ground_truth_csr, calc_ranking_results, Metric, metrics_name_config
+    test_ur = {7: {5, 1, 9}, 3: {2}, 11: set()}
+    ptr, idx = ground_truth_csr(test_ur, [3, 7, 11])
+    assert ptr.tolist() == [0, 1, 4, 4] and idx.tolist() == [2, 1, 5, 9] and idx.dtype == np.int32
+    assert metrics_name_config["hit"] == 'Hit Ratio'
+    import logging, tempfile
+    cfg = dict(logger=logging.getLogger("t"), res_path=tempfile.mkdtemp() + "/", item_num=10, topk=5)
+    with pytest.raises(KeyError):                                      # 'map' has no display name (metrics.py:5-16,38)
+        calc_ranking_results(test_ur, np.zeros((3, 5), np.float32), [3, 7, 11], dict(cfg, metrics=["map"]))
+    with pytest.raises(ValueError):                                    # 'f1' / 'auc' are unreachable (metrics.py:87-92)
+        Metric(dict(cfg, metrics=["f1"])).run(test_ur, np.zeros((3, 5), np.float32), [3, 7, 11])
+    with pytest.raises(RuntimeError):                                  # no CPU fallback for the KPIs either
+        Metric(dict(cfg, metrics=["recall"])).run(test_ur, np.zeros((3, 5), np.float32), [3, 7, 11])
