@@ -18,7 +18,8 @@ c_f64p = C.POINTER(C.c_double)
 vp = C.c_void_p
 
 DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_NAN_LOSS, DRB_ERR_EMPTY_SET, DRB_ERR_NO_DEVICE = range(6)
-OPT_SGD, OPT_ADAM = 0, 1
+OPT_SGD, OPT_ADAM, OPT_ADAGRAD, OPT_RMSPROP = 0, 1, 2, 3
+OPT_KIND = {"sgd": 0, "adam": 1, "adagrad": 2, "rmsprop": 3}
 LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2, "CL": 3, "SL": 4}
 
 

@@ -112,7 +112,9 @@ __device__ __forceinline__ void apply_row(float *theta_row, float *g_row, float 
 // Dense phase-2 sweep: lane groups walk ALL rows of P then Q, R rows in flight each.  Counter, theta
 // and gradient accumulator of the R rows are loaded unconditionally and up front (one memory round
 // trip instead of three dependent ones); an untouched SGD row has cnt == 0 and g == 0, so nothing is
-// written for it.  Adam moves every row (dense optimiser semantics of the reference).
+// written for it.  Adam moves every row (dense optimiser semantics of the reference).  Adagrad / RMSprop
+// (AbstractRecommender.py:57-60, torch defaults) keep ONE state row in the m slot: Adagrad leaves an untouched row
+// alone (g = 0 adds nothing), RMSprop's running square of an untouched row still decays by alpha.
 template <int VEC, int W, int NCH, int OPT>
 __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm, const AdamCoef &ac, int gl, int group,
                                             int groups_per_cta, int chunks)
@@ -139,17 +141,19 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
             if (act[k]) cnt[k] = is_user[k] ? (unsigned long long)__ldcg(p.ws.cntU + it) : __ldcg(p.ws.cntI + it);
             th[k] = load_row<VEC, W, NCH>(th_p[k], gl, chunks, act[k]);
             g[k] = load_row<VEC, W, NCH>(g_p[k], gl, chunks, act[k]);
-            if constexpr (OPT == DRB_OPT_ADAM) {
+            if constexpr (OPT != DRB_OPT_SGD) {
                 m_p[k] = (is_user[k] ? p.ws.mP : p.ws.mQ) + o;
-                v_p[k] = (is_user[k] ? p.ws.vP : p.ws.vQ) + o;
                 m[k] = load_row<VEC, W, NCH>(m_p[k], gl, chunks, act[k]);
+            }
+            if constexpr (OPT == DRB_OPT_ADAM) {
+                v_p[k] = (is_user[k] ? p.ws.vP : p.ws.vQ) + o;
                 v[k] = load_row<VEC, W, NCH>(v_p[k], gl, chunks, act[k]);
             }
         }
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const bool touched = cnt[k] != 0;
-            if (!act[k] || (OPT == DRB_OPT_SGD && !touched && !p.dense_grad)) continue;
+            if (!act[k] || ((OPT == DRB_OPT_SGD || OPT == DRB_OPT_ADAGRAD) && !touched && !p.dense_grad)) continue;
             const float ca = (float)(unsigned)(cnt[k] & 0xffffffffull), cb = p.neg_mult * (float)(unsigned)(cnt[k] >> 32);
             const float ia = is_user[k] ? nm.inv_u : nm.inv_i, ib = nm.inv_j;
 #pragma unroll
@@ -166,6 +170,14 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
                     }
                     if constexpr (OPT == DRB_OPT_SGD) {
                         t.v[e] = x - p.lr * gg;
+                    } else if constexpr (OPT == DRB_OPT_ADAGRAD) {   // sum += g^2; theta -= lr g / (sqrt(sum) + 1e-10)
+                        float ss = m[k].c[ch].v[e] + gg * gg;
+                        t.v[e] = x - p.lr * (gg / (sqrtf(ss) + 1e-10f));
+                        m[k].c[ch].v[e] = ss;
+                    } else if constexpr (OPT == DRB_OPT_RMSPROP) {   // sq = .99 sq + .01 g^2; theta -= lr g / (sqrt(sq) + 1e-8)
+                        float sq = m[k].c[ch].v[e] * 0.99f + (1.f - 0.99f) * gg * gg;
+                        t.v[e] = x - p.lr * (gg / (sqrtf(sq) + 1e-8f));
+                        m[k].c[ch].v[e] = sq;
                     } else {
                         float mm = m[k].c[ch].v[e], vv = v[k].c[ch].v[e];
                         mm = mm + (gg - mm) * (1.f - p.beta1);
@@ -177,10 +189,8 @@ __device__ __forceinline__ void dense_sweep(const StepParams &p, const Norms &nm
                     }
                 }
                 st_row<VEC>(th_p[k] + c * VEC, t);
-                if constexpr (OPT == DRB_OPT_ADAM) {
-                    st_row<VEC>(m_p[k] + c * VEC, m[k].c[ch]);
-                    st_row<VEC>(v_p[k] + c * VEC, v[k].c[ch]);
-                }
+                if constexpr (OPT != DRB_OPT_SGD) st_row<VEC>(m_p[k] + c * VEC, m[k].c[ch]);
+                if constexpr (OPT == DRB_OPT_ADAM) st_row<VEC>(v_p[k] + c * VEC, v[k].c[ch]);
                 if (touched) {
                     Vec<VEC> z;
 #pragma unroll
@@ -496,12 +506,18 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                 ac.bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, t));
             }
             const bool dense = p.dense_hint >= 0 ? (p.dense_hint != 0)
-                                                 : ((p.opt == DRB_OPT_ADAM) || (3 * nb >= ((long long)p.U + p.I) / 4));
-            if (dense) {
+                                                 : ((p.opt != DRB_OPT_SGD) || (3 * nb >= ((long long)p.U + p.I) / 4));
+            if (dense || p.opt != DRB_OPT_SGD) {   // stateful optimisers always sweep (claim mode is SGD only)
                 if (p.opt == DRB_OPT_SGD)
                     dense_sweep<VEC, W, NCH, DRB_OPT_SGD>(p, nm, ac, gl, group, GROUPS, chunks);
-                else
+                else if (p.opt == DRB_OPT_ADAM)
                     dense_sweep<VEC, W, NCH, DRB_OPT_ADAM>(p, nm, ac, gl, group, GROUPS, chunks);
+                else if constexpr (GEN) {          // launch_steps routes these two to the GEN instantiation
+                    if (p.opt == DRB_OPT_ADAGRAD)
+                        dense_sweep<VEC, W, NCH, DRB_OPT_ADAGRAD>(p, nm, ac, gl, group, GROUPS, chunks);
+                    else
+                        dense_sweep<VEC, W, NCH, DRB_OPT_RMSPROP>(p, nm, ac, gl, group, GROUPS, chunks);
+                }
             } else {
                 // claim mode (SGD only): the first group to swap a row's counter to zero applies it
                 for (long long t0 = (long long)blockIdx.x * tile; t0 < nb; t0 += (long long)gridDim.x * tile) {
@@ -594,7 +610,8 @@ static StepKernel pick_kernel(int F, bool gen)
 
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
-    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR);
+    // GEN instantiation: any loss but BPR, and the Adagrad / RMSprop sweeps (kept out of the hot BPR + SGD/Adam kernel)
+    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM);
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
     // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
     // split multi-GPU / LightGCN / NeuMF paths)
@@ -618,7 +635,7 @@ int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
     long long tiles = (p.batch + tile - 1) / tile;
     long long rows_work = ((long long)p.U + p.I + 63) / 64;
     bool dense = p.dense_hint >= 0 ? (p.dense_hint != 0)
-                                   : ((p.opt == DRB_OPT_ADAM) || (3 * p.batch >= ((long long)p.U + p.I) / 4));
+                                   : ((p.opt != DRB_OPT_SGD) || (3 * p.batch >= ((long long)p.U + p.I) / 4));
     long long want_grid = (dense && p.apply) ? (tiles > rows_work ? tiles : rows_work) : tiles;
     int grid = (int)(want_grid < 1 ? 1 : (want_grid > max_grid ? max_grid : want_grid));
     if (p.phases & 1)
@@ -665,7 +682,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
 {
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
-    DRB_REQUIRE(h->opt == DRB_OPT_SGD || h->opt == DRB_OPT_ADAM, "unknown optimizer id %d", h->opt);
+    DRB_REQUIRE(h->opt >= DRB_OPT_SGD && h->opt <= DRB_OPT_RMSPROP, "unknown optimizer id %d", h->opt);
     DRB_REQUIRE(h->loss >= DRB_LOSS_BPR && h->loss <= DRB_LOSS_SL, "unknown loss id %d", h->loss);
     DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0 || n == 0, "steps [%lld,%lld) exceed %lld triples", first,
                 first + nsteps, n);

@@ -40,11 +40,11 @@ inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w)
     t.cntU = (unsigned *)take(sizeof(unsigned) * (size_t)U);
     t.cntI = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)I);
     t.mP = t.vP = t.mQ = t.vQ = nullptr;
-    if (opt == DRB_OPT_ADAM) {
+    if (opt != DRB_OPT_SGD) {  // Adam: m and v; Adagrad / RMSprop: one state table each, in the m slot
         t.mP = (float *)take(sizeof(float) * (size_t)U * F);
-        t.vP = (float *)take(sizeof(float) * (size_t)U * F);
+        if (opt == DRB_OPT_ADAM) t.vP = (float *)take(sizeof(float) * (size_t)U * F);
         t.mQ = (float *)take(sizeof(float) * (size_t)I * F);
-        t.vQ = (float *)take(sizeof(float) * (size_t)I * F);
+        if (opt == DRB_OPT_ADAM) t.vQ = (float *)take(sizeof(float) * (size_t)I * F);
     }
     if (w) *w = t;
     return off;

@@ -118,13 +118,18 @@ class AbstractRecommender(object):
     def eval(self):
         return self.train(False)
 
+    SUPPORTED_OPTIMIZERS = ('sgd', 'adam')
+
     def _optimizer_name(self):
         """AbstractRecommender.py:48-67: unknown names fall back to Adam with a log line."""
         name = str(self.optimizer).lower()
-        if name in ('sgd', 'adam'):
+        if name in self.SUPPORTED_OPTIMIZERS:
             return name
-        if name in ('adagrad', 'rmsprop', 'sparse_adam'):
-            raise NotImplementedError(f"optimizer '{name}' is outside the B200 hot path (sgd / adam are native)")
+        if name == 'sparse_adam':       # what optim.SparseAdam.step() raises on nn.Embedding's dense gradients (:61-62)
+            raise RuntimeError('SparseAdam does not support dense gradients, please consider Adam instead')
+        if name in ('adagrad', 'rmsprop'):
+            raise NotImplementedError(f"optimizer '{name}' is outside the B200 hot path of {type(self).__name__} "
+                                      f"(native: {', '.join(self.SUPPORTED_OPTIMIZERS)})")
         if self.logger is not None:
             self.logger.info('Received unrecognized optimizer, set default Adam optimizer')
         return 'adam'
@@ -164,91 +169,6 @@ class GeneralRecommender(AbstractRecommender):
 
     def _loader_plan(self, train_loader):
         return loader_plan(train_loader)
-
-    def fit(self, train_loader):
-        raise NotImplementedError
-
-    def rank(self, test_loader):
-        raise NotImplementedError
-
-    def full_rank(self, u):
-        raise NotImplementedError
-
-    def predict(self, u, i):
-        raise NotImplementedError
-
-    # -- nn.Module look-alikes used by drivers
-    def train(self, mode=True):
-        self.training = mode
-        return self
-
-    def eval(self):
-        return self.train(False)
-
-    def _optimizer_name(self):
-        """AbstractRecommender.py:48-67: unknown names fall back to Adam with a log line."""
-        name = str(self.optimizer).lower()
-        if name in ('sgd', 'adam'):
-            return name
-        if name in ('adagrad', 'rmsprop', 'sparse_adam'):
-            raise NotImplementedError(f"optimizer '{name}' is outside the B200 hot path (sgd / adam are native)")
-        if self.logger is not None:
-            self.logger.info('Received unrecognized optimizer, set default Adam optimizer')
-        return 'adam'
-
-    SUPPORTED_LOSSES = ('BPR',)
-
-    def _check_loss_type(self):
-        lt = str(self.loss_type).upper()
-        if lt in self.SUPPORTED_LOSSES:
-            return
-        if lt in ('CL', 'SL', 'HL', 'TL', 'BPR'):
-            raise NotImplementedError(f"loss_type '{lt}' is outside the B200 hot path of {type(self).__name__} "
-                                      f"(native: {', '.join(self.SUPPORTED_LOSSES)})")
-        raise NotImplementedError(f'Invalid loss type: {self.loss_type}...')
-
-
-class GeneralRecommender(AbstractRecommender):
-    def __init__(self, config):
-        super().__init__()
-        gpu = str(config.get('gpu', '') or '')
-        if gpu and not torch.cuda.is_initialized() and 'LOCAL_RANK' not in os.environ:
-            os.environ['CUDA_VISIBLE_DEVICES'] = gpu             # AbstractRecommender.py:99
-        ops.require_cuda()
-        local = int(os.environ.get('LOCAL_RANK', torch.cuda.current_device()))
-        self.device = torch.device('cuda', local if local < torch.cuda.device_count() else 0)
-        torch.cuda.set_device(self.device)
-        self.logger = config['logger']
-        self.steps_per_launch = int(config.get('steps_per_launch', 0))   # 0 = whole epoch in one launch
-        self.show_progress = bool(config.get('progress', True))
-        # 'torch' (default): the DataLoader's own CPU permutation -> the reference's batches bit for bit;
-        # 'device': torch.randperm on the GPU seeded from the global RNG (same distribution, no 8-byte/triple H2D)
-        self.shuffle_engine = str(config.get('shuffle_engine', 'torch'))
-        # one process per GPU (torchrun): user-sharded training / ranking, see daisyrec_b200/parallel.py
-        import torch.distributed as dist
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.rank_id = dist.get_rank() if self.world > 1 else 0
-
-    # subclasses provide: _tables() -> (P, Q); _hyper(); _workspace()
-    def _loader_plan(self, train_loader):
-        """Decode a DataLoader into (triples ndarray, batch_size, shuffle, drop_last) or None."""
-        ds = getattr(train_loader, 'dataset', None)
-        data = getattr(ds, 'data', None)
-        bs = getattr(train_loader, 'batch_size', None)
-        if not isinstance(data, np.ndarray) or data.ndim != 2 or data.shape[1] != 3 or bs is None:
-            return None
-        sampler = getattr(train_loader, 'sampler', None)
-        if not isinstance(getattr(train_loader, 'batch_sampler', None), BatchSampler):
-            return None
-        if isinstance(sampler, RandomSampler) and not sampler.replacement and sampler._num_samples is None:
-            shuffle, gen = True, sampler.generator
-        elif isinstance(sampler, SequentialSampler):
-            shuffle, gen = False, None
-        else:
-            return None
-        if gen is not None:
-            return None
-        return data, int(bs), shuffle, bool(train_loader.drop_last), train_loader.generator
 
     def fit(self, train_loader):
         self._check_loss_type()

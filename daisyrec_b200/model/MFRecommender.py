@@ -20,6 +20,7 @@ from .AbstractRecommender import GeneralRecommender, _Table, _init_table, _INIT
 class MF(GeneralRecommender):
     # the pair-wise criteria of AbstractRecommender.py:83-88 and the point-wise ones of :79-82 (batch[2] = label)
     SUPPORTED_LOSSES = ('BPR', 'HL', 'TL', 'CL', 'SL')
+    SUPPORTED_OPTIMIZERS = ('sgd', 'adam', 'adagrad', 'rmsprop')     # AbstractRecommender.py:53-60
 
     def __init__(self, config):
         """Same keys as the reference (MFRecommender.py:46-59): lr, reg_1, reg_2, epochs, topk,

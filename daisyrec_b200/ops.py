@@ -31,7 +31,7 @@ def require_cuda():
 
 
 def hyper(lr, reg_1, reg_2, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8, loss="BPR"):
-    return L.Hyper(lr, reg_1, reg_2, L.OPT_SGD if opt == "sgd" else L.OPT_ADAM, beta1, beta2, eps, L.LOSS_KIND[loss.upper()])
+    return L.Hyper(lr, reg_1, reg_2, L.OPT_KIND[opt], beta1, beta2, eps, L.LOSS_KIND[loss.upper()])
 
 
 def device_query():
@@ -220,11 +220,12 @@ def gather_triples(d_triples, d_perm=None):
 
 # ------------------------------------------------------------------ training
 class MFWorkspace:
-    """Device scratch of the step kernel: gradient accumulators, row counters, Adam moments."""
+    """Device scratch of the step kernel: gradient accumulators, row counters, optimiser state (Adam m, v; Adagrad /
+    RMSprop one table)."""
 
     def __init__(self, user_num, item_num, factors, opt, device):
         self.U, self.I, self.F = user_num, item_num, factors
-        self.opt = L.OPT_SGD if opt == "sgd" else L.OPT_ADAM
+        self.opt = L.OPT_KIND[opt]
         nbytes = L.lib().drb_mf_workspace_bytes(user_num, item_num, factors, self.opt)
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.reset()

@@ -40,6 +40,8 @@ extern "C" {
 
 #define DRB_OPT_SGD 0         /* optim.SGD(lr)   AbstractRecommender.py:55-56                     */
 #define DRB_OPT_ADAM 1        /* optim.Adam(lr)  AbstractRecommender.py:53-54 (dense, torch defaults) */
+#define DRB_OPT_ADAGRAD 2     /* optim.Adagrad(lr) :57-58 (torch defaults; MF step only)          */
+#define DRB_OPT_RMSPROP 3     /* optim.RMSprop(lr) :59-60 (torch defaults, dense; MF step only)   */
 
 #define DRB_LOSS_BPR 0        /* BPRLoss   daisy/utils/loss.py:5-13   -log(1e-10 + sigmoid(pos - neg))           */
 #define DRB_LOSS_HL 1         /* HingeLoss daisy/utils/loss.py:16-23  clamp(1 - (pos - neg), min=0)    (MF only)  */

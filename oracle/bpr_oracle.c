@@ -260,7 +260,8 @@ void orc_mf_predict(const float *P, const float *Q, int32_t F, const int32_t *u,
  *                (norm == 0 -> zero subgradient; sgn(0) = 0)
  *   update       optim.SGD, no momentum / weight decay (AbstractRecommender.py:55-56,126):
  *                theta -= lr * g     -- or optim.Adam defaults (:53-54): dense, every row moves.
- * opt: 0 = SGD, 1 = Adam (state m,v are table-sized, step_count is the 1-based step).
+ * opt: 0 = SGD, 1 = Adam (state m,v are table-sized, step_count is the 1-based step), 2 = Adagrad, 3 = RMSprop
+ *      (MF only; one table-sized state each, kept in m).
  * apply: 0 = loss only (calc_loss), 1 = also update.
  * A NaN loss leaves the tables untouched and returns NaN (AbstractRecommender.py:122-123).
  * parts[8] (optional): bpr, l1_u, l1_i, l1_j, fro_u, fro_i, fro_j, total.
@@ -332,6 +333,31 @@ static void adam_dense(float *theta, float *m, float *v, const double *g, int64_
     }
 }
 
+/* torch.optim.Adagrad defaults (lr_decay 0, eps 1e-10, initial accumulator 0; AbstractRecommender.py:57-58):
+ *   sum += g*g; theta -= lr * g / (sqrt(sum) + eps)            -- state in m
+ * torch.optim.RMSprop defaults (alpha 0.99, eps 1e-8, no momentum, not centered; :59-60):
+ *   sq = alpha*sq + (1-alpha) g*g; theta -= lr * g / (sqrt(sq) + eps)   -- state in m; dense (sq of untouched rows decays) */
+static void adagrad_dense(float *theta, float *sum, const double *g, int64_t n, const orc_hyper *h)
+{
+    for (int64_t k = 0; k < n; k++) {
+        float gk = (float)g[k];
+        sum[k] = sum[k] + gk * gk;
+        float std = sqrtf(sum[k]) + 1e-10f;
+        theta[k] = theta[k] - h->lr * (gk / std);
+    }
+}
+
+static void rmsprop_dense(float *theta, float *sq, const double *g, int64_t n, const orc_hyper *h)
+{
+    const float alpha = 0.99f;
+    for (int64_t k = 0; k < n; k++) {
+        float gk = (float)g[k];
+        sq[k] = sq[k] * alpha + (1.f - alpha) * gk * gk;
+        float avg = sqrtf(sq[k]) + 1e-8f;
+        theta[k] = theta[k] - h->lr * (gk / avg);
+    }
+}
+
 double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, const int32_t *bu, const int32_t *bi,
                        const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP,
                        float *mQ, float *vQ, int64_t step_count, double *parts)
@@ -400,6 +426,12 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
             P[k] = P[k] - h->lr * (float)gP[k];
         for (int64_t k = 0; k < (int64_t)I * F; k++)
             Q[k] = Q[k] - h->lr * (float)gQ[k];
+    } else if (h->opt == 2) {
+        adagrad_dense(P, mP, gP, (int64_t)U * F, h);
+        adagrad_dense(Q, mQ, gQ, (int64_t)I * F, h);
+    } else if (h->opt == 3) {
+        rmsprop_dense(P, mP, gP, (int64_t)U * F, h);
+        rmsprop_dense(Q, mQ, gQ, (int64_t)I * F, h);
     } else {
         adam_dense(P, mP, vP, gP, (int64_t)U * F, h, step_count);
         adam_dense(Q, mQ, vQ, gQ, (int64_t)I * F, h, step_count);

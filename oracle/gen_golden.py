@@ -254,6 +254,51 @@ def gen_mf_pointwise():
     _save("mf_pointwise", **out)
 
 
+def gen_mf_optim():
+    """optim.Adagrad / optim.RMSprop (AbstractRecommender.py:57-60, torch defaults) behind MF.calc_loss, 3 steps each."""
+    import torch
+    from daisy.model.MFRecommender import MF
+    out = {}
+    cases = [  # U, I, F, B, lr, reg1, reg2, opt, seed, loss
+        (40, 60, 32, 128, 0.01, 0.001, 0.001, "adagrad", 21, "BPR"),
+        (40, 60, 64, 256, 0.001, 0.001, 0.001, "rmsprop", 22, "BPR"),
+        (13, 9, 6, 50, 0.01, 0.0, 0.0, "adagrad", 23, "HL"),
+        (25, 30, 100, 200, 0.001, 0.01, 0.02, "rmsprop", 24, "CL"),
+    ]
+    for k, (U, I, F, B, lr, r1, r2, opt, seed, loss_type) in enumerate(cases):
+        cfg = rh.make_config("mf", user_num=U, item_num=I, factors=F, lr=lr, reg_1=r1, reg_2=r2, optimizer=opt,
+                             epochs=1, loss_type=loss_type)
+        torch.manual_seed(seed)
+        model = MF(cfg)
+        with torch.no_grad():
+            model.embed_user.weight.mul_(30.0)
+            model.embed_item.weight.mul_(30.0)
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        assert type(optim).__name__.lower() == opt
+        rng = np.random.default_rng(seed)
+        P = [model.embed_user.weight.detach().numpy().copy()]
+        Q = [model.embed_item.weight.detach().numpy().copy()]
+        batches, losses = [], []
+        for step in range(3):
+            third = rng.integers(0, 2, size=B) if loss_type == "CL" else rng.integers(I, size=B)
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), third]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            P.append(model.embed_user.weight.detach().numpy().copy())
+            Q.append(model.embed_item.weight.detach().numpy().copy())
+        out.update({f"c{k}_P": np.stack(P), f"c{k}_Q": np.stack(Q), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64), f"c{k}_opt": np.array(opt), f"c{k}_losskind": np.array(loss_type),
+                    f"c{k}_hyper": np.array([lr, r1, r2], np.float64)})
+        print(f"mf_optim case {k} ({opt}/{loss_type}): losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("mf_optim", **out)
+
+
 # --------------------------------------------------------------------------- rank
 def gen_mf_rank():
     """MF.rank / full_rank / predict (MFRecommender.py:99-133) on fixed random tables; candidate
@@ -515,7 +560,7 @@ def gen_sampler_pop():
     _save("sampler_pop", **out)
 
 
-ALL = {"mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+ALL = {"mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

@@ -25,11 +25,12 @@ class Hyper(C.Structure):
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("loss", C.c_int32)]
 
 
+OPT_KIND = {"sgd": 0, "adam": 1, "adagrad": 2, "rmsprop": 3}
 LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2, "CL": 3, "SL": 4}
 
 
 def hyper(lr=0.01, reg_1=0.001, reg_2=0.001, opt="sgd", beta1=0.9, beta2=0.999, eps=1e-8, loss="BPR"):
-    return Hyper(lr, reg_1, reg_2, 0 if opt == "sgd" else 1, beta1, beta2, eps, LOSS_KIND[loss.upper()])
+    return Hyper(lr, reg_1, reg_2, OPT_KIND[opt], beta1, beta2, eps, LOSS_KIND[loss.upper()])
 
 
 _lib = None

@@ -191,3 +191,17 @@ def test_metrics_mirror_host_logic():
         Metric(dict(cfg, metrics=["f1"])).run(test_ur, np.zeros((3, 5), np.float32), [3, 7, 11])
     with pytest.raises(RuntimeError):                                  # no CPU fallback for the KPIs either
         Metric(dict(cfg, metrics=["recall"])).run(test_ur, np.zeros((3, 5), np.float32), [3, 7, 11])
+
+
+def test_optimizer_names_mirror():
+    from daisyrec_b200.model.MFRecommender import MF
+    from daisyrec_b200.model.AbstractRecommender import GeneralRecommender
+    assert MF.SUPPORTED_OPTIMIZERS == ('sgd', 'adam', 'adagrad', 'rmsprop') and GeneralRecommender.SUPPORTED_OPTIMIZERS == ('sgd', 'adam')
+    m = MF.__new__(MF)
+    m.logger = None
+    for name, want in (('adagrad', 'adagrad'), ('RMSprop', 'rmsprop'), ('nonsense', 'adam')):
+        m.optimizer = name
+        assert m._optimizer_name() == want
+    m.optimizer = 'sparse_adam'
+    with pytest.raises(RuntimeError):
+        m._optimizer_name()
