@@ -47,7 +47,15 @@ class LightGCN(GeneralRecommender):
         self.restore_item_e = None
 
         m = self.interaction_matrix
-        row_ptr, col, val = ops.lgcn_norm_adj(np.asarray(m.row), np.asarray(m.col), self.user_num, self.item_num)
+        # optional B200 key 'adj_builder': 'host' (default; numpy restatement of get_norm_adj_mat, values bit-identical to
+        # scipy's) | 'device' (sorted CSR + transpose + D^-1/2 A D^-1/2 built by csr.cu; 1/sqrt instead of pow: fp32
+        # values equal except on rare rounding ties)
+        if str(config.get('adj_builder', 'host')) == 'device':
+            row_ptr, col, val = ops.lgcn_build_adj(torch.from_numpy(np.ascontiguousarray(m.row, np.int32)).to(self.device),
+                                                   torch.from_numpy(np.ascontiguousarray(m.col, np.int32)).to(self.device),
+                                                   self.user_num, self.item_num)
+        else:
+            row_ptr, col, val = ops.lgcn_norm_adj(np.asarray(m.row), np.asarray(m.col), self.user_num, self.item_num)
         self.graph = ops.LgcnGraph(row_ptr, col, val, self.device)
         self._ws = None
         self._opt_steps = 0

@@ -175,6 +175,35 @@ def sampler_explode_pointwise(d_coo_u, d_coo_i, d_label, d_js):
     return rows
 
 
+# ------------------------------------------------------------------ CSR / adjacency builders
+def csr_build(d_row, d_col, n_rows, n_cols):
+    """COO int32 pairs on the device -> (row_ptr int64[n_rows+1], col int32[nnz_unique]) sorted + duplicate-free."""
+    _dev(d_row, torch.int32, "row"); _dev(d_col, torch.int32, "col")
+    nnz = d_row.numel()
+    ws = torch.empty(L.lib().drb_csr_workspace_bytes(n_rows, nnz), dtype=torch.uint8, device=d_row.device)
+    row_ptr = torch.empty(n_rows + 1, dtype=torch.int64, device=d_row.device)
+    col = torch.empty(max(nnz, 1), dtype=torch.int32, device=d_row.device)
+    kept = C.c_int64(0)
+    L.check(L.lib().drb_csr_build(_ptr(d_row), _ptr(d_col), nnz, n_rows, n_cols, _ptr(ws), _ptr(row_ptr), _ptr(col),
+                                  C.byref(kept), _stream()))
+    return row_ptr, col[:kept.value]
+
+
+def lgcn_build_adj(d_coo_u, d_coo_i, user_num, item_num):
+    """Train COO on the device -> A_hat CSR (row_ptr i64, col i32, val f32) of get_norm_adj_mat, built on the device."""
+    ui_ptr, ui_col = csr_build(d_coo_u, d_coo_i, user_num, item_num)
+    iu_ptr, iu_col = csr_build(d_coo_i, d_coo_u, item_num, user_num)
+    nnz = ui_col.numel()
+    assert iu_col.numel() == nnz
+    dev = d_coo_u.device
+    adj_ptr = torch.empty(user_num + item_num + 1, dtype=torch.int64, device=dev)
+    adj_col = torch.empty(max(2 * nnz, 1), dtype=torch.int32, device=dev)
+    adj_val = torch.empty(max(2 * nnz, 1), dtype=torch.float32, device=dev)
+    L.check(L.lib().drb_lgcn_build_adj(_ptr(ui_ptr), _ptr(ui_col), _ptr(iu_ptr), _ptr(iu_col), user_num, item_num, nnz,
+                                       _ptr(adj_ptr), _ptr(adj_col), _ptr(adj_val), _stream()))
+    return adj_ptr, adj_col[:2 * nnz], adj_val[:2 * nnz]
+
+
 # ------------------------------------------------------------------ evaluation KPIs
 def rank_metrics(d_preds, d_gt_ptr, d_gt_idx, ks, item_num, d_item_pop=None):
     """calc_ranking_results' numbers for rank()'s device output: -> float64 CUDA tensor [len(ks), 8] (L.KPI_NAMES)."""
@@ -371,6 +400,10 @@ class LgcnGraph:
     """Device copy of the normalised adjacency + its segment list."""
 
     def __init__(self, row_ptr, col, val, device):
+        d_row_ptr = d_col = d_val = None
+        if isinstance(row_ptr, torch.Tensor):                    # lgcn_build_adj's device arrays: only the segment
+            d_row_ptr, d_col, d_val = row_ptr, col, val          # list is derived on the host (from row_ptr)
+            row_ptr = row_ptr.cpu().numpy()
         n = len(row_ptr) - 1
         row_ptr = np.ascontiguousarray(row_ptr, np.int64)
         nseg = int(L.lib().drb_lgcn_segment_count(row_ptr.ctypes.data, n))
@@ -378,9 +411,12 @@ class LgcnGraph:
         seg_ptr = np.empty(nseg + 1, np.int64)
         L.check(L.lib().drb_lgcn_segments(row_ptr.ctypes.data, n, seg_row.ctypes.data, seg_ptr.ctypes.data))
         self.n, self.nseg = n, nseg
-        self.row_ptr = torch.from_numpy(row_ptr).to(device)
-        self.col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).to(device)
-        self.val = torch.from_numpy(np.ascontiguousarray(val, np.float32)).to(device)
+        if d_row_ptr is not None:
+            self.row_ptr, self.col, self.val = d_row_ptr.to(device), d_col.to(device), d_val.to(device)
+        else:
+            self.row_ptr = torch.from_numpy(row_ptr).to(device)
+            self.col = torch.from_numpy(np.ascontiguousarray(col, np.int32)).to(device)
+            self.val = torch.from_numpy(np.ascontiguousarray(val, np.float32)).to(device)
         self.seg_row = torch.from_numpy(seg_row).to(device)
         self.seg_ptr = torch.from_numpy(seg_ptr).to(device)
 

@@ -1,5 +1,5 @@
 """Boundary producers around the hot path, with the reference's function names
-(daisy/utils/utils.py:19-34,53-85).
+(daisy/utils/utils.py:19-34,53-85,125-144).
 
 ``build_candidates_set`` reproduces the reference's candidate lists bit for bit (same global
 numpy RNG stream, ground-truth ids appended in ``list(set)`` order) but finds the k-th
@@ -34,6 +34,31 @@ def get_ur(df):
     for u in sorted(groups, key=first_seen.__getitem__):
         ur[u] = set(groups[u].tolist())
     return ur
+
+
+def get_inter_matrix(df, config, form='coo'):
+    """daisy/utils/utils.py:125-144: the whole sparse interaction matrix (scipy), what LightGCN's config['inter_matrix']
+    holds (run_examples/test.py:89)."""
+    import scipy.sparse as sp
+    src, tar = df[config['UID_NAME']].values, df[config['IID_NAME']].values
+    data = df[config['INTER_NAME']].values
+    mat = sp.coo_matrix((data, (src, tar)), shape=(config['user_num'], config['item_num']))
+    if form == 'coo':
+        return mat
+    elif form == 'csr':
+        return mat.tocsr()
+    raise NotImplementedError(f'Sparse matrix format [{form}] has not been implemented...')
+
+
+def build_train_csr(df, config):
+    """Sorted, duplicate-free user->item CSR of the train set, built on the device from the two DataFrame columns
+    (drb_csr_build): the same object as ``csr_from_ur(get_ur(df))`` without the dict-of-sets walk.  Hand it to the
+    sampler / MF as ``config['train_csr']``.  -> (row_ptr int64[user_num+1], col int32) numpy arrays."""
+    ops.require_cuda()
+    d_u = torch.from_numpy(np.ascontiguousarray(df[config['UID_NAME']].values, dtype=np.int32)).cuda()
+    d_i = torch.from_numpy(np.ascontiguousarray(df[config['IID_NAME']].values, dtype=np.int32)).cuda()
+    row_ptr, col = ops.csr_build(d_u, d_i, config['user_num'], config['item_num'])
+    return row_ptr.cpu().numpy(), col.cpu().numpy()
 
 
 def build_candidates_set(test_ur, train_ur, config, drop_past_inter=True):

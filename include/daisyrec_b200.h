@@ -275,6 +275,21 @@ int drb_mf_predict(const float *d_P, const float *d_Q, int32_t factors, const in
 int drb_mf_rank_host(const float *d_P, const float *d_Q, int32_t factors, const int64_t *h_users, int64_t n_users,
                      const int64_t *h_cands, int32_t cand_num, int32_t topk, float *h_out);
 
+/* ---- producers of the hot path's inputs, on the device -----------------------------------------
+ * One sorted, duplicate-free CSR of the train interactions replaces get_ur (daisy/utils/utils.py:19-34), the
+ * per-user setdiff1d input of the sampler (daisy/utils/sampler.py:84-89) and get_inter_matrix (utils.py:125-144);
+ * with its transpose it yields LightGCN's normalised adjacency (daisy/model/LightGCNRecommender.py:73-107).
+ * drb_csr_build: COO pairs (any order, duplicates allowed, int32) -> row_ptr i64[n_rows+1] + ascending unique columns
+ *   (d_col_out needs room for nnz entries; *h_nnz_unique receives the number kept).  n_cols <= 2^20.  Synchronises.
+ * drb_lgcn_build_adj: user->item CSR + item->user CSR (same nnz) -> A_hat as CSR over U+I nodes (adj_ptr i64[U+I+1],
+ *   adj_col i32[2 nnz] ascending, adj_val f32[2 nnz] = float32((deg_r+1e-7)^-1/2 * (deg_c+1e-7)^-1/2), fp64 inside). */
+size_t drb_csr_workspace_bytes(int32_t n_rows, int64_t nnz);
+int drb_csr_build(const int32_t *d_row, const int32_t *d_col, int64_t nnz, int32_t n_rows, int32_t n_cols, void *d_ws,
+                  int64_t *d_row_ptr, int32_t *d_col_out, int64_t *h_nnz_unique, void *stream);
+int drb_lgcn_build_adj(const int64_t *d_ui_ptr, const int32_t *d_ui_col, const int64_t *d_iu_ptr, const int32_t *d_iu_col,
+                       int32_t user_num, int32_t item_num, int64_t nnz, int64_t *d_adj_ptr, int32_t *d_adj_col,
+                       float *d_adj_val, void *stream);
+
 /* ---- evaluation: calc_ranking_results / Metric.run ------------------------------------------------
  * daisy/utils/metrics.py:18-57 (cut-off loop), :59-96 (dispatch), :98-251 (the KPIs).
  * d_preds: rank()'s float32 [n_users, ld] output; ground truth as CSR aligned with its rows
