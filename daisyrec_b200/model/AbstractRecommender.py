@@ -195,12 +195,7 @@ class GeneralRecommender(AbstractRecommender):
     def _fit_epoch_bulk(self, plan, epoch):
         data, bs, shuffle, drop_last, gen = plan
         T = data.shape[0]
-        d_triples = getattr(data, '_drb_device', None)
-        if d_triples is None or d_triples.device != self.device:
-            if getattr(self, '_triples_key', None) != (id(data), T):
-                self._triples_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.int32)).to(self.device)
-                self._triples_key = (id(data), T)
-            d_triples = self._triples_dev
+        d_triples = self._device_triples(data)
         if shuffle and self.shuffle_engine == 'device':
             torch.empty((), dtype=torch.int64).random_(generator=gen)                 # _base_seed, as the DataLoader draws it
             g = torch.Generator(device=self.device)
