@@ -88,12 +88,13 @@ def test_generic_loader_and_calc_loss_paths():
 
 def test_unsupported_options_fail_loudly():
     from daisyrec_b200.model.MFRecommender import MF
-    cfg = _config(user_num=10, item_num=10, loss_type='CL')
-    m = MF(cfg)
-    with pytest.raises(NotImplementedError):
-        m.fit([])
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):                           # AbstractRecommender.py:90-91
         MF(_config(user_num=10, item_num=10, loss_type='nope')).fit([])
+    with pytest.raises(RuntimeError):                                  # optim.SparseAdam.step() on dense gradients
+        MF(_config(user_num=10, item_num=10, optimizer='sparse_adam')).fit([])
+    with pytest.raises(NotImplementedError):                           # point-wise rows come from the sampler, not the fused draw
+        MF(_config(user_num=10, item_num=10, loss_type='CL', neg_sampling='fused',
+                   train_ur={u: {0} for u in range(10)})).fit([])
 
 
 def test_edge_cases_small_inputs():
