@@ -77,7 +77,7 @@ class BasicNegtiveSampler(AbstractSampler):
 
     def _pointwise(self, d_coo_u, d_coo_i, d_js):
         """CL / SL rows (sampler.py:58-59, :93-98): positives (u, i, rating) then negatives (u, j, 0), int32."""
-        label = np.ascontiguousarray(self.df[self.inter_name].values).astype(np.int32)
+        label = np.array(self.df[self.inter_name].values).astype(np.int32)
         d_rows = ops.sampler_explode_pointwise(d_coo_u, d_coo_i, torch.from_numpy(label).cuda(), d_js)
         out = d_rows.cpu().numpy().view(TripleArray)
         out._drb_device = d_rows
@@ -86,8 +86,8 @@ class BasicNegtiveSampler(AbstractSampler):
     def sampling(self):
         if self.loss_type not in ('BPR', 'HL', 'TL', 'CL', 'SL'):
             raise NotImplementedError
-        coo_u = np.ascontiguousarray(self.df[self.uid_name].values, dtype=np.int32)
-        coo_i = np.ascontiguousarray(self.df[self.iid_name].values, dtype=np.int32)
+        coo_u = np.array(self.df[self.uid_name].values, dtype=np.int32)        # a writable copy: pandas >= 3
+        coo_i = np.array(self.df[self.iid_name].values, dtype=np.int32)        # hands out read-only views
         if self.num_ng == 0:
             if self.loss_type in ('CL', 'SL'):
                 ops.require_cuda()

@@ -55,8 +55,8 @@ def build_train_csr(df, config):
     (drb_csr_build): the same object as ``csr_from_ur(get_ur(df))`` without the dict-of-sets walk.  Hand it to the
     sampler / MF as ``config['train_csr']``.  -> (row_ptr int64[user_num+1], col int32) numpy arrays."""
     ops.require_cuda()
-    d_u = torch.from_numpy(np.ascontiguousarray(df[config['UID_NAME']].values, dtype=np.int32)).cuda()
-    d_i = torch.from_numpy(np.ascontiguousarray(df[config['IID_NAME']].values, dtype=np.int32)).cuda()
+    d_u = torch.from_numpy(np.array(df[config['UID_NAME']].values, dtype=np.int32)).cuda()
+    d_i = torch.from_numpy(np.array(df[config['IID_NAME']].values, dtype=np.int32)).cuda()
     row_ptr, col = ops.csr_build(d_u, d_i, config['user_num'], config['item_num'])
     return row_ptr.cpu().numpy(), col.cpu().numpy()
 
