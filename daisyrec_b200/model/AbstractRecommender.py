@@ -17,6 +17,7 @@ from torch.utils.data import RandomSampler, SequentialSampler, BatchSampler
 from tqdm import tqdm
 
 from .. import ops
+from ..utils.sampler import fingerprint
 
 
 class _Table:
@@ -223,14 +224,17 @@ class GeneralRecommender(AbstractRecommender):
         return current_loss
 
     def _device_triples(self, data):
-        T = data.shape[0]
+        """Device copy of the loader's [T,3] rows: the sampler's own device twin when the host array still carries the stamp
+        it was attached with, else an upload cached per (array, stamp) -- an in-place edit of the host rows re-uploads."""
+        stamp = fingerprint(data)
         d_triples = getattr(data, '_drb_device', None)
-        if d_triples is None or d_triples.device != self.device:
-            if getattr(self, '_triples_key', None) != (id(data), T):
-                self._triples_dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.int32)).to(self.device)
-                self._triples_key = (id(data), T)
-            d_triples = self._triples_dev
-        return d_triples
+        if d_triples is not None and d_triples.device == self.device and getattr(data, '_drb_stamp', None) == stamp:
+            return d_triples
+        if getattr(self, '_triples_key', None) != (id(data), stamp):
+            host = np.ascontiguousarray(data, dtype=np.int32)
+            self._triples_dev = torch.from_numpy(host if host.flags.writeable else host.copy()).to(self.device)
+            self._triples_key = (id(data), stamp)
+        return self._triples_dev
 
     def _fit_epoch_sharded(self, plan, epoch):
         """N > 1: same global batches as the single-GPU run; this rank trains the triples of its users."""

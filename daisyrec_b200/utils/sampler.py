@@ -15,12 +15,31 @@ import torch
 from .. import ops
 
 
+def fingerprint(a):
+    """Cheap content stamp of a host index array: shape, an int64 sum over <= 65 536 evenly strided elements and the two
+    end rows.  It lets fit() notice that a host array whose device copy is cached was edited in place (shuffled, filtered,
+    relabelled) and re-upload it; a stamp, not a checksum."""
+    flat = np.asarray(a).reshape(-1)
+    step = max(1, flat.size // 65536)
+    return (tuple(a.shape), int(flat[::step].sum(dtype=np.int64)), flat[:3].tobytes(), flat[-3:].tobytes())
+
+
 class TripleArray(np.ndarray):
-    """int32 [T,3] host array that remembers its device twin (saves fit() a 12*T-byte H2D)."""
+    """int32 [T,3] host array that remembers its device twin (saves fit() a 12*T-byte H2D).  Views / copies forget
+    the twin; an in-place edit is caught by the stamp taken when the twin was attached."""
     _drb_device = None
+    _drb_stamp = None
 
     def __array_finalize__(self, obj):
         self._drb_device = None
+        self._drb_stamp = None
+
+    @staticmethod
+    def attach(host, device_tensor):
+        out = host.view(TripleArray)
+        out._drb_device = device_tensor
+        out._drb_stamp = fingerprint(out)
+        return out
 
 
 def csr_from_ur(ur, user_num):
@@ -79,9 +98,7 @@ class BasicNegtiveSampler(AbstractSampler):
         """CL / SL rows (sampler.py:58-59, :93-98): positives (u, i, rating) then negatives (u, j, 0), int32."""
         label = np.array(self.df[self.inter_name].values).astype(np.int32)
         d_rows = ops.sampler_explode_pointwise(d_coo_u, d_coo_i, torch.from_numpy(label).cuda(), d_js)
-        out = d_rows.cpu().numpy().view(TripleArray)
-        out._drb_device = d_rows
-        return out
+        return TripleArray.attach(d_rows.cpu().numpy(), d_rows)
 
     def sampling(self):
         if self.loss_type not in ('BPR', 'HL', 'TL', 'CL', 'SL'):
@@ -127,6 +144,4 @@ class BasicNegtiveSampler(AbstractSampler):
         if self.loss_type in ('CL', 'SL'):
             return self._pointwise(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
         d_tr = ops.sampler_explode(torch.from_numpy(coo_u).cuda(), torch.from_numpy(coo_i).cuda(), d_js)
-        out = d_tr.cpu().numpy().view(TripleArray)
-        out._drb_device = d_tr
-        return out
+        return TripleArray.attach(d_tr.cpu().numpy(), d_tr)

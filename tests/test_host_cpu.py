@@ -205,3 +205,28 @@ def test_optimizer_names_mirror():
     m.optimizer = 'sparse_adam'
     with pytest.raises(RuntimeError):
         m._optimizer_name()
+
+
+def test_device_twin_is_dropped_after_an_in_place_edit():
+    """fit() trusts the sampler's device twin only while the host rows still carry the stamp taken at attach time."""
+    from daisyrec_b200.utils.sampler import TripleArray, fingerprint
+    from daisyrec_b200.model.AbstractRecommender import GeneralRecommender
+    rows = np.arange(3 * 5000, dtype=np.int32).reshape(-1, 3)
+    twin = torch.from_numpy(rows.copy())                               # stands in for the CUDA tensor
+    arr = TripleArray.attach(rows, twin)
+    assert isinstance(arr, TripleArray) and arr._drb_device is twin and arr._drb_stamp == fingerprint(rows)
+    assert arr[10:20]._drb_device is None and arr.copy()._drb_device is None        # views / copies forget the twin
+    m = GeneralRecommender.__new__(GeneralRecommender)
+    m.device = torch.device('cpu')
+    assert m._device_triples(arr) is twin                                           # untouched -> the twin itself
+    np.random.default_rng(0).shuffle(arr)                                           # in-place row shuffle
+    up = m._device_triples(arr)
+    assert up is not twin and np.array_equal(up.numpy(), np.asarray(arr))           # re-uploaded from the edited rows
+    assert m._device_triples(arr) is up                                             # cached per (array, stamp)
+    arr[::7, 2] += 1
+    assert np.array_equal(m._device_triples(arr).numpy(), np.asarray(arr))
+    plain = np.asarray(arr).copy()
+    plain.flags.writeable = False                                                   # pandas >= 3 hands out read-only views
+    assert np.array_equal(m._device_triples(plain).numpy(), plain)
+    empty = np.zeros((0, 3), np.int32)
+    assert fingerprint(empty)[0] == (0, 3) and m._device_triples(empty).shape == (0, 3)
