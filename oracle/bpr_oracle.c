@@ -358,9 +358,18 @@ static void rmsprop_dense(float *theta, float *sq, const double *g, int64_t n, c
     }
 }
 
-double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, const int32_t *bu, const int32_t *bi,
-                       const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP,
-                       float *mQ, float *vQ, int64_t step_count, double *parts)
+/* FM's first-order terms (daisy/model/FMRecommender.py:46-49,66-67): u_bias [U], i_bias [I], bias_ [1] and their
+ * optimiser state (m / v like the tables).  NULL = plain MF. */
+typedef struct {
+    float *ub, *ib, *b0;
+    float *m_ub, *v_ub, *m_ib, *v_ib, *m_b0, *v_b0;
+} orc_fm_bias;
+
+static void dense_update(float *theta, float *m, float *v, const double *g, int64_t n, const orc_hyper *h, int64_t step_count);
+
+static double mf_step_impl(float *P, float *Q, int32_t U, int32_t I, int32_t F, const int32_t *bu, const int32_t *bi,
+                           const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP,
+                           float *mQ, float *vQ, int64_t step_count, double *parts, const orc_fm_bias *fm)
 {
     float *coef = (float *)malloc(sizeof(float) * 2 * (size_t)(B > 0 ? B : 1));
     double bpr = 0.0, l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
@@ -368,6 +377,11 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
     for (int64_t t = 0; t < B; t++) {
         const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = pw ? NULL : Q + (int64_t)bj[t] * F;
         float pos = orc_dot(p, qi, F), neg = pw ? (float)bj[t] : orc_dot(p, qj, F);
+        if (fm) {                          /* pred += u_bias(user) + i_bias(item) + bias_  (FMRecommender.py:66-67) */
+            pos += (fm->ub[bu[t]] + fm->ib[bi[t]]) + fm->b0[0];
+            if (!pw)
+                neg += (fm->ub[bu[t]] + fm->ib[bj[t]]) + fm->b0[0];
+        }
         bpr += (double)pair_loss(h->loss, pos, neg, &coef[2 * t], &coef[2 * t + 1]);
         for (int f = 0; f < F; f++) {
             l1u += fabsf(p[f]);
@@ -397,12 +411,22 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
     }
     double *gP = (double *)calloc((size_t)U * F, sizeof(double));
     double *gQ = (double *)calloc((size_t)I * F, sizeof(double));
+    double *gub = fm ? (double *)calloc((size_t)U, sizeof(double)) : NULL;
+    double *gib = fm ? (double *)calloc((size_t)I, sizeof(double)) : NULL;
+    double gb0 = 0.0;
     float inu = nu > 0 ? (float)(1.0 / nu) : 0.f, ini = ni > 0 ? (float)(1.0 / ni) : 0.f,
           inj = nj > 0 ? (float)(1.0 / nj) : 0.f;
     for (int64_t t = 0; t < B; t++) {
         const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F;
         double *gu = gP + (int64_t)bu[t] * F, *gi = gQ + (int64_t)bi[t] * F;
         float cp = coef[2 * t], cn = coef[2 * t + 1];
+        if (fm) {                          /* biases are not regularised (FMRecommender.py:76-95) */
+            gub[bu[t]] += (double)cp + (double)cn;
+            gib[bi[t]] += (double)cp;
+            if (!pw)
+                gib[bj[t]] += (double)cn;
+            gb0 += (double)cp + (double)cn;
+        }
         if (pw) {
             for (int f = 0; f < F; f++) {
                 float sp = (p[f] > 0) - (p[f] < 0), si = (qi[f] > 0) - (qi[f] < 0);
@@ -421,25 +445,75 @@ double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, cons
             gj[f] += (double)(cn * p[f]) + (double)(h->reg_1 * sj) + (double)(h->reg_2 * qj[f] * inj);
         }
     }
-    if (h->opt == 0) {
-        for (int64_t k = 0; k < (int64_t)U * F; k++)
-            P[k] = P[k] - h->lr * (float)gP[k];
-        for (int64_t k = 0; k < (int64_t)I * F; k++)
-            Q[k] = Q[k] - h->lr * (float)gQ[k];
-    } else if (h->opt == 2) {
-        adagrad_dense(P, mP, gP, (int64_t)U * F, h);
-        adagrad_dense(Q, mQ, gQ, (int64_t)I * F, h);
-    } else if (h->opt == 3) {
-        rmsprop_dense(P, mP, gP, (int64_t)U * F, h);
-        rmsprop_dense(Q, mQ, gQ, (int64_t)I * F, h);
-    } else {
-        adam_dense(P, mP, vP, gP, (int64_t)U * F, h, step_count);
-        adam_dense(Q, mQ, vQ, gQ, (int64_t)I * F, h, step_count);
+    dense_update(P, mP, vP, gP, (int64_t)U * F, h, step_count);
+    dense_update(Q, mQ, vQ, gQ, (int64_t)I * F, h, step_count);
+    if (fm) {
+        dense_update(fm->ub, fm->m_ub, fm->v_ub, gub, U, h, step_count);
+        dense_update(fm->ib, fm->m_ib, fm->v_ib, gib, I, h, step_count);
+        dense_update(fm->b0, fm->m_b0, fm->v_b0, &gb0, 1, h, step_count);
+        free(gub);
+        free(gib);
     }
     free(gP);
     free(gQ);
     free(coef);
     return (double)loss;
+}
+
+static void dense_update(float *theta, float *m, float *v, const double *g, int64_t n, const orc_hyper *h, int64_t step_count)
+{
+    if (h->opt == 0) {
+        for (int64_t k = 0; k < n; k++)
+            theta[k] = theta[k] - h->lr * (float)g[k];
+    } else if (h->opt == 2) {
+        adagrad_dense(theta, m, g, n, h);
+    } else if (h->opt == 3) {
+        rmsprop_dense(theta, m, g, n, h);
+    } else {
+        adam_dense(theta, m, v, g, n, h, step_count);
+    }
+}
+
+double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, const int32_t *bu, const int32_t *bi,
+                       const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP,
+                       float *mQ, float *vQ, int64_t step_count, double *parts)
+{
+    return mf_step_impl(P, Q, U, I, F, bu, bi, bj, B, h, apply, mP, vP, mQ, vQ, step_count, parts, NULL);
+}
+
+/* ------------------------------------------------------------------------------------
+ * daisy/model/FMRecommender.py:61-97 -- FM.forward / calc_loss + backward + optimizer.step: the MF step above with
+ * pred = <p_u, q_i> + ((u_bias[u] + i_bias[i]) + bias_) in fp32 (:66-67: the three first-order terms are summed first,
+ * then added to the factor product); the regulariser is MF's (factor rows only).  bias [U + I + 1] = u_bias, i_bias,
+ * bias_ packed; bias_state [2 * (U + I + 1)] = their m then v (Adam) / state (Adagrad, RMSprop), or NULL for SGD.
+ * ---------------------------------------------------------------------------------- */
+double orc_fm_step(float *P, float *Q, float *bias, int32_t U, int32_t I, int32_t F, const int32_t *bu, const int32_t *bi,
+                   const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP, float *mQ,
+                   float *vQ, float *bias_state, int64_t step_count, double *parts)
+{
+    orc_fm_bias fm;
+    int64_t nb = (int64_t)U + I + 1;
+    fm.ub = bias;
+    fm.ib = bias + U;
+    fm.b0 = bias + U + I;
+    fm.m_ub = bias_state ? bias_state : NULL;
+    fm.m_ib = bias_state ? bias_state + U : NULL;
+    fm.m_b0 = bias_state ? bias_state + U + I : NULL;
+    fm.v_ub = bias_state ? bias_state + nb : NULL;
+    fm.v_ib = bias_state ? bias_state + nb + U : NULL;
+    fm.v_b0 = bias_state ? bias_state + nb + U + I : NULL;
+    return mf_step_impl(P, Q, U, I, F, bu, bi, bj, B, h, apply, mP, vP, mQ, vQ, step_count, parts, &fm);
+}
+
+/* FM.rank / full_rank / predict scores (FMRecommender.py:99-131): <p_u, q_c> + ((u_bias[u] + i_bias[c]) + bias_), then
+ * argsort(descending) -- stable by position like orc_mf_rank.  items NULL: all item ids (full_rank). */
+void orc_fm_scores(const float *P, const float *Q, const float *bias, int32_t U, int32_t I, int32_t F, int64_t user,
+                   const int64_t *items, int64_t n, float *scores)
+{
+    for (int64_t k = 0; k < n; k++) {
+        int64_t c = items ? items[k] : k;
+        scores[k] = orc_dot(P + user * F, Q + c * F, F) + ((bias[user] + bias[U + c]) + bias[U + I]);
+    }
 }
 
 /* daisy/model/AbstractRecommender.py:112-128 -- the step loop of one epoch over a given

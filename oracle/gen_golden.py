@@ -337,6 +337,70 @@ def gen_mf_rank():
     _save("mf_rank", **out)
 
 
+# --------------------------------------------------------------------------- FM
+def gen_fm():
+    """FM (daisy/model/FMRecommender.py:16-131): MF's factor product + u_bias + i_bias + bias_; 3 training steps per case
+    (biases are zero-initialised (:58-59), so they are set to random values first), then rank / full_rank / predict."""
+    import torch
+    from daisy.model.FMRecommender import FM
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [  # U, I, F, B, lr, reg1, reg2, opt, seed, loss
+        (40, 60, 8, 64, 0.01, 0.001, 0.001, "sgd", 31, "BPR"),
+        (40, 60, 32, 256, 0.01, 0.0, 0.0, "sgd", 32, "CL"),
+        (25, 30, 100, 200, 0.001, 0.01, 0.02, "adam", 33, "TL"),
+        (13, 9, 6, 50, 0.001, 0.001, 0.001, "adam", 34, "BPR"),
+        (30, 500, 64, 128, 0.01, 0.001, 0.001, "sgd", 35, "HL"),
+    ]
+    for k, (U, I, F, B, lr, r1, r2, opt, seed, loss_type) in enumerate(cases):
+        cfg = rh.make_config("fm", user_num=U, item_num=I, factors=F, lr=lr, reg_1=r1, reg_2=r2, optimizer=opt,
+                             epochs=1, loss_type=loss_type, topk=10, cand_num=100)
+        torch.manual_seed(seed)
+        model = FM(cfg)
+        with torch.no_grad():
+            model.embed_user.weight.mul_(30.0)
+            model.embed_item.weight.mul_(30.0)
+            model.u_bias.weight.normal_(0, 0.3)
+            model.i_bias.weight.normal_(0, 0.3)
+            model.bias_.fill_(0.25)
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+
+        def snap():
+            return (model.embed_user.weight.detach().numpy().copy(), model.embed_item.weight.detach().numpy().copy(),
+                    np.concatenate([model.u_bias.weight.detach().numpy().ravel(), model.i_bias.weight.detach().numpy().ravel(),
+                                    model.bias_.detach().numpy().ravel()]).astype(np.float32))
+        snaps, batches, losses = [snap()], [], []
+        for step in range(3):
+            third = rng.integers(0, 2, size=B) if loss_type == "CL" else rng.integers(I, size=B)
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), third]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            snaps.append(snap())
+        n, C, K = min(U, 20), 100, 10
+        users = rng.permutation(U)[:n].astype(np.int64)
+        cands = rng.integers(I, size=(n, C)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(users[r]), cands[r]] for r in range(n)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        with torch.no_grad():
+            preds = model.rank(loader)
+            full = np.stack([model.full_rank(int(u)) for u in users[:4]])
+            pp = np.array([model.predict(int(users[q]), int(cands[q][0])) for q in range(4)], np.float32)
+        out.update({f"c{k}_P": np.stack([s_[0] for s_ in snaps]), f"c{k}_Q": np.stack([s_[1] for s_ in snaps]),
+                    f"c{k}_bias": np.stack([s_[2] for s_ in snaps]), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64), f"c{k}_opt": np.array(opt), f"c{k}_losskind": np.array(loss_type),
+                    f"c{k}_hyper": np.array([lr, r1, r2], np.float64), f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32),
+                    f"c{k}_preds": preds, f"c{k}_full": full, f"c{k}_pred_pairs": pp})
+        print(f"fm case {k} ({loss_type}/{opt}): losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("fm", **out)
+
+
 # --------------------------------------------------------------------------- LightGCN
 def gen_lightgcn():
     """LightGCN (LightGCNRecommender.py:73-211): normalised adjacency, forward propagation, 3 training steps
@@ -560,7 +624,7 @@ def gen_sampler_pop():
     _save("sampler_pop", **out)
 
 
-ALL = {"mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+ALL = {"fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

@@ -45,6 +45,7 @@ def lib():
         _lib.orc_dot.restype = C.c_float
         _lib.orc_mf_bpr_step.restype = C.c_double
         _lib.orc_mf_bpr_epoch.restype = C.c_double
+        _lib.orc_fm_step.restype = C.c_double
     return _lib
 
 
@@ -197,6 +198,25 @@ def mf_bpr_step(P, Q, bu, bi, bj, hp, apply=True, adam_state=None, step_count=1)
                                  None if mQ is None else _f32(mQ), None if vQ is None else _f32(vQ),
                                  C.c_int64(step_count), _p(parts, C.c_double))
     return loss, parts
+
+
+def fm_step(P, Q, bias, bu, bi, bj, hp, apply=True, state=None, bias_state=None, step_count=1):
+    """daisy/model/FMRecommender.py:61-97.  bias = [u_bias (U), i_bias (I), bias_ (1)] float32, updated in place."""
+    parts = np.zeros(8, np.float64)
+    m = [None] * 4 if state is None else list(state)
+    loss = lib().orc_fm_step(_f32(P), _f32(Q), _f32(bias), P.shape[0], Q.shape[0], P.shape[1], _i32(bu), _i32(bi), _i32(bj),
+                             C.c_int64(len(bu)), C.byref(hp), 1 if apply else 0, *[None if a is None else _f32(a) for a in m],
+                             None if bias_state is None else _f32(bias_state), C.c_int64(step_count), _p(parts, C.c_double))
+    return loss, parts
+
+
+def fm_scores(P, Q, bias, user, items=None):
+    n = Q.shape[0] if items is None else len(items)
+    out = np.empty(n, np.float32)
+    it = None if items is None else np.ascontiguousarray(items, np.int64)
+    lib().orc_fm_scores(_f32(P), _f32(Q), _f32(bias), P.shape[0], Q.shape[0], P.shape[1], C.c_int64(int(user)),
+                        None if it is None else _i64(it), C.c_int64(n), _f32(out))
+    return out
 
 
 def mf_bpr_epoch(P, Q, triples, perm, batch, hp, adam_state=None, first_step_count=1):
