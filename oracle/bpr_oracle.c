@@ -474,6 +474,12 @@ static void dense_update(float *theta, float *m, float *v, const double *g, int6
     }
 }
 
+/* the optimiser switch (SGD / Adam / Adagrad / RMSprop, torch defaults) for the other oracle files */
+void orc_dense_update(float *theta, float *m, float *v, const double *g, int64_t n, const orc_hyper *h, int64_t step_count)
+{
+    dense_update(theta, m, v, g, n, h, step_count);
+}
+
 double orc_mf_bpr_step(float *P, float *Q, int32_t U, int32_t I, int32_t F, const int32_t *bu, const int32_t *bi,
                        const int32_t *bj, int64_t B, const orc_hyper *h, int32_t apply, float *mP, float *vP,
                        float *mQ, float *vQ, int64_t step_count, double *parts)

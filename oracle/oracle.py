@@ -14,7 +14,7 @@ _SO = os.path.join(_HERE, "_build", "libbpr_oracle.so")
 
 
 def build(force=False):
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("bpr_oracle.c", "eval_oracle.c", "Makefile"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("bpr_oracle.c", "eval_oracle.c", "ngcf_oracle.c", "Makefile"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -290,6 +290,29 @@ def lgcn_bpr_step(E0, U, I, L, row_ptr, col, val, bu, bi, bj, hp, apply=True, ad
 
 
 # ---------------------------------------------------------------- NeuMF
+# ---------------------------------------------------------------- NGCF (ngcf_oracle.c)
+def ngcf_param_count(dims):
+    dims = np.ascontiguousarray(dims, np.int32)
+    lib().orc_ngcf_param_count.restype = C.c_int64
+    return int(lib().orc_ngcf_param_count(_i32(dims), len(dims) - 1))
+
+
+def ngcf_forward(E0, W, U, I, dims, row_ptr, col, val):
+    """NGCF.forward: [U + I, sum(dims)] concatenated layer outputs."""
+    dims = np.ascontiguousarray(dims, np.int32)
+    out = np.empty((U + I, int(dims.sum())), np.float32)
+    lib().orc_ngcf_forward(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val), _f32(out))
+    return out
+
+
+def ngcf_bpr_step(E0, W, U, I, dims, row_ptr, col, val, bu, bi, bj, hp, apply=True, state=None, step_count=1):
+    dims = np.ascontiguousarray(dims, np.int32)
+    lib().orc_ngcf_bpr_step.restype = C.c_double
+    return lib().orc_ngcf_bpr_step(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val),
+                                   _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), 1 if apply else 0,
+                                   None if state is None else _f32(state), C.c_int64(step_count))
+
+
 def neumf_param_count(F, L):
     lib().orc_neumf_param_count.restype = C.c_int64
     return int(lib().orc_neumf_param_count(F, L))
