@@ -533,6 +533,90 @@ def gen_ngcf():
     _save("ngcf", **out)
 
 
+# --------------------------------------------------------------------------- NFM
+def gen_nfm():
+    """NFM (NFMRecommender.py:14-209) with dropout = 0: bi-interaction + [BatchNorm] + MLP + broadcast biases + prediction;
+    3 training steps (separate positive / negative forward calls => separate batch statistics), eval-mode ranking."""
+    import torch
+    from daisy.model.NFMRecommender import NFM
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    # compat shim (torch >= 2: F.dropout(x, p=0) hands back x itself, so the in-place `fm += ...` of :120 invalidates the
+    # activation's saved output and backward() raises; the torch the reference was written for returned a new tensor).
+    # Same arithmetic, only the aliasing differs.  Restored after the run.
+    _drop_fwd = torch.nn.Dropout.forward
+    torch.nn.Dropout.forward = lambda self, x: x.clone() if self.p == 0 else _drop_fwd(self, x)
+    out = {}
+    cases = [  # U, I, F, L, bn, act, B, lr, reg1, reg2, opt, seed
+        (40, 60, 8, 2, True, "relu", 64, 0.01, 0.0, 0.0, "sgd", 51),
+        (40, 60, 30, 2, True, "relu", 128, 0.001, 0.001, 0.002, "adam", 52),         # assets/nfm.yaml shape
+        (25, 30, 12, 1, False, "tanh", 50, 0.01, 0.001, 0.001, "sgd", 53),
+        (30, 45, 16, 3, True, "sigmoid", 96, 0.01, 0.0, 0.0, "sgd", 54),
+        (20, 20, 6, 2, False, "relu", 33, 0.001, 0.0, 0.001, "adam", 55),
+    ]
+    ACT = {"relu": 0, "sigmoid": 1, "tanh": 2}
+    for k, (U, I, F, L, bn, act, B, lr, r1, r2, opt, seed) in enumerate(cases):
+        cfg = rh.make_config("nfm", user_num=U, item_num=I, factors=F, num_layers=L, batch_norm=bn, act_function=act, dropout=0.0,
+                             lr=lr, reg_1=r1, reg_2=r2, optimizer=opt, epochs=1, topk=10, cand_num=40)
+        torch.manual_seed(seed)
+        model = NFM(cfg)
+        with torch.no_grad():
+            model.embed_user.weight.mul_(3.0)
+            model.embed_item.weight.mul_(3.0)
+            model.u_bias.weight.normal_(0, 0.3)
+            model.i_bias.weight.normal_(0, 0.3)
+            model.bias_.fill_(0.25)
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        bns = [m for m in list(model.FM_layers) + list(model.deep_layers) if isinstance(m, torch.nn.BatchNorm1d)]
+
+        def snap():
+            net = []
+            for m in list(model.FM_layers) + list(model.deep_layers):
+                if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.Linear)):
+                    net += [m.weight, m.bias]
+            net.append(model.prediction.weight)
+            return (model.embed_user.weight.detach().numpy().copy(), model.embed_item.weight.detach().numpy().copy(),
+                    np.concatenate([model.u_bias.weight.detach().numpy().ravel(), model.i_bias.weight.detach().numpy().ravel(),
+                                    model.bias_.detach().numpy().ravel()]).astype(np.float32),
+                    np.concatenate([w.detach().numpy().ravel() for w in net]).astype(np.float32),
+                    np.concatenate([np.concatenate([m.running_mean.numpy(), m.running_var.numpy()]) for m in bns]).astype(np.float32)
+                    if bns else np.zeros(0, np.float32))
+        snaps, batches, losses = [snap()], [], []
+        model.train()
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            snaps.append(snap())
+        model.eval()
+        users = rng.permutation(U)[:9].astype(np.int64)
+        cands = rng.integers(I, size=(9, 40)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), c] for u, c in zip(users, cands)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        with torch.no_grad():
+            preds = model.rank(loader)
+            full = np.stack([model.full_rank(int(u)) for u in users[:4]])
+            # predict() feeds a 1-D row to BatchNorm1d, which rejects it (:155-157): only callable without batch_norm
+            pp = np.zeros(0, np.float32) if bn else \
+                np.array([model.predict(int(users[q]), int(cands[q][0])) for q in range(4)], np.float32)
+        out.update({f"c{k}_P": np.stack([s_[0] for s_ in snaps]), f"c{k}_Q": np.stack([s_[1] for s_ in snaps]),
+                    f"c{k}_bias": np.stack([s_[2] for s_ in snaps]), f"c{k}_N": np.stack([s_[3] for s_ in snaps]),
+                    f"c{k}_R": np.stack([s_[4] for s_ in snaps]), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64),
+                    f"c{k}_hyper": np.array([L, 1 if bn else 0, ACT[act], lr, r1, r2, 0 if opt == "sgd" else 1], np.float64),
+                    f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32), f"c{k}_preds": preds, f"c{k}_full": full,
+                    f"c{k}_pred_pairs": pp})
+        print(f"nfm case {k} (L={L} bn={bn} {act}/{opt}): losses {losses}")
+    torch.nn.Dropout.forward = _drop_fwd
+    out["ncases"] = np.array(len(cases))
+    _save("nfm", **out)
+
+
 # --------------------------------------------------------------------------- NeuMF
 def _neumf_flat(model):
     """4 tables + the flat tower block in module-registration order (layer weight, bias, ..., predict weight, bias)."""
@@ -693,7 +777,7 @@ def gen_sampler_pop():
     _save("sampler_pop", **out)
 
 
-ALL = {"ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+ALL = {"nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ _SO = os.path.join(_HERE, "_build", "libbpr_oracle.so")
 
 
 def build(force=False):
-    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("bpr_oracle.c", "eval_oracle.c", "ngcf_oracle.c", "Makefile"))
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("bpr_oracle.c", "eval_oracle.c", "ngcf_oracle.c", "nfm_oracle.c", "Makefile"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -311,6 +311,29 @@ def ngcf_bpr_step(E0, W, U, I, dims, row_ptr, col, val, bu, bi, bj, hp, apply=Tr
     return lib().orc_ngcf_bpr_step(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val),
                                    _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), 1 if apply else 0,
                                    None if state is None else _f32(state), C.c_int64(step_count))
+
+
+# ---------------------------------------------------------------- NFM (nfm_oracle.c)
+def nfm_param_count(F, L, bn):
+    lib().orc_nfm_param_count.restype = C.c_int64
+    return int(lib().orc_nfm_param_count(F, L, 1 if bn else 0))
+
+
+def nfm_bpr_step(P, Q, bias, N, R, L, bn, act, bu, bi, bj, hp, apply=True, state=None, step_count=1):
+    """In place on P, Q, bias, N (net block) and R (BatchNorm running statistics).  Returns the loss."""
+    lib().orc_nfm_bpr_step.restype = C.c_double
+    return lib().orc_nfm_bpr_step(_f32(P), _f32(Q), _f32(bias), _f32(N), _f32(R) if R.size else None, P.shape[0], Q.shape[0],
+                                  P.shape[1], L, 1 if bn else 0, act, _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)),
+                                  C.byref(hp), 1 if apply else 0, None if state is None else _f32(state), C.c_int64(step_count))
+
+
+def nfm_scores(P, Q, bias, N, R, L, bn, act, users, items):
+    users = np.ascontiguousarray(users, np.int32)
+    items = np.ascontiguousarray(items, np.int32)
+    out = np.empty(len(users), np.float32)
+    lib().orc_nfm_scores(_f32(P), _f32(Q), _f32(bias), _f32(N), _f32(R) if R.size else None, P.shape[0], Q.shape[0], P.shape[1],
+                         L, 1 if bn else 0, act, _i32(users), _i32(items), C.c_int64(len(users)), _f32(out))
+    return out
 
 
 def neumf_param_count(F, L):
