@@ -25,13 +25,11 @@ def get_ur(df):
     us, its = users[order], items[order]
     cuts = np.flatnonzero(np.diff(us)) + 1
     starts = np.concatenate([[0], cuts])
-    # dict insertion order of the reference = first appearance of each user in df
-    first_seen = {}
-    for u in users.tolist():
-        if u not in first_seen:
-            first_seen[u] = len(first_seen)
     groups = {int(us[s]): its[s:e] for s, e in zip(starts, np.concatenate([cuts, [len(us)]]))}
-    for u in sorted(groups, key=first_seen.__getitem__):
+    # dict insertion order of the reference = first appearance of each user in df; the items of a user are added in df
+    # order (stable sort), so each set goes through the same insertions as the reference's `ur[u].add(i)` loop
+    uniq, first_idx = np.unique(users, return_index=True)
+    for u in uniq[np.argsort(first_idx, kind='stable')].tolist():
         ur[u] = set(groups[u].tolist())
     return ur
 

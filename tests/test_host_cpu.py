@@ -92,6 +92,8 @@ def test_csr_from_ur_and_get_ur():
     for u, i in zip(df["user"], df["item"]):
         ref.setdefault(int(u), set()).add(int(i))
     assert dict(ur) == ref and list(ur.keys()) == list(ref.keys())
+    # list(set) order feeds build_candidates_set (utils.py:72-80): same insertions => same iteration order as the reference
+    assert all(list(ur[u]) == list(ref[u]) for u in ref)
     row_ptr, col = csr_from_ur(ur, 30)
     rp2, col2 = csr_from_coo(df["user"].values.astype(np.int32), df["item"].values.astype(np.int32), 30)
     assert np.array_equal(row_ptr, rp2) and np.array_equal(col, col2)
