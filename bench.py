@@ -1,32 +1,36 @@
 #!/usr/bin/env python
-"""bench.py -- BPR-MF training throughput on the BASELINE.json workload (driver contract).
+"""bench.py -- BPR training throughput on the BASELINE.json workloads (driver contract).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--shape ml-20m]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--shape ml-20m] [--configs LIST]
 
-One "step" = one synchronous BPR-MF training step over one batch of ``--batch`` triples (u,i,j)
+One "step" = one synchronous BPR-MF training step over one batch of ``--batch`` triples (u,i,j) per GPU
 (the reference's zero_grad + calc_loss + backward + optimizer.step, AbstractRecommender.py:119-128).
-Workload at N=1: BASELINE.json configs[1] -- MF + BPR, synthetic ML-20M shape (138,493 x 26,744,
-20 M interactions, num_ng=4 -> 80 M triples/epoch), factors=64, fp32, SGD lr .01, reg .001/.001.
-Metric: BPR user-item pairs (= training triples) per second, whole job.
+Headline workload: BASELINE.json configs[1] -- MF + BPR, synthetic ML-20M shape (138,493 x 26,744, 20 M interactions,
+num_ng=4 -> 80 M triples/epoch), factors=64, fp32, SGD lr .01, reg .001/.001.  Metric: BPR user-item pairs
+(= training triples) per second, whole job.
 
-Own arm (default):
-  value      K steps timed with CUDA events around the persistent step-kernel launches, index planes and
-             tables resident in HBM.  Steps walk the epoch's batches; launches cover one epoch's worth of
-             steps at most (what MF.fit does), so K steps = ceil(K / steps_per_epoch) launches.
-  e2e        the same metric through the public API with HOST batches: MF.fit_host_batches(pinned host index planes)
-             -- every step's index arrays are copied H2D and every step's loss is read back D2H inside the timed
-             region, the copy of batch s+1 overlapping the kernel of batch s; the blocking per-batch
-             MF.train_step loop (the reference's loop shape) is reported beside it.
-  roofline   algorithmic bytes (24*F+12 per triple) / event-timed launch duration vs the
-             measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline  oracle/torch_port.py (the reference's algorithm on PyTorch-CPU) on this host's cores.
-Reference arm (--impl reference): the same port timed alone on the host cores (rank 0 only).
+Own arm
+  value      K steps timed with CUDA events around the persistent step-kernel launches; index planes and tables resident
+             in HBM (N > 1: per-GPU batch fixed, user-row-sharded P, replicated Q; max over ranks).
+  e2e        the reference's plug-in call, wall clock: MF(cfg).fit(get_dataloader(BasicDataset(host_triples), B,
+             shuffle=True)) for one full epoch from PINNED host triples -- upload, epoch permutation, gather, every step,
+             loss read-back -- median of 3, for both shuffle engines (N > 1: the native sharded step loop fed from pinned
+             host shares, H2D per step + loss D2H per step).  `fit_host_batches` (per-step H2D / D2H) is kept beside it.
+  roofline   algorithmic bytes (24*F+12 per triple) / event-timed launch duration vs MEASURED_PEAKS.json.
+  configs    driver-visible lines for the other BASELINE configs and the kernels either side of the step: C3 NeuMF bf16
+             tower, C4 LightGCN L=3, C5 shape on one GPU (and row-sharded when N > 1), rank / full_rank / sampling.
+  parity_check (N > 1)  3 global steps on a 48 K-triple slice: sharded run vs the single-GPU kernel on the same batches.
+  cpu_baseline  the REAL reference (oracle/_ref = /root/reference installed unmodified, oracle/build_ref.py) running
+             daisy.model.MFRecommender.MF.fit over its own DataLoader on this host's cores, bounded sample, in a
+             subprocess with the GPUs hidden.
+Reference arm (--impl reference): the same real-reference run for K steps after W warm-up steps (rank 0 only).
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -38,6 +42,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "bpr_train_triples_per_sec"
 UNIT = "triples/s"
+HYPER = dict(lr=0.01, reg_1=0.001, reg_2=0.001)
 
 
 # ------------------------------------------------------------------------------- helpers
@@ -108,17 +113,16 @@ def measured_peaks():
 
 
 def profiled_traffic(factors, batch):
-    """dram bytes per STEP from the committed ncu capture (profiles/traffic.json), else None; the caller scales it to
-    the steps of its average launch."""
+    """dram bytes per STEP from the committed ncu capture (profiles/traffic.json), else None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
             t = json.load(open(p))
             if t.get("factors") == factors and t.get("batch") == batch:
-                return t.get("dram_bytes_per_step")
+                return t.get("dram_bytes_per_step"), t.get("source", "profiles/traffic.json")
         except Exception:  # noqa: BLE001
             pass
-    return None
+    return None, None
 
 
 def build_workload(shape, device, num_ng, seed, sampler):
@@ -140,98 +144,371 @@ def build_workload(shape, device, num_ng, seed, sampler):
     return d, triples
 
 
-def time_cpu_port(P0, Q0, planes_cpu, batch, hyper, budget_s, max_steps, warmup=1):
-    """Time oracle/torch_port.py steps of `batch` triples on the host cores within ~budget_s."""
-    from oracle.torch_port import TorchMFBaseline
-    m = TorchMFBaseline(P0, Q0, hyper["lr"], hyper["reg_1"], hyper["reg_2"], "sgd")
-    n = planes_cpu[0].numel()
-    nb = max(1, n // batch)
-
-    def run(s):
-        lo = (s % nb) * batch
-        b = [p[lo:lo + batch].to(torch.int64) for p in planes_cpu]
-        return m.step(*b)
-
-    for s in range(warmup):
-        run(s)
-    t0 = time.perf_counter()
-    done = 0
-    while done < max_steps:
-        run(warmup + done)
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return done * batch / dt, done, dt
+def workload_config(args, world):
+    """The workload both arms are measured on (identical dict in the own and the reference arm)."""
+    from daisyrec_b200.utils.synthetic import SHAPES
+    U, I, nnz = SHAPES[args.shape]
+    T = nnz * args.num_ng
+    return {"workload": f"MF+BPR synthetic {args.shape} shape ({U}x{I}, nnz={nnz}, num_ng={args.num_ng} -> {T} "
+                        f"triples/epoch), factors={args.factors}, SGD lr=0.01 reg=0.001/0.001",
+            "batch_size": args.batch, "global_batch": args.batch * world, "factors": args.factors,
+            "triples_per_epoch": T, "optimizer": "sgd",
+            "parallelism": "single GPU" if world == 1 else f"user-row-sharded P x{world}, replicated Q",
+            "l2": "index planes (12 B/triple, all K steps) exceed L2 and are streamed once; the factor tables "
+                  "(42 MB at F=64) are persistent model state reused by every step and stay L2-resident by design"}
 
 
-# ------------------------------------------------------------------------------- reference arm
+def timed_ms(fn, warm, reps):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def mf_config(U, I, F, **kw):
+    import logging
+    cfg = dict(gpu="", logger=logging.getLogger("bench"), epochs=1, topk=50, user_num=U, item_num=I, factors=F,
+               loss_type="BPR", optimizer="default", init_method="default", early_stop=False, progress=False, **HYPER)
+    cfg.update(kw)
+    return cfg
+
+
+# ------------------------------------------------------------------------------- reference arm (real daisyRec on the CPU)
+class TimedLoader:
+    """Pass-through around the reference's own DataLoader that notes when batch `warmup` is requested (= the moment the
+    step before it finished) and when the epoch ends: the K steps in between run inside the reference's fit() loop
+    untouched (tqdm, zero_grad, calc_loss, isnan, backward, optimizer.step, loss.item(); AbstractRecommender.py:112-128)."""
+
+    def __init__(self, loader, warmup):
+        self.loader, self.warmup = loader, warmup
+        self.t0 = self.t1 = None
+        self.steps = 0
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        k = 0
+        it = iter(self.loader)
+        while True:
+            if k == self.warmup:
+                self.t0 = time.perf_counter()
+            try:
+                b = next(it)
+            except StopIteration:
+                self.t1 = time.perf_counter()
+                self.steps = k - self.warmup
+                return
+            k += 1
+            yield b
+
+
+def reference_root():
+    p = os.path.join(ROOT, "oracle", "_ref")
+    return p if os.path.isfile(os.path.join(p, "daisy", "model", "MFRecommender.py")) else None
+
+
+def reference_fit(rows, U, I, F, batch, warmup, steps, num_workers, seed):
+    batch = min(batch, max(256, rows.shape[0] // max(1, warmup + steps)))
+    """daisy.model.MFRecommender.MF(config).fit(get_dataloader(BasicDataset(rows), batch, shuffle=True, num_workers)) on the
+    CPU; rows = (warmup+steps)*batch sampler triples.  -> (seconds for the `steps` timed steps, steps)."""
+    from oracle import ref_harness as RH
+    RH.use_root(reference_root())
+    RH.import_reference()
+    from daisy.model.MFRecommender import MF
+    from daisy.utils.dataset import BasicDataset, get_dataloader
+    cfg = RH.make_config("mf", factors=F, epochs=1, batch_size=batch, user_num=U, item_num=I, **HYPER)
+    RH.seed_everything(seed)
+    model = MF(cfg)
+    assert model.device == "cpu", "the reference arm must run with the GPUs hidden"
+    n = (warmup + steps) * batch
+    loader = get_dataloader(BasicDataset(rows[:n]), batch_size=batch, shuffle=True, num_workers=num_workers)
+    tl = TimedLoader(loader, warmup)
+    model.fit(tl)
+    return tl.t1 - tl.t0, tl.steps
+
+
+def reference_rows(args, n_rows):
+    """First n_rows triples of one seeded epoch permutation of the workload (CPU only)."""
+    if args.rows_file:
+        rows = np.load(args.rows_file)
+    else:
+        d, triples = build_workload(args.shape, "cpu", args.num_ng, args.seed, "oracle")
+        g = torch.Generator()
+        g.manual_seed(args.seed)
+        perm = torch.randperm(triples.shape[0], generator=g)[:n_rows]
+        rows = triples[perm].numpy()
+    if rows.shape[0] < n_rows:                                       # wrap (more steps than the sample holds)
+        rows = np.concatenate([rows] * ((n_rows + rows.shape[0] - 1) // rows.shape[0]))
+    return np.ascontiguousarray(rows[:n_rows], dtype=np.int32)
+
+
 def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
         return 0
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""            # before any CUDA call: the reference picks 'cuda' when it sees one
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    dev = "cuda" if torch.cuda.is_available() else "cpu"     # data generation only; the timed path is CPU
-    from daisyrec_b200.utils.synthetic import SHAPES, init_tables
+    from daisyrec_b200.utils.synthetic import SHAPES
     U, I, _ = SHAPES[args.shape]
-    d, triples = build_workload(args.shape, dev, args.num_ng, args.seed, "oracle")
-    T = triples.shape[0]
-    g = torch.Generator(); g.manual_seed(args.seed)
-    perm = torch.randperm(T, generator=g)
-    tr = triples.cpu()[perm]
-    planes = [tr[:, k].contiguous() for k in range(3)]
-    P0, Q0 = init_tables(U, I, args.factors, args.seed, "cpu")
-    hyper = dict(lr=0.01, reg_1=0.001, reg_2=0.001)
-    # calibrate: shrink the per-step sample so that K+W steps fit the time budget
-    budget = args.ref_budget
-    batch = args.batch
-    tps1, _, dt1 = time_cpu_port(P0, Q0, planes, batch, hyper, 1e9, 1, warmup=1)
-    per_step = batch / tps1
-    total = per_step * (args.steps + args.warmup)
-    if total > budget:
-        batch = max(256, int(batch * budget / total) // 256 * 256)
-    from oracle.torch_port import TorchMFBaseline
-    m = TorchMFBaseline(P0, Q0, hyper["lr"], hyper["reg_1"], hyper["reg_2"], "sgd")
-    nb = max(1, T // batch)
-
-    def step(s):
-        lo = (s % nb) * batch
-        return m.step(*[p[lo:lo + batch].to(torch.int64) for p in planes])
-
-    for s in range(args.warmup):
-        step(s)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step(args.warmup + s)
-    dt = time.perf_counter() - t0
-    value = args.steps * batch / dt
-    sample = (f"{args.steps} steps x {batch} triples of the same epoch (own arm batch {args.batch}"
-              f"{'' if batch == args.batch else ', shrunk to fit the time budget'}), dense fp32 autograd + SGD, "
-              f"torch {torch.__version__} CPU, {cores} threads")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, d, T, batch),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    world = max(world, args.gpus)
+    cfg = workload_config(args, world)
+    if reference_root() is None:
+        return run_reference_port(args, cfg, cores)
+    W, K, F = args.warmup, args.steps, args.factors
+    Bg = args.batch * world                                           # the own arm's global step
+    rows = reference_rows(args, (W + K) * min(Bg, 4 << 20))            # larger global batches get a shrunk sample anyway
+    # calibrate with ONE step (at most 1 M triples, scaled linearly); shrink the per-step sample only if K+W steps of the own
+    # arm's global batch would not fit the time budget.  --quick: the caller sized the sample, no calibration.
+    batch = Bg
+    if not args.quick:
+        Bc = min(Bg, 1 << 20)
+        dt1, _ = reference_fit(rows, U, I, F, Bc, 0, 1, 0, args.seed)
+        per_step = dt1 * Bg / Bc
+        if per_step * (W + K) > args.ref_budget:
+            batch = max(256, int(Bg * args.ref_budget / (per_step * (W + K))) // 256 * 256)
+    dt, done = reference_fit(rows, U, I, F, batch, W, K, args.ref_workers, args.seed)
+    value = done * batch / dt
+    extra = {}
+    if not args.quick:
+        d0, k0 = reference_fit(rows, U, I, F, batch, 1, 2, 0, args.seed)
+        extra["num_workers_0"] = {"value": k0 * batch / d0, "steps": k0, "batch": batch}
+        db, kb = reference_fit(rows, U, I, F, 256, 20, 200, args.ref_workers, args.seed)
+        extra["batch_256"] = {"value": kb * 256 / db, "steps": kb, "batch": 256, "ms_per_step": db / kb * 1e3,
+                              "note": "the reference's default batch_size (assets/basic.yaml)"}
+    sample = (f"{done} steps x {batch} triples after {W} warm-up steps inside daisy.model.MFRecommender.MF.fit over "
+              f"get_dataloader(BasicDataset, batch_size={batch}, shuffle=True, num_workers={args.ref_workers}) "
+              f"(own arm global batch {Bg}{'' if batch == Bg else ', per-step sample shrunk to fit the time budget'}); "
+              f"unmodified reference installed in oracle/_ref, torch {torch.__version__} CPU, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": dt / max(1, done) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample, **extra},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
 
 
-def workload_config(args, d, T, batch, extra=None):
-    cfg = {"workload": f"MF+BPR synthetic {args.shape} shape ({d['user_num']}x{d['item_num']}, nnz={d['nnz']}, "
-                       f"num_ng={args.num_ng} -> {T} triples/epoch), factors={args.factors}, SGD lr=0.01 reg=0.001/0.001",
-           "batch_size": batch, "factors": args.factors, "triples_per_epoch": T, "optimizer": "sgd",
-           "l2": "index planes (12 B/triple, all K steps) exceed L2 and are streamed once; the factor tables "
-                 "(42 MB at F=64) are persistent model state reused by every step and stay L2-resident by design"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def run_reference_port(args, cfg, cores):
+    """oracle/_ref missing (the recipe never ran where /root/reference exists): time the pinned PyTorch-CPU port."""
+    from daisyrec_b200.utils.synthetic import SHAPES, init_tables
+    from oracle.torch_port import TorchMFBaseline
+    U, I, _ = SHAPES[args.shape]
+    W, K, B = args.warmup, args.steps, args.batch
+    rows = torch.from_numpy(reference_rows(args, (W + K) * B)).to(torch.int64)
+    P0, Q0 = init_tables(U, I, args.factors, args.seed, "cpu")
+    m = TorchMFBaseline(P0, Q0, optimizer="sgd", **HYPER)
+
+    def step(s):
+        r = rows[s * B:(s + 1) * B]
+        return m.step(r[:, 0].contiguous(), r[:, 1].contiguous(), r[:, 2].contiguous())
+
+    for s in range(W):
+        step(s)
+    t0 = time.perf_counter()
+    for s in range(K):
+        step(W + s)
+    dt = time.perf_counter() - t0
+    value = K * B / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{K} steps x {B} triples, oracle/torch_port.py (oracle/_ref absent)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
 
 
-# ------------------------------------------------------------------------------- own arm
+def cpu_baseline_subprocess(args, rows, steps=2, warmup=1):
+    """The reference arm on a bounded sample, GPUs hidden, in a child process -> its cpu_baseline dict."""
+    with tempfile.TemporaryDirectory(prefix="drb_bench_") as tmp:
+        f = os.path.join(tmp, "rows.npy")
+        np.save(f, rows)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--quick", "--rows-file", f,
+               "--steps", str(steps), "--warmup", str(warmup), "--batch", str(args.batch), "--factors", str(args.factors),
+               "--shape", args.shape, "--ref-budget", str(args.cpu_budget), "--gpus", "1"]
+        try:
+            r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                               timeout=max(120.0, 6 * args.cpu_budget))
+            for ln in reversed(r.stdout.strip().splitlines()):
+                if ln.startswith("{"):
+                    return json.loads(ln)["cpu_baseline"]
+            return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                    "sample": f"failed rc={r.returncode}: {r.stderr.strip()[-300:]}"}
+        except Exception as e:  # noqa: BLE001
+            return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
+
+
+# ------------------------------------------------------------------------------- secondary configs (driver-visible)
+def roof(achieved_gbs, kernel, alg_bytes, note=None):
+    peak, src = measured_peaks()
+    r = {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
+         "kernel": kernel, "algorithmic_bytes": alg_bytes, "peak_source": src}
+    if note:
+        r["note"] = note
+    return r
+
+
+def cfg_c3_neumf(args, dev, d, planes):
+    """BASELINE config 3: NeuMF + BPR, ML-20M shape, F=32, tower 128->64->32, Adam, bf16 tcgen05 tower."""
+    from daisyrec_b200 import ops
+    U, I = d["user_num"], d["item_num"]
+    F, L, B = 32, 2, args.batch
+    D = F * 2 ** (L - 1)
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    tabs = [(torch.randn(s, device=dev, generator=g) * 0.05).contiguous() for s in ((U, F), (I, F), (U, D), (I, D))]
+    W = (torch.randn(ops.neumf_param_count(F, L), device=dev, generator=g) * 0.1).contiguous()
+    hp = ops.hyper(0.001, 0.001, 0.001, "adam")
+    bu, bi, bj = (p_[:4 * B] for p_ in planes)
+    out = {}
+    for name, td in (("bf16", 1), ("fp32", 0)):
+        ws = ops.NeumfWorkspace(U, I, F, L, "adam", 2 * B, dev)
+        step = [0]
+
+        def fn():
+            ops.neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, B, step[0] % 4, 1, hp, adam_step0=step[0], check=False,
+                                      tower_dtype=td)
+            step[0] += 1
+        ms = timed_ms(fn, 3, 8 if td else 4)
+        bpt = 3 * (F + D) * 4 * 2 + 12
+        out[name] = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": B,
+                     "roofline": roof(B * bpt / ms / 1e6, "neumf tower + head + table sweeps (per step)", bpt)}
+        del ws
+    res = out["bf16"]
+    res["workload"] = f"NeuMF+BPR synthetic ml-20m shape, factors={F}, num_layers={L} (tower {2*D}->{D}->{F}), Adam, bf16 tcgen05 tower"
+    res["fp32_tower"] = out["fp32"]
+    return res
+
+
+def cfg_c4_lightgcn(args, dev):
+    """BASELINE config 4: LightGCN L=3 + BPR, Amazon-Book shape, F=64, Adam."""
+    from daisyrec_b200 import ops
+    from daisyrec_b200.utils.synthetic import SHAPES, make_interactions
+    U, I, nnz = SHAPES["amazon-book"]
+    F, L = 64, 3
+    d = make_interactions(U, I, nnz, seed=args.seed, device=dev)
+    adj = ops.lgcn_build_adj(d["coo_u"], d["coo_i"], U, I)
+    graph = ops.LgcnGraph(*adj, dev)
+    nnzA = int(adj[1].numel())
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    E0 = (torch.randn(U + I, F, device=dev, generator=g) * 0.05).contiguous()
+    hp = ops.hyper(0.01, 0.0, 0.0, "adam")
+    out = {"workload": f"LightGCN+BPR synthetic amazon-book shape ({U}x{I}, nnz={d['nnz']}), factors={F}, num_layers={L}, Adam",
+           "spmm_segments": graph.nseg, "adjacency_nnz": nnzA}
+    for B in (65536, 1 << 20):
+        idx = torch.randint(0, d["coo_u"].numel(), (4 * B,), device=dev, generator=g)
+        bu, bi = d["coo_u"][idx].contiguous(), d["coo_i"][idx].contiguous()
+        bj = torch.randint(0, I, (4 * B,), device=dev, dtype=torch.int32, generator=g)
+        ws = ops.LgcnWorkspace(U, I, F, "adam", dev)
+        step = [0]
+
+        def fn():
+            ops.lgcn_bpr_train_steps(E0, ws, graph, L, bu, bi, bj, B, step[0] % 4, 1, hp, adam_step0=step[0], check=False)
+            step[0] += 1
+        ms = timed_ms(fn, 3, 10)
+        alg = 2 * L * (nnzA * (8 + 4 * F) + (U + I) * 4 * F) + B * (24 * F + 12)
+        out[f"batch_{B}"] = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": B,
+                             "roofline": roof(alg / ms / 1e6, "spmm_seg_kernel x 2L + BPR phases + Adam sweep (per step)", alg,
+                                              "upper-bound algorithmic bytes: neighbour-row gathers are mostly L2 hits")}
+        del ws
+    out["value"], out["unit"], out["ms_per_step"] = out["batch_65536"]["value"], UNIT, out["batch_65536"]["ms_per_step"]
+    return out
+
+
+def cfg_c5_single(args, dev, steps=24):
+    """BASELINE config 5's shape on ONE GPU: MF + BPR, Netflix shape, F=128 -- tables (255 MB) >> L2: the HBM regime."""
+    from daisyrec_b200 import ops
+    from daisyrec_b200.utils.synthetic import init_tables
+    a5 = argparse.Namespace(**vars(args)); a5.shape, a5.factors = "netflix", 128
+    d, triples = build_workload("netflix", dev, args.num_ng, args.seed, "cuda")
+    U, I, F, B = d["user_num"], d["item_num"], 128, args.batch
+    T = triples.shape[0]
+    g = torch.Generator(device=dev); g.manual_seed(args.seed)
+    perm = torch.randperm(T, generator=g, device=dev)[:(steps + 4) * B].contiguous()
+    bu, bi, bj = ops.gather_triples(triples, perm)
+    del triples, perm
+    P, Q = init_tables(U, I, F, args.seed, dev)
+    ws = ops.MFWorkspace(U, I, F, "sgd", dev)
+    hp = ops.hyper(**HYPER)
+    ops.mf_bpr_train_steps(P, Q, ws, bu, bi, bj, B, 0, 4, hp, check=False)
+    ms = timed_ms(lambda: ops.mf_bpr_train_steps(P, Q, ws, bu, bi, bj, B, 4, steps, hp, check=False), 1, 2) / steps
+    bpt = 24 * F + 12
+    return {"workload": workload_config(a5, 1)["workload"], "value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
+            "batch": B, "n_gpus": 1, "roofline": roof(B * bpt / ms / 1e6, "mf_bpr_steps_kernel", bpt)}
+
+
+def cfg_inference(args, dev, d, P, Q):
+    """rank (4 096 users x 1 000 candidates, top-50), full_rank_users (4 096 users x all items), KPIs of the rank output."""
+    from daisyrec_b200 import ops
+    U, I, F = d["user_num"], d["item_num"], P.shape[1]
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    n, C, K = 4096, 1000, 50
+    users = torch.randint(0, U, (n,), device=dev, generator=g)
+    cands = torch.randint(0, I, (n, C), device=dev, generator=g)
+    ms_r = timed_ms(lambda: ops.mf_rank(P, Q, users, cands, K), 2, 10)
+    alg_r = n * (C * (4 * F + 8) + 4 * F + 4 * K)
+    ms_f = timed_ms(lambda: ops.mf_full_rank(P, Q, users, K), 1, 5)
+    alg_f = n * (I * 4 * F + 4 * F + 8 * K)
+    return {"rank": {"users": n, "cand_num": C, "topk": K, "ms": ms_r, "users_per_s": n / ms_r * 1e3,
+                     "roofline": roof(alg_r / ms_r / 1e6, "rank_kernel", alg_r, "per user: cand_num x (row + id) + own row + out")},
+            "full_rank_users": {"users": n, "item_num": I, "topk": K, "ms": ms_f, "users_per_s": n / ms_f * 1e3,
+                                "roofline": roof(alg_f / ms_f / 1e6, "rank_kernel (chunked merge)", alg_f,
+                                                 "item table (6.8 MB) is L2-resident: algorithmic bytes are L2 reads")}}
+
+
+def cfg_sampling(args, dev, d):
+    """BasicNegtiveSampler.sampling() at the ML-20M shape: host MT19937 replay + k-th complement + explode."""
+    from daisyrec_b200 import ops
+    U, I, G = d["user_num"], d["item_num"], args.num_ng
+    row_ptr_h = d["row_ptr"].cpu().numpy()
+    t0 = time.perf_counter()
+    draws = ops.sampler_draw_mt19937(ops.mt19937_seed(args.seed), row_ptr_h, U, I, G)
+    t_host = time.perf_counter() - t0
+    d_draws = torch.from_numpy(draws).to(dev)
+    ms_k = timed_ms(lambda: ops.sampler_kth_complement(d["row_ptr"], d["col"], d_draws, I), 1, 5)
+    js = ops.sampler_kth_complement(d["row_ptr"], d["col"], d_draws, I)
+    ms_e = timed_ms(lambda: ops.sampler_explode(d["coo_u"], d["coo_i"], js), 1, 3)
+    nnz = d["coo_u"].numel()
+    T = nnz * G
+    alg_e = T * 12 + nnz * 8
+    return {"triples": T, "host_mt19937_draws_s": t_host, "kth_complement_ms": ms_k, "explode_ms": ms_e,
+            "triples_per_s": T / (t_host + (ms_k + ms_e) * 1e-3),
+            "roofline": roof(alg_e / ms_e / 1e6, "explode_kernel", alg_e, "12 B written per triple + 8 B read per COO row")}
+
+
+def run_configs(args, dev, d, planes, P, Q, which):
+    out = {}
+
+    def section(name, fn):
+        if which != ["all"] and name not in which:
+            return
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001  (keep the headline line whatever a secondary config does)
+            import traceback
+            out[name] = {"error": repr(e), "trace": traceback.format_exc()[-400:]}
+        torch.cuda.empty_cache()
+
+    section("c3_neumf", lambda: cfg_c3_neumf(args, dev, d, planes))
+    section("c4_lightgcn", lambda: cfg_c4_lightgcn(args, dev))
+    section("inference", lambda: cfg_inference(args, dev, d, P, Q))
+    section("sampling", lambda: cfg_sampling(args, dev, d))
+    return out
+
+
+# ------------------------------------------------------------------------------- own arm, one GPU
 def run_own(args):
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
@@ -241,12 +518,12 @@ def run_own(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        from daisyrec_b200.parallel import run_sharded_bench
-        return run_sharded_bench(args, rank, local, world, dev)
+        return run_sharded(args, rank, local, world, dev)
     from daisyrec_b200 import ops
     from daisyrec_b200.model.MFRecommender import MF
+    from daisyrec_b200.utils.dataset import BasicDataset, get_dataloader
     from daisyrec_b200.utils.synthetic import init_tables
-    import logging
+    which = [w for w in args.configs.split(",") if w]
 
     d, triples = build_workload(args.shape, dev, args.num_ng, args.seed, "cuda")
     U, I, F, B = d["user_num"], d["item_num"], args.factors, args.batch
@@ -256,11 +533,10 @@ def run_own(args):
     bu, bi, bj = ops.gather_triples(triples, perm)
     del perm
     spe = (T + B - 1) // B                                           # steps per epoch
+    ncpu = min(T, 3 * B)                                             # the CPU baseline's sample: 3 batches of this epoch
+    cpu_rows = torch.stack([bu[:ncpu], bi[:ncpu], bj[:ncpu]], 1).cpu().numpy()
 
-    cfg = dict(gpu="", logger=logging.getLogger("bench"), lr=0.01, reg_1=0.001, reg_2=0.001, epochs=1, topk=50,
-               user_num=U, item_num=I, factors=F, loss_type="BPR", optimizer="default", init_method="default",
-               early_stop=False, progress=False)
-    model = MF(cfg)
+    model = MF(mf_config(U, I, F))
     P0, Q0 = init_tables(U, I, F, args.seed, dev)
     model.load_state_dict({"embed_user.weight": P0, "embed_item.weight": Q0})
     model._begin_fit("sgd")
@@ -300,74 +576,270 @@ def run_own(args):
     if not np.isfinite(nan_check):
         raise RuntimeError("bench: loss became non-finite during the timed steps")
 
-    # ---- end to end through the public API with HOST batches (pinned): every step's index arrays are copied
-    #      H2D inside the timed region and every step's loss is read back D2H.
-    #      e2e      = MF.fit_host_batches: the copy of batch s+1 overlaps the kernel of batch s (pipelined)
-    #      e2e_sync = MF.train_step per batch with a blocking loss read, exactly the reference's loop shape
-    ke = max(1, min(args.steps, args.e2e_steps, spe - 1))
-    planes = [t[:ke * B].cpu().pin_memory() for t in (bu, bi, bj)]
-    wk = min(3, ke)
-    model.fit_host_batches(*[p_[:wk * B] for p_ in planes], B, wk)   # warm-up
+    # ---- end to end = the reference's plug-in call (run_examples/test.py:91-95): fit(DataLoader) over PINNED host triples,
+    #      one full epoch, wall clock: upload + id check + epoch permutation + gather + all steps + loss read-back
+    host_t = torch.empty((T, 3), dtype=torch.int32).pin_memory()
+    host_t.copy_(triples)
+    host_np = host_t.numpy()
+    del triples
+    torch.cuda.empty_cache()
+    e2e_runs = {}
+    for engine in ("torch", "device"):
+        walls = []
+        for rep in range(args.e2e_reps + 1):                        # first repetition = warm-up (allocator, page-in)
+            torch.manual_seed(args.seed + rep)
+            m = MF(mf_config(U, I, F, shuffle_engine=engine))
+            loader = get_dataloader(BasicDataset(host_np), batch_size=B, shuffle=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.fit(loader)
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+            del m, loader
+        walls = walls[1:]
+        med = float(np.median(walls))
+        e2e_runs[engine] = {"value": T / med, "wall_s_median": med, "wall_s": walls, "epochs_per_run": 1,
+                            "h2d_bytes_per_step": (12 + (8 if engine == "torch" else 0)) * B, "steps": spe}
+    from daisyrec_b200.model.AbstractRecommender import DEFAULT_SHUFFLE_ENGINE as default_engine
+    e2e_main = e2e_runs[default_engine]
+
+    # fit_host_batches: per-step H2D of the batch + per-step loss D2H (pipelined), >= 0.25 s of steps
+    ke = spe - 1
+    planes_h = [t[:ke * B].cpu().pin_memory() for t in (bu, bi, bj)]
+    model.fit_host_batches(*[p_[:3 * B] for p_ in planes_h], B, 3)   # warm-up
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    rounds = max(1, args.steps // ke)
-    for _ in range(rounds):
-        host_losses = model.fit_host_batches(*planes, B, ke)
-    e1.record()
+    rounds, t0 = 0, time.perf_counter()
+    while True:
+        host_losses = model.fit_host_batches(*planes_h, B, ke)
+        rounds += 1
+        if time.perf_counter() - t0 >= 0.25 and rounds >= 2:
+            break
     torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
-    e2e_value = rounds * ke * B / e2e_ms * 1e3
+    hb_s = time.perf_counter() - t0
     assert bool(torch.isfinite(host_losses).all())
-    ks = min(ke, 16)
-    host = [[p_[s * B:(s + 1) * B] for p_ in planes] for s in range(ks)]
-    model.train_step(host[0])
-    torch.cuda.synchronize()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for s in range(ks):
-        model.train_step(host[s])
-    f1.record()
-    torch.cuda.synchronize()
     t_e1 = time.time()
-    e2e_sync_value = ks * B / f0.elapsed_time(f1) * 1e3
     clk = clocks.stop(t_region0, t_e1)
 
-    # ---- CPU baseline (bounded sample) on this host's cores
-    torch.set_num_threads(os.cpu_count() or 1)
-    planes_cpu = [t[:min(T, 4 * B)].cpu() for t in (bu, bi, bj)]
-    P0c, Q0c = init_tables(U, I, F, args.seed, "cpu")
-    cpu_tps, cpu_steps, cpu_dt = time_cpu_port(P0c, Q0c, planes_cpu, B, dict(lr=0.01, reg_1=0.001, reg_2=0.001),
-                                               args.cpu_budget, 8)
+    # ---- the other BASELINE configs + the kernels either side of the step
+    cfgs = {}
+    if which != ["none"]:
+        cfgs = run_configs(args, dev, d, (bu, bi, bj), P, Q, which)
+        if which == ["all"] or "c5_netflix_1gpu" in which:
+            del bu, bi, bj, planes_h
+            torch.cuda.empty_cache()
+            try:
+                cfgs["c5_netflix_1gpu"] = cfg_c5_single(args, dev)
+            except Exception as e:  # noqa: BLE001
+                cfgs["c5_netflix_1gpu"] = {"error": repr(e)}
+
+    # ---- CPU baseline: the real reference's fit on this host's cores (child process, GPUs hidden, bounded sample)
+    cpu = cpu_baseline_subprocess(args, cpu_rows)
+
     peak, peak_src = measured_peaks()
     bytes_per_triple = 24 * F + 12
     avg_launch_ms = ms / len(evs)
     avg_launch_triples = done_triples / len(evs)
     achieved = avg_launch_triples * bytes_per_triple / (avg_launch_ms * 1e-3) / 1e9
+    traffic, traffic_src = profiled_traffic(F, B)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, d, T, B, {"parallelism": "single GPU", "steps_per_epoch": spe}),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1), "steps_per_epoch": spe,
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8,
-                    "steps": rounds * ke,
-                    "api": "MF.fit_host_batches(pinned host index planes): per step H2D of the batch + step kernel + "
-                           "D2H of the loss; copy of batch s+1 overlaps the kernel of batch s",
-                    "per_step_blocking": {"value": e2e_sync_value, "steps": ks,
-                                          "api": "MF.train_step(host batch) with a blocking loss read per step"}},
+            "e2e": {"value": e2e_main["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_main["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": 8.0 / spe, "steps": spe * args.e2e_reps, "wall_s_median": e2e_main["wall_s_median"],
+                    "api": "MF(config).fit(get_dataloader(BasicDataset(pinned host int32[T,3]), batch_size, shuffle=True)): one "
+                           "epoch per run, wall clock around fit() incl. the 12 B/triple upload, id range check, epoch "
+                           "permutation, gather, all steps and the epoch-loss read-back; median of "
+                           f"{args.e2e_reps} runs after one warm-up run; shuffle_engine={default_engine!r} (the default)",
+                    "engines": e2e_runs,
+                    "fit_host_batches": {"value": rounds * ke * B / hb_s, "steps": rounds * ke, "wall_s": hb_s,
+                                         "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 8,
+                                         "api": "MF.fit_host_batches(pinned host planes): per step H2D of the batch + step "
+                                                "kernel + D2H of the loss, copy of batch s+1 under the kernel of batch s"}},
             "gpu_launches": launches,
             "gpu_launches_note": "persistent cooperative kernel: one launch runs up to steps_per_epoch synchronous steps",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (lambda t_: None if t_ is None else t_ * (args.steps / len(evs)))(profiled_traffic(F, B)),
-                         "traffic_note": "dram__bytes_read+write per step from profiles/r01b (ncu --set full) x steps per launch",
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_triple": bytes_per_triple,
+                         "traffic": None if traffic is None else traffic * (args.steps / len(evs)),
+                         "traffic_note": f"dram__bytes_read+write per step ({traffic_src}) x steps per launch; the 85 MB "
+                                         "working set is L2-resident, so the limiter at this shape is L2/issue, not HBM -- "
+                                         "configs.c5_netflix_1gpu is the HBM-regime figure",
+                         "peak_source": peak_src, "algorithmic_bytes_per_triple": bytes_per_triple,
                          "kernel": "mf_bpr_steps_kernel", "avg_launch_ms": avg_launch_ms},
-            "cpu_baseline": {"value": cpu_tps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{cpu_steps} steps x {B} triples of the same workload in {cpu_dt:.1f} s "
-                                       f"(oracle/torch_port.py: dense fp32 autograd + SGD, torch {torch.__version__} CPU)"}}
+            "cpu_baseline": cpu,
+            "configs": cfgs}
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------- own arm, N GPUs (one process each)
+def sharded_parity_check(d, triples, perm, bounds, rank, world, dev, F, seed, comm):
+    """3 global steps on a 48 K-triple slice: every rank trains its share (sharded path), rank 0 also runs the single-GPU
+    kernel on the same global batches (the single-GPU run is the pinned oracle of N > 1).  All ranks return the verdict."""
+    import torch.distributed as dist
+    from daisyrec_b200 import ops
+    from daisyrec_b200.parallel import ShardedTrainer, allgather_rows
+    from daisyrec_b200.utils.synthetic import init_tables
+    U, I = d["user_num"], d["item_num"]
+    Bs, K = 16384, 3
+    sl = perm[:Bs * K].contiguous()
+    P0, Q0 = init_tables(U, I, F, seed + 1, dev)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.clone(), bounds, rank, world, ops.hyper(**HYPER), comm=comm)
+    m = tr.prepare_epoch(triples, sl, Bs)
+    assert m == K
+    losses = tr.train_steps(0, K).clone()
+    tr.check_nan()
+    P_all = allgather_rows(tr.P[:hi - lo], torch.arange(lo, hi, device=dev), U)
+    qsum = tr.Q.view(torch.int32).to(torch.int64).sum().reshape(1)
+    qs = [torch.zeros_like(qsum) for _ in range(world)]
+    dist.all_gather(qs, qsum)
+    q_same = all(int(q.item()) == int(qs[0].item()) for q in qs)
+    verdict = torch.zeros(4, dtype=torch.float64, device=dev)
+    if rank == 0:
+        P1, Q1 = P0.clone(), Q0.clone()
+        ws = ops.MFWorkspace(U, I, F, "sgd", dev)
+        bu, bi, bj = ops.gather_triples(triples, sl)
+        ref = ops.mf_bpr_train_steps(P1, Q1, ws, bu, bi, bj, Bs, 0, K, ops.hyper(**HYPER))
+        rel = float(((losses - ref).abs() / ref.abs()).max().item())
+        dP = float((P_all - P1).abs().max().item())
+        dQ = float((tr.Q - Q1).abs().max().item())
+        moved = float((P1 - P0).abs().max().item())
+        verdict = torch.tensor([rel, max(dP, dQ), moved, 1.0 if q_same else 0.0], dtype=torch.float64, device=dev)
+    dist.broadcast(verdict, 0)
+    rel, dtab, moved, qok = (float(x) for x in verdict.tolist())
+    ok = rel <= 1e-5 and dtab <= 1e-6 and qok == 1.0 and moved > 0
+    return {"ok": ok, "max_rel_loss": rel, "max_abs_table": dtab, "q_replicas_identical": bool(qok), "steps": K,
+            "global_batch": Bs, "max_abs_update": moved,
+            "how": "sharded N-rank run vs the single-GPU step kernel on the same 3 global batches (tolerances: loss rel 1e-5, "
+                   "tables abs 1e-6; item replicas compared bit for bit across ranks)"}
+
+
+def run_sharded(args, rank, local, world, dev):
+    """Weak scaling: per-GPU batch fixed (args.batch), global batch = world * batch."""
+    import torch.distributed as dist
+    from daisyrec_b200 import ops
+    from daisyrec_b200.parallel import ShardedTrainer, partition_users
+    from daisyrec_b200.utils.synthetic import init_tables
+
+    def shape_run(shape, F, steps, warmup, with_e2e):
+        a = argparse.Namespace(**vars(args)); a.shape, a.factors = shape, F
+        d, triples = build_workload(shape, dev, args.num_ng, args.seed, "cuda")     # identical on every rank
+        U, I = d["user_num"], d["item_num"]
+        T = triples.shape[0]
+        Bg = args.batch * world
+        deg = (d["row_ptr"][1:] - d["row_ptr"][:-1]).cpu().numpy()
+        bounds = partition_users(deg, world)
+        g = torch.Generator(device=dev); g.manual_seed(args.seed)
+        perm = torch.randperm(T, generator=g, device=dev)
+        parity = sharded_parity_check(d, triples, perm, bounds, rank, world, dev, F, args.seed, args.comm)
+        P0, Q0 = init_tables(U, I, F, args.seed, dev)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.contiguous(), bounds, rank, world, ops.hyper(**HYPER), comm=args.comm)
+        del P0
+        spe = tr.prepare_epoch(triples, perm, Bg)
+        del perm, triples
+        torch.cuda.empty_cache()
+        local_counts = np.diff(tr.offsets_host)
+        scratch_losses = torch.empty(spe + 1, dtype=torch.float64, device=dev)
+
+        def run(first, k):
+            n_loc, s = 0, first
+            while k > 0:
+                pos = s % spe
+                seg = min(k, spe - pos)
+                tr.train_steps(pos, seg, scratch_losses)
+                n_loc += int(local_counts[pos:pos + seg].sum())
+                s += seg
+                k -= seg
+            return n_loc
+
+        run(0, warmup)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        n_loc = run(warmup, steps)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        t1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([n_loc], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        tr.check_nan()
+        res = {"d": d, "T": T, "spe": spe, "ms": float(ms.item()), "value": float(tot.item()) / float(ms.item()) * 1e3,
+               "t0": t0, "t1": t1, "parity": parity, "cfg": workload_config(a, world)}
+        if with_e2e:
+            # e2e: pinned host share of every global batch of one epoch segment -> native loop (H2D per step, loss D2H per step)
+            ke = min(spe - 1, 64)
+            offs = tr.offsets_host[:ke + 1].copy()
+            nloc = int(offs[-1])
+            h = [t[:nloc].cpu().pin_memory() for t in (tr.bu, tr.bi, tr.bj)]
+            tr.train_steps_host(*h, offs, 0, min(3, ke))
+            torch.cuda.synchronize(); dist.barrier()
+            rounds, tw0 = 0, time.perf_counter()
+            stop = torch.zeros(1, device=dev)
+            while True:
+                hl = tr.train_steps_host(*h, offs, 0, ke)
+                rounds += 1
+                stop[0] = 1.0 if (time.perf_counter() - tw0 >= 0.25 and rounds >= 2) else 0.0
+                dist.all_reduce(stop, op=dist.ReduceOp.MIN)              # every rank leaves after the same round
+                if float(stop.item()) > 0:
+                    break
+            torch.cuda.synchronize(); dist.barrier()
+            wall = torch.tensor([time.perf_counter() - tw0], dtype=torch.float64, device=dev)
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+            etot = torch.tensor([float(nloc) * rounds], dtype=torch.float64, device=dev)
+            dist.all_reduce(etot, op=dist.ReduceOp.SUM)
+            assert bool(torch.isfinite(hl).all())
+            res["e2e"] = {"value": float(etot.item()) / float(wall.item()), "unit": UNIT,
+                          "h2d_bytes_per_step": 12.0 * float(etot.item()) / (rounds * ke), "d2h_bytes_per_step": 8 * world,
+                          "steps": rounds * ke, "wall_s": float(wall.item()),
+                          "api": "ShardedTrainer.train_steps_host(pinned host shares): native loop, per global step H2D of "
+                                 "each rank's share + phase 1 + exchange + phase 2 + D2H of the global loss; copy of step "
+                                 "s+1 under step s"}
+            res["t1"] = time.time()
+        del tr
+        torch.cuda.empty_cache()
+        return res
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    main = shape_run(args.shape, args.factors, args.steps, args.warmup, True)
+    c5 = None
+    if args.c5 == "on" or (args.c5 == "auto" and world >= 8):
+        c5 = shape_run("netflix", 128, max(100, args.steps), max(10, args.warmup), False)
+    if rank == 0:
+        clk = clocks.stop(main["t0"], main["t1"])
+        peak, peak_src = measured_peaks()
+        F = args.factors
+        bpt = 24 * F + 12
+        achieved = main["value"] / world * bpt / 1e9                      # per-GPU algorithmic GB/s of the step
+        exchange = ("ONE grouped NCCL all-reduce of gQ/counters/norms enqueued by the library between the phase-1 and "
+                    "phase-2 kernels" if args.comm == "nccl" else
+                    "in-kernel peer exchange over NVLink (no NCCL, no relaunch per step)")
+        line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": main["cfg"],
+                "steps_per_epoch": main["spe"], "exchange": exchange, "comm": args.comm,
+                "clocks": clk, "e2e": main["e2e"], "parity_check": main["parity"],
+                "gpu_launches": 2 * args.steps if args.comm == "nccl" else 1,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_triple": bpt,
+                             "kernel": "mf_bpr_steps_kernel (per GPU)"}}
+        if c5 is not None:
+            b5 = 24 * 128 + 12
+            a5 = c5["value"] / world * b5 / 1e9
+            line["configs"] = {"c5": {"workload": c5["cfg"]["workload"], "value": c5["value"], "unit": UNIT, "n_gpus": world,
+                                      "ms_per_step": c5["ms"] / max(100, args.steps), "steps": max(100, args.steps),
+                                      "per_gpu_batch": args.batch, "parity_check": c5["parity"],
+                                      "roofline": roof(a5, "mf_bpr_steps_kernel (per GPU)", b5)}}
+        ok = main["parity"]["ok"] and (c5 is None or c5["parity"]["ok"])
+        print(json.dumps(line), flush=True)
+    else:
+        ok = main["parity"]["ok"] and (c5 is None or c5["parity"]["ok"])
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 3
 
 
 def main():
@@ -381,9 +853,15 @@ def main():
     ap.add_argument("--shape", default="ml-20m")
     ap.add_argument("--num-ng", dest="num_ng", type=int, default=4)
     ap.add_argument("--seed", type=int, default=2022)
-    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=64)
-    ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=12.0)
-    ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=120.0)
+    ap.add_argument("--e2e-reps", dest="e2e_reps", type=int, default=3)
+    ap.add_argument("--configs", default="all", help="all | none | comma list of c3_neumf,c4_lightgcn,c5_netflix_1gpu,inference,sampling")
+    ap.add_argument("--c5", default="auto", choices=["auto", "on", "off"], help="N > 1: also run config 5 (netflix F=128)")
+    ap.add_argument("--comm", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=45.0)
+    ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=330.0)
+    ap.add_argument("--ref-workers", dest="ref_workers", type=int, default=4, help="DataLoader workers of the reference (test.py:94)")
+    ap.add_argument("--rows-file", dest="rows_file", default=None, help="reference arm: .npy of sampler triples to train on")
+    ap.add_argument("--quick", action="store_true", help="reference arm: main measurement only")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 8 if args.steps is None else args.steps

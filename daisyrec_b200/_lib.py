@@ -34,6 +34,7 @@ SIGNATURES = {
     "drb_version": (C.c_int, []),
     "drb_last_error": (C.c_char_p, []),
     "drb_device_query": (C.c_int, [c_i32p, c_i32p, c_i32p, c_i64p]),
+    "drb_index_range_check": (C.c_int, [vp, C.c_int32, C.c_int64, C.c_int32, c_i64p, c_i64p, vp]),
     "drb_mt19937_seed": (C.c_int, [vp, C.c_uint32]),
     "drb_sampler_draw_mt19937": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, c_i32p]),
     "drb_sampler_draw_philox": (C.c_int, [C.c_uint64, C.c_uint64, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]),
@@ -75,6 +76,9 @@ SIGNATURES = {
     "drb_comm_destroy": (C.c_int, []),
     "drb_mf_bpr_train_steps_sharded": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int64,
                                                  C.c_int64, C.POINTER(Hyper), C.c_int64, vp, vp]),
+    "drb_mf_bpr_train_steps_sharded_host": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp,
+                                                      C.c_int64, C.c_int64, C.POINTER(Hyper), C.c_int64, vp, C.c_int64, vp,
+                                                      vp, vp]),
     "drb_neumf_param_count": (C.c_int64, [C.c_int32, C.c_int32]),
     "drb_neumf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "drb_neumf_workspace_init": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp]),

@@ -100,6 +100,28 @@ extern "C" int drb_comm_destroy(void)
     return DRB_OK;
 }
 
+// One synchronous GLOBAL step on this rank's share [d_b* .. d_b* + count) of the global batch:
+//   phase 1 (local triples) -> ONE grouped all-reduce of {gQ, cntI, acc} -> phase 2 (local P rows + the replicated Q).
+static int sharded_step(float *d_P_local, float *d_Q, void *d_ws, int32_t U_local, int32_t I, int32_t F, const int32_t *d_bu,
+                        const int32_t *d_bi, const int32_t *d_bj, int64_t count, const drb_hyper *hyper, int64_t adam_step,
+                        double *d_loss, const int64_t *lay, cudaStream_t st)
+{
+    char *ws = (char *)d_ws;
+    double *acc = (double *)(ws + lay[0]);
+    float *gq = (float *)(ws + lay[2]);
+    unsigned long long *cnt_i = (unsigned long long *)(ws + lay[4]);
+    int rc = drb_mf_bpr_phase(d_P_local, d_Q, d_ws, U_local, I, F, d_bu, d_bi, d_bj, 0, count, 1, hyper, adam_step, d_loss,
+                              (void *)st);
+    if (rc != DRB_OK) return rc;
+    DRB_NCCL(g_nccl.GroupStart());
+    DRB_NCCL(g_nccl.AllReduce(gq, gq, (size_t)I * F, ncclFloat32, ncclSum, g_comm, st));
+    DRB_NCCL(g_nccl.AllReduce(cnt_i, cnt_i, (size_t)I, ncclUint64, ncclSum, g_comm, st));
+    DRB_NCCL(g_nccl.AllReduce(acc, acc, 8, ncclFloat64, ncclSum, g_comm, st));
+    DRB_NCCL(g_nccl.GroupEnd());
+    return drb_mf_bpr_phase(d_P_local, d_Q, d_ws, U_local, I, F, d_bu, d_bi, d_bj, 0, count, 2, hyper, adam_step, d_loss,
+                            (void *)st);
+}
+
 // n_steps synchronous GLOBAL steps on this rank's shard: step s trains local triples [h_step_offsets[s], h_step_offsets[s+1]).
 extern "C" int drb_mf_bpr_train_steps_sharded(float *d_P_local, float *d_Q, void *d_ws, int32_t U_local, int32_t I, int32_t F,
                                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj,
@@ -113,23 +135,79 @@ extern "C" int drb_mf_bpr_train_steps_sharded(float *d_P_local, float *d_Q, void
     int64_t lay[8];
     int rc = drb_mf_workspace_layout(U_local, I, F, hyper->opt, lay);
     if (rc != DRB_OK) return rc;
-    char *ws = (char *)d_ws;
-    double *acc = (double *)(ws + lay[0]);
-    float *gq = (float *)(ws + lay[2]);
-    unsigned long long *cnt_i = (unsigned long long *)(ws + lay[4]);
     for (int64_t s = 0; s < n_steps; ++s) {
         const int64_t b = h_step_offsets[first_step + s], e = h_step_offsets[first_step + s + 1];
-        rc = drb_mf_bpr_phase(d_P_local, d_Q, d_ws, U_local, I, F, d_bu, d_bi, d_bj, b, e - b, 1, hyper, adam_step0 + s,
-                              d_step_loss + s, stream);
-        if (rc != DRB_OK) return rc;
-        DRB_NCCL(g_nccl.GroupStart());
-        DRB_NCCL(g_nccl.AllReduce(gq, gq, (size_t)I * F, ncclFloat32, ncclSum, g_comm, st));
-        DRB_NCCL(g_nccl.AllReduce(cnt_i, cnt_i, (size_t)I, ncclUint64, ncclSum, g_comm, st));
-        DRB_NCCL(g_nccl.AllReduce(acc, acc, 8, ncclFloat64, ncclSum, g_comm, st));
-        DRB_NCCL(g_nccl.GroupEnd());
-        rc = drb_mf_bpr_phase(d_P_local, d_Q, d_ws, U_local, I, F, d_bu, d_bi, d_bj, b, e - b, 2, hyper, adam_step0 + s,
-                              d_step_loss + s, stream);
+        rc = sharded_step(d_P_local, d_Q, d_ws, U_local, I, F, d_bu + b, d_bi + b, d_bj + b, e - b, hyper, adam_step0 + s,
+                          d_step_loss + s, lay, st);
         if (rc != DRB_OK) return rc;
     }
     return DRB_OK;
+}
+
+// The same global steps fed from HOST (pinned) planes holding this rank's share of every global batch: the H2D copy of the
+// share of step s+1 (copy stream) overlaps the kernels and the collective of step s; every step's global loss is read
+// back to the host.  Mirrors drb_mf_bpr_train_steps_host for N > 1.  d_stage: 2 slots x 3 planes x stride int32, where
+// stride = max local share rounded up to 4.
+extern "C" int drb_mf_bpr_train_steps_sharded_host(float *d_P_local, float *d_Q, void *d_ws, int32_t U_local, int32_t I,
+                                                   int32_t F, const int32_t *h_bu, const int32_t *h_bi, const int32_t *h_bj,
+                                                   const int64_t *h_step_offsets, int64_t first_step, int64_t n_steps,
+                                                   const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage,
+                                                   int64_t stage_stride, double *d_step_loss, double *h_step_loss,
+                                                   void *stream)
+{
+    DRB_REQUIRE(g_comm != nullptr, "train_steps_sharded_host: call drb_comm_init first");
+    DRB_REQUIRE(d_P_local && d_Q && d_ws && h_bu && h_bi && h_bj && h_step_offsets && hyper && d_stage && d_step_loss &&
+                    h_step_loss && n_steps >= 0 && stage_stride > 0 && stage_stride % 4 == 0,
+                "train_steps_sharded_host: bad arguments");
+    if (n_steps == 0) return DRB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t lay[8];
+    int rc = drb_mf_workspace_layout(U_local, I, F, hyper->opt, lay);
+    if (rc != DRB_OK) return rc;
+    static thread_local cudaStream_t copy_st = nullptr;
+    if (!copy_st) DRB_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+    cudaEvent_t ready[2], freed[2], start;
+    for (int k = 0; k < 2; ++k) {
+        DRB_CUDA(cudaEventCreateWithFlags(&ready[k], cudaEventDisableTiming));
+        DRB_CUDA(cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming));
+    }
+    DRB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    DRB_CUDA(cudaEventRecord(start, st));
+    DRB_CUDA(cudaStreamWaitEvent(copy_st, start, 0));
+    for (int64_t s = 0; s < n_steps && rc == DRB_OK; ++s) {
+        const int slot = (int)(s & 1);
+        int32_t *sb = d_stage + (size_t)slot * 3 * stage_stride;
+        const int64_t b = h_step_offsets[first_step + s], cnt = h_step_offsets[first_step + s + 1] - b;
+        if (cnt > stage_stride) {
+            set_error("train_steps_sharded_host: local share %lld exceeds the staging stride %lld", (long long)cnt,
+                      (long long)stage_stride);
+            rc = DRB_ERR_INVALID;
+            break;
+        }
+        const size_t bytes = sizeof(int32_t) * (size_t)cnt;
+        if (s >= 2) DRB_CUDA(cudaStreamWaitEvent(copy_st, freed[slot], 0));
+        if (cnt > 0) {
+            DRB_CUDA(cudaMemcpyAsync(sb, h_bu + b, bytes, cudaMemcpyHostToDevice, copy_st));
+            DRB_CUDA(cudaMemcpyAsync(sb + stage_stride, h_bi + b, bytes, cudaMemcpyHostToDevice, copy_st));
+            DRB_CUDA(cudaMemcpyAsync(sb + 2 * stage_stride, h_bj + b, bytes, cudaMemcpyHostToDevice, copy_st));
+        }
+        DRB_CUDA(cudaEventRecord(ready[slot], copy_st));
+        DRB_CUDA(cudaStreamWaitEvent(st, ready[slot], 0));
+        rc = sharded_step(d_P_local, d_Q, d_ws, U_local, I, F, sb, sb + stage_stride, sb + 2 * stage_stride, cnt, hyper,
+                          adam_step0 + s, d_step_loss + s, lay, st);
+        if (rc != DRB_OK) break;
+        DRB_CUDA(cudaEventRecord(freed[slot], st));
+        DRB_CUDA(cudaMemcpyAsync(h_step_loss + s, d_step_loss + s, sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    cudaStreamSynchronize(copy_st);
+    if (rc == DRB_OK) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    for (int k = 0; k < 2; ++k) {
+        cudaEventDestroy(ready[k]);
+        cudaEventDestroy(freed[k]);
+    }
+    cudaEventDestroy(start);
+    return rc;
 }

@@ -20,6 +20,10 @@ from .. import ops
 from ..utils.sampler import fingerprint
 
 
+# 'torch': the DataLoader's own permutation (the reference's batches bit for bit); 'device': torch.randperm on the GPU
+DEFAULT_SHUFFLE_ENGINE = 'torch'
+
+
 class _Table:
     """Stand-in for nn.Embedding: ``.weight`` is the raw fp32 [rows, factors] table."""
 
@@ -50,14 +54,23 @@ _INIT = {
 }
 
 
-def epoch_permutation(n, shuffle, generator=None):
-    """Index order of one DataLoader epoch (torch/utils/data/dataloader.py:706-710 draws
-    ``_base_seed``; sampler.py RandomSampler.__iter__ draws a seed, seeds a private generator and
-    yields ``torch.randperm(n, generator)``).  Consumes the global torch RNG identically."""
+def epoch_seed(shuffle, generator=None):
+    """The DataLoader's RNG protocol for one epoch (torch/utils/data/dataloader.py:706-710 draws ``_base_seed``;
+    sampler.py RandomSampler.__iter__ draws the seed of a private generator).  Consumes the global torch RNG exactly as
+    iterating the loader would.  -> the RandomSampler's seed, or None without shuffling."""
     torch.empty((), dtype=torch.int64).random_(generator=generator)           # _base_seed (discarded)
     if not shuffle:
         return None
-    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return int(torch.empty((), dtype=torch.int64).random_().item())
+
+
+def epoch_permutation(n, shuffle, generator=None, seed=None):
+    """Index order of one DataLoader epoch: ``torch.randperm(n, generator)`` of a private generator seeded as
+    RandomSampler.__iter__ seeds it (``seed`` given: already drawn with epoch_seed)."""
+    if seed is None:
+        seed = epoch_seed(shuffle, generator)
+    if not shuffle or seed is None:
+        return None
     g = torch.Generator()
     g.manual_seed(seed)
     return torch.randperm(n, generator=g)
@@ -162,7 +175,7 @@ class GeneralRecommender(AbstractRecommender):
         self.show_progress = bool(config.get('progress', True))
         # 'torch' (default): the DataLoader's own CPU permutation -> the reference's batches bit for bit;
         # 'device': torch.randperm on the GPU seeded from the global RNG (same distribution, no 8-byte/triple H2D)
-        self.shuffle_engine = str(config.get('shuffle_engine', 'torch'))
+        self.shuffle_engine = str(config.get('shuffle_engine', DEFAULT_SHUFFLE_ENGINE))
         # one process per GPU (torchrun): user-sharded training / ranking, see daisyrec_b200/parallel.py
         import torch.distributed as dist
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -228,13 +241,19 @@ class GeneralRecommender(AbstractRecommender):
         it was attached with, else an upload cached per (array, stamp) -- an in-place edit of the host rows re-uploads."""
         stamp = fingerprint(data)
         d_triples = getattr(data, '_drb_device', None)
-        if d_triples is not None and d_triples.device == self.device and getattr(data, '_drb_stamp', None) == stamp:
-            return d_triples
-        if getattr(self, '_triples_key', None) != (id(data), stamp):
-            host = np.ascontiguousarray(data, dtype=np.int32)
-            self._triples_dev = torch.from_numpy(host if host.flags.writeable else host.copy()).to(self.device)
-            self._triples_key = (id(data), stamp)
-        return self._triples_dev
+        if not (d_triples is not None and d_triples.device == self.device and getattr(data, '_drb_stamp', None) == stamp):
+            if getattr(self, '_triples_key', None) != (id(data), stamp):
+                host = np.ascontiguousarray(data, dtype=np.int32)
+                self._triples_dev = torch.from_numpy(host if host.flags.writeable else host.copy()).to(self.device)
+                self._triples_key = (id(data), stamp)
+            d_triples = self._triples_dev
+        if d_triples.is_cuda and getattr(self, '_range_ok', None) != (id(data), stamp):
+            # nn.Embedding's IndexError (the kernels index raw tables): one pass over the ids per uploaded array
+            pointwise = str(self.loss_type).upper() in ('CL', 'SL')
+            ops.check_index_range(d_triples, (self.user_num, self.item_num, (1 << 62) if pointwise else self.item_num),
+                                  ('user', 'item', 'label' if pointwise else 'negative item'))
+            self._range_ok = (id(data), stamp)
+        return d_triples
 
     def _fit_epoch_sharded(self, plan, epoch):
         """N > 1: same global batches as the single-GPU run; this rank trains the triples of its users."""
@@ -242,7 +261,13 @@ class GeneralRecommender(AbstractRecommender):
         T = data.shape[0]
         d_triples = self._device_triples(data)
         trainer = self._sharded_trainer(d_triples)
-        perm = epoch_permutation(T, shuffle, gen)                  # identical on every rank (same torch seed)
+        # every rank advances its own RNG as the DataLoader would, but rank 0's seed decides the epoch's order: the ranks
+        # keep disjoint shares of ONE permutation whatever their RNG histories were
+        from ..parallel import broadcast_int
+        seed = epoch_seed(shuffle, gen)
+        if shuffle:
+            seed = broadcast_int(seed, self.device)
+        perm = epoch_permutation(T, shuffle, gen, seed=seed)
         d_perm = None if perm is None else perm.to(self.device)
         nsteps = trainer.prepare_epoch(d_triples, d_perm, bs)
         if drop_last and T % bs:

@@ -44,6 +44,12 @@ class MF(GeneralRecommender):
         wi = _init_table(self.item_num, self.factors, None)
         _INIT[self.initializer](wu)
         _INIT[self.initializer](wi)
+        if self.world > 1:
+            # every rank drew the tables from its own CPU RNG; rank 0's draw is THE model (replicas of Q must start
+            # bit-identical and the shards of P must come from one table whatever the ranks' RNG histories were)
+            from ..parallel import broadcast_cpu_
+            broadcast_cpu_(wu, self.device)
+            broadcast_cpu_(wi, self.device)
         self.embed_item = _Table(wi.to(self.device))
         if self.world > 1:
             # user rows are sharded at fit()/rank() time, once the interaction counts are known
@@ -243,10 +249,13 @@ class MF(GeneralRecommender):
         if len(users) == 0:
             return np.zeros((0,), np.float32)
         k = min(self.topk, cands.shape[1])
+        if users.min() < 0 or users.max() >= self.user_num:
+            raise IndexError('index out of range in self: test user id outside [0, user_num)')
         if self.world > 1:
             return self._rank_sharded(users, cands, k)
-        out = ops.mf_rank(self.embed_user.weight, self.embed_item.weight,
-                          torch.from_numpy(users).to(self.device), torch.from_numpy(np.ascontiguousarray(cands)).to(self.device), k)
+        d_cands = torch.from_numpy(np.ascontiguousarray(cands)).to(self.device)
+        ops.check_index_range(d_cands.reshape(-1, 1), (self.item_num,), ('candidate item',))
+        out = ops.mf_rank(self.embed_user.weight, self.embed_item.weight, torch.from_numpy(users).to(self.device), d_cands, k)
         return out.cpu().numpy()
 
     def _rank_sharded(self, users, cands, k):

@@ -54,8 +54,10 @@ class NeuMF(GeneralRecommender):
         with torch.no_grad():
             for e in embs:
                 init(e.weight)
+            bare = {'normal': torch.nn.init.normal_, 'uniform': torch.nn.init.uniform_,
+                    'xavier_normal': torch.nn.init.xavier_normal_, 'xavier_uniform': torch.nn.init.xavier_uniform_}
             for lin in linears:
-                init(lin.weight)
+                bare[self.initializer](lin.weight)      # :88-90 passes NO param config to the hidden layers: 'normal' is N(0, 1)
             init(predict.weight)
             for lin in linears + [predict]:
                 lin.bias.zero_()

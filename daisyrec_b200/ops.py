@@ -40,6 +40,21 @@ def device_query():
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), l2_bytes=l2.value)
 
 
+def check_index_range(ids, bounds, what):
+    """IndexError (what nn.Embedding raises in the reference) when a column of the device index array ``ids`` [n, len(bounds)]
+    holds an id outside [0, bounds[c]).  One kernel + one 64-byte read-back."""
+    if not (isinstance(ids, torch.Tensor) and ids.is_cuda and ids.is_contiguous() and ids.dtype in (torch.int32, torch.int64)):
+        raise TypeError("check_index_range: expected a contiguous CUDA int32 / int64 tensor")
+    ncols = len(bounds)
+    n = ids.numel() // ncols
+    hi = (C.c_int64 * 4)(*([int(b) for b in bounds] + [0] * (4 - ncols)))
+    bad = (C.c_int64 * 4)()
+    L.check(L.lib().drb_index_range_check(_ptr(ids), ids.element_size(), n, ncols, hi, bad, _stream()))
+    for c in range(ncols):
+        if bad[c]:
+            raise IndexError(f"index out of range in self: {bad[c]} {what[c]} id(s) outside [0, {int(bounds[c])})")
+
+
 # ------------------------------------------------------------------ sampler
 def mt19937_seed(seed):
     st = np.zeros(625, np.uint32)

@@ -17,9 +17,6 @@ torch.distributed (NCCL on GPUs, gloo in the CPU tests of the host logic) is plu
 libdaisyrec_b200.so.
 """
 import ctypes as C
-import os
-import time
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -84,6 +81,23 @@ def allgather_rows(local_rows, local_pos, total_rows, group=None):
     return out
 
 
+def broadcast_cpu_(t, device, group=None):
+    """In-place broadcast of a CPU tensor from rank 0 (staged through `device` when the backend is NCCL)."""
+    if dist.get_backend(group) == "nccl":
+        d = t.to(device)
+        dist.broadcast(d, 0, group=group)
+        t.copy_(d)
+    else:
+        dist.broadcast(t, 0, group=group)
+    return t
+
+
+def broadcast_int(value, device, group=None):
+    """Rank 0's python int on every rank (seeds, sizes)."""
+    t = torch.tensor([int(value)], dtype=torch.int64)
+    return int(broadcast_cpu_(t, device, group).item())
+
+
 # --------------------------------------------------------------------------------------- device side
 _NATIVE_COMM = {"ready": False}
 
@@ -123,7 +137,9 @@ class ShardedTrainer:
         if self.comm == "nccl":
             init_native_comm(group)
         self.ops = ops
-        self.P, self.Q = P_local, Q
+        self.Q = Q
+        # a rank that owns no user still takes part in every collective: give the kernels one dummy row to point at
+        self.P = P_local if P_local.shape[0] > 0 else torch.zeros((1, Q.shape[1]), dtype=Q.dtype, device=Q.device)
         self.bounds, self.rank, self.world, self.group = np.asarray(bounds, np.int64), rank, world, group
         self.lo, self.hi = int(self.bounds[rank]), int(self.bounds[rank + 1])
         self.U_local, self.I, self.F = P_local.shape[0], Q.shape[0], Q.shape[1]
@@ -140,6 +156,7 @@ class ShardedTrainer:
         self.loss = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.opt_steps = 0
         self.offsets_host = None
+        self._stage = None
 
     # ---- train feed
     def prepare_epoch(self, d_triples, d_perm, batch_global):
@@ -193,6 +210,25 @@ class ShardedTrainer:
                 losses[k] = self.loss[0]
         return losses[:n_steps]
 
+    def train_steps_host(self, h_bu, h_bi, h_bj, h_offsets, first, n_steps):
+        """Global steps fed from pinned HOST planes holding this rank's share of every global batch (native loop: the
+        H2D of step s+1 overlaps step s, one loss D2H per step).  Returns the per-step GLOBAL losses (pinned CPU fp64)."""
+        if self.comm != "nccl":
+            raise RuntimeError("train_steps_host needs the native NCCL communicator")
+        offs = np.ascontiguousarray(h_offsets, np.int64)
+        widest = int(np.diff(offs[first:first + n_steps + 1]).max()) if n_steps > 0 else 0
+        stride = max(4, (widest + 3) // 4 * 4)
+        if self._stage is None or self._stage.numel() < 6 * stride:
+            self._stage = torch.empty(6 * stride, dtype=torch.int32, device=self.dev)
+        d_loss = torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
+        h_loss = torch.empty(max(1, n_steps), dtype=torch.float64).pin_memory()
+        L.check(L.lib().drb_mf_bpr_train_steps_sharded_host(
+            _ptr(self.P), _ptr(self.Q), _ptr(self.ws.buf), max(1, self.U_local), self.I, self.F, h_bu.data_ptr(),
+            h_bi.data_ptr(), h_bj.data_ptr(), offs.ctypes.data, first, n_steps, C.byref(self.hp), self.opt_steps,
+            _ptr(self._stage), stride, _ptr(d_loss), h_loss.data_ptr(), _stream()))
+        self.opt_steps += n_steps
+        return h_loss[:n_steps]
+
     def step_host(self, h_bu, h_bi, h_bj, stage):
         """End-to-end step from pinned HOST arrays holding this rank's share of the global batch."""
         n = len(h_bu)
@@ -207,112 +243,3 @@ class ShardedTrainer:
         status = int(np.frombuffer(hdr[144:148].tobytes(), np.int32)[0])   # WsHeader: barrier 8 + acc 128 + nan_step 8
         if status == L.DRB_ERR_NAN_LOSS:
             raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
-
-
-# --------------------------------------------------------------------------------------- bench (N > 1)
-def run_sharded_bench(args, rank, local, world, dev):
-    """Weak-scaling arm of bench.py: per-GPU batch fixed (args.batch), global batch = world * batch."""
-    import json
-    from . import ops
-    from .utils.synthetic import init_tables
-    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    import sys
-    if sys_path_root not in sys.path:
-        sys.path.insert(0, sys_path_root)
-    import bench as B
-
-    d, triples = B.build_workload(args.shape, dev, args.num_ng, args.seed, "cuda")     # identical on every rank
-    U, I, F = d["user_num"], d["item_num"], args.factors
-    T = triples.shape[0]
-    Bg = args.batch * world
-    deg = (d["row_ptr"][1:] - d["row_ptr"][:-1]).cpu().numpy()
-    bounds = partition_users(deg, world)
-    g = torch.Generator(device=dev); g.manual_seed(args.seed)
-    perm = torch.randperm(T, generator=g, device=dev)
-    P0, Q0 = init_tables(U, I, F, args.seed, dev)
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.contiguous(), bounds, rank, world, ops.hyper(0.01, 0.001, 0.001))
-    spe = tr.prepare_epoch(triples, perm, Bg)
-    del perm
-    local_counts = np.diff(tr.offsets_host)
-
-    scratch_losses = torch.empty(spe + 1, dtype=torch.float64, device=dev)
-
-    def run(first, k):
-        """k global steps starting at `first`, walking the epoch cyclically; one native call per epoch segment."""
-        n_loc, s = 0, first
-        while k > 0:
-            pos = s % spe
-            seg = min(k, spe - pos)
-            tr.train_steps(pos, seg, scratch_losses)
-            n_loc += int(local_counts[pos:pos + seg].sum())
-            s += seg
-            k -= seg
-        return n_loc
-
-    clocks = B.ClockSampler(local) if rank == 0 else None
-    run(0, args.warmup)
-    torch.cuda.synchronize(); dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    e0.record()
-    n_loc = run(args.warmup, args.steps)
-    e1.record()
-    torch.cuda.synchronize(); dist.barrier()
-    t1 = time.time()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    tot = torch.tensor([n_loc], dtype=torch.float64, device=dev)
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    tr.check_nan()
-    value = float(tot.item()) / float(ms.item()) * 1e3
-
-    # e2e: pinned host share of each global batch -> H2D + step + D2H loss
-    ke = max(1, min(args.steps, args.e2e_steps))
-    host = []
-    for s in range(ke + 2):
-        b, e = int(tr.offsets_host[(args.warmup + s) % spe]), int(tr.offsets_host[(args.warmup + s) % spe + 1])
-        host.append([t[b:e].cpu().pin_memory() for t in (tr.bu, tr.bi, tr.bj)])
-    stage = torch.empty(3 * (max(len(h[0]) for h in host) + 4) + 4, dtype=torch.int32, device=dev)
-    for s in range(2):
-        tr.step_host(*host[s], stage)
-    torch.cuda.synchronize(); dist.barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    n_e = 0
-    for s in range(2, ke + 2):
-        tr.step_host(*host[s], stage)
-        n_e += len(host[s][0])
-    f1.record()
-    torch.cuda.synchronize(); dist.barrier()
-    t2 = time.time()
-    ems = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    etot = torch.tensor([n_e], dtype=torch.float64, device=dev)
-    dist.all_reduce(etot, op=dist.ReduceOp.SUM)
-    h2d = torch.tensor([12.0 * n_e / ke], dtype=torch.float64, device=dev)
-    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        clk = clocks.stop(t0, t2)
-        peak, peak_src = B.measured_peaks()
-        bpt = 24 * F + 12
-        achieved = value / world * bpt / 1e9                      # per-GPU algorithmic GB/s of the fused step
-        line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": float(ms.item()) / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": B.workload_config(args, d, T, args.batch, {
-                    "parallelism": f"user-row-sharded P x{world}, replicated Q, per step ONE grouped NCCL all-reduce of "
-                                   "gQ/counters/norms enqueued by the library between the phase-1 and phase-2 kernels",
-                    "global_batch": Bg, "per_gpu_batch": args.batch, "steps_per_epoch": spe}),
-                "clocks": clk,
-                "e2e": {"value": float(etot.item()) / float(ems.item()) * 1e3, "unit": B.UNIT,
-                        "h2d_bytes_per_step": float(h2d.item()), "d2h_bytes_per_step": 8 * world, "steps": ke,
-                        "api": "ShardedTrainer.step_host(rank-local host batch): H2D + phase1 + all-reduce + phase2 + D2H loss"},
-                "gpu_launches": 2 * args.steps,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_triple": bpt,
-                             "kernel": "mf_bpr_steps_kernel (phase 1 + phase 2 launches, per GPU)"}}
-        print(json.dumps(line), flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
-    return 0

@@ -21,6 +21,8 @@ def fingerprint(a):
     relabelled) and re-upload it; a stamp, not a checksum."""
     flat = np.asarray(a).reshape(-1)
     step = max(1, flat.size // 65536)
+    while step > 1 and step % 3 == 0:        # [T,3] rows: a stride that is a multiple of 3 would only ever see one column
+        step += 1
     return (tuple(a.shape), int(flat[::step].sum(dtype=np.int64)), flat[:3].tobytes(), flat[-3:].tobytes())
 
 

@@ -65,6 +65,12 @@ int drb_version(void);
 const char *drb_last_error(void);
 /* sm_count, compute capability, L2 bytes of the current device */
 int drb_device_query(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *l2_bytes);
+/* Range check of an index array [n_rows, n_cols] (elem_bytes 4 = int32, 8 = int64; n_cols <= 4) resident on the device:
+ * h_bad[c] = number of ids in column c outside [0, h_hi[c]).  The kernels index raw tables where the reference's
+ * nn.Embedding raises IndexError (torch/nn/functional.py: embedding), so fit() / rank() call this once per uploaded
+ * array and raise the same exception.  Synchronises the stream. */
+int drb_index_range_check(const void *d_ids, int32_t elem_bytes, int64_t n_rows, int32_t n_cols, const int64_t *h_hi,
+                          int64_t *h_bad, void *stream);
 
 /* ---- pair-wise sampler: BasicNegtiveSampler.sampling(), uniform + BPR branch ------
  * daisy/utils/sampler.py:55-103 (js table :63,84-89; explode :91,99-101).
@@ -258,6 +264,15 @@ int drb_mf_bpr_train_steps_sharded(float *d_P_local, float *d_Q, void *d_ws, int
                                    int32_t factors, const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj,
                                    const int64_t *h_step_offsets, int64_t first_step, int64_t n_steps,
                                    const drb_hyper *hyper, int64_t adam_step0, double *d_step_loss, void *stream);
+/* The same global steps from HOST (pinned) planes holding this rank's share of every global batch (the N > 1 form of
+ * drb_mf_bpr_train_steps_host; the reference's per-step `.to(device)` + `loss.item()`, AbstractRecommender.py:116-128):
+ * the H2D copy of step s+1 overlaps step s; h_step_loss[s] receives the GLOBAL loss of step s.  d_stage: 2 x 3 x
+ * stage_stride int32 (stage_stride = largest local share rounded up to a multiple of 4).  Synchronises the stream. */
+int drb_mf_bpr_train_steps_sharded_host(float *d_P_local, float *d_Q, void *d_ws, int32_t user_num_local, int32_t item_num,
+                                        int32_t factors, const int32_t *h_bu, const int32_t *h_bi, const int32_t *h_bj,
+                                        const int64_t *h_step_offsets, int64_t first_step, int64_t n_steps,
+                                        const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage, int64_t stage_stride,
+                                        double *d_step_loss, double *h_step_loss, void *stream);
 
 /* ---- inference ------------------------------------------------------------------------
  * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,

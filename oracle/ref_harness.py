@@ -1,10 +1,11 @@
 """Import harness for the REAL reference (AmazingDD/daisyRec at /root/reference).
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``daisyrec_b200/`` may import this file.
-It only works in the build container (``/root/reference`` does not exist on the GPU
-box); its sole jobs are (1) validating the restatements in ``oracle/`` against the
-reference itself and (2) generating the golden fixtures in ``tests/golden/`` via
-``oracle/gen_golden.py``.
+Its jobs: (1) validating the restatements in ``oracle/`` against the reference itself,
+(2) generating the golden fixtures in ``tests/golden/`` via ``oracle/gen_golden.py`` (both in
+the build container, from ``/root/reference``), and (3) letting ``bench.py --impl reference`` /
+the ``cpu_baseline`` leg time the reference's own ``fit`` on the GPU box's host cores from the
+installed copy ``oracle/_ref`` (``oracle/build_ref.py``).
 
 The reference does not run unmodified on numpy 2.3 / pandas 3.0 / scipy 1.18
 (SURVEY.md facts 10, Appendix B).  Three behavioural shims are applied *here*, in
@@ -24,7 +25,26 @@ import os
 import random
 import sys
 
-REF_ROOT = os.environ.get("DAISY_REF_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+INSTALLED_ROOT = os.path.join(_HERE, "_ref")          # oracle/build_ref.py: the reference package, installed unmodified
+
+
+def _default_root():
+    env = os.environ.get("DAISY_REF_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/daisy"):         # build container: the source tree (has data/ml-100k too)
+        return "/root/reference"
+    return INSTALLED_ROOT                              # GPU box: only the installed copy travels
+
+
+REF_ROOT = _default_root()
+
+
+def use_root(path):
+    """Point the harness at another copy of the reference (bench.py times the installed copy everywhere)."""
+    global REF_ROOT
+    REF_ROOT = path
 
 
 def available() -> bool:

@@ -232,3 +232,49 @@ def test_device_twin_is_dropped_after_an_in_place_edit():
     assert np.array_equal(m._device_triples(plain).numpy(), plain)
     empty = np.zeros((0, 3), np.int32)
     assert fingerprint(empty)[0] == (0, 3) and m._device_triples(empty).shape == (0, 3)
+
+
+def test_fingerprint_sees_every_column():
+    """A stride that is a multiple of 3 would sample one column of the [T,3] rows only (T = 65536*k hits it)."""
+    from daisyrec_b200.utils.sampler import fingerprint
+    rows = np.zeros((65536 * 3, 3), np.int32)
+    base = fingerprint(rows)
+    for col in range(3):
+        edited = rows.copy()
+        edited[5:-5, col] += 1                                            # leave the end rows (stamped separately) alone
+        assert fingerprint(edited) != base, col
+
+
+def test_epoch_seed_and_permutation_follow_the_dataloader():
+    """epoch_seed + epoch_permutation consume the global RNG exactly as iterating DataLoader(shuffle=True) does."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from daisyrec_b200.model.AbstractRecommender import epoch_permutation, epoch_seed
+    n = 1000
+    torch.manual_seed(7)
+    order = torch.cat([b[0] for b in DataLoader(TensorDataset(torch.arange(n)), batch_size=64, shuffle=True)])
+    after = torch.get_rng_state()
+    torch.manual_seed(7)
+    assert torch.equal(epoch_permutation(n, True, seed=epoch_seed(True)), order)
+    assert torch.equal(torch.get_rng_state(), after)
+    torch.manual_seed(7)
+    assert torch.equal(epoch_permutation(n, True), order)
+
+
+def test_reference_arm_times_the_installed_reference(tmp_path):
+    """bench.py --impl reference runs the REAL daisy MF.fit (oracle/_ref) over its own DataLoader; config is the own arm's."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    if bench.reference_root() is None:
+        pytest.skip("oracle/_ref not installed (no /root/reference in this container)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--shape", "tiny", "--batch",
+                        "2048", "--steps", "3", "--warmup", "1", "--quick"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "reference" and line["value"] > 0
+    assert line["steps"] == 3 and line["gpu_launches"] == 0
+    ns = type("A", (), dict(shape="tiny", num_ng=4, factors=64, batch=2048))
+    assert line["config"] == bench.workload_config(ns, 1)                  # same_config with the own arm

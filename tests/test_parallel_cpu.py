@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from daisyrec_b200.parallel import partition_users, owner_of, allgather_rows, allreduce_step_buffers
+from daisyrec_b200.parallel import (partition_users, owner_of, allgather_rows, allreduce_step_buffers, broadcast_cpu_,
+                                    broadcast_int)
 
 
 def test_partition_users_balances_weight():
@@ -53,6 +54,19 @@ def _worker(rank, world, port, out):
         # a rank with no rows still participates
         empty = allgather_rows(rows[:0] if rank == 1 else rows, mine[:0] if rank == 1 else mine, 5)
         ok = ok and torch.equal(empty[[0, 3, 4]], want[[0, 3, 4]])
+        # RNG-dependent state comes from rank 0 whatever the ranks drew themselves (model init, epoch seed)
+        torch.manual_seed(100 + rank)                                      # deliberately different RNG histories
+        w = torch.empty(7, 3).normal_()
+        mine_before = w.clone()
+        broadcast_cpu_(w, torch.device("cpu"))
+        g = torch.Generator(); g.manual_seed(100)
+        ok = ok and torch.equal(w, torch.empty(7, 3).normal_(generator=g)) and (rank == 0 or not torch.equal(w, mine_before))
+        from daisyrec_b200.model.AbstractRecommender import epoch_seed, epoch_permutation
+        seed = broadcast_int(epoch_seed(True), torch.device("cpu"))
+        perm = epoch_permutation(1000, True, seed=seed)
+        both = [torch.empty_like(perm) for _ in range(world)]
+        dist.all_gather(both, perm)
+        ok = ok and torch.equal(both[0], both[1]) and sorted(perm.tolist()) == list(range(1000))
         out[rank] = ok
     finally:
         dist.destroy_process_group()
