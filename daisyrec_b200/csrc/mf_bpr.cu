@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
             if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1; } else { mbar_wait(&s_bar[1], par1); par1 ^= 1; }
             const int cnt = (int)min((long long)tile, nb - t_i * tile);
             const int32_t *xu = s_idx[buf][0], *xi = s_idx[buf][1], *xj = s_idx[buf][2];
-            float t_loss = 0.f, t_l1u = 0.f, t_l1i = 0.f, t_l1j = 0.f, t_s2u = 0.f, t_s2i = 0.f, t_s2j = 0.f;
+            float t_loss = 0.f, t_l1u = 0.f, t_l1i = 0.f, t_l1j = 0.f, t_s2u = 0.f, t_s2i = 0.f, t_s2j = 0.f, t_gb0 = 0.f;
 
             for (int tb = 0; tb < cnt; tb += GROUPS * UNR) {
                 Row<VEC, W, NCH> rp[UNR], rqi[UNR], rqj[UNR];
@@ -332,6 +332,11 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                 for (int r = 0; r < UNR; ++r) {
                     ps[r] = dot_rows<VEC, W, NCH>(rp[r], rqi[r]);
                     ns[r] = dot_rows<VEC, W, NCH>(rp[r], rqj[r]);
+                    if (GEN && p.bias != nullptr) {   // FM: pred += (u_bias(user) + i_bias(item)) + bias_  (FMRecommender.py:66-67)
+                        const float ub = __ldcg(p.bias + iu[r]), b0 = __ldcg(p.bias + p.U + p.I);
+                        ps[r] += (ub + __ldcg(p.bias + p.U + ii[r])) + b0;
+                        ns[r] += (ub + __ldcg(p.bias + p.U + ij[r])) + b0;
+                    }
                     if (pw) ns[r] = lab[r];         // pair_loss receives the label in place of the negative score
                 }
                 // The scalar chain (sigmoid -> log -> coefficient, ~40 instructions) would be replayed by all W lanes for
@@ -441,15 +446,24 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                             red_add_u32(p.ws.cntU + iu[r], 1u);
                             red_add_u64(p.ws.cntI + ii[r], 1ull);
                             if (!pw) red_add_u64(p.ws.cntI + ij[r], 1ull << 32);
+                            if (GEN && p.bias != nullptr) {   // d loss / d (u_bias, i_bias, bias_): no regulariser (:76-95)
+                                const float cboth = pw ? c : c + cn[r];
+                                asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p.ws.gB + iu[r]), "f"(cboth) : "memory");
+                                asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p.ws.gB + p.U + ii[r]), "f"(c) : "memory");
+                                if (!pw)
+                                    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p.ws.gB + p.U + ij[r]), "f"(cn[r]) : "memory");
+                                t_gb0 += cboth;
+                            }
                         }
                     }
                 }
             }
             // per-thread fp32 partials cover <= tile/GROUPS triples: warp-reduce, widen to fp64 in smem
             {
-                float tv[7] = {t_loss, t_l1u, t_l1i, t_l1j, t_s2u, t_s2i, t_s2j};
+                float tv[8] = {t_loss, t_l1u, t_l1i, t_l1j, t_s2u, t_s2i, t_s2j, t_gb0};
                 const int nv = has_reg ? 7 : 1;
-                for (int k = 0; k < nv; ++k) {
+                for (int k = 0; k < 8; ++k) {
+                    if (k >= nv && !(GEN && k == 7 && p.bias != nullptr)) continue;
                     float v = tv[k];
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
         }
         // CTA reduction of the 7 partial sums -> one fp64 atomic each
         __syncthreads();
-        if (tid < (has_reg ? 7 : 1)) {
+        if (tid < (has_reg ? 7 : 1) || (GEN && tid == 7 && p.bias != nullptr)) {
             double v = 0;
             for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
             if (v != 0.0) atomicAdd(&acc[tid], v);
@@ -562,6 +576,41 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
                 }
             }
         }
+        if (GEN && p.apply && p.bias != nullptr) {
+            // FM's U + I + 1 first-order scalars: the same optimiser switch, no regulariser; the accumulator is cleared
+            const double gb0 = ((const volatile double *)acc)[7];
+            float step_size = 0.f, bc2_sqrt = 1.f;
+            if (p.opt == DRB_OPT_ADAM) {
+                double t = (double)(p.adam_step0 + s + 1);
+                step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, t)));
+                bc2_sqrt = (float)sqrt(1.0 - pow((double)p.beta2, t));
+            }
+            const long long nbias = (long long)p.U + p.I + 1;
+            for (long long k = (long long)blockIdx.x * kThreads + tid; k < nbias; k += (long long)gridDim.x * kThreads) {
+                const float g = (k == nbias - 1) ? (float)gb0 : __ldcg(p.ws.gB + k);
+                float th = __ldcg(p.bias + k);
+                if (p.opt == DRB_OPT_SGD) {
+                    th = th - p.lr * g;
+                } else if (p.opt == DRB_OPT_ADAGRAD) {
+                    const float ss = __ldcg(p.ws.mB + k) + g * g;
+                    th = th - p.lr * (g / (sqrtf(ss) + 1e-10f));
+                    __stcg(p.ws.mB + k, ss);
+                } else if (p.opt == DRB_OPT_RMSPROP) {
+                    const float sq = __ldcg(p.ws.mB + k) * 0.99f + (1.f - 0.99f) * g * g;
+                    th = th - p.lr * (g / (sqrtf(sq) + 1e-8f));
+                    __stcg(p.ws.mB + k, sq);
+                } else {
+                    float mm = __ldcg(p.ws.mB + k), vv = __ldcg(p.ws.vB + k);
+                    mm = mm + (g - mm) * (1.f - p.beta1);
+                    vv = vv * p.beta2 + (1.f - p.beta2) * g * g;
+                    th = th - step_size * (mm / (sqrtf(vv) / bc2_sqrt + p.eps));
+                    __stcg(p.ws.mB + k, mm);
+                    __stcg(p.ws.vB + k, vv);
+                }
+                __stcg(p.bias + k, th);
+                if (k != nbias - 1 && g != 0.f) __stcg(p.ws.gB + k, 0.f);
+            }
+        }
         if (s + 1 < p.n_steps) grid_barrier(&hdr->barrier, epoch);
     }
 }
@@ -611,7 +660,7 @@ static StepKernel pick_kernel(int F, bool gen)
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
     // GEN instantiation: any loss but BPR, and the Adagrad / RMSprop sweeps (kept out of the hot BPR + SGD/Adam kernel)
-    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM);
+    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr);
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
     // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
     // split multi-GPU / LightGCN / NeuMF paths)
@@ -678,7 +727,7 @@ extern "C" int drb_mf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F
 
 static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu,
                        const int32_t *bi, const int32_t *bj, long long n, long long batch, long long first, long long nsteps,
-                       const drb_hyper *h, long long adam_step0, double *d_step_loss, int apply)
+                       const drb_hyper *h, long long adam_step0, double *d_step_loss, int apply, float *d_bias = nullptr)
 {
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
@@ -687,7 +736,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0 || n == 0, "steps [%lld,%lld) exceed %lld triples", first,
                 first + nsteps, n);
     p.P = P; p.Q = Q;
-    carve(d_ws, U, I, F, h->opt, &p.ws);
+    carve(d_ws, U, I, F, h->opt, &p.ws, d_bias != nullptr);
     p.bu = bu; p.bi = bi; p.bj = bj;
     p.n = n; p.batch = batch; p.first_step = first; p.n_steps = nsteps;
     p.U = U; p.I = I; p.F = F; p.tile = kTileMax;
@@ -709,6 +758,7 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.neg_out = nullptr;
     p.neg_seed = 0ull;
     p.loss = h->loss;
+    p.bias = d_bias;
     return DRB_OK;
 }
 
@@ -766,6 +816,38 @@ extern "C" int drb_mf_bpr_loss(const float *d_P, const float *d_Q, void *d_ws, i
                          d_loss, 0);
     if (rc != DRB_OK) return rc;
     return launch_steps(p, (cudaStream_t)stream);
+}
+
+// ---- FM (daisy/model/FMRecommender.py:61-97): the MF step with first-order terms; d_bias = [u_bias (U), i_bias (I), bias_]
+extern "C" size_t drb_fm_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_t opt)
+{
+    return carve(nullptr, U, I, F, opt, nullptr, 1);
+}
+
+extern "C" int drb_fm_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F, int32_t opt, void *stream)
+{
+    DRB_REQUIRE(d_ws != nullptr && U > 0 && I > 0 && F > 0, "fm_workspace_init: bad arguments");
+    DRB_CUDA(cudaMemsetAsync(d_ws, 0, carve(nullptr, U, I, F, opt, nullptr, 1), (cudaStream_t)stream));
+    return DRB_OK;
+}
+
+extern "C" int drb_fm_train_steps(float *d_P, float *d_Q, float *d_bias, void *d_ws, int32_t U, int32_t I, int32_t F,
+                                  const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
+                                  int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                                  int32_t apply, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream)
+{
+    DRB_REQUIRE(d_bias != nullptr, "fm_train_steps: the bias vector is required");
+    StepParams p;
+    int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu, d_bi, d_bj, n, batch, first_step, n_steps, hyper, adam_step0,
+                         d_step_loss, apply ? 1 : 0, d_bias);
+    if (rc != DRB_OK) return rc;
+    if (n_steps == 0) return DRB_OK;
+    DRB_REQUIRE(apply || n_steps == 1, "fm_train_steps: apply=0 evaluates the loss of ONE batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_steps(p, st);
+    if (rc != DRB_OK) return rc;
+    if (sync_and_check) return check_nan(d_ws, st, nan_step);
+    return DRB_OK;
 }
 
 extern "C" int drb_mf_bpr_train_step_host(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,

@@ -51,7 +51,8 @@ template <int VEC, int W, int NCH, int MODE>
 __global__ void __launch_bounds__(kRankThreads) rank_kernel(const float *__restrict__ P, const float *__restrict__ Q, int F,
                                                             const int64_t *__restrict__ users,
                                                             const int64_t *__restrict__ cands, int count, int K, int nkeys,
-                                                            float *__restrict__ out_f, int64_t *__restrict__ out_i)
+                                                            float *__restrict__ out_f, int64_t *__restrict__ out_i,
+                                                            const float *__restrict__ bias, int U, int I)
 {
     extern __shared__ unsigned long long keys[];
     constexpr int GPW = 32 / W, GROUPS = (kRankThreads / 32) * GPW;
@@ -75,6 +76,8 @@ __global__ void __launch_bounds__(kRankThreads) rank_kernel(const float *__restr
             if (ok) item = (MODE == 0) ? crow[done + c] : (long long)(done + c);
             Row<VEC, W, NCH> q = load_row<VEC, W, NCH>(Q + (size_t)item * F, gl, chunks, ok);
             float s = dot_rows<VEC, W, NCH>(p, q);
+            // FM (FMRecommender.py:113,129): scores += (u_bias(u) + i_bias(c)) + bias_
+            if (bias != nullptr) s += (bias[users[row]] + bias[U + item]) + bias[U + I];
             if (ok && gl == 0) keys[lo + c] = make_key(s, (unsigned)(done + c));
         }
         __syncthreads();
@@ -126,7 +129,8 @@ __global__ void __launch_bounds__(kRankThreads) topk_scores_kernel(const float *
 
 template <int VEC, int W, int NCH>
 __global__ void predict_kernel(const float *__restrict__ P, const float *__restrict__ Q, int F, const int32_t *__restrict__ u,
-                               const int32_t *__restrict__ it, long long n, float *__restrict__ out)
+                               const int32_t *__restrict__ it, long long n, float *__restrict__ out,
+                               const float *__restrict__ bias, int U, int I)
 {
     constexpr int GPW = 32 / W;
     const int lane = threadIdx.x & 31, gl = lane % W;
@@ -141,13 +145,15 @@ __global__ void predict_kernel(const float *__restrict__ P, const float *__restr
         Row<VEC, W, NCH> a = load_row<VEC, W, NCH>(P + (size_t)uu * F, gl, chunks, ok);
         Row<VEC, W, NCH> b = load_row<VEC, W, NCH>(Q + (size_t)ii * F, gl, chunks, ok);
         float s = dot_rows<VEC, W, NCH>(a, b);
+        if (bias != nullptr) s += (bias[uu] + bias[U + ii]) + bias[U + I];     // FM.forward (FMRecommender.py:66-67)
         if (ok && gl == 0) out[t] = s;
     }
 }
 
 typedef void (*RankKernel)(const float *, const float *, int, const int64_t *, const int64_t *, int, int, int, float *,
-                           int64_t *);
-typedef void (*PredictKernel)(const float *, const float *, int, const int32_t *, const int32_t *, long long, float *);
+                           int64_t *, const float *, int, int);
+typedef void (*PredictKernel)(const float *, const float *, int, const int32_t *, const int32_t *, long long, float *,
+                              const float *, int, int);
 
 template <int VEC, int MODE>
 static RankKernel pick_rank_v(int W, int NCH)
@@ -179,7 +185,8 @@ static PredictKernel pick_predict_v(int W, int NCH)
 }
 
 static int launch_rank(int mode, const float *P, const float *Q, int F, const int64_t *users, long long n,
-                       const int64_t *cands, int count, int K, float *out_f, int64_t *out_i, cudaStream_t st)
+                       const int64_t *cands, int count, int K, float *out_f, int64_t *out_i, cudaStream_t st,
+                       const float *bias = nullptr, int U = 0, int I = 0)
 {
     DRB_REQUIRE(P && Q && users && F > 0 && count > 0 && K > 0 && n >= 0, "rank: bad arguments");
     DRB_REQUIRE(K <= count, "rank: topk=%d exceeds the %d scored ids", K, count);
@@ -192,7 +199,7 @@ static int launch_rank(int mode, const float *P, const float *Q, int F, const in
     while (nkeys < 2 * K) nkeys <<= 1;
     size_t smem = sizeof(unsigned long long) * (size_t)nkeys;
     DRB_REQUIRE(n <= 0x7fffffffLL, "rank: too many users in one call");
-    k<<<(unsigned)n, kRankThreads, smem, st>>>(P, Q, F, users, cands, count, K, nkeys, out_f, out_i);
+    k<<<(unsigned)n, kRankThreads, smem, st>>>(P, Q, F, users, cands, count, K, nkeys, out_f, out_i, bias, U, I);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }
@@ -236,10 +243,10 @@ extern "C" int drb_topk_from_scores(const float *d_scores, const int64_t *d_cand
     return DRB_OK;
 }
 
-extern "C" int drb_mf_predict(const float *d_P, const float *d_Q, int32_t F, const int32_t *d_u, const int32_t *d_i,
-                              int64_t n, float *d_out, void *stream)
+static int launch_predict(const float *d_P, const float *d_Q, int32_t F, const int32_t *d_u, const int32_t *d_i, int64_t n,
+                          float *d_out, void *stream, const float *d_bias, int U, int I)
 {
-    DRB_REQUIRE(d_P && d_Q && d_u && d_i && d_out && F > 0 && n >= 0, "mf_predict: bad arguments");
+    DRB_REQUIRE(d_P && d_Q && d_u && d_i && d_out && F > 0 && n >= 0, "predict: bad arguments");
     if (n == 0) return DRB_OK;
     RowGeom g = row_geom(F);
     PredictKernel k = g.vec == 4 ? pick_predict_v<4>(g.width, g.nch)
@@ -248,9 +255,39 @@ extern "C" int drb_mf_predict(const float *d_P, const float *d_Q, int32_t F, con
     long long per_block = (256 / 32) * (32 / g.width);
     long long blocks = (n + per_block - 1) / per_block, cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    k<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_P, d_Q, F, d_u, d_i, n, d_out);
+    k<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_P, d_Q, F, d_u, d_i, n, d_out, d_bias, U, I);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
+}
+
+extern "C" int drb_mf_predict(const float *d_P, const float *d_Q, int32_t F, const int32_t *d_u, const int32_t *d_i,
+                              int64_t n, float *d_out, void *stream)
+{
+    return launch_predict(d_P, d_Q, F, d_u, d_i, n, d_out, stream, nullptr, 0, 0);
+}
+
+// ---- FM inference (daisy/model/FMRecommender.py:99-131): MF's kernels with score += (u_bias[u] + i_bias[c]) + bias_
+extern "C" int drb_fm_rank(const float *d_P, const float *d_Q, const float *d_bias, int32_t U, int32_t I, int32_t F,
+                           const int64_t *d_users, int64_t n_users, const int64_t *d_cands, int32_t cand_num, int32_t topk,
+                           float *d_out, void *stream)
+{
+    DRB_REQUIRE(d_cands && d_out && d_bias && U > 0 && I > 0, "fm_rank: bad arguments");
+    return launch_rank(0, d_P, d_Q, F, d_users, n_users, d_cands, cand_num, topk, d_out, nullptr, (cudaStream_t)stream, d_bias,
+                       U, I);
+}
+
+extern "C" int drb_fm_full_rank(const float *d_P, const float *d_Q, const float *d_bias, int32_t U, int32_t I, int32_t F,
+                                const int64_t *d_users, int64_t n_users, int32_t topk, int64_t *d_out, void *stream)
+{
+    DRB_REQUIRE(d_out && d_bias && U > 0 && I > 0, "fm_full_rank: bad arguments");
+    return launch_rank(1, d_P, d_Q, F, d_users, n_users, nullptr, I, topk, nullptr, d_out, (cudaStream_t)stream, d_bias, U, I);
+}
+
+extern "C" int drb_fm_predict(const float *d_P, const float *d_Q, const float *d_bias, int32_t U, int32_t I, int32_t F,
+                              const int32_t *d_u, const int32_t *d_i, int64_t n, float *d_out, void *stream)
+{
+    DRB_REQUIRE(d_bias && U > 0 && I > 0, "fm_predict: bad arguments");
+    return launch_predict(d_P, d_Q, F, d_u, d_i, n, d_out, stream, d_bias, U, I);
 }
 
 extern "C" int drb_mf_rank_host(const float *d_P, const float *d_Q, int32_t F, const int64_t *h_users, int64_t n_users,

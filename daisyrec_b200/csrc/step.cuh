@@ -6,7 +6,7 @@ namespace drb {
 
 struct WsHeader {
     unsigned long long barrier;  // grid barrier ticket counter          } reset before every phase-1 launch
-    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, -]  }
+    double acc[2][8];            // [parity][bpr, l1u, l1i, l1j, s2u, s2i, s2j, g(bias_)]  }
     long long nan_step;          // step whose loss was NaN               } sticky in split (multi-GPU) mode
     int status;
     int pad[13];
@@ -20,11 +20,14 @@ struct Workspace {
     unsigned *cntU;
     unsigned long long *cntI;
     float *mP, *vP, *mQ, *vQ;
+    // FM's first-order terms (FMRecommender.py:46-49): gradient accumulator and optimiser state of the packed
+    // [u_bias (U), i_bias (I), bias_ (1)] vector; nullptr for plain MF
+    float *gB, *mB, *vB;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w)
+inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w, int fm = 0)
 {
     size_t off = 0;
     char *b = (char *)base;
@@ -45,6 +48,13 @@ inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w)
         if (opt == DRB_OPT_ADAM) t.vP = (float *)take(sizeof(float) * (size_t)U * F);
         t.mQ = (float *)take(sizeof(float) * (size_t)I * F);
         if (opt == DRB_OPT_ADAM) t.vQ = (float *)take(sizeof(float) * (size_t)I * F);
+    }
+    t.gB = t.mB = t.vB = nullptr;
+    if (fm) {   // appended, so the MF part of the layout (drb_mf_workspace_layout) is the same with and without biases
+        const size_t nb = (size_t)U + I + 1;
+        t.gB = (float *)take(sizeof(float) * nb);
+        if (opt != DRB_OPT_SGD) t.mB = (float *)take(sizeof(float) * nb);
+        if (opt == DRB_OPT_ADAM) t.vB = (float *)take(sizeof(float) * nb);
     }
     if (w) *w = t;
     return off;
@@ -79,6 +89,8 @@ struct StepParams {
     int32_t *neg_out;      // optional: the drawn negatives are written here (aligned with bu/bi) for inspection
     unsigned long long neg_seed;
     int loss;              // DRB_LOSS_BPR / _HL / _TL (pair-wise criterion, AbstractRecommender.py:79-93)
+    // FM (FMRecommender.py:61-68): pred += (u_bias[u] + i_bias[item]) + bias_; bias = packed [U + I + 1]; nullptr = MF
+    float *bias;
 };
 
 

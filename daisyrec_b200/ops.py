@@ -360,6 +360,60 @@ def mf_bpr_train_steps_host(P, Q, ws, h_bu, h_bi, h_bj, batch, n_steps, hp, adam
     return h_loss[:n_steps]
 
 
+# ------------------------------------------------------------------ FM
+class FMWorkspace:
+    """MF workspace + gradient accumulator / optimiser state of the packed bias vector."""
+
+    def __init__(self, user_num, item_num, factors, opt, device):
+        self.U, self.I, self.F = user_num, item_num, factors
+        self.opt = L.OPT_KIND[opt]
+        self.buf = torch.empty(L.lib().drb_fm_workspace_bytes(user_num, item_num, factors, self.opt), dtype=torch.uint8,
+                               device=device)
+        L.check(L.lib().drb_fm_workspace_init(_ptr(self.buf), user_num, item_num, factors, self.opt, _stream()))
+
+
+def fm_train_steps(P, Q, bias, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True):
+    _dev(P, torch.float32, "P"); _dev(Q, torch.float32, "Q"); _dev(bias, torch.float32, "bias")
+    for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
+        _dev(t, torch.int32, nm)
+    if bias.numel() != ws.U + ws.I + 1:
+        raise ValueError("bias must hold user_num + item_num + 1 floats")
+    losses = torch.empty(max(n_steps, 1), dtype=torch.float64, device=P.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_fm_train_steps(_ptr(P), _ptr(Q), _ptr(bias), _ptr(ws.buf), ws.U, ws.I, ws.F, _ptr(bu), _ptr(bi), _ptr(bj),
+                                    bu.numel(), batch, first_step, n_steps, C.byref(hp), adam_step0, 1 if apply else 0,
+                                    _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]
+
+
+def fm_rank(P, Q, bias, users, cands, topk):
+    _dev(users, torch.int64, "users"); _dev(cands, torch.int64, "cands"); _dev(bias, torch.float32, "bias")
+    n, Cn = cands.shape
+    out = torch.empty((n, topk), dtype=torch.float32, device=P.device)
+    L.check(L.lib().drb_fm_rank(_ptr(P), _ptr(Q), _ptr(bias), P.shape[0], Q.shape[0], P.shape[1], _ptr(users), n, _ptr(cands),
+                                Cn, topk, _ptr(out), _stream()))
+    return out
+
+
+def fm_full_rank(P, Q, bias, users, topk):
+    _dev(users, torch.int64, "users"); _dev(bias, torch.float32, "bias")
+    out = torch.empty((users.numel(), topk), dtype=torch.int64, device=P.device)
+    L.check(L.lib().drb_fm_full_rank(_ptr(P), _ptr(Q), _ptr(bias), P.shape[0], Q.shape[0], P.shape[1], _ptr(users),
+                                     users.numel(), topk, _ptr(out), _stream()))
+    return out
+
+
+def fm_predict(P, Q, bias, u, i):
+    _dev(u, torch.int32, "u"); _dev(i, torch.int32, "i"); _dev(bias, torch.float32, "bias")
+    out = torch.empty(u.numel(), dtype=torch.float32, device=P.device)
+    L.check(L.lib().drb_fm_predict(_ptr(P), _ptr(Q), _ptr(bias), P.shape[0], Q.shape[0], P.shape[1], _ptr(u), _ptr(i),
+                                   u.numel(), _ptr(out), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------ inference
 def mf_rank(P, Q, users, cands, topk):
     _dev(users, torch.int64, "users"); _dev(cands, torch.int64, "cands")

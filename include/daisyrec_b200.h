@@ -176,6 +176,28 @@ int drb_mf_bpr_train_steps_host(float *d_P, float *d_Q, void *d_ws, int32_t user
                                 int64_t n, int64_t batch, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
                                 int32_t *d_stage, double *d_loss, double *h_loss, int64_t *nan_step, void *stream);
 
+/* ---- FM (daisy/model/FMRecommender.py:16-131) -----------------------------
+ * FM.forward :61-68 = MF's factor product + (u_bias[u] + i_bias[i]) + bias_ (the three first-order terms are summed first,
+ * fp32); FM.calc_loss :70-97 regularises the factor rows only, exactly as MF does; backward + optimizer.step as for MF,
+ * the biases take the plain loss gradient.  d_bias = packed fp32 [u_bias (user_num), i_bias (item_num), bias_ (1)]
+ * (== FM.u_bias.weight, FM.i_bias.weight, FM.bias_).  The workspace is the MF workspace plus the bias accumulator and
+ * optimiser state.  All DRB_LOSS_* / DRB_OPT_* kinds; apply=0 evaluates the loss of one batch (n_steps must be 1). */
+size_t drb_fm_workspace_bytes(int32_t user_num, int32_t item_num, int32_t factors, int32_t opt);
+int drb_fm_workspace_init(void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t opt, void *stream);
+int drb_fm_train_steps(float *d_P, float *d_Q, float *d_bias, void *d_ws, int32_t user_num, int32_t item_num,
+                       int32_t factors, const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
+                       int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                       int32_t apply, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+/* FM.rank :103-121 / FM.full_rank :123-131 / FM.predict :97-101: the MF kernels with the first-order terms added to
+ * every score before the sort key is built. */
+int drb_fm_rank(const float *d_P, const float *d_Q, const float *d_bias, int32_t user_num, int32_t item_num,
+                int32_t factors, const int64_t *d_users, int64_t n_users, const int64_t *d_cands, int32_t cand_num,
+                int32_t topk, float *d_out, void *stream);
+int drb_fm_full_rank(const float *d_P, const float *d_Q, const float *d_bias, int32_t user_num, int32_t item_num,
+                     int32_t factors, const int64_t *d_users, int64_t n_users, int32_t topk, int64_t *d_out, void *stream);
+int drb_fm_predict(const float *d_P, const float *d_Q, const float *d_bias, int32_t user_num, int32_t item_num,
+                   int32_t factors, const int32_t *d_u, const int32_t *d_i, int64_t n, float *d_out, void *stream);
+
 /* ---- multi-GPU (one process per GPU; user-sharded P, replicated Q) ---------------
  * There is no multi-device path in the reference (single process, AbstractRecommender.py:99-100);
  * these entry points split the synchronous step where the exchange has to happen:

@@ -357,6 +357,7 @@ def gen_fm():
                              epochs=1, loss_type=loss_type, topk=10, cand_num=100)
         torch.manual_seed(seed)
         model = FM(cfg)
+        init_tabs = (model.embed_user.weight.detach().numpy().copy(), model.embed_item.weight.detach().numpy().copy())
         with torch.no_grad():
             model.embed_user.weight.mul_(30.0)
             model.embed_item.weight.mul_(30.0)
@@ -395,7 +396,8 @@ def gen_fm():
                     f"c{k}_bias": np.stack([s_[2] for s_ in snaps]), f"c{k}_batches": np.stack(batches),
                     f"c{k}_loss": np.array(losses, np.float64), f"c{k}_opt": np.array(opt), f"c{k}_losskind": np.array(loss_type),
                     f"c{k}_hyper": np.array([lr, r1, r2], np.float64), f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32),
-                    f"c{k}_preds": preds, f"c{k}_full": full, f"c{k}_pred_pairs": pp})
+                    f"c{k}_preds": preds, f"c{k}_full": full, f"c{k}_pred_pairs": pp,
+                    f"c{k}_P_init": init_tabs[0], f"c{k}_Q_init": init_tabs[1]})
         print(f"fm case {k} ({loss_type}/{opt}): losses {losses}")
     out["ncases"] = np.array(len(cases))
     _save("fm", **out)
