@@ -488,6 +488,23 @@ def cfg_sampling(args, dev, d):
             "roofline": roof(alg_e / ms_e / 1e6, "explode_kernel", alg_e, "12 B written per triple + 8 B read per COO row")}
 
 
+def cfg_shuffle(args, dev, d):
+    """The DataLoader's epoch permutation of the 80 M triples, bit-exact on the device: MT19937 stream + parallel Fisher-Yates."""
+    from daisyrec_b200 import ops
+    T = d["coo_u"].numel() * args.num_ng
+    ms_mt = timed_ms(lambda: ops.mt19937_stream(args.seed, T, dev), 1, 3)
+    ms_all = timed_ms(lambda: ops.randperm_torch(args.seed, T, dev), 1, 3)
+    t0 = time.perf_counter()
+    g = torch.Generator(); g.manual_seed(args.seed)
+    ref = torch.randperm(T, generator=g)
+    t_cpu = time.perf_counter() - t0
+    same = bool(torch.equal(ops.randperm_torch(args.seed, T, dev).cpu(), ref))
+    return {"n": T, "mt19937_stream_ms": ms_mt, "randperm_total_ms": ms_all, "fisher_yates_ms": ms_all - ms_mt,
+            "torch_cpu_randperm_s": t_cpu, "equals_torch_randperm": same,
+            "roofline": roof(T * 4 / ms_mt / 1e6, "mt19937_stream_kernel (one CTA: the sequence is sequential across 624-word blocks)", T * 4,
+                             "latency-bound by construction; reported for completeness")}
+
+
 def run_configs(args, dev, d, planes, P, Q, which):
     out = {}
 
@@ -505,6 +522,7 @@ def run_configs(args, dev, d, planes, P, Q, which):
     section("c4_lightgcn", lambda: cfg_c4_lightgcn(args, dev))
     section("inference", lambda: cfg_inference(args, dev, d, P, Q))
     section("sampling", lambda: cfg_sampling(args, dev, d))
+    section("shuffle", lambda: cfg_shuffle(args, dev, d))
     return out
 
 
@@ -584,9 +602,9 @@ def run_own(args):
     del triples
     torch.cuda.empty_cache()
     e2e_runs = {}
-    for engine in ("torch", "device"):
+    for engine in ("torch", "torch-cpu", "device"):
         walls = []
-        for rep in range(args.e2e_reps + 1):                        # first repetition = warm-up (allocator, page-in)
+        for rep in range((1 if engine == "torch-cpu" else args.e2e_reps) + 1):   # first repetition = warm-up (allocator, page-in)
             torch.manual_seed(args.seed + rep)
             m = MF(mf_config(U, I, F, shuffle_engine=engine))
             loader = get_dataloader(BasicDataset(host_np), batch_size=B, shuffle=True)
@@ -599,7 +617,7 @@ def run_own(args):
         walls = walls[1:]
         med = float(np.median(walls))
         e2e_runs[engine] = {"value": T / med, "wall_s_median": med, "wall_s": walls, "epochs_per_run": 1,
-                            "h2d_bytes_per_step": (12 + (8 if engine == "torch" else 0)) * B, "steps": spe}
+                            "h2d_bytes_per_step": (12 + (8 if engine == "torch-cpu" else 0)) * B, "steps": spe}
     from daisyrec_b200.model.AbstractRecommender import DEFAULT_SHUFFLE_ENGINE as default_engine
     e2e_main = e2e_runs[default_engine]
 

@@ -20,8 +20,12 @@ from .. import ops
 from ..utils.sampler import fingerprint
 
 
-# 'torch': the DataLoader's own permutation (the reference's batches bit for bit); 'device': torch.randperm on the GPU
+# 'torch': the DataLoader's own permutation -- the reference's batches bit for bit -- computed ON THE DEVICE
+#          (drb_randperm_torch: MT19937 stream + parallel Fisher-Yates, same result as torch.randperm on the CPU generator);
+# 'torch-cpu': the same permutation from torch.randperm on the host (what the line above is tested against);
+# 'device': torch.randperm on the GPU, seeded from the global RNG (same distribution, another order)
 DEFAULT_SHUFFLE_ENGINE = 'torch'
+RANDPERM_DEVICE_MAX = 0xFFFFFFFF // 20          # ATen switches algorithm above this n; the host path covers it
 
 
 class _Table:
@@ -210,14 +214,7 @@ class GeneralRecommender(AbstractRecommender):
         data, bs, shuffle, drop_last, gen = plan
         T = data.shape[0]
         d_triples = self._device_triples(data)
-        if shuffle and self.shuffle_engine == 'device':
-            torch.empty((), dtype=torch.int64).random_(generator=gen)                 # _base_seed, as the DataLoader draws it
-            g = torch.Generator(device=self.device)
-            g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
-            d_perm = torch.randperm(T, generator=g, device=self.device)
-        else:
-            perm = epoch_permutation(T, shuffle, gen)
-            d_perm = None if perm is None else perm.to(self.device, non_blocking=False)
+        d_perm = self._device_permutation(T, shuffle, gen)
         bu, bi, bj = ops.gather_triples(d_triples, d_perm)
         n_use = (T // bs) * bs if drop_last else T
         nsteps = (n_use + bs - 1) // bs
@@ -235,6 +232,20 @@ class GeneralRecommender(AbstractRecommender):
         pbar.set_postfix(loss=current_loss)
         pbar.close()
         return current_loss
+
+    def _device_permutation(self, T, shuffle, gen, seed=None):
+        """The epoch's index order as a device int64 tensor (None = sequential); consumes the global RNG like the DataLoader."""
+        if seed is None:
+            seed = epoch_seed(shuffle, gen)
+        if not shuffle:
+            return None
+        if self.shuffle_engine == 'device':
+            g = torch.Generator(device=self.device)
+            g.manual_seed(seed)
+            return torch.randperm(T, generator=g, device=self.device)
+        if self.shuffle_engine == 'torch' and T < RANDPERM_DEVICE_MAX:
+            return ops.randperm_torch(seed, T, self.device)
+        return epoch_permutation(T, shuffle, gen, seed=seed).to(self.device, non_blocking=False)
 
     def _device_triples(self, data):
         """Device copy of the loader's [T,3] rows: the sampler's own device twin when the host array still carries the stamp
@@ -267,8 +278,7 @@ class GeneralRecommender(AbstractRecommender):
         seed = epoch_seed(shuffle, gen)
         if shuffle:
             seed = broadcast_int(seed, self.device)
-        perm = epoch_permutation(T, shuffle, gen, seed=seed)
-        d_perm = None if perm is None else perm.to(self.device)
+        d_perm = self._device_permutation(T, shuffle, gen, seed=seed if shuffle else 0)
         nsteps = trainer.prepare_epoch(d_triples, d_perm, bs)
         if drop_last and T % bs:
             nsteps -= 1

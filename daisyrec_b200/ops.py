@@ -249,6 +249,21 @@ def rank_metrics_host(preds, gt_ptr, gt_idx, ks, item_num, item_pop=None):
     return out
 
 
+# ------------------------------------------------------------------ epoch permutation
+def mt19937_stream(seed, n, device):
+    out = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+    L.check(L.lib().drb_mt19937_stream(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), n, _ptr(out), _stream()))
+    return out[:n]
+
+
+def randperm_torch(seed, n, device):
+    """torch.randperm(n, generator=G) for a CPU generator G with G.manual_seed(seed) -- computed on the device, bit-exact."""
+    perm = torch.empty(max(n, 1), dtype=torch.int64, device=device)
+    ws = torch.empty(L.lib().drb_randperm_workspace_bytes(n), dtype=torch.uint8, device=device)
+    L.check(L.lib().drb_randperm_torch(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), n, _ptr(perm), _ptr(ws), _stream()))
+    return perm[:n]
+
+
 # ------------------------------------------------------------------ train feed
 def gather_triples(d_triples, d_perm=None):
     _dev(d_triples, torch.int32, "triples")

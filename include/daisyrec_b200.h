@@ -176,6 +176,16 @@ int drb_mf_bpr_train_steps_host(float *d_P, float *d_Q, void *d_ws, int32_t user
                                 int64_t n, int64_t batch, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
                                 int32_t *d_stage, double *d_loss, double *h_loss, int64_t *nan_step, void *stream);
 
+/* ---- the DataLoader's epoch order on the device (daisy/utils/dataset.py:5-8 get_dataloader(shuffle=True)) ----------
+ * torch's RandomSampler yields torch.randperm(n, generator=G) of a private CPU generator G seeded per epoch; ATen's
+ * randperm_cpu is a Fisher-Yates walk over MT19937 words.  drb_randperm_torch returns THAT permutation (bit-exact, int64)
+ * computed on the device: a one-CTA MT19937 stream + a parallel Fisher-Yates with deterministic reservations (one
+ * cooperative launch).  n < 2^32/20 (ATen's branch).  d_ws: drb_randperm_workspace_bytes(n) bytes of scratch.
+ * drb_mt19937_stream: the first n tempered 32-bit outputs of at::mt19937(seed) (= numpy's legacy stream for the same seed). */
+size_t drb_randperm_workspace_bytes(int64_t n);
+int drb_mt19937_stream(uint64_t seed, int64_t n, uint32_t *d_out, void *stream);
+int drb_randperm_torch(uint64_t seed, int64_t n, int64_t *d_perm, void *d_ws, void *stream);
+
 /* ---- FM (daisy/model/FMRecommender.py:16-131) -----------------------------
  * FM.forward :61-68 = MF's factor product + (u_bias[u] + i_bias[i]) + bias_ (the three first-order terms are summed first,
  * fp32); FM.calc_loss :70-97 regularises the factor rows only, exactly as MF does; backward + optimizer.step as for MF,

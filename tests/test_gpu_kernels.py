@@ -307,3 +307,59 @@ def test_rank_vs_oracle_bit_exact(ops, orc, F, I, C, K):
     assert np.array_equal(gotf, orc.mf_full_rank(P, Q, users[:6], K))
     u32, i32 = users.astype(np.int32), cands[:, 0].astype(np.int32)
     assert np.array_equal(ops.mf_predict(dev(P), dev(Q), dev(u32), dev(i32)).cpu().numpy(), orc.mf_predict(P, Q, u32, i32))
+
+
+# ------------------------------------------------------------------ the DataLoader's epoch order on the device
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 623, 624, 625, 1000, 4097, 100_003, 3_000_000])
+def test_randperm_torch_is_bit_exact(n):
+    """drb_randperm_torch == torch.randperm(n, generator=CPU generator seeded the same) for every n (MT19937 stream +
+    parallel Fisher-Yates with deterministic reservations vs ATen's sequential walk)."""
+    from daisyrec_b200 import ops
+    for seed in (0, 2022, (1 << 40) + 17, (1 << 63) - 5):
+        g = torch.Generator()
+        g.manual_seed(seed)
+        want = torch.randperm(n, generator=g)
+        got = ops.randperm_torch(seed, n, "cuda").cpu()
+        assert torch.equal(got, want), (n, seed)
+        if n > 100_000:
+            break
+
+
+def test_mt19937_stream_matches_numpy():
+    from daisyrec_b200 import ops
+    for seed, n in ((5, 1), (7, 624), (11, 625), (2022, 200_000)):
+        want = np.random.RandomState(seed).randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint32)
+        got = ops.mt19937_stream(seed, n, "cuda").cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, want), (seed, n)
+
+
+def test_fit_shuffle_engines_agree():
+    """shuffle_engine='torch' (permutation computed on the device) trains on exactly the batches of 'torch-cpu'
+    (torch.randperm on the host generator): identical step order => bitwise-identical epoch losses are not guaranteed
+    (atomics), but the permutation is, and the losses agree to fp32 accumulation noise."""
+    import logging
+    from daisyrec_b200.model import MF
+    from daisyrec_b200.model.AbstractRecommender import epoch_permutation
+    from daisyrec_b200.utils.dataset import BasicDataset, get_dataloader
+    rng = np.random.default_rng(3)
+    U, I, T = 300, 200, 50_000
+    data = np.stack([rng.integers(U, size=T), rng.integers(I, size=T), rng.integers(I, size=T)], 1).astype(np.int32)
+    tabs = {}
+    for engine in ("torch", "torch-cpu"):
+        cfg = dict(gpu="", logger=logging.getLogger("t"), lr=0.01, reg_1=0.001, reg_2=0.001, epochs=2, topk=10, user_num=U,
+                   item_num=I, factors=32, loss_type="BPR", optimizer="default", init_method="default", early_stop=False,
+                   progress=False, shuffle_engine=engine)
+        torch.manual_seed(99)
+        m = MF(cfg)
+        m.fit(get_dataloader(BasicDataset(data), batch_size=1024, shuffle=True))
+        tabs[engine] = (m.embed_user.weight.cpu().numpy(), m.embed_item.weight.cpu().numpy(), torch.get_rng_state())
+    assert torch.equal(tabs["torch"][2], tabs["torch-cpu"][2])                  # the global RNG moved identically
+    for a, b in zip(tabs["torch"][:2], tabs["torch-cpu"][:2]):
+        assert np.abs(a - b).max() < 5e-6
+    # and the device permutation itself equals the DataLoader protocol's
+    from daisyrec_b200 import ops
+    torch.manual_seed(5)
+    want = epoch_permutation(T, True)
+    torch.manual_seed(5)
+    from daisyrec_b200.model.AbstractRecommender import epoch_seed
+    assert torch.equal(ops.randperm_torch(epoch_seed(True), T, "cuda").cpu(), want)
