@@ -21,12 +21,13 @@
 //                           result equals the sequential order.  ~70 rounds for 80 M elements, 1.2 n cell visits, one
 //                           persistent cooperative launch (two grid barriers per round).
 // Integer kernels: bit-exact by construction; tests compare against torch.randperm itself.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace drb {
 
 constexpr int kMtN = 624, kMtM = 397;
-constexpr int kMtThreads = 256;
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b)
 {
@@ -42,10 +43,22 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// out[0..n) = the first n outputs of at::mt19937(seed) (== numpy's init_genrand + genrand_int32)
-__global__ void __launch_bounds__(kMtThreads) mt19937_stream_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
+// out[0..n) = the first n outputs of at::mt19937(seed) (== numpy's init_genrand + genrand_int32).
+// T threads (one CTA).  Every phase reads its inputs into registers, synchronises, writes, synchronises: the sequential
+// recurrence only ever sees values the walk would have seen.  Fewer threads = cheaper barriers (one warp: __syncwarp),
+// more threads = fewer iterations per phase; the default was picked on the B200 (profiles/r02b).
+template <int T>
+__device__ __forceinline__ void mt_sync()
+{
+    if constexpr (T == 32) __syncwarp(); else __syncthreads();
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) mt19937_stream_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
 {
     __shared__ uint32_t x[kMtN];
+    constexpr int D = kMtN - kMtM;                   // 227
+    constexpr int R = (D + T - 1) / T;               // register slots per phase
     const int tid = threadIdx.x;
     if (tid == 0) {                                  // init_genrand: sequential, 624 steps, once
         uint32_t s = seed;
@@ -55,27 +68,49 @@ __global__ void __launch_bounds__(kMtThreads) mt19937_stream_kernel(uint32_t see
             x[j] = s;
         }
     }
-    __syncthreads();
+    mt_sync<T>();
+    uint32_t v[R];
     for (long long base = 0; base < n; base += kMtN) {
         // phase 1: k in [0, 227) reads old x[k], x[k+1], x[k+397]
-        uint32_t v = 0;
-        if (tid < kMtN - kMtM) v = x[tid + kMtM] ^ mt_twist(x[tid], x[tid + 1]);
-        __syncthreads();
-        if (tid < kMtN - kMtM) x[tid] = v;
-        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = tid + r * T;
+            if (k < D) v[r] = x[k + kMtM] ^ mt_twist(x[k], x[k + 1]);
+        }
+        mt_sync<T>();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = tid + r * T;
+            if (k < D) x[k] = v[r];
+        }
+        mt_sync<T>();
         // phase 2: k in [227, 454) reads new x[k-227] (phase 1) and old x[k], x[k+1]
-        const int k2 = tid + (kMtN - kMtM);
-        if (tid < kMtN - kMtM) v = x[k2 - (kMtN - kMtM)] ^ mt_twist(x[k2], x[k2 + 1]);
-        __syncthreads();
-        if (tid < kMtN - kMtM) x[k2] = v;
-        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = D + tid + r * T;
+            if (k < 2 * D) v[r] = x[k - D] ^ mt_twist(x[k], x[k + 1]);
+        }
+        mt_sync<T>();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = D + tid + r * T;
+            if (k < 2 * D) x[k] = v[r];
+        }
+        mt_sync<T>();
         // phase 3: k in [454, 624) reads new x[k-227] (phase 2), old x[k], old x[k+1] -- x[624] wraps to the NEW x[0]
-        const int k3 = tid + 2 * (kMtN - kMtM);
-        if (k3 < kMtN) v = x[k3 - (kMtN - kMtM)] ^ mt_twist(x[k3], k3 + 1 < kMtN ? x[k3 + 1] : x[0]);
-        __syncthreads();
-        if (k3 < kMtN) x[k3] = v;
-        __syncthreads();
-        for (int k = tid; k < kMtN; k += kMtThreads)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = 2 * D + tid + r * T;
+            if (k < kMtN) v[r] = x[k - D] ^ mt_twist(x[k], k + 1 < kMtN ? x[k + 1] : x[0]);
+        }
+        mt_sync<T>();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = 2 * D + tid + r * T;
+            if (k < kMtN) x[k] = v[r];
+        }
+        mt_sync<T>();
+        for (int k = tid; k < kMtN; k += T)
             if (base + k < n) out[base + k] = mt_temper(x[k]);
     }
 }
@@ -121,7 +156,7 @@ __global__ void __launch_bounds__(kFyThreads) fisher_yates_kernel(FyParams p)
         const unsigned long long hi = (unsigned long long)(~round) << 32;   // newer rounds win the atomicMin
         // ---- reserve: both cells of every candidate iteration receive min(iteration index)
         for (long long e = gtid; e < total; e += gsz) {
-            const long long i = e < f ? (long long)fc[e] : s + (e - f);
+            const long long i = e < f ? (long long)__ldcg(fc + e) : s + (e - f);
             const long long h = i + (long long)(__ldg(p.w + i) % (uint32_t)(n - i));
             const unsigned long long key = hi | (unsigned long long)i;
             atomicMin(p.r + i, key);
@@ -135,7 +170,7 @@ __global__ void __launch_bounds__(kFyThreads) fisher_yates_kernel(FyParams p)
             bool failed = false;
             long long i = 0;
             if (e < total) {
-                i = e < f ? (long long)fc[e] : s + (e - f);
+                i = e < f ? (long long)__ldcg(fc + e) : s + (e - f);
                 const long long h = i + (long long)(__ldg(p.w + i) % (uint32_t)(n - i));
                 const unsigned long long key = hi | (unsigned long long)i;
                 const bool ok = __ldcg(p.r + i) == key && __ldcg(p.r + h) == key;
@@ -198,7 +233,19 @@ extern "C" int drb_mt19937_stream(uint64_t seed, int64_t n, uint32_t *d_out, voi
 {
     DRB_REQUIRE(d_out && n >= 0, "mt19937_stream: bad arguments");
     if (n == 0) return DRB_OK;
-    mt19937_stream_kernel<<<1, kMtThreads, 0, (cudaStream_t)stream>>>((uint32_t)(seed & 0xffffffffull), n, d_out);
+    static int threads = 0;                          // DRB_MT_THREADS: developer override used to pick the default
+    if (!threads) {
+        const char *e = getenv("DRB_MT_THREADS");
+        threads = e ? atoi(e) : 64;
+    }
+    const uint32_t s32 = (uint32_t)(seed & 0xffffffffull);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (threads) {
+        case 32: mt19937_stream_kernel<32><<<1, 32, 0, st>>>(s32, n, d_out); break;
+        case 128: mt19937_stream_kernel<128><<<1, 128, 0, st>>>(s32, n, d_out); break;
+        case 256: mt19937_stream_kernel<256><<<1, 256, 0, st>>>(s32, n, d_out); break;
+        default: mt19937_stream_kernel<64><<<1, 64, 0, st>>>(s32, n, d_out); break;
+    }
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }

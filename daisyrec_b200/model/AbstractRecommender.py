@@ -213,8 +213,18 @@ class GeneralRecommender(AbstractRecommender):
     def _fit_epoch_bulk(self, plan, epoch):
         data, bs, shuffle, drop_last, gen = plan
         T = data.shape[0]
+        # the epoch's order is computed on a side stream while the rows upload (first epoch) / are stamped: the one-CTA
+        # MT19937 stream leaves the copy engines and 147 SMs free
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_side_stream', None) is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        self._side_stream.wait_stream(main)
+        with torch.cuda.stream(self._side_stream):
+            d_perm = self._device_permutation(T, shuffle, gen)
         d_triples = self._device_triples(data)
-        d_perm = self._device_permutation(T, shuffle, gen)
+        main.wait_stream(self._side_stream)
+        if d_perm is not None:
+            d_perm.record_stream(main)
         bu, bi, bj = ops.gather_triples(d_triples, d_perm)
         n_use = (T // bs) * bs if drop_last else T
         nsteps = (n_use + bs - 1) // bs
