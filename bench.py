@@ -712,6 +712,8 @@ def sharded_parity_check(d, triples, perm, bounds, rank, world, dev, F, seed, co
     qs = [torch.zeros_like(qsum) for _ in range(world)]
     dist.all_gather(qs, qsum)
     q_same = all(int(q.item()) == int(qs[0].item()) for q in qs)
+    q_sharded = tr.Q.clone()
+    tr.close()
     verdict = torch.zeros(4, dtype=torch.float64, device=dev)
     if rank == 0:
         P1, Q1 = P0.clone(), Q0.clone()
@@ -720,7 +722,7 @@ def sharded_parity_check(d, triples, perm, bounds, rank, world, dev, F, seed, co
         ref = ops.mf_bpr_train_steps(P1, Q1, ws, bu, bi, bj, Bs, 0, K, ops.hyper(**HYPER))
         rel = float(((losses - ref).abs() / ref.abs()).max().item())
         dP = float((P_all - P1).abs().max().item())
-        dQ = float((tr.Q - Q1).abs().max().item())
+        dQ = float((q_sharded - Q1).abs().max().item())
         moved = float((P1 - P0).abs().max().item())
         verdict = torch.tensor([rel, max(dP, dQ), moved, 1.0 if q_same else 0.0], dtype=torch.float64, device=dev)
     dist.broadcast(verdict, 0)
@@ -817,6 +819,7 @@ def run_sharded(args, rank, local, world, dev):
                                  "each rank's share + phase 1 + exchange + phase 2 + D2H of the global loss; copy of step "
                                  "s+1 under step s"}
             res["t1"] = time.time()
+        tr.close()
         del tr
         torch.cuda.empty_cache()
         return res

@@ -17,7 +17,7 @@ c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)
 vp = C.c_void_p
 
-DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_NAN_LOSS, DRB_ERR_EMPTY_SET, DRB_ERR_NO_DEVICE = range(6)
+DRB_OK, DRB_ERR_INVALID, DRB_ERR_CUDA, DRB_ERR_NAN_LOSS, DRB_ERR_EMPTY_SET, DRB_ERR_NO_DEVICE, DRB_ERR_PEER = range(7)
 OPT_SGD, OPT_ADAM, OPT_ADAGRAD, OPT_RMSPROP = 0, 1, 2, 3
 OPT_KIND = {"sgd": 0, "adam": 1, "adagrad": 2, "rmsprop": 3}
 LOSS_KIND = {"BPR": 0, "HL": 1, "TL": 2, "CL": 3, "SL": 4}
@@ -89,6 +89,15 @@ SIGNATURES = {
     "drb_mf_bpr_train_steps_sharded_host": (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp,
                                                       C.c_int64, C.c_int64, C.POINTER(Hyper), C.c_int64, vp, C.c_int64, vp,
                                                       vp, vp]),
+    "drb_p2p_buffer_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "drb_p2p_q_offset": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "drb_p2p_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp), vp]),
+    "drb_p2p_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "drb_p2p_close": (C.c_int, [vp]),
+    "drb_p2p_free": (C.c_int, [vp]),
+    "drb_mf_bpr_train_steps_p2p": (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp), C.c_int32, C.c_int32,
+                                             vp, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Hyper),
+                                             C.c_int64, vp, C.c_double, C.c_int32, c_i64p, vp]),
     "drb_neumf_param_count": (C.c_int64, [C.c_int32, C.c_int32]),
     "drb_neumf_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
     "drb_neumf_workspace_init": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, vp]),

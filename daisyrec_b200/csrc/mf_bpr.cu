@@ -145,9 +145,10 @@ extern "C" int drb_mf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F
     return DRB_OK;
 }
 
-static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu,
-                       const int32_t *bi, const int32_t *bj, long long n, long long batch, long long first, long long nsteps,
-                       const drb_hyper *h, long long adam_step0, double *d_step_loss, int apply, float *d_bias = nullptr)
+namespace drb {
+int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu, const int32_t *bi,
+                const int32_t *bj, long long n, long long batch, long long first, long long nsteps, const drb_hyper *h,
+                long long adam_step0, double *d_step_loss, int apply, float *d_bias)
 {
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
@@ -179,8 +180,10 @@ static int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int
     p.neg_seed = 0ull;
     p.loss = h->loss;
     p.bias = d_bias;
+    p.step_offsets = nullptr;
     return DRB_OK;
 }
+}  // namespace drb
 
 extern "C" int drb_mf_bpr_train_steps(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
                                       const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,

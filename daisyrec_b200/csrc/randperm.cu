@@ -21,8 +21,6 @@
 //                           result equals the sequential order.  ~70 rounds for 80 M elements, 1.2 n cell visits, one
 //                           persistent cooperative launch (two grid barriers per round).
 // Integer kernels: bit-exact by construction; tests compare against torch.randperm itself.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace drb {
@@ -44,23 +42,22 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 }
 
 // out[0..n) = the first n outputs of at::mt19937(seed) (== numpy's init_genrand + genrand_int32).
-// T threads (one CTA).  Every phase reads its inputs into registers, synchronises, writes, synchronises: the sequential
-// recurrence only ever sees values the walk would have seen.  Fewer threads = cheaper barriers (one warp: __syncwarp),
-// more threads = fewer iterations per phase; the default was picked on the B200 (profiles/r02b).
-template <int T>
-__device__ __forceinline__ void mt_sync()
-{
-    if constexpr (T == 32) __syncwarp(); else __syncthreads();
-}
+// One CTA; thread t (t < 227) owns the state words t, t+227 and t+454 (t < 170).  In the sequential walk
+//   x[k]     = x[k+397] ^ twist(x[k], x[k+1])                 k in [0, 227)    -- all inputs are OLD words
+//   x[k]     = x[k-227] ^ twist(x[k], x[k+1])                 k in [227, 454)  -- x[k-227] is thread t's own NEW word
+//   x[k]     = x[k-227] ^ twist(x[k], x[k+1])                 k in [454, 623)  -- likewise
+//   x[623]   = x[396]   ^ twist(x[623], x[0])                                   -- NEW x[0]: recomputed by its reader
+// every OLD input can be read before anything is written, and every NEW input is a register of the same thread.  So a
+// 624-word block costs: load the old words, ONE barrier, three dependent twists in registers, store + temper + stream the
+// three outputs, ONE barrier -- instead of three load/barrier/store/barrier rounds (58 ms -> see profiles/r02b for 80 M words).
+constexpr int kMtThreads = 256;
 
-template <int T>
-__global__ void __launch_bounds__(T) mt19937_stream_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
+__global__ void __launch_bounds__(kMtThreads) mt19937_stream_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
 {
-    __shared__ uint32_t x[kMtN];
+    __shared__ uint32_t x[kMtN + 1];
     constexpr int D = kMtN - kMtM;                   // 227
-    constexpr int R = (D + T - 1) / T;               // register slots per phase
-    const int tid = threadIdx.x;
-    if (tid == 0) {                                  // init_genrand: sequential, 624 steps, once
+    const int t = threadIdx.x;
+    if (t == 0) {                                    // init_genrand: sequential, 624 steps, once
         uint32_t s = seed;
         x[0] = s;
         for (int j = 1; j < kMtN; ++j) {
@@ -68,50 +65,35 @@ __global__ void __launch_bounds__(T) mt19937_stream_kernel(uint32_t seed, long l
             x[j] = s;
         }
     }
-    mt_sync<T>();
-    uint32_t v[R];
+    __syncthreads();
+    const bool a1 = t < D, a3 = t + 2 * D < kMtN, last = t + 2 * D == kMtN - 1;
     for (long long base = 0; base < n; base += kMtN) {
-        // phase 1: k in [0, 227) reads old x[k], x[k+1], x[k+397]
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = tid + r * T;
-            if (k < D) v[r] = x[k + kMtM] ^ mt_twist(x[k], x[k + 1]);
+        uint32_t v1 = 0, v2 = 0, v3 = 0;
+        if (a1) {
+            const uint32_t o0 = x[t], o1 = x[t + 1], om = x[t + kMtM];
+            const uint32_t p0 = x[t + D], p1 = x[t + D + 1];
+            v1 = om ^ mt_twist(o0, o1);
+            v2 = v1 ^ mt_twist(p0, p1);
+            if (a3) {
+                const uint32_t q0 = x[t + 2 * D];
+                uint32_t q1;
+                if (last) q1 = x[kMtM] ^ mt_twist(x[0], x[1]);   // the NEW x[0], recomputed from old words
+                else q1 = x[t + 2 * D + 1];
+                v3 = v2 ^ mt_twist(q0, q1);
+            }
         }
-        mt_sync<T>();
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = tid + r * T;
-            if (k < D) x[k] = v[r];
+        __syncthreads();                             // every old word has been read
+        if (a1) {
+            x[t] = v1;
+            x[t + D] = v2;
+            if (base + t < n) out[base + t] = mt_temper(v1);
+            if (base + t + D < n) out[base + t + D] = mt_temper(v2);
+            if (a3) {
+                x[t + 2 * D] = v3;
+                if (base + t + 2 * D < n) out[base + t + 2 * D] = mt_temper(v3);
+            }
         }
-        mt_sync<T>();
-        // phase 2: k in [227, 454) reads new x[k-227] (phase 1) and old x[k], x[k+1]
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = D + tid + r * T;
-            if (k < 2 * D) v[r] = x[k - D] ^ mt_twist(x[k], x[k + 1]);
-        }
-        mt_sync<T>();
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = D + tid + r * T;
-            if (k < 2 * D) x[k] = v[r];
-        }
-        mt_sync<T>();
-        // phase 3: k in [454, 624) reads new x[k-227] (phase 2), old x[k], old x[k+1] -- x[624] wraps to the NEW x[0]
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = 2 * D + tid + r * T;
-            if (k < kMtN) v[r] = x[k - D] ^ mt_twist(x[k], k + 1 < kMtN ? x[k + 1] : x[0]);
-        }
-        mt_sync<T>();
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = 2 * D + tid + r * T;
-            if (k < kMtN) x[k] = v[r];
-        }
-        mt_sync<T>();
-        for (int k = tid; k < kMtN; k += T)
-            if (base + k < n) out[base + k] = mt_temper(x[k]);
+        __syncthreads();
     }
 }
 
@@ -233,19 +215,7 @@ extern "C" int drb_mt19937_stream(uint64_t seed, int64_t n, uint32_t *d_out, voi
 {
     DRB_REQUIRE(d_out && n >= 0, "mt19937_stream: bad arguments");
     if (n == 0) return DRB_OK;
-    static int threads = 0;                          // DRB_MT_THREADS: developer override used to pick the default
-    if (!threads) {
-        const char *e = getenv("DRB_MT_THREADS");
-        threads = e ? atoi(e) : 64;
-    }
-    const uint32_t s32 = (uint32_t)(seed & 0xffffffffull);
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (threads) {
-        case 32: mt19937_stream_kernel<32><<<1, 32, 0, st>>>(s32, n, d_out); break;
-        case 128: mt19937_stream_kernel<128><<<1, 128, 0, st>>>(s32, n, d_out); break;
-        case 256: mt19937_stream_kernel<256><<<1, 256, 0, st>>>(s32, n, d_out); break;
-        default: mt19937_stream_kernel<64><<<1, 64, 0, st>>>(s32, n, d_out); break;
-    }
+    mt19937_stream_kernel<<<1, kMtThreads, 0, (cudaStream_t)stream>>>((uint32_t)(seed & 0xffffffffull), n, d_out);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
 }

@@ -91,9 +91,15 @@ struct StepParams {
     int loss;              // DRB_LOSS_BPR / _HL / _TL (pair-wise criterion, AbstractRecommender.py:79-93)
     // FM (FMRecommender.py:61-68): pred += (u_bias[u] + i_bias[item]) + bias_; bias = packed [U + I + 1]; nullptr = MF
     float *bias;
+    // multi-GPU persistent mode: step s trains local triples [step_offsets[s], step_offsets[s+1]) (device array; the union
+    // of the ranks' ranges is the global batch s).  nullptr = uniform batches of `batch` triples.
+    const long long *step_offsets;
 };
 
 
+int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu, const int32_t *bi,
+                const int32_t *bj, long long n, long long batch, long long first, long long nsteps, const drb_hyper *h,
+                long long adam_step0, double *d_step_loss, int apply, float *d_bias = nullptr);
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status = false);
 int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step);
 

@@ -203,7 +203,7 @@ __device__ __forceinline__ int draw_negative(const StepParams &p, int u, unsigne
 struct NoExchange {
     static constexpr bool kActive = false;
     __device__ __forceinline__ void begin_step(StepParams &, long long, double *&) {}
-    __device__ __forceinline__ bool after_phase1(const StepParams &, long long, double *, unsigned long long &) { return true; }
+    __device__ __forceinline__ bool after_phase1(const StepParams &, long long, double *&, unsigned long long &) { return true; }
     template <int VEC, int W, int NCH>
     __device__ __forceinline__ void item_slice(const StepParams &, long long, const Norms &, const AdamCoef &, int, int, int,
                                                int, unsigned long long &) {}
@@ -265,8 +265,8 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
 
     for (long long s = 0; s < p.n_steps; ++s) {
         const long long step = p.first_step + s;
-        const long long base = step * p.batch;
-        const long long nb = min(p.batch, p.n - base);
+        const long long base = p.step_offsets ? __ldg(p.step_offsets + step) : step * p.batch;
+        const long long nb = p.step_offsets ? __ldg(p.step_offsets + step + 1) - base : min(p.batch, p.n - base);
         const long long ntiles = (nb + tile - 1) / tile;
         double *acc = hdr->acc[s & 1];
         const bool has_reg = (p.reg1 != 0.f) || (p.reg2 != 0.f);

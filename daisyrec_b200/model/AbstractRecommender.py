@@ -215,16 +215,22 @@ class GeneralRecommender(AbstractRecommender):
         T = data.shape[0]
         # the epoch's order is computed on a side stream while the rows upload (first epoch) / are stamped: the one-CTA
         # MT19937 stream leaves the copy engines and 147 SMs free
-        main = torch.cuda.current_stream(self.device)
-        if getattr(self, '_side_stream', None) is None:
-            self._side_stream = torch.cuda.Stream(self.device)
-        self._side_stream.wait_stream(main)
-        with torch.cuda.stream(self._side_stream):
+        exact_on_device = shuffle and self.shuffle_engine == 'torch' and T < RANDPERM_DEVICE_MAX
+        if exact_on_device:
+            # buffers are allocated on the main stream and kept for the model's lifetime (no cross-stream allocator traffic)
+            if getattr(self, '_perm_bufs', None) is None or self._perm_bufs[0].numel() < T:
+                self._perm_bufs = ops.randperm_workspace(T, self.device)
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, '_side_stream', None) is None:
+                self._side_stream = torch.cuda.Stream(self.device)
+            self._side_stream.wait_stream(main)
+            with torch.cuda.stream(self._side_stream):
+                d_perm = self._device_permutation(T, shuffle, gen)
+            d_triples = self._device_triples(data)
+            main.wait_stream(self._side_stream)
+        else:
+            d_triples = self._device_triples(data)
             d_perm = self._device_permutation(T, shuffle, gen)
-        d_triples = self._device_triples(data)
-        main.wait_stream(self._side_stream)
-        if d_perm is not None:
-            d_perm.record_stream(main)
         bu, bi, bj = ops.gather_triples(d_triples, d_perm)
         n_use = (T // bs) * bs if drop_last else T
         nsteps = (n_use + bs - 1) // bs
@@ -254,7 +260,7 @@ class GeneralRecommender(AbstractRecommender):
             g.manual_seed(seed)
             return torch.randperm(T, generator=g, device=self.device)
         if self.shuffle_engine == 'torch' and T < RANDPERM_DEVICE_MAX:
-            return ops.randperm_torch(seed, T, self.device)
+            return ops.randperm_torch(seed, T, self.device, out=getattr(self, '_perm_bufs', None))
         return epoch_permutation(T, shuffle, gen, seed=seed).to(self.device, non_blocking=False)
 
     def _device_triples(self, data):

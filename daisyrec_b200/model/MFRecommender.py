@@ -59,6 +59,9 @@ class MF(GeneralRecommender):
         self._ws = None
         self._opt_steps = 0
         self._stage = None
+        # optional B200 key (torchrun only): 'p2p' = one persistent launch per epoch with the exchange inside the kernel over
+        # peer-mapped memory; 'nccl' = phase 1 -> grouped NCCL all-reduce -> phase 2 per step (also the automatic fallback)
+        self.sharded_comm = str(config.get('sharded_comm', 'p2p'))
         # optional B200 key: 'table' (default; the reference's per-user-once negatives, taken from the loader's triples) |
         # 'fused' (throughput mode: a fresh negative per triple and step is drawn inside the step kernel from the
         # complement of the user's train row; the loader's third column is ignored)
@@ -104,6 +107,9 @@ class MF(GeneralRecommender):
         lo, hi = int(bounds[self.rank_id]), int(bounds[self.rank_id + 1])
         self.embed_user = _Table(self._P_full_cpu[lo:hi].contiguous().to(self.device))
         self._P_full_cpu = None
+        if self._trainer is not None:
+            self._trainer.close()
+            self.embed_item = _Table(self._trainer.Q)
         self._trainer = None
 
     def _default_bounds(self):
@@ -117,7 +123,8 @@ class MF(GeneralRecommender):
             self._shard(partition_users(w, self.world))
         if self._trainer is None:
             self._trainer = ShardedTrainer(self.embed_user.weight, self.embed_item.weight, self._bounds, self.rank_id,
-                                           self.world, self._hp, self._optimizer_name())
+                                           self.world, self._hp, self._optimizer_name(), comm=self.sharded_comm)
+            self.embed_item = _Table(self._trainer.Q)             # p2p: the replica lives in the peer-visible buffer
         return self._trainer
 
     def gather_user_table(self):
@@ -140,6 +147,9 @@ class MF(GeneralRecommender):
         self._hp = self._hyper(opt)
         self._opt_steps = 0
         if self.world > 1:
+            if self._trainer is not None:
+                self._trainer.close()                              # keeps a private copy of Q; frees the peer buffers
+                self.embed_item = _Table(self._trainer.Q)
             self._trainer = None                                   # fresh optimiser state per fit()
             return
         self._ws = ops.MFWorkspace(self.user_num, self.item_num, self.factors, opt, self.device)

@@ -256,10 +256,15 @@ def mt19937_stream(seed, n, device):
     return out[:n]
 
 
-def randperm_torch(seed, n, device):
+def randperm_workspace(n, device):
+    """(perm int64 [n], scratch) for randperm_torch(out=...): lets a caller keep them across epochs."""
+    return (torch.empty(max(n, 1), dtype=torch.int64, device=device),
+            torch.empty(L.lib().drb_randperm_workspace_bytes(n), dtype=torch.uint8, device=device))
+
+
+def randperm_torch(seed, n, device, out=None):
     """torch.randperm(n, generator=G) for a CPU generator G with G.manual_seed(seed) -- computed on the device, bit-exact."""
-    perm = torch.empty(max(n, 1), dtype=torch.int64, device=device)
-    ws = torch.empty(L.lib().drb_randperm_workspace_bytes(n), dtype=torch.uint8, device=device)
+    perm, ws = out if out is not None else randperm_workspace(n, device)
     L.check(L.lib().drb_randperm_torch(C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), n, _ptr(perm), _ptr(ws), _stream()))
     return perm[:n]
 

@@ -133,11 +133,18 @@ class ShardedTrainer:
         from . import ops
         # comm = "nccl": the library enqueues kernels + one grouped NCCL all-reduce per step itself (no host round trip);
         # comm = "torch": per-step torch.distributed collectives (also what the gloo CPU tests of the host logic exercise)
+        # comm = "p2p": ONE persistent launch per epoch segment, the exchange inside the kernel over peer-mapped memory (csrc/p2p.cu)
         self.comm = comm if (comm == "torch" or dist.get_backend(group) == "nccl") else "torch"
+        if self.comm == "p2p" and (hp.opt not in (L.OPT_SGD, L.OPT_ADAM) or hp.loss != 0 or Q.shape[1] % 4 or Q.shape[1] > 128
+                                   or world > 8):
+            self.comm = "nccl"                                    # outside the peer kernel's instantiations
         if self.comm == "nccl":
             init_native_comm(group)
         self.ops = ops
         self.Q = Q
+        self._xbuf = None
+        if self.comm == "p2p":
+            self._open_peer_buffers(Q, rank, world, group)
         # a rank that owns no user still takes part in every collective: give the kernels one dummy row to point at
         self.P = P_local if P_local.shape[0] > 0 else torch.zeros((1, Q.shape[1]), dtype=Q.dtype, device=Q.device)
         self.bounds, self.rank, self.world, self.group = np.asarray(bounds, np.int64), rank, world, group
@@ -157,6 +164,54 @@ class ShardedTrainer:
         self.opt_steps = 0
         self.offsets_host = None
         self._stage = None
+        self.peer_timeout_s = 20.0
+
+    # ---- peer exchange buffers (comm = "p2p")
+    def _open_peer_buffers(self, Q, rank, world, group):
+        I, F = Q.shape
+        lib = L.lib()
+        nbytes = lib.drb_p2p_buffer_bytes(I, F)
+        own, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        L.check(lib.drb_p2p_alloc(nbytes, C.byref(own), handle))
+        self._xbuf, self._xbytes = own.value, nbytes
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=Q.device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)                  # torch.distributed moves the 64-byte handles, nothing else
+        self._peer_ptrs = (C.c_void_p * world)()
+        self._opened = []
+        for q in range(world):
+            if q == rank:
+                self._peer_ptrs[q] = own.value
+                continue
+            h = (C.c_uint8 * 64)(*every[q].cpu().tolist())
+            ptr = C.c_void_p()
+            L.check(lib.drb_p2p_open(h, C.byref(ptr)))
+            self._peer_ptrs[q] = ptr.value
+            self._opened.append(ptr.value)
+        # the item-table replica lives inside the exchange buffer (peers store their slices straight into it)
+        q_off = lib.drb_p2p_q_offset(I, F)
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (I * F,), "typestr": "<f4", "data": (own.value + q_off, False), "version": 2}
+        self._q_owner = _Mem()
+        q_view = torch.as_tensor(self._q_owner, device=Q.device).view(I, F)
+        q_view.copy_(Q)
+        self.Q = q_view
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                                  # every replica is initialised before anyone's first launch
+
+    def close(self):
+        """Unmap the peers' buffers and free the own one (collective: nobody may still be inside a launch)."""
+        if self._xbuf is None:
+            return
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        q_copy = self.Q.clone()
+        for ptr in self._opened:
+            L.lib().drb_p2p_close(C.c_void_p(ptr))
+        dist.barrier(group=self.group)
+        L.lib().drb_p2p_free(C.c_void_p(self._xbuf))
+        self._xbuf, self._opened, self.Q = None, [], q_copy
 
     # ---- train feed
     def prepare_epoch(self, d_triples, d_perm, batch_global):
@@ -174,6 +229,7 @@ class ShardedTrainer:
                                                  _ptr(self._planes[0]), _ptr(self._planes[1]), _ptr(self._planes[2]),
                                                  _stream()))
         self.offsets_host = self.step_offsets.cpu().numpy()
+        self.batch_global = int(batch_global)
         self.bu, self.bi, self.bj = self._planes[0], self._planes[1], self._planes[2]
         return m
 
@@ -197,7 +253,17 @@ class ShardedTrainer:
         """Global steps first .. first+n_steps-1 of the prepared epoch; returns the per-step global losses (device)."""
         if losses is None:
             losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
-        if self.comm == "nccl":
+        if self.comm == "p2p":
+            bad = C.c_int64(-1)
+            per_rank = max(1, self.batch_global // self.world)
+            rc = L.lib().drb_mf_bpr_train_steps_p2p(_ptr(self.P), _ptr(self.ws.buf), max(1, self.U_local), self.I, self.F,
+                                                    self._peer_ptrs, self.rank, self.world, _ptr(self.bu), _ptr(self.bi),
+                                                    _ptr(self.bj), _ptr(self.step_offsets), int(self.offsets_host[-1]),
+                                                    per_rank, first, n_steps, C.byref(self.hp), self.opt_steps, _ptr(losses),
+                                                    C.c_double(self.peer_timeout_s), 0, C.byref(bad), _stream())
+            L.check(rc)
+            self.opt_steps += n_steps
+        elif self.comm == "nccl":
             offs = np.ascontiguousarray(self.offsets_host, np.int64)
             L.check(L.lib().drb_mf_bpr_train_steps_sharded(_ptr(self.P), _ptr(self.Q), _ptr(self.ws.buf), max(1, self.U_local),
                                                            self.I, self.F, _ptr(self.bu), _ptr(self.bi), _ptr(self.bj),
@@ -213,8 +279,10 @@ class ShardedTrainer:
     def train_steps_host(self, h_bu, h_bi, h_bj, h_offsets, first, n_steps):
         """Global steps fed from pinned HOST planes holding this rank's share of every global batch (native loop: the
         H2D of step s+1 overlaps step s, one loss D2H per step).  Returns the per-step GLOBAL losses (pinned CPU fp64)."""
+        if self.comm == "p2p":
+            return self._train_steps_host_p2p(h_bu, h_bi, h_bj, h_offsets, first, n_steps)
         if self.comm != "nccl":
-            raise RuntimeError("train_steps_host needs the native NCCL communicator")
+            raise RuntimeError("train_steps_host needs the native NCCL communicator or the peer kernel")
         offs = np.ascontiguousarray(h_offsets, np.int64)
         widest = int(np.diff(offs[first:first + n_steps + 1]).max()) if n_steps > 0 else 0
         stride = max(4, (widest + 3) // 4 * 4)
@@ -227,6 +295,34 @@ class ShardedTrainer:
             h_bi.data_ptr(), h_bj.data_ptr(), offs.ctypes.data, first, n_steps, C.byref(self.hp), self.opt_steps,
             _ptr(self._stage), stride, _ptr(d_loss), h_loss.data_ptr(), _stream()))
         self.opt_steps += n_steps
+        return h_loss[:n_steps]
+
+    def _train_steps_host_p2p(self, h_bu, h_bi, h_bj, h_offsets, first, n_steps, chunk=8):
+        """Peer-kernel form: the host shares are copied in chunks of `chunk` global steps (side stream) under the persistent
+        launch of the chunk before; the losses of a chunk come back with one D2H."""
+        offs = np.ascontiguousarray(h_offsets, np.int64)
+        assert np.array_equal(offs, self.offsets_host[:len(offs)]), "host shares must follow the prepared epoch's offsets"
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.dev)
+        d_loss = torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
+        h_loss = torch.empty(max(1, n_steps), dtype=torch.float64).pin_memory()
+        self._copy_stream.wait_stream(main)
+        spans = [(s, min(chunk, first + n_steps - s)) for s in range(first, first + n_steps, chunk)]
+        ready = []
+        for s0, k in spans:                                          # enqueue every copy; each chunk's launch waits for its own
+            b, e = int(offs[s0]), int(offs[s0 + k])
+            with torch.cuda.stream(self._copy_stream):
+                for dst, src in ((self.bu, h_bu), (self.bi, h_bi), (self.bj, h_bj)):
+                    dst[b:e].copy_(src[b:e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            ready.append(ev)
+        for (s0, k), ev in zip(spans, ready):
+            main.wait_event(ev)
+            self.train_steps(s0, k, d_loss[s0 - first:])
+            h_loss[s0 - first:s0 - first + k].copy_(d_loss[s0 - first:s0 - first + k], non_blocking=True)
+        main.synchronize()
         return h_loss[:n_steps]
 
     def step_host(self, h_bu, h_bi, h_bj, stage):
@@ -243,3 +339,6 @@ class ShardedTrainer:
         status = int(np.frombuffer(hdr[144:148].tobytes(), np.int32)[0])   # WsHeader: barrier 8 + acc 128 + nan_step 8
         if status == L.DRB_ERR_NAN_LOSS:
             raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+        if status == L.DRB_ERR_PEER:
+            raise RuntimeError("multi-GPU peer exchange timed out: a rank did not reach the rendezvous (see DESIGN.md, "
+                               "multi-GPU section); the NCCL step (sharded_comm='nccl') is the fallback")

@@ -37,6 +37,7 @@ extern "C" {
 #define DRB_ERR_NAN_LOSS 3    /* loss became NaN: ValueError of AbstractRecommender.py:122-123    */
 #define DRB_ERR_EMPTY_SET 4   /* a user has no un-interacted item: numpy "a cannot be empty"      */
 #define DRB_ERR_NO_DEVICE 5   /* no sm_100 device / kernel image not loadable on this device     */
+#define DRB_ERR_PEER 6        /* multi-GPU peer exchange: a rank did not reach the rendezvous in time */
 
 #define DRB_OPT_SGD 0         /* optim.SGD(lr)   AbstractRecommender.py:55-56                     */
 #define DRB_OPT_ADAM 1        /* optim.Adam(lr)  AbstractRecommender.py:53-54 (dense, torch defaults) */
@@ -305,6 +306,30 @@ int drb_mf_bpr_train_steps_sharded_host(float *d_P_local, float *d_Q, void *d_ws
                                         const int64_t *h_step_offsets, int64_t first_step, int64_t n_steps,
                                         const drb_hyper *hyper, int64_t adam_step0, int32_t *d_stage, int64_t stage_stride,
                                         double *d_step_loss, double *h_step_loss, void *stream);
+
+/* Peer-exchange form of the sharded step (csrc/p2p.cu): ONE persistent cooperative launch per rank runs n_steps global steps;
+ * between phase 1 and phase 2 the ranks rendezvous through flags in peer-mapped memory, every rank reduces, updates and
+ * broadcasts ITS slice of the item table over NVLink (peer loads / stores), no NCCL call and no relaunch per step.
+ *   drb_p2p_buffer_bytes / drb_p2p_q_offset : size of a rank's exchange buffer, offset of its item-table replica inside it
+ *   drb_p2p_alloc  : cudaMalloc + zero + 64-byte CUDA IPC handle (the host all-gathers the handles)
+ *   drb_p2p_open / _close : map / unmap a peer's buffer;  drb_p2p_free : release the own buffer
+ *   drb_mf_bpr_train_steps_p2p : h_peer_bufs[q] = rank q's buffer as mapped here (own buffer at [rank]); step s trains local
+ *     triples [d_step_offsets[s], d_step_offsets[s+1]) (DEVICE array from drb_shard_gather_triples); steps_done = global steps
+ *     already run on these buffers (rendezvous flags carry absolute step numbers; also Adam's step count).  BPR, SGD / Adam,
+ *     factors a multiple of 4 up to 128.  A rank that does not reach a rendezvous within peer_timeout_s (<= 0: 20 s) ends
+ *     the launch with DRB_ERR_PEER on every rank instead of hanging the GPUs. */
+size_t drb_p2p_buffer_bytes(int32_t item_num, int32_t factors);
+size_t drb_p2p_q_offset(int32_t item_num, int32_t factors);
+int drb_p2p_alloc(size_t bytes, void **d_ptr, uint8_t *h_handle64);
+int drb_p2p_open(const uint8_t *h_handle64, void **d_ptr);
+int drb_p2p_close(void *d_ptr);
+int drb_p2p_free(void *d_ptr);
+int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t user_num_local, int32_t item_num, int32_t factors,
+                               void *const *h_peer_bufs, int32_t rank, int32_t world, const int32_t *d_bu,
+                               const int32_t *d_bi, const int32_t *d_bj, const int64_t *d_step_offsets, int64_t n_local,
+                               int64_t batch_per_rank, int64_t first_step, int64_t n_steps, const drb_hyper *hyper,
+                               int64_t steps_done, double *d_step_loss, double peer_timeout_s, int32_t sync_and_check,
+                               int64_t *bad_step, void *stream);
 
 /* ---- inference ------------------------------------------------------------------------
  * MF.rank  daisy/model/MFRecommender.py:106-123: per user, score cand_num candidates,

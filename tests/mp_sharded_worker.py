@@ -28,8 +28,8 @@ def main():
     data = np.stack([users, rng.integers(I, size=T), rng.integers(I, size=T)], 1).astype(np.int32)
     cfg = dict(gpu='', logger=logging.getLogger('w'), lr=0.01, reg_1=0.001, reg_2=0.001, epochs=2, topk=20, user_num=U,
                item_num=I, factors=F, loss_type='BPR', optimizer='default', init_method='default', early_stop=False,
-               progress=False)
-    torch.manual_seed(11)
+               progress=False, sharded_comm=os.environ.get("DRB_SHARDED_COMM", "p2p"))
+    torch.manual_seed(11 + 1000 * rank)          # different RNG histories per rank: rank 0's draws must win (broadcast)
     model = MF(cfg)
     P0 = model._P_full_cpu.numpy().copy()
     Q0 = model.embed_item.weight.cpu().numpy().copy()
@@ -57,7 +57,7 @@ def main():
         errP, errQ = np.abs(P - Po).max(), np.abs(Q - Qo).max()
         want = orc.mf_rank(P, Q, tu, cands, 20)
         ok = same_q and errP < 1e-5 and errQ < 1e-5 and np.array_equal(preds, want)
-        print(f"[mp_sharded_worker] world={world} same_q={same_q} errP={errP:.2e} errQ={errQ:.2e} "
+        print(f"[mp_sharded_worker] world={world} comm={model._trainer.comm if model._trainer else None} same_q={same_q} errP={errP:.2e} errQ={errQ:.2e} "
               f"rank_equal={np.array_equal(preds, want)} -> {'OK' if ok else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -20,14 +20,15 @@ def _physical_gpus():
         return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("comm", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [2])
-def test_sharded_training_matches_oracle(world):
+def test_sharded_training_matches_oracle(world, comm):
     if _physical_gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    env = dict(os.environ)
+    env = dict(os.environ, DRB_SHARDED_COMM=comm)
     env.pop("CUDA_VISIBLE_DEVICES", None)      # an earlier test may have mirrored config['gpu'] into it
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "tests", "mp_sharded_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "-> OK" in r.stdout
+    assert "-> OK" in r.stdout and f"comm={comm}" in r.stdout
