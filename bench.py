@@ -702,7 +702,7 @@ def sharded_parity_check(d, triples, perm, bounds, rank, world, dev, F, seed, co
     sl = perm[:Bs * K].contiguous()
     P0, Q0 = init_tables(U, I, F, seed + 1, dev)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.clone(), bounds, rank, world, ops.hyper(**HYPER), comm=comm)
+    tr = ShardedTrainer(P0[lo:hi].clone(), Q0.clone(), bounds, rank, world, ops.hyper(**HYPER), comm=comm)   # clone: a slice's .contiguous() aliases P0
     m = tr.prepare_epoch(triples, sl, Bs)
     assert m == K
     losses = tr.train_steps(0, K).clone()

@@ -27,17 +27,20 @@ namespace drb {
 constexpr int kMaxLayers = 8;
 
 struct NeumfDims {
-    int U, I, F, L, D;
+    int U, I, F, L, D, mode;
     int n[kMaxLayers + 1];              // n[0] = 2D, n[l] = n[l-1]/2, n[L] = F
     long long w_off[kMaxLayers], b_off[kMaxLayers], wp_off, bp_off, nW;
     long long act_off[kMaxLayers + 1];  // offset of A_l inside the activation buffer, in units of R floats
     long long act_cols;                 // sum_l n[l]
 };
 
-static bool make_dims(NeumfDims &d, int U, int I, int F, int L)
+// mode (config['model_name'], NeuMFRecommender.py:48-50,97-116,118-137): 0 'NeuMF' / 'NeuMF-pre' (predict over
+// cat(GMF, tower) = 2F inputs), 1 'GMF' (predict over the GMF product, F inputs; the tower exists but is never run),
+// 2 'MLP' (predict over the tower output, F inputs).  All four tables and every tower layer are parameters in every mode.
+static bool make_dims(NeumfDims &d, int U, int I, int F, int L, int mode = 0)
 {
-    if (U <= 0 || I <= 0 || F <= 0 || L < 1 || L > kMaxLayers || (F % 4) != 0) return false;
-    d.U = U; d.I = I; d.F = F; d.L = L; d.D = F << (L - 1);
+    if (U <= 0 || I <= 0 || F <= 0 || L < 1 || L > kMaxLayers || (F % 4) != 0 || mode < 0 || mode > 2) return false;
+    d.U = U; d.I = I; d.F = F; d.L = L; d.D = F << (L - 1); d.mode = mode;
     d.n[0] = 2 * d.D;
     long long o = 0, a = 0;
     for (int l = 0; l < L; ++l) {
@@ -45,7 +48,7 @@ static bool make_dims(NeumfDims &d, int U, int I, int F, int L)
         d.w_off[l] = o; o += (long long)d.n[l] * d.n[l + 1];
         d.b_off[l] = o; o += d.n[l + 1];
     }
-    d.wp_off = o; o += 2 * F;
+    d.wp_off = o; o += (mode == 0 ? 2 : 1) * F;
     d.bp_off = o; o += 1;
     d.nW = o;
     for (int l = 0; l <= L; ++l) { d.act_off[l] = a; a += d.n[l]; }
@@ -207,13 +210,25 @@ static int launch_gemm(int dtype, long long M, int N, int K, const float *A, lon
 // masks from torch's global RNG; here they are counter-based: keep(layer, step, element) = Philox4x32-10(seed;
 // element/4, layer, step) word (element%4) >= p * 2^32.  Counter-based masks can be regenerated in the backward pass
 // (layer 0) instead of being stored.  Kept values are scaled by 1/(1-p) like torch.
+// Parity mode: `bits[layer]` points at HOST-generated keep masks for this step -- the very tensors
+// torch.empty(B, n_l).bernoulli_(1 - p) yields on the CPU generator, in the reference's draw order, bit-packed (bit e of
+// the [2B, n_l] row-major mask; rows [0,B) from the pos forward, [B,2B) from the neg forward) -- and takes precedence.
 struct Drop {
     float p, inv_keep;
     uint32_t k0, k1, step, thresh;
+    const uint32_t *bits[kMaxLayers];
 };
 
 __device__ __forceinline__ float4 drop4(float4 v, const Drop &d, unsigned long long chunk, uint32_t layer)
 {
+    if (d.bits[0] != nullptr) {
+        const uint32_t m = (__ldg(d.bits[layer] + (chunk >> 3)) >> ((unsigned)(chunk & 7ull) * 4u)) & 0xFu;
+        v.x = (m & 1u) ? v.x * d.inv_keep : 0.f;
+        v.y = (m & 2u) ? v.y * d.inv_keep : 0.f;
+        v.z = (m & 4u) ? v.z * d.inv_keep : 0.f;
+        v.w = (m & 8u) ? v.w * d.inv_keep : 0.f;
+        return v;
+    }
     uint32_t c[4] = {(uint32_t)chunk, (uint32_t)(chunk >> 32), layer, d.step};
     philox4x32(c, d.k0, d.k1);
     v.x = c[0] >= d.thresh ? v.x * d.inv_keep : 0.f;
@@ -282,7 +297,7 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
                                                          const float *__restrict__ wp, const float *__restrict__ AL,
                                                          const int32_t *__restrict__ bu, const int32_t *__restrict__ bi,
                                                          const int32_t *__restrict__ bj, long long B, int F, int D, int has_reg,
-                                                         int apply, int W, float *__restrict__ gUG, float *__restrict__ gIG,
+                                                         int apply, int W, int mode, float *__restrict__ gUG, float *__restrict__ gIG,
                                                          float *__restrict__ gWp, float *__restrict__ dZL,
                                                          unsigned *__restrict__ cntU, unsigned long long *__restrict__ cntI,
                                                          double *__restrict__ red)
@@ -292,13 +307,17 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int gpw = 32 / W, gl = lane % W, gw = lane / W;
     const int chunks = F / 4, dchunks = D / 4;
+    // predict layer: mode 0 over cat(GMF, h) [2F], mode 1 over GMF [F], mode 2 over h [F]
+    const bool use_g = mode != 2, use_h = mode != 1;
+    const int pw = (mode == 0 ? 2 : 1) * F, hoff = mode == 0 ? F : 0;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = threadIdx.x; k < 2 * F + 1; k += blockDim.x) s_gw[k] = 0.f;
     if (threadIdx.x < 11) s_red[threadIdx.x] = 0.0;
     __syncthreads();
     float acc[11] = {};
     float4 gwa = make_float4(0.f, 0.f, 0.f, 0.f), gwb = gwa;   // predict-layer gradient partials of this lane's chunk
     const bool one_chunk = chunks <= W;                        // F <= 128: each lane owns at most one chunk
-    const float bp = wp[2 * F];
+    const float bp = wp[pw];
     const long long groups = (long long)gridDim.x * nwarp * gpw;
     const long long g0 = ((long long)blockIdx.x * nwarp + warp) * gpw + gw;
     const long long rounds = (B + groups - 1) / groups;
@@ -311,8 +330,9 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
         float sp = 0.f, sn = 0.f;
         for (int c = gl; c < chunks; c += W) {
             float4 a = ldcg4(ug + 4 * c), b = ldcg4(igi + 4 * c), d = ldcg4(igj + 4 * c);
-            float4 w0 = *reinterpret_cast<const float4 *>(wp + 4 * c), w1 = *reinterpret_cast<const float4 *>(wp + F + 4 * c);
-            float4 h0 = *reinterpret_cast<const float4 *>(hp + 4 * c), h1 = *reinterpret_cast<const float4 *>(hn + 4 * c);
+            float4 w0 = use_g ? *reinterpret_cast<const float4 *>(wp + 4 * c) : z4;
+            float4 w1 = use_h ? *reinterpret_cast<const float4 *>(wp + hoff + 4 * c) : z4;
+            float4 h0 = use_h ? *reinterpret_cast<const float4 *>(hp + 4 * c) : z4, h1 = use_h ? *reinterpret_cast<const float4 *>(hn + 4 * c) : z4;
             sp = fmaf(w0.x, a.x * b.x, sp); sp = fmaf(w1.x, h0.x, sp); sn = fmaf(w0.x, a.x * d.x, sn); sn = fmaf(w1.x, h1.x, sn);
             sp = fmaf(w0.y, a.y * b.y, sp); sp = fmaf(w1.y, h0.y, sp); sn = fmaf(w0.y, a.y * d.y, sn); sn = fmaf(w1.y, h1.y, sn);
             sp = fmaf(w0.z, a.z * b.z, sp); sp = fmaf(w1.z, h0.z, sp); sn = fmaf(w0.z, a.z * d.z, sn); sn = fmaf(w1.z, h1.z, sn);
@@ -342,8 +362,9 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
         if (!apply || !ok) continue;
         for (int cc = gl; cc < chunks; cc += W) {
             float4 a = ldcg4(ug + 4 * cc), b = ldcg4(igi + 4 * cc), d = ldcg4(igj + 4 * cc);
-            float4 w0 = *reinterpret_cast<const float4 *>(wp + 4 * cc), w1 = *reinterpret_cast<const float4 *>(wp + F + 4 * cc);
-            float4 h0 = *reinterpret_cast<const float4 *>(hp + 4 * cc), h1 = *reinterpret_cast<const float4 *>(hn + 4 * cc);
+            float4 w0 = use_g ? *reinterpret_cast<const float4 *>(wp + 4 * cc) : z4;
+            float4 w1 = use_h ? *reinterpret_cast<const float4 *>(wp + hoff + 4 * cc) : z4;
+            float4 h0 = use_h ? *reinterpret_cast<const float4 *>(hp + 4 * cc) : z4, h1 = use_h ? *reinterpret_cast<const float4 *>(hn + 4 * cc) : z4;
             // predict-layer weight gradient: dp * cat(GMF, h) summed over pos (+c) and neg (-c)
             float4 ga = make_float4(c * (a.x * b.x) - c * (a.x * d.x), c * (a.y * b.y) - c * (a.y * d.y),
                                     c * (a.z * b.z) - c * (a.z * d.z), c * (a.w * b.w) - c * (a.w * d.w));
@@ -352,23 +373,27 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
                 gwa.x += ga.x; gwa.y += ga.y; gwa.z += ga.z; gwa.w += ga.w;
                 gwb.x += gb.x; gwb.y += gb.y; gwb.z += gb.z; gwb.w += gb.w;
             } else {
-                atomicAdd(&s_gw[4 * cc], ga.x); atomicAdd(&s_gw[4 * cc + 1], ga.y); atomicAdd(&s_gw[4 * cc + 2], ga.z); atomicAdd(&s_gw[4 * cc + 3], ga.w);
-                atomicAdd(&s_gw[F + 4 * cc], gb.x); atomicAdd(&s_gw[F + 4 * cc + 1], gb.y); atomicAdd(&s_gw[F + 4 * cc + 2], gb.z); atomicAdd(&s_gw[F + 4 * cc + 3], gb.w);
+                if (use_g) { atomicAdd(&s_gw[4 * cc], ga.x); atomicAdd(&s_gw[4 * cc + 1], ga.y); atomicAdd(&s_gw[4 * cc + 2], ga.z); atomicAdd(&s_gw[4 * cc + 3], ga.w); }
+                if (use_h) { atomicAdd(&s_gw[hoff + 4 * cc], gb.x); atomicAdd(&s_gw[hoff + 4 * cc + 1], gb.y); atomicAdd(&s_gw[hoff + 4 * cc + 2], gb.z); atomicAdd(&s_gw[hoff + 4 * cc + 3], gb.w); }
             }
             // GMF table gradients (one RED.ADD.F32x4 per row chunk)
-            Vec<4> v;
-            v.v[0] = c * w0.x * b.x - c * w0.x * d.x; v.v[1] = c * w0.y * b.y - c * w0.y * d.y;
-            v.v[2] = c * w0.z * b.z - c * w0.z * d.z; v.v[3] = c * w0.w * b.w - c * w0.w * d.w;
-            red_row<4>(gUG + (size_t)u * F + 4 * cc, v);
-            v.v[0] = c * w0.x * a.x; v.v[1] = c * w0.y * a.y; v.v[2] = c * w0.z * a.z; v.v[3] = c * w0.w * a.w;
-            red_row<4>(gIG + (size_t)i * F + 4 * cc, v);
-            v.v[0] = -v.v[0]; v.v[1] = -v.v[1]; v.v[2] = -v.v[2]; v.v[3] = -v.v[3];
-            red_row<4>(gIG + (size_t)j * F + 4 * cc, v);
-            // dZ_L = dp * w1 * relu'(h)
-            *reinterpret_cast<float4 *>(dZL + (size_t)t * F + 4 * cc) =
-                make_float4(h0.x > 0.f ? c * w1.x : 0.f, h0.y > 0.f ? c * w1.y : 0.f, h0.z > 0.f ? c * w1.z : 0.f, h0.w > 0.f ? c * w1.w : 0.f);
-            *reinterpret_cast<float4 *>(dZL + (size_t)(B + t) * F + 4 * cc) =
-                make_float4(h1.x > 0.f ? -c * w1.x : 0.f, h1.y > 0.f ? -c * w1.y : 0.f, h1.z > 0.f ? -c * w1.z : 0.f, h1.w > 0.f ? -c * w1.w : 0.f);
+            if (use_g) {
+                Vec<4> v;
+                v.v[0] = c * w0.x * b.x - c * w0.x * d.x; v.v[1] = c * w0.y * b.y - c * w0.y * d.y;
+                v.v[2] = c * w0.z * b.z - c * w0.z * d.z; v.v[3] = c * w0.w * b.w - c * w0.w * d.w;
+                red_row<4>(gUG + (size_t)u * F + 4 * cc, v);
+                v.v[0] = c * w0.x * a.x; v.v[1] = c * w0.y * a.y; v.v[2] = c * w0.z * a.z; v.v[3] = c * w0.w * a.w;
+                red_row<4>(gIG + (size_t)i * F + 4 * cc, v);
+                v.v[0] = -v.v[0]; v.v[1] = -v.v[1]; v.v[2] = -v.v[2]; v.v[3] = -v.v[3];
+                red_row<4>(gIG + (size_t)j * F + 4 * cc, v);
+            }
+            if (use_h) {
+                // dZ_L = dp * w1 * relu'(h)
+                *reinterpret_cast<float4 *>(dZL + (size_t)t * F + 4 * cc) =
+                    make_float4(h0.x > 0.f ? c * w1.x : 0.f, h0.y > 0.f ? c * w1.y : 0.f, h0.z > 0.f ? c * w1.z : 0.f, h0.w > 0.f ? c * w1.w : 0.f);
+                *reinterpret_cast<float4 *>(dZL + (size_t)(B + t) * F + 4 * cc) =
+                    make_float4(h1.x > 0.f ? -c * w1.x : 0.f, h1.y > 0.f ? -c * w1.y : 0.f, h1.z > 0.f ? -c * w1.z : 0.f, h1.w > 0.f ? -c * w1.w : 0.f);
+            }
         }
         if (gl == 0) {
             red_add_u32(cntU + u, 1u);
@@ -377,8 +402,8 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
         }
     }
     if (apply && one_chunk && gl < chunks) {
-        atomicAdd(&s_gw[4 * gl], gwa.x); atomicAdd(&s_gw[4 * gl + 1], gwa.y); atomicAdd(&s_gw[4 * gl + 2], gwa.z); atomicAdd(&s_gw[4 * gl + 3], gwa.w);
-        atomicAdd(&s_gw[F + 4 * gl], gwb.x); atomicAdd(&s_gw[F + 4 * gl + 1], gwb.y); atomicAdd(&s_gw[F + 4 * gl + 2], gwb.z); atomicAdd(&s_gw[F + 4 * gl + 3], gwb.w);
+        if (use_g) { atomicAdd(&s_gw[4 * gl], gwa.x); atomicAdd(&s_gw[4 * gl + 1], gwa.y); atomicAdd(&s_gw[4 * gl + 2], gwa.z); atomicAdd(&s_gw[4 * gl + 3], gwa.w); }
+        if (use_h) { atomicAdd(&s_gw[hoff + 4 * gl], gwb.x); atomicAdd(&s_gw[hoff + 4 * gl + 1], gwb.y); atomicAdd(&s_gw[hoff + 4 * gl + 2], gwb.z); atomicAdd(&s_gw[hoff + 4 * gl + 3], gwb.w); }
     }
     // block reduction of the scalars
     const int nv = has_reg ? 11 : 1;
@@ -391,7 +416,7 @@ __global__ void __launch_bounds__(256) neumf_head_kernel(const float *__restrict
     __syncthreads();
     if (threadIdx.x < nv && s_red[threadIdx.x] != 0.0) atomicAdd(red + threadIdx.x, s_red[threadIdx.x]);
     if (apply)
-        for (int k = threadIdx.x; k < 2 * F; k += blockDim.x)
+        for (int k = threadIdx.x; k < pw; k += blockDim.x)
             if (s_gw[k] != 0.f) atomicAdd(gWp + k, s_gw[k]);
     // the bias gradient of the predict layer is sum(+c) + sum(-c) == 0 exactly for a pairwise loss
 }
@@ -499,8 +524,10 @@ __global__ void neumf_update_w_kernel(float *__restrict__ W, float *__restrict__
 __global__ void neumf_score_kernel(const float *__restrict__ UG, const float *__restrict__ IG, const float *__restrict__ wp,
                                    const float *__restrict__ AL, const int64_t *__restrict__ users,
                                    const int64_t *__restrict__ items, long long row0, long long rows, int per_user, int F,
-                                   float *__restrict__ scores)
+                                   int mode, float *__restrict__ scores)
 {
+    const bool use_g = mode != 2, use_h = mode != 1;
+    const int pw = (mode == 0 ? 2 : 1) * F, hoff = mode == 0 ? F : 0;
     const int lane = threadIdx.x & 31;
     long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long r = warp; r < rows; r += nw) {
@@ -509,12 +536,12 @@ __global__ void neumf_score_kernel(const float *__restrict__ UG, const float *__
         long long it = items ? items[g] : (g % per_user);
         float s = 0.f;
         for (int f = lane; f < F; f += 32) {
-            s = fmaf(wp[f], __ldcg(UG + (size_t)u * F + f) * __ldcg(IG + (size_t)it * F + f), s);
-            s = fmaf(wp[F + f], AL[(size_t)r * F + f], s);
+            if (use_g) s = fmaf(wp[f], __ldcg(UG + (size_t)u * F + f) * __ldcg(IG + (size_t)it * F + f), s);
+            if (use_h) s = fmaf(wp[hoff + f], AL[(size_t)r * F + f], s);
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) scores[g] = s + wp[2 * F];
+        if (lane == 0) scores[g] = s + wp[pw];
     }
 }
 
@@ -548,17 +575,28 @@ static int tower_forward(const NeumfDims &d, const float *W, float *acts, long l
 
 using namespace drb;
 
-extern "C" int64_t drb_neumf_param_count(int32_t F, int32_t L)
+extern "C" int64_t drb_neumf_param_count(int32_t F, int32_t L, int32_t mode)
+{
+    NeumfDims d;
+    if (!make_dims(d, 1, 1, F, L, mode)) return -1;
+    return d.nW;
+}
+
+// words (uint32) of host-generated dropout keep-masks one step of `batch` triples consumes: layer l's [2*batch, n_l] mask
+// bit-packed and padded to a word, layers in order (n_0 = 2D, n_l = n_{l-1}/2)
+extern "C" int64_t drb_neumf_mask_words(int32_t F, int32_t L, int64_t batch)
 {
     NeumfDims d;
     if (!make_dims(d, 1, 1, F, L)) return -1;
-    return d.nW;
+    int64_t w = 0;
+    for (int l = 0; l < L; ++l) w += (2 * batch * d.n[l] + 31) / 32;
+    return w;
 }
 
 extern "C" size_t drb_neumf_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_t L, int32_t opt, int64_t max_rows)
 {
     NeumfDims d;
-    if (!make_dims(d, U, I, F, L)) return 0;
+    if (!make_dims(d, U, I, F, L)) return 0;      // mode 0 has the largest parameter block: one layout for every mode
     return carve_neumf(nullptr, d, opt, max_rows, nullptr);
 }
 
@@ -581,13 +619,14 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
                                          const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
                                          int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *h,
                                          int64_t adam_step0, int32_t apply, int32_t tower_dtype, float dropout,
-                                         uint64_t dropout_seed, double *d_step_loss, int32_t sync_and_check,
-                                         int64_t *nan_step, void *stream)
+                                         uint64_t dropout_seed, const uint32_t *d_drop_masks, int32_t mode,
+                                         double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream)
 {
-    NeumfDims d;
+    NeumfDims d, dlay;
     DRB_REQUIRE(tower_dtype == 0 || tower_dtype == 1, "neumf: tower_dtype must be 0 (fp32) or 1 (bf16 tcgen05)");
     DRB_REQUIRE(dropout >= 0.f && dropout < 1.f, "neumf: dropout must be in [0, 1)");
-    DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf: bad dims (factors must be a positive multiple of 4, 1 <= num_layers <= 8)");
+    DRB_REQUIRE(make_dims(d, U, I, F, L, mode) && make_dims(dlay, U, I, F, L, 0),
+                "neumf: bad dims (factors must be a positive multiple of 4, 1 <= num_layers <= 8, mode 0..2)");
     DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_bu && d_bi && d_bj && h && d_step_loss, "neumf: null argument");
     DRB_REQUIRE(batch > 0 && 2 * batch <= max_rows, "neumf: batch %lld needs 2*batch <= max_rows=%lld", (long long)batch,
                 (long long)max_rows);
@@ -596,8 +635,10 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
     if (n_steps == 0) return DRB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     NeumfWs w;
-    carve_neumf(d_ws, d, h->opt, max_rows, &w);
+    carve_neumf(d_ws, dlay, h->opt, max_rows, &w);
     const int has_reg = (h->reg_1 != 0.f) || (h->reg_2 != 0.f);
+    const bool use_tower = mode != 1;
+    const int64_t mask_words = d_drop_masks ? drb_neumf_mask_words(F, L, batch) : 0;
     DRB_CUDA(cudaMemsetAsync(w.hdrG, 0, 512, st));            // both headers: clear a stale NaN flag
     for (int64_t s = 0; s < n_steps; ++s) {
         const int64_t base = (first_step + s) * batch, B = (n - base < batch) ? n - base : batch;
@@ -609,25 +650,37 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         drop.k0 = (uint32_t)dropout_seed; drop.k1 = (uint32_t)(dropout_seed >> 32);
         drop.step = (uint32_t)(adam_step0 + s);
         drop.thresh = (uint32_t)fmin(4294967295.0, (double)dropout * 4294967296.0);
+        for (int l = 0; l < kMaxLayers; ++l) drop.bits[l] = nullptr;
+        if (d_drop_masks && dropout > 0.f) {                  // parity mode: this step's host-generated masks, per layer
+            DRB_REQUIRE(B == batch, "neumf: host dropout masks need full batches (n must be a multiple of batch)");
+            const uint32_t *mp = d_drop_masks + (size_t)s * (size_t)mask_words;
+            for (int l = 0; l < d.L; ++l) {
+                drop.bits[l] = mp;
+                mp += (2 * batch * d.n[l] + 31) / 32;
+            }
+        }
+        int rc = DRB_OK;
         // forward
-        neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts, drop);
-        DRB_CUDA(cudaGetLastError());
-        int rc = tower_forward(d, d_W, w.acts, R, R, tower_dtype, drop, st);
-        if (rc != DRB_OK) return rc;
+        if (use_tower) {
+            neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts, drop);
+            DRB_CUDA(cudaGetLastError());
+            rc = tower_forward(d, d_W, w.acts, R, R, tower_dtype, drop, st);
+            if (rc != DRB_OK) return rc;
+        }
         const float *AL = w.acts + d.act_off[d.L] * R;
         float *dZ = w.dA;                                        // dZ_L [R, F]
         int hw = 1;
         while (hw < F / 4 && hw < 32) hw <<= 1;                  // lanes per triple in the head kernel
         neumf_head_kernel<<<grid1d(B, 8 * (32 / hw), 8), 256, sizeof(float) * (2 * F + 1), st>>>(
-            d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, hw, w.gUG, w.gIG,
+            d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, hw, mode, w.gUG, w.gIG,
             w.gW + d.wp_off, dZ, w.cntU, w.cntI, w.red);
         DRB_CUDA(cudaGetLastError());
         neumf_finalize_kernel<<<1, 1, 0, st>>>(w.red, h->reg_1, h->reg_2, w.hdrG, w.hdrM, d_step_loss + s, first_step + s);
         DRB_CUDA(cudaGetLastError());
         if (!apply) break;
-        // tower backward
+        // tower backward ('GMF': the tower takes no part in the prediction, its parameters have no gradient)
         float *cur = w.dA, *nxt = w.dB;
-        for (int l = d.L - 1; l >= 0; --l) {
+        for (int l = d.L - 1; l >= 0 && use_tower; --l) {
             const float *Aprev = w.acts + d.act_off[l] * R;
             // gW_l[out,in] += dZ^T A_{l-1}, computed as (A_{l-1}^T dZ)^T: the wide dimension (in) fills the 128-row MMA tile
             // and the narrow one (out) becomes N, so the TMEM footprint per CTA is small and more CTAs overlap
@@ -647,8 +700,10 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
             if (rc != DRB_OK) return rc;
             float *t = cur; cur = nxt; nxt = t;
         }
-        neumf_scatter_kernel<<<grid1d(B * (d.D / 4), 256), 256, 0, st>>>(cur, bu, bi, bj, B, d.D, w.gUM, w.gIM, drop);
-        DRB_CUDA(cudaGetLastError());
+        if (use_tower) {
+            neumf_scatter_kernel<<<grid1d(B * (d.D / 4), 256), 256, 0, st>>>(cur, bu, bi, bj, B, d.D, w.gUM, w.gIM, drop);
+            DRB_CUDA(cudaGetLastError());
+        }
         // apply: table pairs through the MF dense sweep, tower block through the small dense kernel
         StepParams p;
         p.bu = bu; p.bi = bi; p.bj = bj; p.n = B; p.batch = B; p.first_step = 0; p.n_steps = 1;
@@ -684,25 +739,27 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
 extern "C" int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
                                 void *d_ws, int32_t U, int32_t I, int32_t F, int32_t L, int32_t opt, int64_t max_rows,
                                 const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,
-                                int32_t tower_dtype, float *d_scores, void *stream)
+                                int32_t tower_dtype, int32_t mode, float *d_scores, void *stream)
 {
-    NeumfDims d;
-    DRB_REQUIRE(make_dims(d, U, I, F, L), "neumf_scores: bad dims");
+    NeumfDims d, dlay;
+    DRB_REQUIRE(make_dims(d, U, I, F, L, mode) && make_dims(dlay, U, I, F, L, 0), "neumf_scores: bad dims");
     DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_users && d_scores && per_user > 0 && max_rows > 0,
                 "neumf_scores: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     NeumfWs w;
-    carve_neumf(d_ws, d, opt, max_rows, &w);   // same layout as training: only the dA/dB scratch is touched here
+    carve_neumf(d_ws, dlay, opt, max_rows, &w);   // same layout as training: only the dA/dB scratch is touched here
     const long long total = (long long)n_users * per_user;
     for (long long row0 = 0; row0 < total; row0 += max_rows) {
         long long rows = total - row0 < max_rows ? total - row0 : max_rows;
-        neumf_gather_pairs_kernel<<<grid1d(rows * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, d_users, d_items, row0, rows,
-                                                                                   per_user, d.D, w.dA);
-        DRB_CUDA(cudaGetLastError());
+        if (mode != 1) {
+            neumf_gather_pairs_kernel<<<grid1d(rows * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, d_users, d_items, row0, rows,
+                                                                                       per_user, d.D, w.dA);
+            DRB_CUDA(cudaGetLastError());
+        }
         // use dA as A_0 and dB as ping-pong for the hidden layers (independent of the optimiser layout)
         const float *in = w.dA;
         float *bufs[2] = {w.dB, w.dA};
-        for (int l = 0; l < d.L; ++l) {
+        for (int l = 0; l < d.L && mode != 1; ++l) {
             float *out = bufs[l & 1];
             int rc = launch_gemm<false, true, 1>(tower_dtype, rows, d.n[l + 1], d.n[l], in, d.n[l], d_W + d.w_off[l], d.n[l],
                                                  out, d.n[l + 1], d_W + d.b_off[l], nullptr, 0, st);
@@ -710,7 +767,7 @@ extern "C" int drb_neumf_scores(const float *d_UG, const float *d_IG, const floa
             in = out;
         }
         neumf_score_kernel<<<grid1d(rows * 32, 256), 256, 0, st>>>(d_UG, d_IG, d_W + d.wp_off, in, d_users, d_items, row0, rows,
-                                                                  per_user, F, d_scores);
+                                                                  per_user, F, mode, d_scores);
         DRB_CUDA(cudaGetLastError());
     }
     return DRB_OK;

@@ -548,8 +548,15 @@ def lgcn_bpr_train_steps(E0, ws, graph, num_layers, bu, bi, bj, batch, first_ste
 
 
 # ------------------------------------------------------------------ NeuMF
-def neumf_param_count(factors, num_layers):
-    return int(L.lib().drb_neumf_param_count(factors, num_layers))
+NEUMF_MODE = {"NeuMF": 0, "NeuMF-pre": 0, "GMF": 1, "MLP": 2}       # config['model_name'] (NeuMFRecommender.py:48-50)
+
+
+def neumf_param_count(factors, num_layers, mode=0):
+    return int(L.lib().drb_neumf_param_count(factors, num_layers, mode))
+
+
+def neumf_mask_words(factors, num_layers, batch):
+    return int(L.lib().drb_neumf_mask_words(factors, num_layers, batch))
 
 
 class NeumfWorkspace:
@@ -565,7 +572,12 @@ class NeumfWorkspace:
 
 
 def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True,
-                          tower_dtype=0, dropout=0.0, dropout_seed=0):
+                          tower_dtype=0, dropout=0.0, dropout_seed=0, drop_masks=None, mode=0):
+    """drop_masks: int32 CUDA tensor [n_steps * neumf_mask_words(F, L, batch)] of host-generated keep-masks (parity mode)."""
+    if drop_masks is not None:
+        _dev(drop_masks, torch.int32, "drop_masks")
+        if drop_masks.numel() < n_steps * neumf_mask_words(ws.F, ws.Ln, batch):
+            raise ValueError("drop_masks too short for n_steps batches")
     for t in list(tabs) + [W]:
         _dev(t, torch.float32, "table")
     for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
@@ -575,7 +587,8 @@ def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, h
     rc = L.lib().drb_neumf_bpr_train_steps(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf),
                                            ws.U, ws.I, ws.F, ws.Ln, ws.max_rows, _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(),
                                            batch, first_step, n_steps, C.byref(hp), adam_step0, 1 if apply else 0,
-                                           tower_dtype, C.c_float(dropout), C.c_uint64(dropout_seed), _ptr(losses),
+                                           tower_dtype, C.c_float(dropout), C.c_uint64(dropout_seed),
+                                           None if drop_masks is None else _ptr(drop_masks), mode, _ptr(losses),
                                            1 if check else 0, C.byref(nan_step), _stream())
     if rc == L.DRB_ERR_NAN_LOSS:
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
@@ -583,7 +596,7 @@ def neumf_bpr_train_steps(tabs, W, ws, bu, bi, bj, batch, first_step, n_steps, h
     return losses[:n_steps]
 
 
-def neumf_scores(tabs, W, ws, users, items, per_user, tower_dtype=0):
+def neumf_scores(tabs, W, ws, users, items, per_user, tower_dtype=0, mode=0):
     """scores [n_users, per_user]: items = int64 [n_users, per_user] candidate ids, or None for all item ids."""
     _dev(users, torch.int64, "users")
     if items is not None:
@@ -591,7 +604,8 @@ def neumf_scores(tabs, W, ws, users, items, per_user, tower_dtype=0):
     out = torch.empty((users.numel(), per_user), dtype=torch.float32, device=W.device)
     L.check(L.lib().drb_neumf_scores(_ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), _ptr(W), _ptr(ws.buf), ws.U,
                                      ws.I, ws.F, ws.Ln, ws.opt, ws.max_rows, _ptr(users), users.numel(),
-                                     None if items is None else _ptr(items), per_user, tower_dtype, _ptr(out), _stream()))
+                                     None if items is None else _ptr(items), per_user, tower_dtype, mode, _ptr(out),
+                                     _stream()))
     return out
 
 

@@ -250,18 +250,27 @@ int drb_lgcn_bpr_train_steps(float *d_E0, void *d_ws, int32_t user_num, int32_t 
                              int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0, int32_t apply,
                              double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 
-/* ---- NeuMF + BPR (daisy/model/NeuMFRecommender.py, model_name 'NeuMF') -----------------------------
+/* ---- NeuMF + BPR (daisy/model/NeuMFRecommender.py) -------------------------------------------------
  * Tables: UG [U,F], IG [I,F] (embed_*_GMF), UM [U,D], IM [I,D] (embed_*_MLP), D = F * 2^(L-1);
  * W: the tower as ONE flat fp32 block in module-registration order -- per layer weight [out,in] then bias [out]
- * (in = 2D / 2^l), then predict_layer weight [2F] and bias [1]  (NeuMFRecommender.py:58-71).
+ * (in = 2D / 2^l), then predict_layer weight and bias [1]  (NeuMFRecommender.py:58-71).
+ * mode = config['model_name'] (:48-50, :118-137): 0 'NeuMF' / 'NeuMF-pre' (predict over cat(GMF, tower), weight [2F]),
+ *        1 'GMF' (predict over the GMF product, weight [F]; the tower is never run and takes no gradient),
+ *        2 'MLP' (predict over the tower output, weight [F]).  All four tables are regularised in every mode (:154-167).
  * max_rows: rows of activation scratch (>= 2 * batch for training; any size for scoring).
  * drb_neumf_bpr_train_steps  calc_loss :139-169 (regulariser quirk of :158/:160 included) + backward +
  *                            optimizer.step for n_steps batches; apply = 0: calc_loss of one batch.
- *                            dropout (config['dropout'], :61): counter-based Philox masks keyed by dropout_seed and the
- *                            global step -- same distribution as nn.Dropout, not torch's RNG stream (parity at dropout = 0).
+ *                            dropout (config['dropout'], :61), two engines:
+ *                            d_drop_masks == NULL: counter-based Philox masks keyed by dropout_seed and the global step
+ *                              (same distribution as nn.Dropout, not torch's RNG stream);
+ *                            d_drop_masks != NULL (parity): the keep-masks nn.Dropout itself would draw, generated on the
+ *                              host by torch in the reference's order and bit-packed -- per step drb_neumf_mask_words()
+ *                              uint32 words: for layer l = 0..L-1 the [2*batch, n_l] row-major mask (rows [0,batch) = the pos
+ *                              forward's mask, [batch, 2*batch) = the neg forward's), padded to a word.
  * drb_neumf_scores           forward :118-137 for (users[r / per_user], items[r]) pairs (items NULL: all item ids):
  *                            what rank / full_rank / predict score with (:171-232); feed to drb_topk_from_scores. */
-int64_t drb_neumf_param_count(int32_t factors, int32_t num_layers);
+int64_t drb_neumf_param_count(int32_t factors, int32_t num_layers, int32_t mode);
+int64_t drb_neumf_mask_words(int32_t factors, int32_t num_layers, int64_t batch);
 size_t drb_neumf_workspace_bytes(int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t opt,
                                  int64_t max_rows);
 int drb_neumf_workspace_init(void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers,
@@ -271,11 +280,12 @@ int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, float *d_IM
                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
                               int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
                               int32_t apply, int32_t tower_dtype, float dropout, uint64_t dropout_seed,
-                              double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+                              const uint32_t *d_drop_masks, int32_t mode, double *d_step_loss, int32_t sync_and_check,
+                              int64_t *nan_step, void *stream);
 int drb_neumf_scores(const float *d_UG, const float *d_IG, const float *d_UM, const float *d_IM, const float *d_W,
                      void *d_ws, int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t opt,
                      int64_t max_rows, const int64_t *d_users, int64_t n_users, const int64_t *d_items, int32_t per_user,
-                     int32_t tower_dtype, float *d_scores, void *stream);
+                     int32_t tower_dtype, int32_t mode, float *d_scores, void *stream);
 /* tower_dtype: 0 = fp32 on CUDA cores (parity path), 1 = bf16 operands on tcgen05 tensor cores with the fp32
  * accumulator in tensor memory (BASELINE config 3).  drb_gemm_test exposes the tower's GEMM dispatcher to the tests:
  * variant 0 NT+bias+ReLU (forward), 1 NN+ReLU-mask (input gradient), 2 NN, 3 TN split-K accumulate (weight gradient). */

@@ -747,26 +747,35 @@ double orc_lgcn_bpr_step(float *E0, int32_t U, int32_t I, int32_t F, int32_t L, 
  *   layer l = 0..L-1: weight [out_l, in_l] row-major, then bias [out_l], with in_l = 2D/2^l, out_l = in_l/2;
  *   then predict weight [2F], predict bias [1].         D = F * 2^(L-1).
  * ================================================================================== */
-static int64_t neumf_param_count(int F, int L)
+/* mode = config['model_name'] (NeuMFRecommender.py:48-50,63-68): 0 'NeuMF' / 'NeuMF-pre' predict over cat(GMF, tower) [2F],
+ * 1 'GMF' predict over the GMF product [F] (the tower is never called), 2 'MLP' predict over the tower output [F]. */
+static int64_t neumf_param_count_m(int F, int L, int mode)
 {
     int64_t D = (int64_t)F << (L - 1), n = 0, in = 2 * D;
     for (int l = 0; l < L; l++) { n += in * (in / 2) + in / 2; in /= 2; }
-    return n + 2 * F + 1;
+    return n + (mode == 0 ? 2 : 1) * F + 1;
 }
+static int64_t neumf_param_count(int F, int L) { return neumf_param_count_m(F, L, 0); }
 
 int64_t orc_neumf_param_count(int32_t F, int32_t L) { return neumf_param_count(F, L); }
+int64_t orc_neumf_param_count_ex(int32_t F, int32_t L, int32_t mode) { return neumf_param_count_m(F, L, mode); }
 
 /* forward of one (u, item) pair; acts[] receives the activations of every layer (concatenated), returns pred */
-static float neumf_forward_one(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int F,
-                               int L, int u, int it, float *x0, float *acts, float *gmf)
+/* keep (train mode, nn.Dropout in front of every Linear, :61): this row's keep factors (0 or 1/(1-p)), the L layer inputs
+ * concatenated [2D, D, ..., 2F]; NULL = no dropout.  x0 and the hidden activations are stored AFTER the mask (the next
+ * Linear's input); a dropped or non-positive unit is 0 there, which is all relu' needs in the backward pass. */
+static float neumf_forward_ex(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int F,
+                              int L, int u, int it, float *x0, float *acts, float *gmf, int mode, const float *keep)
 {
     int D = F << (L - 1);
     for (int f = 0; f < F; f++) gmf[f] = UG[(int64_t)u * F + f] * IG[(int64_t)it * F + f];
     for (int d = 0; d < D; d++) { x0[d] = UM[(int64_t)u * D + d]; x0[D + d] = IM[(int64_t)it * D + d]; }
+    if (keep) for (int k = 0; k < 2 * D; k++) x0[k] *= keep[k];
     const float *in = x0;
     int n_in = 2 * D;
     const float *w = W;
     float *out = acts;
+    const float *kp = keep ? keep + 2 * D : NULL;
     for (int l = 0; l < L; l++) {
         int n_out = n_in / 2;
         const float *b = w + (int64_t)n_in * n_out;
@@ -775,17 +784,26 @@ static float neumf_forward_one(const float *UG, const float *IG, const float *UM
             for (int k = 0; k < n_in; k++) acc += (double)(w[(int64_t)o * n_in + k] * in[k]);
             float z = (float)acc + b[o];
             out[o] = z > 0.f ? z : 0.f;
+            if (kp && l + 1 < L) out[o] *= kp[o];
         }
+        if (kp) kp += n_out;
         w = b + n_out;
         in = out;
         out += n_out;
         n_in = n_out;
     }
-    /* predict layer: weight [2F] over cat(GMF, MLP out), bias */
+    /* predict layer (:126-137): over cat(GMF, tower out) / GMF / tower out, then bias */
     double acc = 0.0;
-    for (int f = 0; f < F; f++) acc += (double)(w[f] * gmf[f]);
-    for (int f = 0; f < F; f++) acc += (double)(w[F + f] * in[f]);
-    return (float)acc + w[2 * F];
+    const int hoff = mode == 0 ? F : 0;
+    if (mode != 2) for (int f = 0; f < F; f++) acc += (double)(w[f] * gmf[f]);
+    if (mode != 1) for (int f = 0; f < F; f++) acc += (double)(w[hoff + f] * in[f]);
+    return (float)acc + w[(mode == 0 ? 2 : 1) * F];
+}
+
+static float neumf_forward_one(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int F,
+                               int L, int u, int it, float *x0, float *acts, float *gmf)
+{
+    return neumf_forward_ex(UG, IG, UM, IM, W, F, L, u, it, x0, acts, gmf, 0, NULL);
 }
 
 void orc_neumf_predict(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int32_t F,
@@ -809,15 +827,29 @@ static void update_block(float *theta, float *m, float *v, const double *g, int6
 
 /* One NeuMF BPR step.  tables: UG[U,F] IG[I,F] UM[U,D] IM[I,D]; W flat tower block.  state (Adam): m,v blocks in the
  * order UG, IG, UM, IM, W (each table-sized), may be NULL for SGD.  Returns the loss. */
+double orc_neumf_bpr_step_ex(float *UG, float *IG, float *UM, float *IM, float *W, int32_t U, int32_t I, int32_t F, int32_t L,
+                             const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B, const orc_hyper *h,
+                             int32_t apply, float **m, float **v, int64_t step_count, int32_t mode, const float *keep);
+
 double orc_neumf_bpr_step(float *UG, float *IG, float *UM, float *IM, float *W, int32_t U, int32_t I, int32_t F, int32_t L,
                           const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B, const orc_hyper *h,
                           int32_t apply, float **m, float **v, int64_t step_count)
 {
+    return orc_neumf_bpr_step_ex(UG, IG, UM, IM, W, U, I, F, L, bu, bi, bj, B, h, apply, m, v, step_count, 0, NULL);
+}
+
+/* mode as above; keep: [2B, n_keep] keep factors (0 or 1/(1-p)), row r = side * B + t (side 0 = the pos forward, which
+ * draws its masks first, 1 = the neg forward), n_keep = sum of the L layer input widths; NULL = eval / dropout 0. */
+double orc_neumf_bpr_step_ex(float *UG, float *IG, float *UM, float *IM, float *W, int32_t U, int32_t I, int32_t F, int32_t L,
+                             const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B, const orc_hyper *h,
+                             int32_t apply, float **m, float **v, int64_t step_count, int32_t mode, const float *keep)
+{
     const float gamma = 1e-10f;
     const int D = F << (L - 1);
-    int n_act = 0;
-    { int in = 2 * D; for (int l = 0; l < L; l++) { n_act += in / 2; in /= 2; } }
-    const int64_t nW = neumf_param_count(F, L);
+    int n_act = 0, n_keep = 0;
+    { int in = 2 * D; for (int l = 0; l < L; l++) { n_act += in / 2; n_keep += in; in /= 2; } }
+    const int use_g = mode != 2, use_h = mode != 1, hoff = mode == 0 ? F : 0, pw = (mode == 0 ? 2 : 1) * F;
+    const int64_t nW = neumf_param_count_m(F, L, mode);
     /* per-row storage of x0 / activations / gmf for pos and neg */
     size_t per = (size_t)(2 * D + n_act + F);
     float *buf = (float *)malloc(sizeof(float) * per * 2 * (size_t)(B > 0 ? B : 1));
@@ -825,8 +857,10 @@ double orc_neumf_bpr_step(float *UG, float *IG, float *UM, float *IM, float *W, 
     double bpr = 0, l1[5] = {0, 0, 0, 0, 0}, s2[5] = {0, 0, 0, 0, 0};   /* UG_u, UM_u, IG_i, IM_i, IG_j */
     for (int64_t t = 0; t < B; t++) {
         float *rp = buf + per * (size_t)(2 * t), *rn = rp + per;
-        float pos = neumf_forward_one(UG, IG, UM, IM, W, F, L, bu[t], bi[t], rp, rp + 2 * D, rp + 2 * D + n_act);
-        float neg = neumf_forward_one(UG, IG, UM, IM, W, F, L, bu[t], bj[t], rn, rn + 2 * D, rn + 2 * D + n_act);
+        const float *kpos = (keep && use_h) ? keep + (int64_t)t * n_keep : NULL;
+        const float *kneg = (keep && use_h) ? keep + (int64_t)(B + t) * n_keep : NULL;
+        float pos = neumf_forward_ex(UG, IG, UM, IM, W, F, L, bu[t], bi[t], rp, rp + 2 * D, rp + 2 * D + n_act, mode, kpos);
+        float neg = neumf_forward_ex(UG, IG, UM, IM, W, F, L, bu[t], bj[t], rn, rn + 2 * D, rn + 2 * D + n_act, mode, kneg);
         float x = pos - neg;
         float s = 1.f / (1.f + expf(-x));
         bpr += (double)(-logf(gamma + s));
@@ -868,16 +902,21 @@ double orc_neumf_bpr_step(float *UG, float *IG, float *UM, float *IM, float *W, 
             float dp = side == 0 ? coef[t] : -coef[t];                     /* dL/dpred */
             /* predict layer */
             const float *hL = acts + (n_act - F);
+            const float *kr = (keep && use_h) ? keep + (int64_t)(side * B + t) * n_keep : NULL;
             for (int f = 0; f < F; f++) {
-                gW[woff[L] + f] += (double)(dp * gmf[f]);
-                gW[woff[L] + F + f] += (double)(dp * hL[f]);
-                gUG[(int64_t)u * F + f] += (double)(dp * wp[f] * IG[(int64_t)it * F + f]);
-                gIG[(int64_t)it * F + f] += (double)(dp * wp[f] * UG[(int64_t)u * F + f]);
+                if (use_g) {
+                    gW[woff[L] + f] += (double)(dp * gmf[f]);
+                    gUG[(int64_t)u * F + f] += (double)(dp * wp[f] * IG[(int64_t)it * F + f]);
+                    gIG[(int64_t)it * F + f] += (double)(dp * wp[f] * UG[(int64_t)u * F + f]);
+                }
+                if (use_h) gW[woff[L] + hoff + f] += (double)(dp * hL[f]);
             }
-            gW[woff[L] + 2 * F] += (double)dp;
+            gW[woff[L] + pw] += (double)dp;
+            if (!use_h) continue;                                         /* 'GMF': the tower is not part of the graph */
             /* tower backward */
-            for (int f = 0; f < F; f++) dcur[f] = dp * wp[F + f];
+            for (int f = 0; f < F; f++) dcur[f] = dp * wp[hoff + f];
             int a_off = n_act;                                            /* end of layer l's activations */
+            int k_off = n_keep;                                           /* end of layer l's keep factors */
             for (int l = L - 1; l >= 0; l--) {
                 int n_in = nin[l], n_out = n_in / 2;
                 a_off -= n_out;
@@ -894,6 +933,8 @@ double orc_neumf_bpr_step(float *UG, float *IG, float *UM, float *IM, float *W, 
                         dprev[k] += dz * w[(int64_t)o * n_in + k];
                     }
                 }
+                k_off -= n_in;
+                if (kr) for (int k = 0; k < n_in; k++) dprev[k] *= kr[k_off + k];   /* through this layer's Dropout */
                 float *tmp = dcur; dcur = dprev; dprev = tmp;
             }
             for (int d = 0; d < D; d++) {
@@ -925,9 +966,20 @@ double orc_neumf_bpr_step(float *UG, float *IG, float *UM, float *IM, float *W, 
 }
 
 /* NeuMF.rank :178-209 / full_rank :211-232: scores through the full tower; ties by lower position / item id */
+void orc_neumf_rank_ex(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int32_t F,
+                       int32_t L, const int64_t *users, int64_t n_users, const int64_t *cands, int32_t cand_num,
+                       int32_t item_num, int32_t topk, float *out_f, int64_t *out_i, int32_t mode);
+
 void orc_neumf_rank(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int32_t F, int32_t L,
                     const int64_t *users, int64_t n_users, const int64_t *cands, int32_t cand_num, int32_t item_num,
                     int32_t topk, float *out_f, int64_t *out_i)
+{
+    orc_neumf_rank_ex(UG, IG, UM, IM, W, F, L, users, n_users, cands, cand_num, item_num, topk, out_f, out_i, 0);
+}
+
+void orc_neumf_rank_ex(const float *UG, const float *IG, const float *UM, const float *IM, const float *W, int32_t F,
+                       int32_t L, const int64_t *users, int64_t n_users, const int64_t *cands, int32_t cand_num,
+                       int32_t item_num, int32_t topk, float *out_f, int64_t *out_i, int32_t mode)
 {
     int D = F << (L - 1);
     int cnt = cands ? cand_num : item_num;
@@ -936,7 +988,7 @@ void orc_neumf_rank(const float *UG, const float *IG, const float *UM, const flo
     for (int64_t r = 0; r < n_users; r++) {
         for (int k = 0; k < cnt; k++) {
             int it = cands ? (int)cands[r * cand_num + k] : k;
-            sc[k].s = neumf_forward_one(UG, IG, UM, IM, W, F, L, (int)users[r], it, x0, x0 + 2 * D, x0 + 4 * D);
+            sc[k].s = neumf_forward_ex(UG, IG, UM, IM, W, F, L, (int)users[r], it, x0, x0 + 2 * D, x0 + 4 * D, mode, NULL);
             sc[k].pos = k;
         }
         qsort(sc, (size_t)cnt, sizeof(orc_sc), sc_desc);

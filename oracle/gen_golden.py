@@ -693,6 +693,72 @@ def gen_neumf():
     _save("neumf", **out)
 
 
+def gen_neumf_modes():
+    """The rest of NeuMF's surface (NeuMFRecommender.py:48-50,61,97-137): the reference's DEFAULT dropout (0.5, masks from
+    torch's global CPU generator: one bernoulli_ per Dropout call, pos forward then neg forward) and model_name 'GMF' / 'MLP'
+    / 'NeuMF-pre' (pre-trained GMF + MLP models, the bias-into-weight line :116 included).  Per case: init snapshot, the
+    RNG seed set right before the 3 training steps, batches, losses, snapshots, eval-mode rank / full_rank / predict."""
+    import torch
+    from daisy.model.NeuMFRecommender import NeuMF
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [  # name, U, I, F, L, B, lr, reg1, reg2, opt, dropout, seed
+        ("NeuMF", 40, 60, 24, 2, 64, 0.001, 0.001, 0.001, "default", 0.5, 41),     # assets/neumf.yaml defaults
+        ("NeuMF", 30, 45, 8, 3, 48, 0.01, 0.002, 0.001, "sgd", 0.3, 42),
+        ("GMF", 35, 50, 16, 2, 64, 0.001, 0.001, 0.001, "default", 0.5, 43),
+        ("MLP", 35, 50, 16, 2, 64, 0.001, 0.001, 0.001, "default", 0.5, 44),
+        ("NeuMF-pre", 35, 50, 16, 2, 64, 0.001, 0.001, 0.001, "default", 0.0, 45),   # from the two trained models above
+    ]
+    trained = {}
+    for k, (name, U, I, F, L, B, lr, r1, r2, opt, drop, seed) in enumerate(cases):
+        cfg = rh.make_config("neumf", user_num=U, item_num=I, factors=F, num_layers=L, lr=lr, reg_1=r1, reg_2=r2,
+                             optimizer=opt, dropout=drop, epochs=1, topk=10, cand_num=40, model_name=name,
+                             GMF_model=trained.get("GMF"), MLP_model=trained.get("MLP"))
+        torch.manual_seed(seed)
+        model = NeuMF(cfg)
+        if name != "NeuMF-pre":
+            with torch.no_grad():
+                for t in (model.embed_user_GMF, model.embed_item_GMF, model.embed_user_MLP, model.embed_item_MLP):
+                    t.weight.mul_(3.0)
+        model.train()
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        snaps = [_neumf_flat(model)]
+        batches, losses = [], []
+        torch.manual_seed(seed + 100)                                   # the dropout masks of the 3 steps come from here
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]).long(), torch.from_numpy(b[1]).long(), torch.from_numpy(b[2]).long()])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            snaps.append(_neumf_flat(model))
+        rng_after = torch.get_rng_state().numpy().copy()
+        model.eval()
+        trained[name] = model
+        users = rng.permutation(U)[:7].astype(np.int64)
+        cands = rng.integers(I, size=(7, 40)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), c] for u, c in zip(users, cands)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        with torch.no_grad():
+            preds = model.rank(loader)
+            full = np.stack([model.full_rank(int(u)) for u in users[:3]])
+            pp = np.array([model.predict(int(users[q]), int(cands[q][0])) for q in range(4)], np.float32)
+        for q, tn in enumerate(("UG", "IG", "UM", "IM")):
+            out[f"c{k}_{tn}"] = np.stack([s_[0][q] for s_ in snaps])
+        out.update({f"c{k}_W": np.stack([s_[1] for s_ in snaps]), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64), f"c{k}_name": np.array(name),
+                    f"c{k}_hyper": np.array([U, I, F, L, lr, r1, r2, 0 if opt == "sgd" else 1, seed, drop], np.float64),
+                    f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32), f"c{k}_preds": preds, f"c{k}_full": full,
+                    f"c{k}_pred_pairs": pp, f"c{k}_rng_after": rng_after})
+        print(f"neumf_modes case {k} ({name}, dropout {drop}): losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("neumf_modes", **out)
+
+
 # --------------------------------------------------------------------------- evaluation KPIs
 def gen_metrics():
     """daisy/utils/metrics.py:18-57,59-96,98-251 (calc_ranking_results / Metric.run) on synthetic rank lists:
@@ -779,7 +845,7 @@ def gen_sampler_pop():
     _save("sampler_pop", **out)
 
 
-ALL = {"nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+ALL = {"neumf_modes": gen_neumf_modes, "nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

@@ -336,9 +336,23 @@ def nfm_scores(P, Q, bias, N, R, L, bn, act, users, items):
     return out
 
 
-def neumf_param_count(F, L):
-    lib().orc_neumf_param_count.restype = C.c_int64
-    return int(lib().orc_neumf_param_count(F, L))
+NEUMF_MODE = {"NeuMF": 0, "NeuMF-pre": 0, "GMF": 1, "MLP": 2}
+
+
+def neumf_param_count(F, L, mode=0):
+    lib().orc_neumf_param_count_ex.restype = C.c_int64
+    return int(lib().orc_neumf_param_count_ex(F, L, mode))
+
+
+def torch_dropout_keep(B, F, L, p):
+    """The keep factors nn.Dropout draws for ONE training step of B triples (NeuMFRecommender.py:61, forward(user, pos) then
+    forward(user, neg), one bernoulli_ per Dropout call on torch's global CPU generator) -> float32 [2B, sum n_l]."""
+    import torch
+    widths = [F * (2 ** (L - i)) for i in range(L)]
+    sides = []
+    for _side in range(2):
+        sides.append(np.concatenate([torch.empty(B, n, dtype=torch.float32).bernoulli_(1.0 - p).numpy() for n in widths], 1))
+    return np.ascontiguousarray(np.concatenate(sides, 0) / np.float32(1.0 - p), np.float32)
 
 
 def neumf_predict(tabs, W, F, L, u, it):
@@ -349,34 +363,35 @@ def neumf_predict(tabs, W, F, L, u, it):
     return out
 
 
-def neumf_bpr_step(tabs, W, F, L, bu, bi, bj, hp, apply=True, adam_state=None, step_count=1):
-    """In-place step on the 4 tables (UG, IG, UM, IM) and the flat tower block W.  adam_state = (m[5], v[5])."""
+def neumf_bpr_step(tabs, W, F, L, bu, bi, bj, hp, apply=True, adam_state=None, step_count=1, mode=0, keep=None):
+    """In-place step on the 4 tables (UG, IG, UM, IM) and the flat tower block W.  adam_state = (m[5], v[5]).
+    mode: NEUMF_MODE; keep: torch_dropout_keep(...) in train mode with dropout > 0."""
     UG, IG, UM, IM = tabs
     PF = C.POINTER(C.c_float)
     m = v = None
     if adam_state is not None:
         m = (PF * 5)(*[_f32(a) for a in adam_state[0]])
         v = (PF * 5)(*[_f32(a) for a in adam_state[1]])
-    lib().orc_neumf_bpr_step.restype = C.c_double
-    return lib().orc_neumf_bpr_step(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), UG.shape[0], IG.shape[0], F, L,
-                                    _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), int(apply), m, v,
-                                    C.c_int64(step_count))
+    lib().orc_neumf_bpr_step_ex.restype = C.c_double
+    return lib().orc_neumf_bpr_step_ex(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), UG.shape[0], IG.shape[0], F, L,
+                                       _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), int(apply), m, v,
+                                       C.c_int64(step_count), mode, None if keep is None else _f32(keep))
 
 
-def neumf_rank(tabs, W, F, L, users, cands, topk):
+def neumf_rank(tabs, W, F, L, users, cands, topk, mode=0):
     UG, IG, UM, IM = tabs
     users = np.ascontiguousarray(users, np.int64)
     cands = np.ascontiguousarray(cands, np.int64)
     out = np.empty((len(users), topk), np.float32)
-    lib().orc_neumf_rank(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i64(users), C.c_int64(len(users)),
-                         _i64(cands), cands.shape[1], IG.shape[0], topk, _f32(out), None)
+    lib().orc_neumf_rank_ex(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i64(users), C.c_int64(len(users)),
+                            _i64(cands), cands.shape[1], IG.shape[0], topk, _f32(out), None, mode)
     return out
 
 
-def neumf_full_rank(tabs, W, F, L, users, topk):
+def neumf_full_rank(tabs, W, F, L, users, topk, mode=0):
     UG, IG, UM, IM = tabs
     users = np.ascontiguousarray(users, np.int64)
     out = np.empty((len(users), topk), np.int64)
-    lib().orc_neumf_rank(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i64(users), C.c_int64(len(users)),
-                         None, 0, IG.shape[0], topk, None, _i64(out))
+    lib().orc_neumf_rank_ex(_f32(UG), _f32(IG), _f32(UM), _f32(IM), _f32(W), F, L, _i64(users), C.c_int64(len(users)),
+                            None, 0, IG.shape[0], topk, None, _i64(out), mode)
     return out

@@ -172,3 +172,98 @@ def test_neumf_dropout_gradient_consistency(ops, tower_dtype):
         tp[2][r, c] += eps; tm[2][r, c] -= eps
         num = (loss_at(W_h, tp) - loss_at(W_h, tm)) / (2 * eps)
         assert abs(num - gUM[r, c]) <= 0.03 * abs(gUM[r, c]) + 0.05, (r, c, num, gUM[r, c])
+
+
+def _neumf_cfg(g, c, **kw):
+    U, I, F, L, lr, r1, r2, opt, seed, drop = g[f"c{c}_hyper"]
+    cfg = dict(gpu="", logger=logging.getLogger("t"), lr=float(lr), reg_1=float(r1), reg_2=float(r2), epochs=1, topk=10,
+               user_num=int(U), item_num=int(I), factors=int(F), num_layers=int(L), dropout=float(drop),
+               model_name=str(g[f"c{c}_name"]), loss_type="BPR", optimizer="sgd" if opt == 0 else "default",
+               init_method="default", early_stop=False, progress=False, GMF_model=None, MLP_model=None)
+    cfg.update(kw)
+    return cfg, int(seed)
+
+
+def test_neumf_default_dropout_and_modes_match_reference():
+    """The reference's default config (dropout 0.5) and model_name GMF / MLP / NeuMF-pre through the class surface: host-drawn
+    torch masks (dropout_engine 'auto' -> 'torch' at these sizes) reproduce the reference's losses, tables and RNG position;
+    NeuMF-pre reproduces the reference's initial state bit for bit, quirk of :116 and nn.Linear's own bias draw included."""
+    from daisyrec_b200.model import NeuMF
+    from daisyrec_b200.utils.dataset import CandidatesDataset, get_dataloader
+    g = golden("neumf_modes")
+    trained = {}
+    for c in range(int(g["ncases"])):
+        name = str(g[f"c{c}_name"])
+        cfg, seed = _neumf_cfg(g, c, GMF_model=trained.get("GMF"), MLP_model=trained.get("MLP"))
+        torch.manual_seed(seed)
+        m = NeuMF(cfg)
+        init = {"embed_user_GMF.weight": g[f"c{c}_UG"][0], "embed_item_GMF.weight": g[f"c{c}_IG"][0],
+                "embed_user_MLP.weight": g[f"c{c}_UM"][0], "embed_item_MLP.weight": g[f"c{c}_IM"][0], "tower": g[f"c{c}_W"][0]}
+        if name == "NeuMF-pre":
+            for k, want in init.items():                                  # copied tables + the reference's predict layer
+                assert np.array_equal(m.state_dict()[k].cpu().numpy(), want), (name, k)
+        else:
+            scale = {k: (3.0 if k != "tower" else 1.0) for k in init}     # the generator spreads the tables by 3x
+            for k, want in init.items():
+                np.testing.assert_allclose(m.state_dict()[k].cpu().numpy() * scale[k], want, rtol=1e-6, atol=0, err_msg=k)
+            m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in init.items()})
+        opt_is_sgd = cfg["optimizer"] == "sgd"
+        bs, losses = g[f"c{c}_batches"], g[f"c{c}_loss"]
+        m.train()
+        torch.manual_seed(seed + 100)
+        for s in range(bs.shape[0]):
+            loss = m.train_step([torch.from_numpy(np.ascontiguousarray(bs[s][k])) for k in range(3)])
+            assert abs(loss - losses[s]) <= 3e-5 * abs(losses[s]), (c, name, s, loss, losses[s])
+            tol = (5e-6 if opt_is_sgd else 1e-4) * (s + 1)
+            for k, fx in (("embed_user_GMF.weight", "UG"), ("embed_item_GMF.weight", "IG"), ("embed_user_MLP.weight", "UM"),
+                          ("embed_item_MLP.weight", "IM"), ("tower", "W")):
+                want = g[f"c{c}_{fx}"][s + 1]
+                got = m.state_dict()[k].cpu().numpy()
+                bad = np.abs(got - want) > tol * max(1.0, np.abs(want).max())
+                assert bad.mean() <= (0.0 if opt_is_sgd else 0.01), (c, name, s, fx, float(bad.mean()))
+        assert np.array_equal(torch.get_rng_state().numpy(), g[f"c{c}_rng_after"]), (c, name)
+        m.eval()
+        trained[name] = m
+        m.load_state_dict({"embed_user_GMF.weight": g[f"c{c}_UG"][-1], "embed_item_GMF.weight": g[f"c{c}_IG"][-1],
+                           "embed_user_MLP.weight": g[f"c{c}_UM"][-1], "embed_item_MLP.weight": g[f"c{c}_IM"][-1],
+                           "tower": g[f"c{c}_W"][-1]})
+        users, cands = g[f"c{c}_users"], g[f"c{c}_cands"].astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), cands[r]] for r, u in enumerate(users)]), batch_size=128,
+                                shuffle=False)
+        assert (m.rank(loader) == g[f"c{c}_preds"]).mean() >= 0.97, (c, name)
+        assert (np.stack([m.full_rank(int(u)) for u in users[:3]]) == g[f"c{c}_full"]).mean() >= 0.9
+        pp = np.array([m.predict(int(users[q]), int(cands[q][0])) for q in range(4)], np.float32)
+        np.testing.assert_allclose(pp, g[f"c{c}_pred_pairs"], rtol=3e-5, atol=3e-6)
+
+
+def test_neumf_modes_match_oracle(ops, orc):
+    """GMF / MLP steps and host-mask dropout on random inputs against the pinned oracle (same masks on both sides)."""
+    rng = np.random.default_rng(4)
+    U, I, F, L, B = 200, 150, 16, 2, 500
+    D = F * 2 ** (L - 1)
+    for name, drop in (("GMF", 0.0), ("MLP", 0.4), ("NeuMF", 0.5)):
+        mode = ops.NEUMF_MODE[name]
+        tabs_h = [(rng.standard_normal(s) * 0.1).astype(np.float32) for s in ((U, F), (I, F), (U, D), (I, D))]
+        W_h = (rng.standard_normal(ops.neumf_param_count(F, L, mode)) * 0.2).astype(np.float32)
+        b = [rng.integers(n, size=B).astype(np.int32) for n in (U, I, I)]
+        keep = None
+        masks = None
+        if drop > 0:
+            torch.manual_seed(3)
+            keep = orc.torch_dropout_keep(B, F, L, drop)
+            words, col = [], 0
+            for n in [F * (2 ** (L - i)) for i in range(L)]:
+                bits = np.packbits((keep[:, col:col + n] != 0).reshape(-1), bitorder="little")
+                words.append(np.pad(bits, (0, (-len(bits)) % 4)).view(np.int32))
+                col += n
+            masks = dev(np.concatenate(words))
+        tabs, W = [dev(t) for t in tabs_h], dev(W_h)
+        ws = ops.NeumfWorkspace(U, I, F, L, "sgd", 2 * B, "cuda")
+        hp = ops.hyper(0.05, 0.001, 0.002, "sgd")
+        loss = ops.neumf_bpr_train_steps(tabs, W, ws, *[dev(x) for x in b], B, 0, 1, hp, dropout=drop, drop_masks=masks,
+                                         mode=mode).item()
+        lo = orc.neumf_bpr_step(tabs_h, W_h, F, L, *b, orc.hyper(0.05, 0.001, 0.002, "sgd"), True, None, 1, mode=mode, keep=keep)
+        assert abs(loss - lo) <= 2e-5 * abs(lo), (name, loss, lo)
+        for q in range(4):
+            np.testing.assert_allclose(tabs[q].cpu().numpy(), tabs_h[q], rtol=0, atol=5e-6, err_msg=f"{name} table {q}")
+        np.testing.assert_allclose(W.cpu().numpy(), W_h, rtol=0, atol=2e-5, err_msg=name)
