@@ -373,7 +373,7 @@ def cfg_c3_neumf(args, dev, d, planes):
     hp = ops.hyper(0.001, 0.001, 0.001, "adam")
     bu, bi, bj = (p_[:4 * B] for p_ in planes)
     out = {}
-    for name, td in (("bf16", 1), ("fp32", 0)):
+    for name, td in (("fused", 2), ("bf16", 1), ("fp32", 0)):
         ws = ops.NeumfWorkspace(U, I, F, L, "adam", 2 * B, dev)
         step = [0]
 
@@ -383,11 +383,15 @@ def cfg_c3_neumf(args, dev, d, planes):
             step[0] += 1
         ms = timed_ms(fn, 3, 8 if td else 4)
         bpt = 3 * (F + D) * 4 * 2 + 12
+        kern = {2: "neumf_fused_kernel (gather + tower fwd/bwd + head + scatter in one CTA per tile) + table sweeps",
+                1: "layer-wise tcgen05 GEMMs + head + table sweeps", 0: "layer-wise fp32 GEMMs + head + table sweeps"}[td]
         out[name] = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": B,
-                     "roofline": roof(B * bpt / ms / 1e6, "neumf tower + head + table sweeps (per step)", bpt)}
+                     "roofline": roof(B * bpt / ms / 1e6, kern, bpt)}
         del ws
-    res = out["bf16"]
-    res["workload"] = f"NeuMF+BPR synthetic ml-20m shape, factors={F}, num_layers={L} (tower {2*D}->{D}->{F}), Adam, bf16 tcgen05 tower"
+    res = out["fused"]
+    res["workload"] = (f"NeuMF+BPR synthetic ml-20m shape, factors={F}, num_layers={L} (tower {2*D}->{D}->{F}), Adam, bf16 tcgen05 "
+                       "tower fused per 64-triple tile (activations in shared / tensor memory)")
+    res["layerwise_bf16_tower"] = out["bf16"]
     res["fp32_tower"] = out["fp32"]
     return res
 

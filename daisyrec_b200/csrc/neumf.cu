@@ -21,6 +21,7 @@
 // tcgen05 (umma_gemm.cuh) and the step becomes bound by streaming the fp32 activations (profiles/r01c).
 #include "step.cuh"
 #include "umma_gemm.cuh"
+#include "neumf_fused.cuh"
 
 namespace drb {
 
@@ -623,8 +624,11 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
                                          double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream)
 {
     NeumfDims d, dlay;
-    DRB_REQUIRE(tower_dtype == 0 || tower_dtype == 1, "neumf: tower_dtype must be 0 (fp32) or 1 (bf16 tcgen05)");
+    DRB_REQUIRE(tower_dtype >= 0 && tower_dtype <= 2,
+                "neumf: tower_dtype must be 0 (fp32), 1 (bf16 tcgen05, layer-wise) or 2 (bf16 tcgen05, fused per tile)");
     DRB_REQUIRE(dropout >= 0.f && dropout < 1.f, "neumf: dropout must be in [0, 1)");
+    const bool fused = tower_dtype == 2 && neumf_fused_supported(F, L, mode, dropout);
+    if (tower_dtype == 2 && !fused) tower_dtype = 1;      // shapes outside the fused kernel: same numerics class, layer-wise
     DRB_REQUIRE(make_dims(d, U, I, F, L, mode) && make_dims(dlay, U, I, F, L, 0),
                 "neumf: bad dims (factors must be a positive multiple of 4, 1 <= num_layers <= 8, mode 0..2)");
     DRB_REQUIRE(d_UG && d_IG && d_UM && d_IM && d_W && d_ws && d_bu && d_bi && d_bj && h && d_step_loss, "neumf: null argument");
@@ -660,8 +664,21 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
             }
         }
         int rc = DRB_OK;
+        if (fused) {
+            // one persistent kernel: gather, both layers, head, all four backward products, scatter (neumf_fused.cuh)
+            FusedParams fp;
+            fp.UG = d_UG; fp.IG = d_IG; fp.UM = d_UM; fp.IM = d_IM; fp.W = d_W;
+            fp.bu = bu; fp.bi = bi; fp.bj = bj; fp.B = B;
+            fp.gUG = w.gUG; fp.gIG = w.gIG; fp.gUM = w.gUM; fp.gIM = w.gIM; fp.gW = w.gW;
+            fp.cntU = w.cntU; fp.cntI = w.cntI; fp.red = w.red; fp.has_reg = has_reg; fp.apply = apply ? 1 : 0;
+            rc = launch_neumf_fused(F, fp, st);
+            if (rc != DRB_OK) return rc;
+            neumf_finalize_kernel<<<1, 1, 0, st>>>(w.red, h->reg_1, h->reg_2, w.hdrG, w.hdrM, d_step_loss + s, first_step + s);
+            DRB_CUDA(cudaGetLastError());
+            if (!apply) break;
+        }
         // forward
-        if (use_tower) {
+        if (use_tower && !fused) {
             neumf_gather_kernel<<<grid1d(R * 2 * (d.D / 4), 256), 256, 0, st>>>(d_UM, d_IM, bu, bi, bj, B, d.D, w.acts, drop);
             DRB_CUDA(cudaGetLastError());
             rc = tower_forward(d, d_W, w.acts, R, R, tower_dtype, drop, st);
@@ -669,18 +686,20 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
         }
         const float *AL = w.acts + d.act_off[d.L] * R;
         float *dZ = w.dA;                                        // dZ_L [R, F]
-        int hw = 1;
-        while (hw < F / 4 && hw < 32) hw <<= 1;                  // lanes per triple in the head kernel
-        neumf_head_kernel<<<grid1d(B, 8 * (32 / hw), 8), 256, sizeof(float) * (2 * F + 1), st>>>(
-            d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, hw, mode, w.gUG, w.gIG,
-            w.gW + d.wp_off, dZ, w.cntU, w.cntI, w.red);
-        DRB_CUDA(cudaGetLastError());
-        neumf_finalize_kernel<<<1, 1, 0, st>>>(w.red, h->reg_1, h->reg_2, w.hdrG, w.hdrM, d_step_loss + s, first_step + s);
-        DRB_CUDA(cudaGetLastError());
-        if (!apply) break;
+        if (!fused) {
+            int hw = 1;
+            while (hw < F / 4 && hw < 32) hw <<= 1;              // lanes per triple in the head kernel
+            neumf_head_kernel<<<grid1d(B, 8 * (32 / hw), 8), 256, sizeof(float) * (2 * F + 1), st>>>(
+                d_UG, d_IG, d_UM, d_IM, d_W + d.wp_off, AL, bu, bi, bj, B, F, d.D, has_reg, apply ? 1 : 0, hw, mode, w.gUG, w.gIG,
+                w.gW + d.wp_off, dZ, w.cntU, w.cntI, w.red);
+            DRB_CUDA(cudaGetLastError());
+            neumf_finalize_kernel<<<1, 1, 0, st>>>(w.red, h->reg_1, h->reg_2, w.hdrG, w.hdrM, d_step_loss + s, first_step + s);
+            DRB_CUDA(cudaGetLastError());
+            if (!apply) break;
+        }
         // tower backward ('GMF': the tower takes no part in the prediction, its parameters have no gradient)
         float *cur = w.dA, *nxt = w.dB;
-        for (int l = d.L - 1; l >= 0 && use_tower; --l) {
+        for (int l = d.L - 1; l >= 0 && use_tower && !fused; --l) {
             const float *Aprev = w.acts + d.act_off[l] * R;
             // gW_l[out,in] += dZ^T A_{l-1}, computed as (A_{l-1}^T dZ)^T: the wide dimension (in) fills the 128-row MMA tile
             // and the narrow one (out) becomes N, so the TMEM footprint per CTA is small and more CTAs overlap
@@ -700,7 +719,7 @@ extern "C" int drb_neumf_bpr_train_steps(float *d_UG, float *d_IG, float *d_UM, 
             if (rc != DRB_OK) return rc;
             float *t = cur; cur = nxt; nxt = t;
         }
-        if (use_tower) {
+        if (use_tower && !fused) {
             neumf_scatter_kernel<<<grid1d(B * (d.D / 4), 256), 256, 0, st>>>(cur, bu, bi, bj, B, d.D, w.gUM, w.gIM, drop);
             DRB_CUDA(cudaGetLastError());
         }

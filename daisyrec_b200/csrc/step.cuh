@@ -90,10 +90,10 @@ struct StepParams {
     unsigned long long neg_seed;
     int loss;              // DRB_LOSS_BPR / _HL / _TL (pair-wise criterion, AbstractRecommender.py:79-93)
     // FM (FMRecommender.py:61-68): pred += (u_bias[u] + i_bias[item]) + bias_; bias = packed [U + I + 1]; nullptr = MF
-    float *bias;
+    float *bias = nullptr;
     // multi-GPU persistent mode: step s trains local triples [step_offsets[s], step_offsets[s+1]) (device array; the union
     // of the ranks' ranges is the global batch s).  nullptr = uniform batches of `batch` triples.
-    const long long *step_offsets;
+    const long long *step_offsets = nullptr;
 };
 
 

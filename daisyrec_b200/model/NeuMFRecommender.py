@@ -81,10 +81,12 @@ class NeuMF(GeneralRecommender):
         self._opt_steps = 0
         self._rows = int(config.get('neumf_scratch_rows', 1 << 16))
         # optional B200 key: 'fp32' (CUDA cores, parity path, default) | 'bf16' (tcgen05 tensor cores, BASELINE config 3)
+        #                   | 'fused' (bf16 tcgen05, the whole tower step of a 64-triple tile inside one CTA: activations stay in
+        #                     shared / tensor memory; factors = 32, num_layers = 2, dropout 0 -- other shapes run as 'bf16')
         td = str(config.get('tower_dtype', 'fp32')).lower()
-        if td not in ('fp32', 'bf16'):
-            raise ValueError(f"tower_dtype must be 'fp32' or 'bf16', got {td!r}")
-        self._tower_dtype = 1 if td == 'bf16' else 0
+        if td not in ('fp32', 'bf16', 'fused'):
+            raise ValueError(f"tower_dtype must be 'fp32', 'bf16' or 'fused', got {td!r}")
+        self._tower_dtype = {'fp32': 0, 'bf16': 1, 'fused': 2}[td]
         # optional B200 key: how nn.Dropout's masks (:61) are produced in train mode.
         #   'torch'  : torch itself draws them on the host, in the reference's order (per step: the pos forward's L masks, then
         #              the neg forward's), from the global CPU generator; they are bit-packed and uploaded -- the reference's

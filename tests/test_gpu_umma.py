@@ -99,3 +99,66 @@ def test_neumf_bf16_tower_step_close_to_fp32(ops):
         rel = np.linalg.norm(d_bf16 - d_fp32) / max(np.linalg.norm(d_fp32), 1e-30)
         cos = float((d_bf16 * d_fp32).sum() / max(np.linalg.norm(d_bf16) * np.linalg.norm(d_fp32), 1e-30))
         assert rel <= 0.15 and cos >= 0.99, (rel, cos)
+
+
+@pytest.mark.parametrize("B,reg", [(64, 0.0), (4096, 0.001), (5000, 0.002), (130, 0.001)])
+def test_neumf_fused_tower_matches_layerwise_bf16(ops, B, reg):
+    """tower_dtype 2 (the whole tower step of a 64-triple tile fused in one CTA: bf16 operand images in shared memory, every
+    accumulator in TMEM, transposed operands read through swapped-stride descriptors) against tower_dtype 1 (the same bf16
+    products as separate GEMM launches).  Both round the same values to bf16 at the same points, so they agree to fp32
+    accumulation-order noise: a wrong descriptor, TMEM column or image offset shows up as an O(1) error in exactly one of
+    {loss (forward), embedding tables (dZ W products), tower block (A^T dZ products, bias / predict sums)}."""
+    rng = np.random.default_rng(B)
+    U, I, F, L = 700, 500, 32, 2
+    D = F * 2 ** (L - 1)
+    tabs_h = [(rng.standard_normal(s) * 0.2).astype(np.float32) for s in ((U, F), (I, F), (U, D), (I, D))]
+    W_h = (rng.standard_normal(ops.neumf_param_count(F, L)) * 0.15).astype(np.float32)
+    b = [torch.from_numpy(rng.integers(m, size=B).astype(np.int32)).cuda() for m in (U, I, I)]
+    hp = ops.hyper(0.01, reg, reg, "sgd")
+    res = []
+    for dtype in (1, 2):
+        tabs = [torch.from_numpy(t).cuda() for t in tabs_h]
+        W = torch.from_numpy(W_h).cuda()
+        ws = ops.NeumfWorkspace(U, I, F, L, "sgd", 2 * B, "cuda")
+        l0 = ops.neumf_bpr_train_steps(tabs, W, ws, *b, B, 0, 1, hp, tower_dtype=dtype, apply=False).item()
+        assert all(np.array_equal(t.cpu().numpy(), h) for t, h in zip(tabs, tabs_h))      # loss-only call changes nothing
+        loss = ops.neumf_bpr_train_steps(tabs, W, ws, *b, B, 0, 1, hp, tower_dtype=dtype).item()
+        assert l0 == loss or abs(l0 - loss) <= 1e-6 * abs(loss)
+        res.append((loss, [t.cpu().numpy() for t in tabs], W.cpu().numpy()))
+    (l1, t1, w1), (l2, t2, w2) = res
+    assert abs(l2 - l1) <= 2e-5 * abs(l1), ("forward", l1, l2)
+    names = ["UG", "IG", "UM", "IM"]
+    for n, init, a, c in zip(names, tabs_h, t1, t2):
+        upd = np.abs(a - init).max()
+        assert np.abs(c - a).max() <= 2e-4 * max(upd, 1e-12) + 1e-9, (n, float(np.abs(c - a).max()), float(upd))
+    n1, n0, n2 = 2 * F, 4 * F, F
+    blocks = {"W1": (0, n1 * n0), "b1": (n1 * n0, n1 * n0 + n1), "W2": (n1 * n0 + n1, n1 * n0 + n1 + n2 * n1),
+              "b2": (n1 * n0 + n1 + n2 * n1, n1 * n0 + n1 + n2 * n1 + n2), "wp": (n1 * n0 + n1 + n2 * n1 + n2, len(W_h))}
+    for n, (lo, hi) in blocks.items():
+        upd = np.abs(w1[lo:hi] - W_h[lo:hi]).max()
+        assert np.abs(w2[lo:hi] - w1[lo:hi]).max() <= 5e-4 * max(upd, 1e-12) + 1e-9, (n, float(np.abs(w2[lo:hi] - w1[lo:hi]).max()), float(upd))
+
+
+def test_neumf_fused_tower_multi_step_training(ops):
+    """Several chained Adam steps over many tiles per CTA (TMEM weight-gradient accumulators carried across tiles, flushed once)."""
+    rng = np.random.default_rng(9)
+    U, I, F, L, B, K = 3000, 2000, 32, 2, 20000, 3
+    D = F * 2 ** (L - 1)
+    tabs_h = [(rng.standard_normal(s) * 0.1).astype(np.float32) for s in ((U, F), (I, F), (U, D), (I, D))]
+    W_h = (rng.standard_normal(ops.neumf_param_count(F, L)) * 0.1).astype(np.float32)
+    b = [torch.from_numpy(rng.integers(m, size=B * K).astype(np.int32)).cuda() for m in (U, I, I)]
+    hp = ops.hyper(0.001, 0.001, 0.001, "adam")
+    out = []
+    for dtype in (1, 2):
+        tabs = [torch.from_numpy(t).cuda() for t in tabs_h]
+        W = torch.from_numpy(W_h).cuda()
+        ws = ops.NeumfWorkspace(U, I, F, L, "adam", 2 * B, "cuda")
+        losses = ops.neumf_bpr_train_steps(tabs, W, ws, *b, B, 0, K, hp, tower_dtype=dtype).cpu().numpy()
+        out.append((losses, W.cpu().numpy(), tabs[2].cpu().numpy()))
+    (la, wa, ta), (lb, wb, tb) = out
+    assert np.all(np.abs(la - lb) <= 1e-4 * np.abs(la)), (la, lb)
+    # Adam normalises every gradient to ~lr: compare the direction of the accumulated update
+    for a, c, init in ((wa, wb, W_h), (ta, tb, tabs_h[2])):
+        da, dc = (a - init).astype(np.float64).ravel(), (c - init).astype(np.float64).ravel()
+        cos = float(da @ dc / max(np.linalg.norm(da) * np.linalg.norm(dc), 1e-30))
+        assert cos >= 0.995, cos
