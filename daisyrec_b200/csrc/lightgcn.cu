@@ -21,6 +21,7 @@
 // stores (deterministic), multi-segment rows are combined with RED.ADD.F32x4.  HBM/L2-bound:
 // algorithmic bytes per product = nnzA*(8 + 4F) + n*4F.
 #include "step.cuh"
+#include "spmm.cuh"
 
 namespace drb {
 
@@ -63,14 +64,6 @@ static size_t carve_lgcn(void *base, int U, int I, int F, int opt, LgcnWs *w)
     return off;
 }
 
-struct Adj {
-    const int64_t *row_ptr;
-    const int32_t *col;
-    const float *val;
-    const int32_t *seg_row;
-    const int64_t *seg_ptr;
-    long long nseg, n;
-};
 
 // Y[r] (+)= sum_e val[e] * X[col[e]]  over the segment's edges;  S[r] += the same (layer-sum accumulator)
 template <int VEC, int W, int NCH>
@@ -122,16 +115,18 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_seg_kernel(Adj a, const flo
         for (int ch = 0; ch < NCH; ++ch) {
             int c = gl + ch * W;
             if (c >= chunks) continue;
-            float *yp = Y + (size_t)r * F + c * VEC, *sp = S + (size_t)r * F + c * VEC;
+            float *yp = Y + (size_t)r * F + c * VEC, *sp = S ? S + (size_t)r * F + c * VEC : nullptr;
             if (!multi) {
                 st_row<VEC>(yp, acc.c[ch]);
-                Vec<VEC> s = ld_row<VEC>(sp);
+                if (sp) {
+                    Vec<VEC> s = ld_row<VEC>(sp);
 #pragma unroll
-                for (int z = 0; z < VEC; ++z) s.v[z] += acc.c[ch].v[z];
-                st_row<VEC>(sp, s);
+                    for (int z = 0; z < VEC; ++z) s.v[z] += acc.c[ch].v[z];
+                    st_row<VEC>(sp, s);
+                }
             } else {
                 red_row<VEC>(yp, acc.c[ch]);
-                red_row<VEC>(sp, acc.c[ch]);
+                if (sp) red_row<VEC>(sp, acc.c[ch]);
             }
         }
     }
@@ -164,7 +159,7 @@ static SpmmKernel pick_spmm_v(int W, int NCH)
     return nullptr;
 }
 
-static int launch_spmm(const Adj &a, const float *X, float *Y, float *S, int F, cudaStream_t st)
+int launch_spmm(const Adj &a, const float *X, float *Y, float *S, int F, cudaStream_t st)
 {
     RowGeom g = row_geom(F);
     SpmmKernel k = g.vec == 4 ? pick_spmm_v<4>(g.width, g.nch) : g.vec == 2 ? pick_spmm_v<2>(g.width, g.nch)

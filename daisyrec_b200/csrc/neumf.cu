@@ -546,6 +546,30 @@ __global__ void neumf_score_kernel(const float *__restrict__ UG, const float *__
     }
 }
 
+// ---- the tower's GEMM dispatcher for the other dense-layer models (ngcf.cu): plain entry points, see gemm.cuh
+int gemm_nt(int dtype, long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb, float *C,
+            long long ldc, cudaStream_t st)
+{
+    return launch_gemm<false, true, 0>(dtype, M, N, K, A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, st);
+}
+int gemm_nn(int dtype, long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb, float *C,
+            long long ldc, cudaStream_t st)
+{
+    return launch_gemm<false, false, 0>(dtype, M, N, K, A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, st);
+}
+int gemm_tn_acc_t(int dtype, long long M, int N, int K, const float *A, long long lda, const float *B, long long ldb, float *C,
+                  long long ldc, cudaStream_t st)
+{
+    return launch_gemm<true, false, 4>(dtype, M, N, K, A, lda, B, ldb, C, ldc, nullptr, nullptr, 0, st);
+}
+int colsum_acc(const float *dZ, long long M, int N, float *gb, cudaStream_t st)
+{
+    DRB_REQUIRE(N <= 256, "colsum: N=%d exceeds 256", N);
+    colsum_kernel<<<sm_count() * 4, 256, 0, st>>>(dZ, M, N, gb);
+    DRB_CUDA(cudaGetLastError());
+    return DRB_OK;
+}
+
 static int grid1d(long long n, int block, int per_sm = 16)
 {
     long long b = (n + block - 1) / block, cap = (long long)sm_count() * per_sm;

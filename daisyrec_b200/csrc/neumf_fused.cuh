@@ -57,7 +57,13 @@ struct FusedLayout {
     static constexpr uint32_t DZ2 = DZ1 + (N1 / 8) * LBO_T;
     static constexpr uint32_t W1 = DZ2 + (N2 / 8) * LBO_T;
     static constexpr uint32_t W2 = W1 + (N0 / 8) * LBO_W1;
-    static constexpr uint32_t TAIL = W2 + (N1 / 8) * LBO_W2;
+    static constexpr uint32_t W_END = W2 + (N1 / 8) * LBO_W2;
+    // fp32 staging of the NEXT tile's gathered rows (cp.async): MLP rows [3][64][D], GMF rows [3][64][F + 4] (padded: the head
+    // reads one row per lane with 128-bit loads)
+    static constexpr uint32_t SM = (W_END + 127) / 128 * 128;
+    static constexpr uint32_t SG = SM + 3 * 64 * D * 4;
+    static constexpr int GROW = F + 4;
+    static constexpr uint32_t TAIL = SG + 3 * 64 * GROW * 4;
     // the gW2 product reads A1^T as an M = 128 operand although only N1 <= 96 feature rows exist: MN-groups beyond N1/8 fall
     // into the images behind A1 (finite bf16 data, rows of the result that nobody reads) -- keep that window inside the buffer
     static constexpr uint32_t SPAN = (A1 + 16 * LBO_T + 256 > TAIL) ? (A1 + 16 * LBO_T + 256) : TAIL;
@@ -119,6 +125,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) neumf_fused_kernel(FusedPara
     __shared__ uint32_t s_tmem;
     __shared__ float s_b1[N1], s_b2[N2], s_wp[2 * F + 1];
     __shared__ float s_pred[2][128];
+    __shared__ int s_idx[2][3][kFusedTile];      // [buffer][u | i | j][triple] of the current and the next tile
     __shared__ float s_colsum[N1 + N2 + 2 * F];  // final cross-thread reduction of the register column sums
     __shared__ double s_red[11];
 
@@ -187,33 +194,82 @@ __global__ void __launch_bounds__(kFusedThreads, 1) neumf_fused_kernel(FusedPara
 
     const long long ntiles = (p.B + kFusedTile - 1) / kFusedTile;
     bool first_tile = true;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+
+    // this thread's slot of a tile's index lists: threads 0..191 load one index each (u | i | j of triple tid % 64)
+    auto load_indices = [&](long long tile_, int buf) {
+        if (tid < 3 * kFusedTile) {
+            const int kind = tid / kFusedTile, r = tid % kFusedTile;
+            const long long t = tile_ * kFusedTile + r;
+            int v = 0;
+            if (t < p.B) v = __ldg((kind == 0 ? p.bu : kind == 1 ? p.bi : p.bj) + t);
+            s_idx[buf][kind][r] = v;
+        }
+    };
+    // asynchronous global -> shared copies (cp.async, 16 bytes per lane) of a tile's gathered rows, straight from the tables
+    constexpr int G = D / 4;                               // lanes per D-float MLP row
+    constexpr int GROUPS = kFusedThreads / G;
+    constexpr int GG = F / 4;                              // lanes per F-float GMF row
+    constexpr int GGROUPS = kFusedThreads / GG;
+    auto prefetch_mlp = [&](long long tile_, int buf) {
+        const int nt_ = (int)min((long long)kFusedTile, p.B - tile_ * kFusedTile);
+        const int gl = tid % G, grp = tid / G;
+        for (int w = grp; w < 3 * kFusedTile; w += GROUPS) {
+            const int kind = w / kFusedTile, r = w % kFusedTile;            // 0: UM[u], 1: IM[i], 2: IM[j]
+            const uint32_t dst = sbase + L::SM + (uint32_t)(w * D + gl * 4) * 4u;
+            if (r < nt_) {
+                const float *src = (kind == 0 ? p.UM : p.IM) + (size_t)s_idx[buf][kind][r] * D + gl * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            } else {
+                *reinterpret_cast<float4 *>(smem + L::SM + (uint32_t)(w * D + gl * 4) * 4u) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto prefetch_gmf = [&](long long tile_, int buf) {
+        const int nt_ = (int)min((long long)kFusedTile, p.B - tile_ * kFusedTile);
+        const int gl = tid % GG, grp = tid / GG;
+        for (int w = grp; w < 3 * kFusedTile; w += GGROUPS) {
+            const int kind = w / kFusedTile, r = w % kFusedTile;            // 0: UG[u], 1: IG[i], 2: IG[j]
+            const uint32_t off = L::SG + (uint32_t)(w * L::GROW + gl * 4) * 4u;
+            if (r < nt_) {
+                const float *src = (kind == 0 ? p.UG : p.IG) + (size_t)s_idx[buf][kind][r] * F + gl * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + off), "l"(src) : "memory");
+            } else {
+                *reinterpret_cast<float4 *>(smem + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if ((long long)blockIdx.x < ntiles) {
+        load_indices(blockIdx.x, 0);
+        __syncthreads();
+        prefetch_mlp(blockIdx.x, 0);
+        prefetch_gmf(blockIdx.x, 0);
+    }
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, cur ^= 1) {
         const long long t0 = tile * kFusedTile;
         const int nt = (int)min((long long)kFusedTile, p.B - t0);           // valid triples in this tile
         const int tr = row & (kFusedTile - 1);                              // triple of this thread's row
         const bool ok = tr < nt;
-        const int u = ok ? __ldg(p.bu + t0 + tr) : 0;
-        const int item = ok ? (pos_row ? __ldg(p.bi + t0 + tr) : __ldg(p.bj + t0 + tr)) : 0;
+        const long long next_tile = tile + gridDim.x;
+        const bool has_next = next_tile < ntiles;
+        if (has_next) load_indices(next_tile, cur ^ 1);                     // in flight while this tile's rows land
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                                    // staged rows + both index lists visible
+        const int u = s_idx[cur][0][tr];
+        const int item = s_idx[cur][pos_row ? 1 : 2][tr];
 
-        // ---------------------------------------------------------------- gather A0 (bf16 K-major image)
+        // ---------------------------------------------------------------- A0: staged fp32 rows -> bf16 K-major image
         {
-            constexpr int G = D / 4;                       // lanes per D-float row
-            constexpr int GROUPS = kFusedThreads / G;
             const int gl = tid % G, grp = tid / G;
             for (int w = grp; w < 3 * kFusedTile; w += GROUPS) {
                 const int kind = w / kFusedTile, r = w % kFusedTile;        // 0: UM[u] -> rows r and r+64; 1: IM[i]; 2: IM[j]
-                const bool valid = r < nt;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    const int uu = __ldg(p.bu + t0 + r);
-                    const float *src = kind == 0 ? p.UM + (size_t)uu * D
-                                                 : p.IM + (size_t)(kind == 1 ? __ldg(p.bi + t0 + r) : __ldg(p.bj + t0 + r)) * D;
-                    v = __ldcg(reinterpret_cast<const float4 *>(src) + gl);
-                    if (p.has_reg && kind < 2) {           // UM_u and IM_i rows enter the regulariser once per triple
-                        const float a = fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
-                        const float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-                        if (kind == 0) { acc_l1[1] += a; acc_s2[1] += s; } else { acc_l1[3] += a; acc_s2[3] += s; }
-                    }
+                const float4 v = *reinterpret_cast<const float4 *>(smem + L::SM + (uint32_t)(w * D + gl * 4) * 4u);
+                if (p.has_reg && kind < 2 && r < nt) {     // UM_u and IM_i rows enter the regulariser once per triple
+                    const float a = fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+                    const float s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+                    if (kind == 0) { acc_l1[1] += a; acc_s2[1] += s; } else { acc_l1[3] += a; acc_s2[3] += s; }
                 }
                 uint2 o;
                 o.x = pack_bf16x2(v.x, v.y);
@@ -228,6 +284,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) neumf_fused_kernel(FusedPara
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (has_next) prefetch_mlp(next_tile, cur ^ 1);      // the MLP staging has been consumed: refill it under the MMAs
 
         // ---------------------------------------------------------------- Z1 = A0 W1^T
         if (tid == 0) {
@@ -290,12 +347,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) neumf_fused_kernel(FusedPara
                 }
             }
             float part = 0.f;
-            const float4 *ug4 = reinterpret_cast<const float4 *>(p.UG + (size_t)u * F + k0);
-            const float4 *ig4 = reinterpret_cast<const float4 *>(p.IG + (size_t)item * F + k0);
+            const float4 *ug4 = reinterpret_cast<const float4 *>(smem + L::SG + (uint32_t)((0 * kFusedTile + tr) * L::GROW + k0) * 4u);
+            const float4 *ig4 =
+                reinterpret_cast<const float4 *>(smem + L::SG + (uint32_t)(((pos_row ? 1 : 2) * kFusedTile + tr) * L::GROW + k0) * 4u);
 #pragma unroll
             for (int c = 0; c < HC / 4; ++c) {
-                const float4 a = ok ? __ldcg(ug4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 b = ok ? __ldcg(ig4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 a = ug4[c];                     // rows beyond the batch were staged as zeros
+                const float4 b = ig4[c];
                 gu[4 * c] = a.x; gu[4 * c + 1] = a.y; gu[4 * c + 2] = a.z; gu[4 * c + 3] = a.w;
                 gi[4 * c] = b.x; gi[4 * c + 1] = b.y; gi[4 * c + 2] = b.z; gi[4 * c + 3] = b.w;
             }
@@ -364,10 +422,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) neumf_fused_kernel(FusedPara
                 }
             }
         }
-        if (!p.apply) { first_tile = false; __syncthreads(); continue; }   // loss only
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (has_next) prefetch_gmf(next_tile, cur ^ 1);      // the GMF staging has been consumed by the head
+        if (!p.apply) { first_tile = false; continue; }      // loss only
 
         // ---------------------------------------------------------------- dA1 = dZ2 W2 ;  gW2^T += A1^T dZ2
         if (tid == 0) {

@@ -149,7 +149,7 @@ class NeuMF(GeneralRecommender):
 
     def load_state_dict(self, sd):
         for k, t in self.state_dict().items():
-            t.copy_(sd[k])
+            t.copy_(torch.as_tensor(sd[k]).reshape(t.shape))
 
     def _hyper(self, opt=None):
         return ops.hyper(self.lr, self.reg_1, self.reg_2, opt or self._optimizer_name())

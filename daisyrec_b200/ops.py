@@ -547,6 +547,52 @@ def lgcn_bpr_train_steps(E0, ws, graph, num_layers, bu, bi, bj, batch, first_ste
     return losses[:n_steps]
 
 
+# ------------------------------------------------------------------ NGCF
+def _dims_arr(dims):
+    return (C.c_int32 * len(dims))(*[int(d) for d in dims])
+
+
+def ngcf_param_count(dims):
+    return int(L.lib().drb_ngcf_param_count(_dims_arr(dims), len(dims) - 1))
+
+
+class NgcfWorkspace:
+    def __init__(self, user_num, item_num, dims, opt, device):
+        self.U, self.I, self.dims = user_num, item_num, [int(d) for d in dims]
+        self.opt = L.OPT_SGD if opt == "sgd" else L.OPT_ADAM
+        nbytes = L.lib().drb_ngcf_workspace_bytes(user_num, item_num, _dims_arr(self.dims), len(self.dims) - 1, self.opt)
+        if nbytes == 0:
+            raise ValueError("NGCF: layer widths must be in 1..256 and 1 <= layers <= 8")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        L.check(L.lib().drb_ngcf_workspace_init(_ptr(self.buf), user_num, item_num, _dims_arr(self.dims), len(self.dims) - 1,
+                                                self.opt, _stream()))
+
+
+def ngcf_forward(E0, W, ws, graph, tower_dtype=0):
+    _dev(E0, torch.float32, "E0"); _dev(W, torch.float32, "W")
+    out = torch.empty((ws.U + ws.I, sum(ws.dims)), dtype=torch.float32, device=E0.device)
+    L.check(L.lib().drb_ngcf_forward(_ptr(E0), _ptr(W), _ptr(ws.buf), ws.U, ws.I, _dims_arr(ws.dims), len(ws.dims) - 1,
+                                     *graph.args(), tower_dtype, _ptr(out), _stream()))
+    return out
+
+
+def ngcf_bpr_train_steps(E0, W, ws, graph, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True,
+                         tower_dtype=0):
+    _dev(E0, torch.float32, "E0"); _dev(W, torch.float32, "W")
+    for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
+        _dev(t, torch.int32, nm)
+    losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=E0.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_ngcf_bpr_train_steps(_ptr(E0), _ptr(W), _ptr(ws.buf), ws.U, ws.I, _dims_arr(ws.dims), len(ws.dims) - 1,
+                                          *graph.args(), _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(), batch, first_step, n_steps,
+                                          C.byref(hp), adam_step0, 1 if apply else 0, tower_dtype, _ptr(losses),
+                                          1 if check else 0, C.byref(nan_step), _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]
+
+
 # ------------------------------------------------------------------ NeuMF
 NEUMF_MODE = {"NeuMF": 0, "NeuMF-pre": 0, "GMF": 1, "MLP": 2}       # config['model_name'] (NeuMFRecommender.py:48-50)
 

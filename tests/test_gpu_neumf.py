@@ -131,8 +131,10 @@ def test_neumf_dropin_class(ops):
     m2 = NeuMF(dict(cfg, dropout=0.5))
     m2.fit(get_dataloader(BasicDataset(data), batch_size=bs.shape[2], shuffle=False))
     assert np.isfinite(m2.tower.cpu().numpy()).all() and m2.rank(loader).shape == (7, 10)
-    with pytest.raises(NotImplementedError):
-        NeuMF(dict(cfg, model_name='GMF'))
+    with pytest.raises(ValueError):
+        NeuMF(dict(cfg, model_name='SomethingElse'))
+    with pytest.raises(ValueError):
+        NeuMF(dict(cfg, model_name='NeuMF-pre'))                      # needs config['GMF_model'] / config['MLP_model']
 
 
 @pytest.mark.parametrize("tower_dtype", [0])
