@@ -194,8 +194,8 @@ class NeuMF(GeneralRecommender):
     def _drop_seed(self):
         """Key of the counter-based (Philox) masks: drawn from torch's global RNG the first time a fit needs it, so that
         torch.manual_seed makes runs reproducible."""
-        if self.dropout <= 0.0 or not self.training:
-            return 0
+        if self.dropout <= 0.0 or not self.training or self._mode == 1:
+            return 0                                                      # 'GMF' never calls a Dropout module: no draw at all
         if getattr(self, '_philox_seed', None) is None:
             self._philox_seed = int(torch.empty((), dtype=torch.int64).random_().item())
         return self._philox_seed

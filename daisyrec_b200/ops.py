@@ -593,6 +593,55 @@ def ngcf_bpr_train_steps(E0, W, ws, graph, bu, bi, bj, batch, first_step, n_step
     return losses[:n_steps]
 
 
+# ------------------------------------------------------------------ NFM
+NFM_ACT = {"relu": 0, "sigmoid": 1, "tanh": 2}
+
+
+def nfm_param_count(factors, num_layers, batch_norm):
+    return int(L.lib().drb_nfm_param_count(factors, num_layers, 1 if batch_norm else 0))
+
+
+class NfmWorkspace:
+    def __init__(self, user_num, item_num, factors, num_layers, batch_norm, opt, max_rows, device):
+        self.U, self.I, self.F, self.Ln, self.bn, self.max_rows = user_num, item_num, factors, num_layers, 1 if batch_norm else 0, int(max_rows)
+        self.opt = L.OPT_SGD if opt == "sgd" else L.OPT_ADAM
+        nbytes = L.lib().drb_nfm_workspace_bytes(user_num, item_num, factors, num_layers, self.bn, self.opt, self.max_rows)
+        if nbytes == 0:
+            raise ValueError("NFM: factors must be in 1..256, 0 <= num_layers <= 8 and max_rows >= 2")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        L.check(L.lib().drb_nfm_workspace_init(_ptr(self.buf), user_num, item_num, factors, num_layers, self.bn, self.opt,
+                                               self.max_rows, _stream()))
+
+
+def nfm_bpr_train_steps(P, Q, bias, N, Rs, ws, act, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True,
+                        check=True, tower_dtype=0):
+    for t in (P, Q, bias, N):
+        _dev(t, torch.float32, "parameter")
+    for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
+        _dev(t, torch.int32, nm)
+    losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=P.device)
+    nan_step = C.c_int64(-1)
+    rc = L.lib().drb_nfm_bpr_train_steps(_ptr(P), _ptr(Q), _ptr(bias), _ptr(N), None if Rs is None or Rs.numel() == 0 else _ptr(Rs),
+                                         _ptr(ws.buf), ws.U, ws.I, ws.F, ws.Ln, ws.bn, act, ws.max_rows, _ptr(bu), _ptr(bi),
+                                         _ptr(bj), bu.numel(), batch, first_step, n_steps, C.byref(hp), adam_step0,
+                                         1 if apply else 0, tower_dtype, _ptr(losses), 1 if check else 0, C.byref(nan_step),
+                                         _stream())
+    if rc == L.DRB_ERR_NAN_LOSS:
+        raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
+    L.check(rc)
+    return losses[:n_steps]
+
+
+def nfm_scores(P, Q, bias, N, Rs, ws, act, u, i, tower_dtype=0):
+    """eval-mode scores of the (u[k], i[k]) pairs (int32 CUDA tensors)."""
+    _dev(u, torch.int32, "u"); _dev(i, torch.int32, "i")
+    out = torch.empty(u.numel(), dtype=torch.float32, device=P.device)
+    L.check(L.lib().drb_nfm_scores(_ptr(P), _ptr(Q), _ptr(bias), _ptr(N), None if Rs is None or Rs.numel() == 0 else _ptr(Rs),
+                                   _ptr(ws.buf), ws.U, ws.I, ws.F, ws.Ln, ws.bn, act, ws.opt, ws.max_rows, _ptr(u), _ptr(i),
+                                   u.numel(), tower_dtype, _ptr(out), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------ NeuMF
 NEUMF_MODE = {"NeuMF": 0, "NeuMF-pre": 0, "GMF": 1, "MLP": 2}       # config['model_name'] (NeuMFRecommender.py:48-50)
 
