@@ -80,7 +80,9 @@ static StepKernel pick_kernel(int F, bool gen)
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
     // GEN instantiation: any loss but BPR, and the Adagrad / RMSprop sweeps (kept out of the hot BPR + SGD/Adam kernel)
-    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr);
+    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
+    DRB_REQUIRE(!p.det || (p.phases == 3 && p.ws.gP64 != nullptr), "deterministic accumulation: single-GPU fused steps with a "
+                "workspace from drb_mf_workspace_bytes_det");
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
     // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
     // split multi-GPU / LightGCN / NeuMF paths)
@@ -148,7 +150,7 @@ extern "C" int drb_mf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F
 namespace drb {
 int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu, const int32_t *bi,
                 const int32_t *bj, long long n, long long batch, long long first, long long nsteps, const drb_hyper *h,
-                long long adam_step0, double *d_step_loss, int apply, float *d_bias)
+                long long adam_step0, double *d_step_loss, int apply, float *d_bias, int det)
 {
     DRB_REQUIRE(P && Q && d_ws && bu && bi && bj && h && d_step_loss, "null pointer argument");
     DRB_REQUIRE(U > 0 && I > 0 && F > 0 && batch > 0 && n >= 0 && first >= 0 && nsteps >= 0, "bad sizes");
@@ -157,7 +159,8 @@ int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int
     DRB_REQUIRE((first + nsteps - 1) * batch < n || nsteps == 0 || n == 0, "steps [%lld,%lld) exceed %lld triples", first,
                 first + nsteps, n);
     p.P = P; p.Q = Q;
-    carve(d_ws, U, I, F, h->opt, &p.ws, d_bias != nullptr);
+    carve(d_ws, U, I, F, h->opt, &p.ws, d_bias != nullptr, det);
+    p.det = det;
     p.bu = bu; p.bi = bi; p.bj = bj;
     p.n = n; p.batch = batch; p.first_step = first; p.n_steps = nsteps;
     p.U = U; p.I = I; p.F = F; p.tile = kTileMax;
@@ -194,6 +197,31 @@ extern "C" int drb_mf_bpr_train_steps(float *d_P, float *d_Q, void *d_ws, int32_
     StepParams p;
     int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu, d_bi, d_bj, n, batch, first_step, n_steps, hyper, adam_step0,
                          d_step_loss, 1);
+    if (rc != DRB_OK) return rc;
+    if (n_steps == 0) return DRB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = launch_steps(p, st);
+    if (rc != DRB_OK) return rc;
+    if (sync_and_check) return check_nan(d_ws, st, nan_step);
+    return DRB_OK;
+}
+
+// Deterministic accumulation (opt-in): the same steps with every cross-thread sum taken in fixed point, so that two runs --
+// and any two orders of the atomics -- give bitwise identical tables and losses.  Workspace: drb_mf_workspace_bytes_det.
+extern "C" size_t drb_mf_workspace_bytes_det(int32_t U, int32_t I, int32_t F, int32_t opt)
+{
+    return carve(nullptr, U, I, F, opt, nullptr, 0, 1);
+}
+
+extern "C" int drb_mf_bpr_train_steps_det(float *d_P, float *d_Q, void *d_ws, int32_t U, int32_t I, int32_t F,
+                                          const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
+                                          int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *hyper,
+                                          int64_t adam_step0, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step,
+                                          void *stream)
+{
+    StepParams p;
+    int rc = fill_params(p, d_P, d_Q, d_ws, U, I, F, d_bu, d_bi, d_bj, n, batch, first_step, n_steps, hyper, adam_step0,
+                         d_step_loss, 1, nullptr, 1);
     if (rc != DRB_OK) return rc;
     if (n_steps == 0) return DRB_OK;
     cudaStream_t st = (cudaStream_t)stream;

@@ -328,7 +328,11 @@ __global__ void nfm_finalize_kernel(WsHeader *hdr, float reg1, float reg2, doubl
     if (isnan(loss)) { hdr->status = DRB_ERR_NAN_LOSS; hdr->nan_step = step; }
 }
 
-// dh = dpred * wp;  gwp += sum dpred * fm;  gbias[u], gbias[U + item], gbias[U + I] += sum_f dh     (one warp per row)
+// One warp per TRIPLE (its pos row t and neg row B + t): dh = dpred * wp;  gwp += sum dpred * fm;  first-order terms:
+// gbias[U + i] += bs_pos, gbias[U + j] += bs_neg, and the user / global terms take bs_pos + bs_neg of the SAME triple -- for BPR
+// dpred_neg = -dpred_pos, so that sum is exactly 0, as it is in the reference (its two embedding backward passes add the same
+// numbers with opposite signs in the same order); adding the halves separately would leave cancellation noise that Adam
+// turns into +-lr steps.
 __global__ void __launch_bounds__(256) nfm_head_bwd_kernel(const float *__restrict__ coef, const float *__restrict__ fm,
                                                            const float *__restrict__ wp, int U, int I,
                                                            const int32_t *__restrict__ bu, const int32_t *__restrict__ bi,
@@ -341,29 +345,36 @@ __global__ void __launch_bounds__(256) nfm_head_bwd_kernel(const float *__restri
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
     float b0 = 0.f;
-    for (long long r = warp; r < R; r += nw) {
-        const long long t = r < B ? r : r - B;
-        const int item = r < B ? bi[t] : bj[t];
-        const float dp = coef[r];
-        float bs = 0.f;
+    for (long long t = warp; t < B; t += nw) {
+        const float dp = coef[t], dn = coef[B + t];
+        float bsp = 0.f, bsn = 0.f;
         for (int f = lane; f < F; f += 32) {
-            const float d = dp * wp[f];
-            dh[r * F + f] = d;
-            bs += d;
-            atomicAdd(&s_gwp[f], dp * fm[r * F + f]);
+            const float w = wp[f];
+            const float d1 = dp * w, d2 = dn * w;
+            dh[t * F + f] = d1;
+            dh[(B + t) * F + f] = d2;
+            bsp += d1;
+            bsn += d2;
+            atomicAdd(&s_gwp[f], dp * fm[t * F + f] + dn * fm[(B + t) * F + f]);
         }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, off);
+        for (int off = 16; off >= 1; off >>= 1) {
+            bsp += __shfl_xor_sync(0xffffffffu, bsp, off);
+            bsn += __shfl_xor_sync(0xffffffffu, bsn, off);
+        }
         if (lane == 0) {
-            atomicAdd(gB + bu[t], bs);
-            atomicAdd(gB + U + item, bs);
-            b0 += bs;
+            const float both = bsp + bsn;
+            if (both != 0.f) atomicAdd(gB + bu[t], both);
+            atomicAdd(gB + U + bi[t], bsp);
+            atomicAdd(gB + U + bj[t], bsn);
+            b0 += both;
         }
     }
     if (lane == 0 && b0 != 0.f) atomicAdd(gB + U + I, b0);
     __syncthreads();
     for (int k = threadIdx.x; k < F; k += blockDim.x)
         if (s_gwp[k] != 0.f) atomicAdd(gwp + k, s_gwp[k]);
+    (void)R;
 }
 
 // tmp = dh * act'(z, h)
@@ -565,7 +576,7 @@ extern "C" int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, fl
         DRB_CUDA(cudaGetLastError());
         if (!apply) break;
         // ---- backward
-        nfm_head_bwd_kernel<<<nfm_grid(R * 32, 256), 256, sizeof(float) * F, st>>>(w.coef, w.fm, wp, U, I, bu, bi, bj, B, R, F, w.dh,
+        nfm_head_bwd_kernel<<<nfm_grid(B * 32, 256), 256, sizeof(float) * F, st>>>(w.coef, w.fm, wp, U, I, bu, bi, bj, B, R, F, w.dh,
                                                                                  w.gN + d.o_wp, w.gB);
         DRB_CUDA(cudaGetLastError());
         for (int l = L - 1; l >= 0; --l) {

@@ -23,11 +23,14 @@ struct Workspace {
     // FM's first-order terms (FMRecommender.py:46-49): gradient accumulator and optimiser state of the packed
     // [u_bias (U), i_bias (I), bias_ (1)] vector; nullptr for plain MF
     float *gB, *mB, *vB;
+    // deterministic accumulation (opt-in): phase 1 adds fixed-point int64 images of every contribution (integer addition is
+    // associative: the sums do not depend on the order the atomics land in), converted to fp32 once before phase 2
+    long long *gP64, *gQ64, *accfx;    // table-shaped accumulators + [8] loss / norm sums; nullptr unless requested
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w, int fm = 0)
+inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w, int fm = 0, int det = 0)
 {
     size_t off = 0;
     char *b = (char *)base;
@@ -55,6 +58,12 @@ inline size_t carve(void *base, int U, int I, int F, int opt, Workspace *w, int 
         t.gB = (float *)take(sizeof(float) * nb);
         if (opt != DRB_OPT_SGD) t.mB = (float *)take(sizeof(float) * nb);
         if (opt == DRB_OPT_ADAM) t.vB = (float *)take(sizeof(float) * nb);
+    }
+    t.gP64 = t.gQ64 = t.accfx = nullptr;
+    if (det) {  // appended after everything else: the other layouts do not move
+        t.gP64 = (long long *)take(sizeof(long long) * (size_t)U * F);
+        t.gQ64 = (long long *)take(sizeof(long long) * (size_t)I * F);
+        t.accfx = (long long *)take(sizeof(long long) * 8);
     }
     if (w) *w = t;
     return off;
@@ -91,6 +100,9 @@ struct StepParams {
     int loss;              // DRB_LOSS_BPR / _HL / _TL (pair-wise criterion, AbstractRecommender.py:79-93)
     // FM (FMRecommender.py:61-68): pred += (u_bias[u] + i_bias[item]) + bias_; bias = packed [U + I + 1]; nullptr = MF
     float *bias = nullptr;
+    // deterministic accumulation: run-to-run bitwise reproducible steps (fixed-point int64 atomics, see Workspace); single GPU,
+    // fused persistent launch only
+    int det = 0;
     // multi-GPU persistent mode: step s trains local triples [step_offsets[s], step_offsets[s+1]) (device array; the union
     // of the ranks' ranges is the global batch s).  nullptr = uniform batches of `batch` triples.
     const long long *step_offsets = nullptr;
@@ -99,7 +111,7 @@ struct StepParams {
 
 int fill_params(StepParams &p, float *P, float *Q, void *d_ws, int U, int I, int F, const int32_t *bu, const int32_t *bi,
                 const int32_t *bj, long long n, long long batch, long long first, long long nsteps, const drb_hyper *h,
-                long long adam_step0, double *d_step_loss, int apply, float *d_bias = nullptr);
+                long long adam_step0, double *d_step_loss, int apply, float *d_bias = nullptr, int det = 0);
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status = false);
 int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step);
 

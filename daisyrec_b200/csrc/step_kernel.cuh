@@ -199,6 +199,13 @@ __device__ __forceinline__ int draw_negative(const StepParams &p, int u, unsigne
     return item < p.I ? item : p.I - 1;   // only reachable for a user who interacted with every item (rejected by the host)
 }
 
+// deterministic mode: contribution -> 2^40 fixed point (|sum| < 8.3e6, resolution 9e-13), scalars -> 2^24
+constexpr double kDetScale = 1099511627776.0, kDetAccScale = 16777216.0;
+__device__ __forceinline__ void det_red(long long *p, float v)
+{
+    red_add_u64(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__double2ll_rn((double)v * kDetScale));
+}
+
 // Exchange policy of the single-GPU kernel: nothing to exchange (every hook is a compile-time no-op).
 struct NoExchange {
     static constexpr bool kActive = false;
@@ -425,9 +432,18 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
                                     gj.v[e] = cn[r] * rp[r].c[ch].v[e];
                                 }
                             }
-                            red_row<VEC>(p.ws.gP + (size_t)iu[r] * F + cc * VEC, gu);
-                            red_row<VEC>(p.ws.gQ + (size_t)ii[r] * F + cc * VEC, gi);
-                            if (!pw) red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
+                            if (GEN && p.det) {
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) {
+                                    det_red(p.ws.gP64 + (size_t)iu[r] * F + cc * VEC + e, gu.v[e]);
+                                    det_red(p.ws.gQ64 + (size_t)ii[r] * F + cc * VEC + e, gi.v[e]);
+                                    if (!pw) det_red(p.ws.gQ64 + (size_t)ij[r] * F + cc * VEC + e, gj.v[e]);
+                                }
+                            } else {
+                                red_row<VEC>(p.ws.gP + (size_t)iu[r] * F + cc * VEC, gu);
+                                red_row<VEC>(p.ws.gQ + (size_t)ii[r] * F + cc * VEC, gi);
+                                if (!pw) red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
+                            }
                         }
                         if (gl == 0) {
                             red_add_u32(p.ws.cntU + iu[r], 1u);
@@ -465,11 +481,34 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
         if (tid < (has_reg ? 7 : 1) || (GEN && tid == 7 && p.bias != nullptr)) {
             double v = 0;
             for (int w = 0; w < kThreads / 32; ++w) v += s_red[tid][w];
-            if (v != 0.0) atomicAdd(&acc[tid], v);
+            if (GEN && p.det) {
+                if (v != 0.0) red_add_u64(reinterpret_cast<unsigned long long *>(p.ws.accfx + tid),
+                                          (unsigned long long)__double2ll_rn(v * kDetAccScale));
+            } else if (v != 0.0) {
+                atomicAdd(&acc[tid], v);
+            }
         }
         }  // phase 1
         if (p.phases == 3) grid_barrier(&hdr->barrier, epoch);
         if (!(p.phases & 2)) break;   // split mode: the host reduces gQ / counters / acc across ranks now
+        if (GEN && p.det) {
+            // fixed-point sums -> the fp32 accumulators phase 2 reads (one rounding per element, whatever order the atomics took)
+            const long long gsz = (long long)gridDim.x * kThreads, gt = (long long)blockIdx.x * kThreads + tid;
+            const long long nP = (long long)p.U * F, nQ = (long long)p.I * F;
+            for (long long k = gt; k < nP + nQ; k += gsz) {
+                long long *src = k < nP ? p.ws.gP64 + k : p.ws.gQ64 + (k - nP);
+                const long long v = __ldcg(src);
+                if (v != 0) {
+                    __stcg((k < nP ? p.ws.gP + k : p.ws.gQ + (k - nP)), (float)((double)v / kDetScale));
+                    __stcg(src, 0ll);
+                }
+            }
+            if (gt < 8) {
+                acc[gt] = (double)__ldcg(p.ws.accfx + gt) / kDetAccScale;
+                __stcg(p.ws.accfx + gt, 0ll);
+            }
+            grid_barrier(&hdr->barrier, epoch);
+        }
         if constexpr (XCH::kActive) {
             // rendezvous with the other ranks; acc[0..7] become the GLOBAL sums (identical on every rank)
             if (!xch.after_phase1(p, s, acc, epoch)) break;

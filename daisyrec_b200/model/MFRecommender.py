@@ -59,6 +59,10 @@ class MF(GeneralRecommender):
         self._ws = None
         self._opt_steps = 0
         self._stage = None
+        # optional B200 key: True = every cross-thread sum of a step in fixed point (bitwise reproducible runs); single GPU
+        self.deterministic = bool(config.get('deterministic', False))
+        if self.deterministic and (self.world > 1 or str(config.get('neg_sampling', 'table')) == 'fused'):
+            raise NotImplementedError("deterministic=True covers single-GPU training on the sampler's triples")
         # optional B200 key (torchrun only): 'p2p' = one persistent launch per epoch with the exchange inside the kernel over
         # peer-mapped memory; 'nccl' = phase 1 -> grouped NCCL all-reduce -> phase 2 per step (also the automatic fallback)
         self.sharded_comm = str(config.get('sharded_comm', 'p2p'))
@@ -152,7 +156,7 @@ class MF(GeneralRecommender):
                 self.embed_item = _Table(self._trainer.Q)
             self._trainer = None                                   # fresh optimiser state per fit()
             return
-        self._ws = ops.MFWorkspace(self.user_num, self.item_num, self.factors, opt, self.device)
+        self._ws = ops.MFWorkspace(self.user_num, self.item_num, self.factors, opt, self.device, deterministic=self.deterministic)
 
     def _ensure_ws(self):
         if self._ws is None:

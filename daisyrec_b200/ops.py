@@ -287,15 +287,20 @@ class MFWorkspace:
     """Device scratch of the step kernel: gradient accumulators, row counters, optimiser state (Adam m, v; Adagrad /
     RMSprop one table)."""
 
-    def __init__(self, user_num, item_num, factors, opt, device):
+    def __init__(self, user_num, item_num, factors, opt, device, deterministic=False):
         self.U, self.I, self.F = user_num, item_num, factors
         self.opt = L.OPT_KIND[opt]
-        nbytes = L.lib().drb_mf_workspace_bytes(user_num, item_num, factors, self.opt)
+        self.det = bool(deterministic)
+        nbytes = (L.lib().drb_mf_workspace_bytes_det if self.det else L.lib().drb_mf_workspace_bytes)(user_num, item_num, factors,
+                                                                                                     self.opt)
         self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         self.reset()
 
     def reset(self):
-        L.check(L.lib().drb_mf_workspace_init(_ptr(self.buf), self.U, self.I, self.F, self.opt, _stream()))
+        if self.det:
+            self.buf.zero_()               # the int64 images behind the regular layout as well
+        else:
+            L.check(L.lib().drb_mf_workspace_init(_ptr(self.buf), self.U, self.I, self.F, self.opt, _stream()))
 
 
 def mf_bpr_train_steps(P, Q, ws, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, check=True, out=None):
@@ -305,9 +310,9 @@ def mf_bpr_train_steps(P, Q, ws, bu, bi, bj, batch, first_step, n_steps, hp, ada
     n = bu.numel()
     losses = out if out is not None else torch.empty(max(n_steps, 1), dtype=torch.float64, device=P.device)
     nan_step = C.c_int64(-1)
-    rc = L.lib().drb_mf_bpr_train_steps(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, _ptr(bu), _ptr(bi), _ptr(bj),
-                                        n, batch, first_step, n_steps, C.byref(hp), adam_step0, _ptr(losses),
-                                        1 if check else 0, C.byref(nan_step), _stream())
+    fn = L.lib().drb_mf_bpr_train_steps_det if getattr(ws, "det", False) else L.lib().drb_mf_bpr_train_steps
+    rc = fn(_ptr(P), _ptr(Q), _ptr(ws.buf), ws.U, ws.I, ws.F, _ptr(bu), _ptr(bi), _ptr(bj), n, batch, first_step, n_steps,
+            C.byref(hp), adam_step0, _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
     if rc == L.DRB_ERR_NAN_LOSS:
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
     L.check(rc)

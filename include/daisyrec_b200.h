@@ -187,6 +187,17 @@ size_t drb_randperm_workspace_bytes(int64_t n);
 int drb_mt19937_stream(uint64_t seed, int64_t n, uint32_t *d_out, void *stream);
 int drb_randperm_torch(uint64_t seed, int64_t n, int64_t *d_perm, void *d_ws, void *stream);
 
+/* Deterministic accumulation (opt-in, SURVEY 7 hard part 3): drb_mf_bpr_train_steps with every cross-thread sum (gradient
+ * rows, loss, norms) accumulated as fixed-point int64 -- integer addition is associative, so tables and losses are bitwise
+ * identical from run to run and independent of the order in which the atomics land.  4 scalar atomics instead of one
+ * RED.128 per row chunk and one extra grid barrier per step: a reproducibility / parity mode, not the throughput path.
+ * The workspace (drb_mf_workspace_bytes_det, initialised with drb_mf_workspace_init on that size) appends the int64 images. */
+size_t drb_mf_workspace_bytes_det(int32_t user_num, int32_t item_num, int32_t factors, int32_t opt);
+int drb_mf_bpr_train_steps_det(float *d_P, float *d_Q, void *d_ws, int32_t user_num, int32_t item_num, int32_t factors,
+                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
+                               int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                               double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
+
 /* ---- FM (daisy/model/FMRecommender.py:16-131) -----------------------------
  * FM.forward :61-68 = MF's factor product + (u_bias[u] + i_bias[i]) + bias_ (the three first-order terms are summed first,
  * fp32); FM.calc_loss :70-97 regularises the factor rows only, exactly as MF does; backward + optimizer.step as for MF,

@@ -56,8 +56,27 @@ def test_ml100k_driver_sequence():
     test_loader = get_dataloader(CandidatesDataset(test_ucands), batch_size=128, shuffle=False, num_workers=0)
     preds = model.rank(test_loader)                                   # test.py:120
     assert preds.dtype == np.float32 and preds.shape == (304, 50)
-    # tables differ from the reference's by fp32 noise -> compare ranking quality, not ids
-    assert (preds == gr["preds"]).mean() > 0.98
+    # After GPU training the tables differ from the reference's by fp32 re-association noise (the reference's own autograd
+    # sums in ANOTHER fp32 order than any other implementation), so a list can differ from the reference's exactly where two
+    # candidates are tied to within that noise.  Checked position by position: wherever the ids differ, the REFERENCE's own
+    # scores (its trained tables gf[P1], gf[Q1], fp64 dot) of the two candidates are closer than the score perturbation the
+    # observed table difference can cause -- i.e. every mismatch is a near-tie, there is no mis-ranking.
+    ref = gr["preds"]
+    assert (preds == ref).mean() > 0.98
+    Pr, Qr = gf["P1"].astype(np.float64), gf["Q1"].astype(np.float64)
+    dP = np.abs(model.embed_user.weight.cpu().numpy() - gf["P1"]).max()
+    dQ = np.abs(model.embed_item.weight.cpu().numpy() - gf["Q1"]).max()
+    noise = 2.0 * cfg['factors'] * (dP * np.abs(Qr).max() + dQ * np.abs(Pr).max()) + 1e-7
+    rows, cols = np.nonzero(preds != ref)
+    users_arr = np.asarray(test_u)
+    for r, k in zip(rows, cols):
+        u = users_arr[r]
+        gap = abs(Pr[u] @ Qr[int(preds[r, k])] - Pr[u] @ Qr[int(ref[r, k])])
+        # the candidate we placed at k is within noise of the reference's k-th candidate, or the lists are shifted by one
+        # around a near-tie: compare against the neighbouring reference positions too
+        near = min(abs(Pr[u] @ Qr[int(preds[r, k])] - Pr[u] @ Qr[int(ref[r, kk])])
+                   for kk in range(max(0, k - 1), min(ref.shape[1], k + 2)))
+        assert min(gap, near) <= noise, (int(r), int(k), float(gap), float(near), float(noise))
     # with the reference's own trained tables the ids are bit-identical
     model.load_state_dict({'embed_user.weight': torch.from_numpy(gf["P1"]).cuda(),
                            'embed_item.weight': torch.from_numpy(gf["Q1"]).cuda()})
@@ -121,3 +140,32 @@ def test_edge_cases_small_inputs():
     model.fit(get_dataloader(BasicDataset(tri), batch_size=256, shuffle=True))          # 24 triples < one batch
     assert np.isfinite(model.embed_user.weight.cpu().numpy()).all()
     assert model.rank(get_dataloader(CandidatesDataset([]), batch_size=128, shuffle=False)).shape[0] == 0
+
+
+def test_deterministic_mode_is_bitwise_reproducible(orc):
+    """deterministic=True: every cross-thread sum of a step is taken in fixed point (integer atomics are associative), so two
+    fits from the same state give bitwise identical tables and epoch losses; the default mode (float RED in arrival order)
+    agrees with it to fp32 noise; and because the oracle accumulates the same sums in fp64, GPU == oracle almost everywhere."""
+    from daisyrec_b200.model.MFRecommender import MF
+    from daisyrec_b200.utils.dataset import BasicDataset, get_dataloader
+    rng = np.random.default_rng(12)
+    U, I, T, B = 400, 300, 40_000, 512
+    users = np.minimum(U - 1, rng.zipf(1.3, size=T) - 1)                 # hot rows: many contributions per row and step
+    data = np.stack([users, rng.integers(I, size=T), rng.integers(I, size=T)], 1).astype(np.int32)
+    runs = []
+    for det in (True, True, False):
+        cfg = _config(user_num=U, item_num=I, factors=64, epochs=2, batch_size=B, deterministic=det)
+        torch.manual_seed(7)
+        m = MF(cfg)
+        P0, Q0 = m.embed_user.weight.cpu().numpy().copy(), m.embed_item.weight.cpu().numpy().copy()
+        m.fit(get_dataloader(BasicDataset(data), batch_size=B, shuffle=False))
+        runs.append((m.embed_user.weight.cpu().numpy(), m.embed_item.weight.cpu().numpy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])       # bitwise
+    for a, b in zip(runs[0], runs[2]):
+        d = np.abs(a - b)
+        assert (d > 5e-6).mean() < 2e-3 and d.max() < 1e-3
+    Po, Qo = P0.copy(), Q0.copy()
+    for _ in range(2):
+        orc.mf_bpr_epoch(Po, Qo, np.ascontiguousarray(data), None, B, orc.hyper(0.01, 0.001, 0.001))
+    for got, want in ((runs[0][0], Po), (runs[0][1], Qo)):
+        assert (got == want).mean() > 0.9 and np.abs(got - want).max() < 1e-4, float((got == want).mean())
