@@ -881,7 +881,7 @@ def main():
     ap.add_argument("--e2e-reps", dest="e2e_reps", type=int, default=3)
     ap.add_argument("--configs", default="all", help="all | none | comma list of c3_neumf,c4_lightgcn,c5_netflix_1gpu,inference,sampling")
     ap.add_argument("--c5", default="auto", choices=["auto", "on", "off"], help="N > 1: also run config 5 (netflix F=128)")
-    ap.add_argument("--comm", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--comm", default="p2p", choices=["nccl", "p2p"], help="N > 1: in-kernel peer exchange (default) or the NCCL step")
     ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=45.0)
     ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=330.0)
     ap.add_argument("--ref-workers", dest="ref_workers", type=int, default=4, help="DataLoader workers of the reference (test.py:94)")
