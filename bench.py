@@ -465,7 +465,20 @@ def cfg_inference(args, dev, d, P, Q):
     alg_r = n * (C * (4 * F + 8) + 4 * F + 4 * K)
     ms_f = timed_ms(lambda: ops.mf_full_rank(P, Q, users, K), 1, 5)
     alg_f = n * (I * 4 * F + 4 * F + 8 * K)
-    return {"rank": {"users": n, "cand_num": C, "topk": K, "ms": ms_r, "users_per_s": n / ms_r * 1e3,
+    preds = ops.mf_rank(P, Q, users, cands, K)
+    lens = torch.randint(1, 21, (n,), device=dev, generator=g)
+    ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(lens, 0)
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), lens)
+    key, _ = torch.sort(rows * I + torch.randint(0, I, (rows.numel(),), device=dev, generator=g))
+    gt_idx = (key % I).to(torch.int32).contiguous()
+    ks = [1, 5, 10, 20, 30, 50]
+    ms_k = timed_ms(lambda: ops.rank_metrics(preds, ptr, gt_idx, ks, I), 2, 10)
+    alg_k = n * K * 4 + rows.numel() * 4 + (n + 1) * 8
+    return {"kpis": {"users": n, "topk": K, "ks": ks, "ms": ms_k, "users_per_s": n / ms_k * 1e3,
+                     "roofline": roof(alg_k / ms_k / 1e6, "kpi_kernel (+ coverage / finish)", alg_k,
+                                      "preds + ground-truth CSR read once; launch-latency-sized at 4 096 users")},
+            "rank": {"users": n, "cand_num": C, "topk": K, "ms": ms_r, "users_per_s": n / ms_r * 1e3,
                      "roofline": roof(alg_r / ms_r / 1e6, "rank_kernel", alg_r, "per user: cand_num x (row + id) + own row + out")},
             "full_rank_users": {"users": n, "item_num": I, "topk": K, "ms": ms_f, "users_per_s": n / ms_f * 1e3,
                                 "roofline": roof(alg_f / ms_f / 1e6, "rank_kernel (chunked merge)", alg_f,

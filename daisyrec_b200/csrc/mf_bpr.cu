@@ -30,6 +30,7 @@
 // only P_u and Q_i take part) at run time; `phases` splits it into phase-1 / phase-2 launches (multi-GPU exchange,
 // LightGCN, NeuMF); `neg_row_ptr` switches on the fused sampler (a fresh negative per triple drawn inside phase 1).
 #include <math.h>
+#include <stdlib.h>
 
 #include "step_kernel.cuh"
 
@@ -62,6 +63,23 @@ static StepKernel pick_kernel_v(int W, int NCH)
     return nullptr;
 }
 
+// the lean MF instantiation exists for the vectorised single-chunk geometries (F = 4 .. 128 in multiples of 4)
+static StepKernel pick_lean(int F)
+{
+    if (F <= 0) return nullptr;
+    RowGeom g = row_geom(F);
+    if (g.vec != 4 || g.nch != 1) return nullptr;
+    switch (g.width) {
+    case 1: return mf_bpr_steps_lean_kernel<4, 1, 1>;
+    case 2: return mf_bpr_steps_lean_kernel<4, 2, 1>;
+    case 4: return mf_bpr_steps_lean_kernel<4, 4, 1>;
+    case 8: return mf_bpr_steps_lean_kernel<4, 8, 1>;
+    case 16: return mf_bpr_steps_lean_kernel<4, 16, 1>;
+    case 32: return mf_bpr_steps_lean_kernel<4, 32, 1>;
+    }
+    return nullptr;
+}
+
 // GEN = false: BPR only (the hot instantiation, no loss-kind branches); GEN = true: HL / TL selected at run time
 static StepKernel pick_kernel(int F, bool gen)
 {
@@ -80,7 +98,10 @@ static StepKernel pick_kernel(int F, bool gen)
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
     // GEN instantiation: any loss but BPR, and the Adagrad / RMSprop sweeps (kept out of the hot BPR + SGD/Adam kernel)
-    StepKernel k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
+    StepKernel k = nullptr;
+    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;   // developer switch: A/B the two instantiations
+    if (!no_lean && step_params_lean(p)) k = pick_lean(p.F);
+    if (k == nullptr) k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
     DRB_REQUIRE(!p.det || (p.phases == 3 && p.ws.gP64 != nullptr), "deterministic accumulation: single-GPU fused steps with a "
                 "workspace from drb_mf_workspace_bytes_det");
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);

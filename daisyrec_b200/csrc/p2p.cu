@@ -16,6 +16,7 @@
 //   rendezvous B  "my slice has landed everywhere" flags; meanwhile the local user rows are swept and X[b^1] is cleared
 //   next step.
 // Two cross-GPU rendezvous per step, no NCCL, no relaunch, no host round trip.
+#include <stdlib.h>
 #include <string.h>
 
 #include "step_kernel.cuh"
@@ -291,28 +292,35 @@ struct P2PExchange {
     }
 };
 
-template <int VEC, int W, int NCH>
+template <int VEC, int W, int NCH, bool LEAN>
 __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_p2p_steps_kernel(StepParams p, P2PParams xp)
 {
     P2PExchange x;
     x.x = xp;
     x.b = 0;
-    bpr_steps_body<VEC, W, NCH, false, P2PExchange>(p, x);
+    bpr_steps_body<VEC, W, NCH, false, P2PExchange, LEAN>(p, x);
 }
 
 typedef void (*P2PKernel)(StepParams, P2PParams);
 
-static P2PKernel pick_p2p(int F)
+template <bool LEAN>
+static P2PKernel pick_p2p_v(int width)
+{
+    switch (width) {
+        case 4: return mf_bpr_p2p_steps_kernel<4, 4, 1, LEAN>;
+        case 8: return mf_bpr_p2p_steps_kernel<4, 8, 1, LEAN>;
+        case 16: return mf_bpr_p2p_steps_kernel<4, 16, 1, LEAN>;
+        case 32: return mf_bpr_p2p_steps_kernel<4, 32, 1, LEAN>;
+        default: return nullptr;
+    }
+}
+
+// lean = 32-bit row offsets (step_params_lean); the exchange policy is the same in both
+static P2PKernel pick_p2p(int F, bool lean = false)
 {
     RowGeom g = row_geom(F);
     if (g.vec != 4 || g.nch != 1) return nullptr;
-    switch (g.width) {
-        case 4: return mf_bpr_p2p_steps_kernel<4, 4, 1>;
-        case 8: return mf_bpr_p2p_steps_kernel<4, 8, 1>;
-        case 16: return mf_bpr_p2p_steps_kernel<4, 16, 1>;
-        case 32: return mf_bpr_p2p_steps_kernel<4, 32, 1>;
-        default: return nullptr;
-    }
+    return lean ? pick_p2p_v<true>(g.width) : pick_p2p_v<false>(g.width);
 }
 
 }  // namespace drb
@@ -380,8 +388,7 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
                 "train_steps_p2p: bad arguments");
     DRB_REQUIRE(hyper->opt == DRB_OPT_SGD || hyper->opt == DRB_OPT_ADAM, "train_steps_p2p: SGD and Adam only");
     DRB_REQUIRE(hyper->loss == DRB_LOSS_BPR, "train_steps_p2p: BPR only (the other pair-wise losses use the NCCL step)");
-    P2PKernel k = pick_p2p(F);
-    DRB_REQUIRE(k != nullptr, "train_steps_p2p: factors=%d unsupported (multiple of 4, at most 128)", F);
+    DRB_REQUIRE(pick_p2p(F) != nullptr, "train_steps_p2p: factors=%d unsupported (multiple of 4, at most 128)", F);
     if (n_steps == 0) return DRB_OK;
     const P2PLayout L = p2p_layout(I, F);
     char *self = (char *)h_peer_bufs[rank];
@@ -394,6 +401,8 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     p.n = n_local;
     p.step_offsets = (const long long *)d_step_offsets;
     p.dense_hint = 1;
+    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;
+    P2PKernel k = pick_p2p(F, !no_lean && step_params_lean(p));
     P2PParams x;
     for (int q = 0; q < kMaxPeers; ++q) x.peer[q] = q < world ? (char *)h_peer_bufs[q] : nullptr;
     x.rank = rank;

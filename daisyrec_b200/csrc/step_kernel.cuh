@@ -199,6 +199,9 @@ __device__ __forceinline__ int draw_negative(const StepParams &p, int u, unsigne
     return item < p.I ? item : p.I - 1;   // only reachable for a user who interacted with every item (rejected by the host)
 }
 
+template <bool LEAN> struct RowOffset { typedef size_t type; };
+template <> struct RowOffset<true> { typedef unsigned type; };
+
 // deterministic mode: contribution -> 2^40 fixed point (|sum| < 8.3e6, resolution 9e-13), scalars -> 2^24
 constexpr double kDetScale = 1099511627776.0, kDetAccScale = 16777216.0;
 __device__ __forceinline__ void det_red(long long *p, float v)
@@ -217,9 +220,14 @@ struct NoExchange {
     __device__ __forceinline__ bool end_step(const StepParams &, long long, unsigned long long &) { return true; }
 };
 
-template <int VEC, int W, int NCH, bool GEN, class XCH>
+// LEAN: the MF hot instantiation (launch_steps picks it when the parameters allow): BPR, no ego / norm tables (LightGCN),
+// no in-kernel negative draw, and 32-bit element offsets into the tables (rows * F < 2^32) -- the same arithmetic on the same
+// operands in the same order as the general body, with ~1/3 fewer instructions per triple.
+template <int VEC, int W, int NCH, bool GEN, class XCH, bool LEAN = false>
 __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
 {
+    static_assert(!(GEN && LEAN), "the lean body is BPR only");
+    using RowOff = typename RowOffset<LEAN>::type;
     constexpr int GPW = 32 / W;                  // lane groups per warp
     constexpr int GROUPS = (kThreads / 32) * GPW;  // lane groups per CTA
     constexpr int UNR = (NCH * VEC <= 4) ? DRB_UNR : 1;  // triples in flight per group
@@ -297,6 +305,7 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
             for (int tb = 0; tb < cnt; tb += GROUPS * UNR) {
                 Row<VEC, W, NCH> rp[UNR], rqi[UNR], rqj[UNR];
                 int iu[UNR], ii[UNR], ij[UNR];
+                RowOff ou[UNR], oi[UNR], oj[UNR];   // element offsets of the three rows (tables and accumulators alike)
                 float lab[UNR];
                 bool ok[UNR];
 #pragma unroll
@@ -311,14 +320,17 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
                         lab[r] = (float)ij[r];
                         ij[r] = 0;
                     }
-                    if (p.neg_row_ptr != nullptr && ok[r]) {
+                    if (!LEAN && p.neg_row_ptr != nullptr && ok[r]) {
                         const long long gt = base + t_i * tile + t;            // position of the triple in the planes
                         ij[r] = draw_negative(p, iu[r], (unsigned long long)gt, (unsigned long long)step);
                         if (p.neg_out != nullptr && gl == 0) p.neg_out[gt] = ij[r];
                     }
-                    rp[r] = load_row<VEC, W, NCH>(p.P + (size_t)iu[r] * F, gl, chunks, ok[r]);
-                    rqi[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ii[r] * F, gl, chunks, ok[r]);
-                    rqj[r] = load_row<VEC, W, NCH>(p.Q + (size_t)ij[r] * F, gl, chunks, ok[r] && !pw);
+                    ou[r] = (RowOff)iu[r] * (RowOff)F;
+                    oi[r] = (RowOff)ii[r] * (RowOff)F;
+                    oj[r] = (RowOff)ij[r] * (RowOff)F;
+                    rp[r] = load_row<VEC, W, NCH>(p.P + ou[r], gl, chunks, ok[r]);
+                    rqi[r] = load_row<VEC, W, NCH>(p.Q + oi[r], gl, chunks, ok[r]);
+                    rqj[r] = load_row<VEC, W, NCH>(p.Q + oj[r], gl, chunks, ok[r] && !pw);
                 }
                 // scores of the UNR triples of this group (every lane of the group ends up with the same values)
                 float ps[UNR], ns[UNR], cs[UNR], cn[UNR];
@@ -397,10 +409,10 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
                     if (has_reg) {
                         float l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
                         Row<VEC, W, NCH> nu_ = rp[r], ni_ = rqi[r], nj_ = rqj[r];
-                        if (p.Pn != nullptr) {   // regulariser on the ego rows (LightGCNRecommender.py:145-146,159)
-                            nu_ = load_row<VEC, W, NCH>(p.Pn + (size_t)iu[r] * F, gl, chunks, true);
-                            ni_ = load_row<VEC, W, NCH>(p.Qn + (size_t)ii[r] * F, gl, chunks, true);
-                            nj_ = load_row<VEC, W, NCH>(p.Qn + (size_t)ij[r] * F, gl, chunks, true);
+                        if (!LEAN && p.Pn != nullptr) {   // regulariser on the ego rows (LightGCNRecommender.py:145-146,159)
+                            nu_ = load_row<VEC, W, NCH>(p.Pn + ou[r], gl, chunks, true);
+                            ni_ = load_row<VEC, W, NCH>(p.Qn + oi[r], gl, chunks, true);
+                            nj_ = load_row<VEC, W, NCH>(p.Qn + oj[r], gl, chunks, true);
                         }
 #pragma unroll
                         for (int ch = 0; ch < NCH; ++ch)
@@ -435,14 +447,14 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
                             if (GEN && p.det) {
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) {
-                                    det_red(p.ws.gP64 + (size_t)iu[r] * F + cc * VEC + e, gu.v[e]);
-                                    det_red(p.ws.gQ64 + (size_t)ii[r] * F + cc * VEC + e, gi.v[e]);
-                                    if (!pw) det_red(p.ws.gQ64 + (size_t)ij[r] * F + cc * VEC + e, gj.v[e]);
+                                    det_red(p.ws.gP64 + ou[r] + cc * VEC + e, gu.v[e]);
+                                    det_red(p.ws.gQ64 + oi[r] + cc * VEC + e, gi.v[e]);
+                                    if (!pw) det_red(p.ws.gQ64 + oj[r] + cc * VEC + e, gj.v[e]);
                                 }
                             } else {
-                                red_row<VEC>(p.ws.gP + (size_t)iu[r] * F + cc * VEC, gu);
-                                red_row<VEC>(p.ws.gQ + (size_t)ii[r] * F + cc * VEC, gi);
-                                if (!pw) red_row<VEC>(p.ws.gQ + (size_t)ij[r] * F + cc * VEC, gj);
+                                red_row<VEC>(p.ws.gP + ou[r] + cc * VEC, gu);
+                                red_row<VEC>(p.ws.gQ + oi[r] + cc * VEC, gi);
+                                if (!pw) red_row<VEC>(p.ws.gQ + oj[r] + cc * VEC, gj);
                             }
                         }
                         if (gl == 0) {
@@ -660,6 +672,21 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_kernel(StepPa
 {
     NoExchange x;
     bpr_steps_body<VEC, W, NCH, GEN, NoExchange>(p, x);
+}
+
+template <int VEC, int W, int NCH>
+__global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_steps_lean_kernel(StepParams p)
+{
+    NoExchange x;
+    bpr_steps_body<VEC, W, NCH, false, NoExchange, true>(p, x);
+}
+
+// the conditions under which the lean body computes what the general one does
+inline bool step_params_lean(const StepParams &p)
+{
+    return p.loss == DRB_LOSS_BPR && p.opt <= DRB_OPT_ADAM && p.bias == nullptr && p.det == 0 && p.Pn == nullptr &&
+           p.Qn == nullptr && p.neg_row_ptr == nullptr && (unsigned long long)p.U * (unsigned)p.F < (1ull << 32) &&
+           (unsigned long long)p.I * (unsigned)p.F < (1ull << 32);
 }
 
 
