@@ -768,13 +768,14 @@ def run_sharded(args, rank, local, world, dev):
         bounds = partition_users(deg, world)
         g = torch.Generator(device=dev); g.manual_seed(args.seed)
         perm = torch.randperm(T, generator=g, device=dev)
-        parity = sharded_parity_check(d, triples, perm, bounds, rank, world, dev, F, args.seed, args.comm)
         P0, Q0 = init_tables(U, I, F, args.seed, dev)
         lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.contiguous(), bounds, rank, world, ops.hyper(**HYPER), comm=args.comm)
+        progress["stage"] = f"{shape}: trainer setup ({comm})"
+        tr = ShardedTrainer(P0[lo:hi].contiguous(), Q0.contiguous(), bounds, rank, world, ops.hyper(**HYPER), comm=comm)
         del P0
         spe = tr.prepare_epoch(triples, perm, Bg)
-        del perm, triples
+        par_sl = perm[:16384 * 3].clone()
+        del perm
         torch.cuda.empty_cache()
         local_counts = np.diff(tr.offsets_host)
         scratch_losses = torch.empty(spe + 1, dtype=torch.float64, device=dev)
@@ -790,8 +791,10 @@ def run_sharded(args, rank, local, world, dev):
                 k -= seg
             return n_loc
 
+        progress["stage"] = f"{shape}: warm-up steps ({comm})"
         run(0, warmup)
         torch.cuda.synchronize(); dist.barrier()
+        progress["stage"] = f"{shape}: timed steps ({comm})"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
@@ -805,8 +808,13 @@ def run_sharded(args, rank, local, world, dev):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         tr.check_nan()
         res = {"d": d, "T": T, "spe": spe, "ms": float(ms.item()), "value": float(tot.item()) / float(ms.item()) * 1e3,
-               "t0": t0, "t1": t1, "parity": parity, "cfg": workload_config(a, world)}
+               "t0": t0, "t1": t1, "parity": None, "cfg": workload_config(a, world), "steps": steps}
+        progress[shape] = res                                    # the watchdog can print from here on
+        progress["stage"] = f"{shape}: parity check ({comm})"
+        res["parity"] = sharded_parity_check(d, triples, par_sl, bounds, rank, world, dev, F, args.seed, comm)
+        del triples
         if with_e2e:
+            progress["stage"] = f"{shape}: e2e host-fed steps ({comm})"
             # e2e: pinned host share of every global batch of one epoch segment -> native loop (H2D per step, loss D2H per step)
             ke = min(spe - 1, 64)
             offs = tr.offsets_host[:ke + 1].copy()
@@ -841,26 +849,35 @@ def run_sharded(args, rank, local, world, dev):
         torch.cuda.empty_cache()
         return res
 
+    comm = args.comm if args.comm != "auto" else ("p2p" if world == 2 else "nccl")
+    progress = {"stage": "start"}
     clocks = ClockSampler(local) if rank == 0 else None
-    main = shape_run(args.shape, args.factors, args.steps, args.warmup, True)
-    c5 = None
-    if args.c5 == "on" or (args.c5 == "auto" and world >= 8):
-        c5 = shape_run("netflix", 128, max(100, args.steps), max(10, args.warmup), False)
-    if rank == 0:
+    printed = threading.Event()
+
+    def emit(main, c5, incomplete=None):
+        """rank 0: the driver's JSON line from whatever has been measured."""
+        if printed.is_set():
+            return
+        printed.set()
+        if main is None:
+            print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "higher_is_better": True, "comm": comm,
+                              "incomplete": incomplete}), flush=True)
+            return
         clk = clocks.stop(main["t0"], main["t1"])
         peak, peak_src = measured_peaks()
         F = args.factors
         bpt = 24 * F + 12
         achieved = main["value"] / world * bpt / 1e9                      # per-GPU algorithmic GB/s of the step
         exchange = ("ONE grouped NCCL all-reduce of gQ/counters/norms enqueued by the library between the phase-1 and "
-                    "phase-2 kernels" if args.comm == "nccl" else
+                    "phase-2 kernels" if comm == "nccl" else
                     "in-kernel peer exchange over NVLink (no NCCL, no relaunch per step)")
         line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": main["cfg"],
-                "steps_per_epoch": main["spe"], "exchange": exchange, "comm": args.comm,
-                "clocks": clk, "e2e": main["e2e"], "parity_check": main["parity"],
-                "gpu_launches": 2 * args.steps if args.comm == "nccl" else 1,
+                "steps_per_epoch": main["spe"], "exchange": exchange, "comm": comm,
+                "clocks": clk, "e2e": main.get("e2e"), "parity_check": main["parity"],
+                "gpu_launches": 2 * args.steps if comm == "nccl" else 1,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_triple": bpt,
                              "kernel": "mf_bpr_steps_kernel (per GPU)"}}
@@ -868,13 +885,34 @@ def run_sharded(args, rank, local, world, dev):
             b5 = 24 * 128 + 12
             a5 = c5["value"] / world * b5 / 1e9
             line["configs"] = {"c5": {"workload": c5["cfg"]["workload"], "value": c5["value"], "unit": UNIT, "n_gpus": world,
-                                      "ms_per_step": c5["ms"] / max(100, args.steps), "steps": max(100, args.steps),
+                                      "ms_per_step": c5["ms"] / c5["steps"], "steps": c5["steps"],
                                       "per_gpu_batch": args.batch, "parity_check": c5["parity"],
                                       "roofline": roof(a5, "mf_bpr_steps_kernel (per GPU)", b5)}}
-        ok = main["parity"]["ok"] and (c5 is None or c5["parity"]["ok"])
+        if incomplete:
+            line["incomplete"] = incomplete
         print(json.dumps(line), flush=True)
-    else:
-        ok = main["parity"]["ok"] and (c5 is None or c5["parity"]["ok"])
+
+    def watchdog():
+        # a stage that never returns (a collective or a mapping call that blocks) must not cost the line: after --watchdog
+        # seconds rank 0 prints what has been measured and every rank leaves without waiting for the others
+        if printed.wait(args.watchdog):
+            return
+        why = f"watchdog after {args.watchdog:.0f} s in stage '{progress.get('stage')}'"
+        if rank == 0:
+            emit(progress.get(args.shape), progress.get("netflix") if progress.get(args.shape) else None, why)
+        sys.stderr.write(f"[bench rank {rank}] {why}\n")
+        sys.stderr.flush()
+        os._exit(0 if progress.get(args.shape) else 4)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    main = shape_run(args.shape, args.factors, args.steps, args.warmup, True)
+    c5 = None
+    if args.c5 == "on" or (args.c5 == "auto" and world >= 8):
+        c5 = shape_run("netflix", 128, max(100, args.steps), max(10, args.warmup), False)
+    ok = main["parity"]["ok"] and (c5 is None or c5["parity"]["ok"])
+    if rank == 0:
+        emit(main, c5)
+    printed.set()
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 3
@@ -894,7 +932,10 @@ def main():
     ap.add_argument("--e2e-reps", dest="e2e_reps", type=int, default=3)
     ap.add_argument("--configs", default="all", help="all | none | comma list of c3_neumf,c4_lightgcn,c5_netflix_1gpu,inference,sampling")
     ap.add_argument("--c5", default="auto", choices=["auto", "on", "off"], help="N > 1: also run config 5 (netflix F=128)")
-    ap.add_argument("--comm", default="p2p", choices=["nccl", "p2p"], help="N > 1: in-kernel peer exchange (default) or the NCCL step")
+    ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="N > 1: auto = in-kernel peer exchange on 2 GPUs (validated), the NCCL step beyond; or force one")
+    ap.add_argument("--watchdog", type=float, default=600.0,
+                    help="N > 1: seconds after which rank 0 prints the line with what has been measured and every rank exits")
     ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=45.0)
     ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=330.0)
     ap.add_argument("--ref-workers", dest="ref_workers", type=int, default=4, help="DataLoader workers of the reference (test.py:94)")

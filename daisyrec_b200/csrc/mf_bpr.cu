@@ -63,20 +63,46 @@ static StepKernel pick_kernel_v(int W, int NCH)
     return nullptr;
 }
 
-// the lean MF instantiation exists for the vectorised single-chunk geometries (F = 4 .. 128 in multiples of 4)
+// The lean MF instantiation.  Its lane geometry is its own: a group of W = F / 16 lanes owns a row, every lane 4 chunks of
+// 4 floats (F = 64: 4 lanes x 64 B).  The index loads, address arithmetic, loss chain and counter updates of a triple are
+// replicated across the lanes of its group, the row arithmetic is not -- so fewer lanes per row means fewer issue slots per
+// triple (8 triples per warp at F = 64 instead of 2) and more rows in flight per warp.  Only the fp32 summation order of the
+// two dot products differs from the canonical geometry (row_geom) that rank / predict / the oracle share.
+static int lean_nch()
+{
+    static const int v = [] {
+        const char *e = getenv("DRB_LEAN_NCH");   // developer switch: 1 | 2 | 4 chunks per lane
+        int n = e ? atoi(e) : 4;
+        return (n == 1 || n == 2 || n == 4) ? n : 4;
+    }();
+    return v;
+}
+void lean_geom(int F, int &W, int &NCH)
+{
+    W = NCH = 0;
+    if (F <= 0 || F % 4 != 0) return;
+    const int chunks = F / 4;
+    for (int n = lean_nch(); n >= 1; n >>= 1) {
+        if (chunks % n != 0) continue;
+        const int w = chunks / n;
+        if (w > 32 || (w & (w - 1)) != 0) continue;
+        W = w;
+        NCH = n;
+        return;
+    }
+    RowGeom g = row_geom(F);              // e.g. F = 100: 25 chunks on 32 lanes
+    if (g.vec == 4 && g.nch == 1) { W = g.width; NCH = 1; }
+}
 static StepKernel pick_lean(int F)
 {
-    if (F <= 0) return nullptr;
-    RowGeom g = row_geom(F);
-    if (g.vec != 4 || g.nch != 1) return nullptr;
-    switch (g.width) {
-    case 1: return mf_bpr_steps_lean_kernel<4, 1, 1>;
-    case 2: return mf_bpr_steps_lean_kernel<4, 2, 1>;
-    case 4: return mf_bpr_steps_lean_kernel<4, 4, 1>;
-    case 8: return mf_bpr_steps_lean_kernel<4, 8, 1>;
-    case 16: return mf_bpr_steps_lean_kernel<4, 16, 1>;
-    case 32: return mf_bpr_steps_lean_kernel<4, 32, 1>;
-    }
+    int W, NCH;
+    lean_geom(F, W, NCH);
+#define DRB_LEAN(w, n) \
+    if (W == w && NCH == n) return mf_bpr_steps_lean_kernel<4, w, n>;
+    DRB_LEAN(1, 1) DRB_LEAN(2, 1) DRB_LEAN(4, 1) DRB_LEAN(8, 1) DRB_LEAN(16, 1) DRB_LEAN(32, 1)
+    DRB_LEAN(1, 2) DRB_LEAN(2, 2) DRB_LEAN(4, 2) DRB_LEAN(8, 2) DRB_LEAN(16, 2) DRB_LEAN(32, 2)
+    DRB_LEAN(1, 4) DRB_LEAN(2, 4) DRB_LEAN(4, 4) DRB_LEAN(8, 4) DRB_LEAN(16, 4) DRB_LEAN(32, 4)
+#undef DRB_LEAN
     return nullptr;
 }
 
@@ -118,11 +144,8 @@ int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
     const int per_sm = cached_per_sm;
     DRB_REQUIRE(per_sm > 0, "step kernel does not fit on an SM");
     const int max_grid = per_sm * sm_count();
-    // tile: as large as possible (<= kTileMax) while still giving every CTA work
-    long long want = (p.batch + max_grid - 1) / max_grid;
-    int tile = (int)((want + 15) / 16 * 16);
-    if (tile < 16) tile = 16;
-    if (tile > kTileMax) tile = kTileMax;
+    // tile: equal tiles of at most kTileMax triples, every CTA the same number of them
+    const int tile = pick_tile((p.batch + max_grid - 1) / max_grid);
     p.tile = tile;
     long long tiles = (p.batch + tile - 1) / tile;
     long long rows_work = ((long long)p.U + p.I + 63) / 64;

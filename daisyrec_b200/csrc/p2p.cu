@@ -303,24 +303,30 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_p2p_steps_kernel(St
 
 typedef void (*P2PKernel)(StepParams, P2PParams);
 
-template <bool LEAN>
-static P2PKernel pick_p2p_v(int width)
-{
-    switch (width) {
-        case 4: return mf_bpr_p2p_steps_kernel<4, 4, 1, LEAN>;
-        case 8: return mf_bpr_p2p_steps_kernel<4, 8, 1, LEAN>;
-        case 16: return mf_bpr_p2p_steps_kernel<4, 16, 1, LEAN>;
-        case 32: return mf_bpr_p2p_steps_kernel<4, 32, 1, LEAN>;
-        default: return nullptr;
-    }
-}
+void lean_geom(int F, int &W, int &NCH);   // mf_bpr.cu
 
-// lean = 32-bit row offsets (step_params_lean); the exchange policy is the same in both
+// lean = the MF hot body (32-bit row offsets, its own lane geometry; step_params_lean); the exchange policy is the same
 static P2PKernel pick_p2p(int F, bool lean = false)
 {
     RowGeom g = row_geom(F);
-    if (g.vec != 4 || g.nch != 1) return nullptr;
-    return lean ? pick_p2p_v<true>(g.width) : pick_p2p_v<false>(g.width);
+    if (g.vec != 4 || g.nch != 1 || g.width < 4) return nullptr;
+    if (lean) {
+        int W, NCH;
+        lean_geom(F, W, NCH);
+#define DRB_P2P(w, n) \
+    if (W == w && NCH == n) return mf_bpr_p2p_steps_kernel<4, w, n, true>;
+        DRB_P2P(4, 1) DRB_P2P(8, 1) DRB_P2P(16, 1) DRB_P2P(32, 1)
+        DRB_P2P(2, 2) DRB_P2P(4, 2) DRB_P2P(8, 2) DRB_P2P(16, 2)
+        DRB_P2P(1, 4) DRB_P2P(2, 4) DRB_P2P(4, 4) DRB_P2P(8, 4)
+#undef DRB_P2P
+    }
+    switch (g.width) {
+        case 4: return mf_bpr_p2p_steps_kernel<4, 4, 1, false>;
+        case 8: return mf_bpr_p2p_steps_kernel<4, 8, 1, false>;
+        case 16: return mf_bpr_p2p_steps_kernel<4, 16, 1, false>;
+        case 32: return mf_bpr_p2p_steps_kernel<4, 32, 1, false>;
+        default: return nullptr;
+    }
 }
 
 }  // namespace drb
@@ -423,10 +429,7 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     }
     DRB_REQUIRE(cached_per_sm > 0, "p2p step kernel does not fit on an SM");
     const int max_grid = cached_per_sm * sm_count();
-    long long want = (batch_per_rank + max_grid - 1) / max_grid;
-    int tile = (int)((want + 15) / 16 * 16);
-    if (tile < 16) tile = 16;
-    if (tile > kTileMax) tile = kTileMax;
+    const int tile = pick_tile((batch_per_rank + max_grid - 1) / max_grid);
     p.tile = tile;
     cudaStream_t st = (cudaStream_t)stream;
     DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, sizeof(WsHeader), st));

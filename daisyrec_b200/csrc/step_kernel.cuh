@@ -5,13 +5,29 @@
 // the phase-2 sweep with a reduce-update-broadcast of this rank's item slice over NVLink.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 
 #include "step.cuh"
 
 namespace drb {
 
 constexpr int kThreads = 256;
-constexpr int kTileMax = 512;  // triples per staged index tile
+constexpr int kTileMax = 1024;  // triples per staged index tile
+
+// Tile size for `per_cta` triples per CTA and step: the fewest equal tiles of at most `cap` triples (a multiple of 16), so every
+// CTA walks the same number of full tiles (default cap 512: 3 543 per CTA -> 7 tiles of 512; DRB_TILE_CAP=1024 -> 4 tiles of 896).
+inline int pick_tile(long long per_cta)
+{
+    static const int cap = [] {
+        const char *e = getenv("DRB_TILE_CAP");   // developer switch
+        int c = e ? atoi(e) : 512;
+        return (c >= 16 && c <= kTileMax) ? c / 16 * 16 : 512;
+    }();
+    if (per_cta < 16) return 16;
+    const long long k = (per_cta + cap - 1) / cap;
+    long long tile = ((per_cta + k - 1) / k + 15) / 16 * 16;
+    return (int)(tile > cap ? cap : tile);
+}
 #ifndef DRB_MINB
 #define DRB_MINB 2             // resident CTAs per SM the register allocator must allow
 #endif

@@ -65,7 +65,7 @@ class MF(GeneralRecommender):
             raise NotImplementedError("deterministic=True covers single-GPU training on the sampler's triples")
         # optional B200 key (torchrun only): 'p2p' = one persistent launch per epoch with the exchange inside the kernel over
         # peer-mapped memory; 'nccl' = phase 1 -> grouped NCCL all-reduce -> phase 2 per step (also the automatic fallback)
-        self.sharded_comm = str(config.get('sharded_comm', 'p2p'))
+        self.sharded_comm = str(config.get('sharded_comm', 'auto'))   # auto: p2p on 2 GPUs, nccl beyond (parallel.py)
         # optional B200 key: 'table' (default; the reference's per-user-once negatives, taken from the loader's triples) |
         # 'fused' (throughput mode: a fresh negative per triple and step is drawn inside the step kernel from the
         # complement of the user's train row; the loader's third column is ignored)

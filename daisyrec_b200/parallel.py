@@ -118,6 +118,18 @@ def init_native_comm(group=None):
     _NATIVE_COMM["ready"] = True
 
 
+_HOST_GROUP = {}
+
+
+def _host_group(group=None):
+    """A gloo (host-only) group over the same ranks, for barriers that must not occupy the GPUs.  Collective on first use."""
+    key = id(group)
+    if key not in _HOST_GROUP:
+        ranks = None if group is None else dist.get_process_group_ranks(group)
+        _HOST_GROUP[key] = dist.new_group(ranks=ranks, backend="gloo")
+    return _HOST_GROUP[key]
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -131,6 +143,10 @@ class ShardedTrainer:
 
     def __init__(self, P_local, Q, bounds, rank, world, hp, opt="sgd", group=None, comm="nccl"):
         from . import ops
+        if comm == "auto":
+            # the peer-exchange kernel is the default where it has been validated on hardware (2 GPUs: parity + 0.91 weak-scaling
+            # efficiency); larger worlds take the NCCL step unless 'p2p' is asked for by name (multi-GPU section)
+            comm = "p2p" if world == 2 else "nccl"
         # comm = "nccl": the library enqueues kernels + one grouped NCCL all-reduce per step itself (no host round trip);
         # comm = "torch": per-step torch.distributed collectives (also what the gloo CPU tests of the host logic exercise)
         # comm = "p2p": ONE persistent launch per epoch segment, the exchange inside the kernel over peer-mapped memory (csrc/p2p.cu)
@@ -177,17 +193,25 @@ class ShardedTrainer:
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=Q.device)
         every = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(every, mine, group=group)                  # torch.distributed moves the 64-byte handles, nothing else
+        handles = [e.cpu().tolist() for e in every]
+        torch.cuda.synchronize()
         self._peer_ptrs = (C.c_void_p * world)()
         self._opened = []
-        for q in range(world):
-            if q == rank:
-                self._peer_ptrs[q] = own.value
-                continue
-            h = (C.c_uint8 * 64)(*every[q].cpu().tolist())
-            ptr = C.c_void_p()
-            L.check(lib.drb_p2p_open(h, C.byref(ptr)))
-            self._peer_ptrs[q] = ptr.value
-            self._opened.append(ptr.value)
+        # Mapping a peer's buffer creates / touches a context on the peer's device.  The ranks take turns, separated by a HOST
+        # barrier (gloo), with every GPU idle: no rank sits in a device-side collective while another one maps its memory.
+        hg = _host_group(group)
+        for turn in range(world):
+            if turn == rank:
+                for q in range(world):
+                    if q == rank:
+                        self._peer_ptrs[q] = own.value
+                        continue
+                    h = (C.c_uint8 * 64)(*handles[q])
+                    ptr = C.c_void_p()
+                    L.check(lib.drb_p2p_open(h, C.byref(ptr)))
+                    self._peer_ptrs[q] = ptr.value
+                    self._opened.append(ptr.value)
+            dist.barrier(group=hg)
         # the item-table replica lives inside the exchange buffer (peers store their slices straight into it)
         q_off = lib.drb_p2p_q_offset(I, F)
 
@@ -205,11 +229,15 @@ class ShardedTrainer:
         if self._xbuf is None:
             return
         torch.cuda.synchronize()
-        dist.barrier(group=self.group)
+        hg = _host_group(self.group)
+        dist.barrier(group=hg)                                     # host barriers: the GPUs stay idle while mappings change
         q_copy = self.Q.clone()
-        for ptr in self._opened:
-            L.lib().drb_p2p_close(C.c_void_p(ptr))
-        dist.barrier(group=self.group)
+        torch.cuda.synchronize()
+        for turn in range(self.world):
+            if turn == self.rank:
+                for ptr in self._opened:
+                    L.lib().drb_p2p_close(C.c_void_p(ptr))
+            dist.barrier(group=hg)
         L.lib().drb_p2p_free(C.c_void_p(self._xbuf))
         self._xbuf, self._opened, self.Q = None, [], q_copy
 

@@ -67,6 +67,15 @@ def _worker(rank, world, port, out):
         both = [torch.empty_like(perm) for _ in range(world)]
         dist.all_gather(both, perm)
         ok = ok and torch.equal(both[0], both[1]) and sorted(perm.tolist()) == list(range(1000))
+        # the host-only group the peer-buffer mapping takes turns on (turn-by-turn barriers, no device work)
+        from daisyrec_b200.parallel import _host_group
+        hg = _host_group(None)
+        order = []
+        for turn in range(world):
+            if turn == rank:
+                order.append(turn)
+            dist.barrier(group=hg)
+        ok = ok and order == [rank] and _host_group(None) is hg and dist.get_backend(hg) == "gloo"
         out[rank] = ok
     finally:
         dist.destroy_process_group()
