@@ -352,6 +352,15 @@ def cpu_baseline_subprocess(args, rows, steps=2, warmup=1):
 
 
 # ------------------------------------------------------------------------------- secondary configs (driver-visible)
+def step_kernel_info(F):
+    """Which instantiation of the step kernel the timed steps ran (the lean one only after its on-device self-check)."""
+    from daisyrec_b200 import ops
+    lean, lanes, chunks = ops.mf_step_variant(F)
+    return {"instantiation": "mf_bpr_steps_lean_kernel" if lean else "mf_bpr_steps_kernel", "lanes_per_row": lanes,
+            "chunks_per_lane": chunks, "selfcheck": "lean == general on a seeded problem (loss 1e-5 rel, tables 1e-5 abs)" if lean
+            else "general instantiation (lean not selected)"}
+
+
 def roof(achieved_gbs, kernel, alg_bytes, note=None):
     peak, src = measured_peaks()
     r = {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
@@ -693,6 +702,7 @@ def run_own(args):
                                                 "kernel + D2H of the loss, copy of batch s+1 under the kernel of batch s"}},
             "gpu_launches": launches,
             "gpu_launches_note": "persistent cooperative kernel: one launch runs up to steps_per_epoch synchronous steps",
+            "step_kernel": step_kernel_info(F),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if traffic is None else traffic * (args.steps / len(evs)),
                          "traffic_note": f"dram__bytes_read+write per step ({traffic_src}) x steps per launch; the 85 MB "
@@ -877,7 +887,7 @@ def run_sharded(args, rank, local, world, dev):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": main["cfg"],
                 "steps_per_epoch": main["spe"], "exchange": exchange, "comm": comm,
                 "clocks": clk, "e2e": main.get("e2e"), "parity_check": main["parity"],
-                "gpu_launches": 2 * args.steps if comm == "nccl" else 1,
+                "gpu_launches": 2 * args.steps if comm == "nccl" else 1, "step_kernel": step_kernel_info(F),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_triple": bpt,
                              "kernel": "mf_bpr_steps_kernel (per GPU)"}}

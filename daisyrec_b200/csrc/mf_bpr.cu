@@ -32,6 +32,10 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "step_kernel.cuh"
 
 namespace drb {
@@ -121,16 +125,9 @@ static StepKernel pick_kernel(int F, bool gen)
     return pick_kernel_v<1, false>(g.width, g.nch);
 }
 
-int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
+// grid / tile choice and the cooperative launch of one chosen instantiation
+static int launch_kernel(StepKernel k, StepParams &p, cudaStream_t st, bool keep_status)
 {
-    // GEN instantiation: any loss but BPR, and the Adagrad / RMSprop sweeps (kept out of the hot BPR + SGD/Adam kernel)
-    StepKernel k = nullptr;
-    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;   // developer switch: A/B the two instantiations
-    if (!no_lean && step_params_lean(p)) k = pick_lean(p.F);
-    if (k == nullptr) k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
-    DRB_REQUIRE(!p.det || (p.phases == 3 && p.ws.gP64 != nullptr), "deterministic accumulation: single-GPU fused steps with a "
-                "workspace from drb_mf_workspace_bytes_det");
-    DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
     // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
     // split multi-GPU / LightGCN / NeuMF paths)
     static thread_local StepKernel cached_k = nullptr;
@@ -160,6 +157,109 @@ int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
     return DRB_OK;
 }
 
+// The lean instantiation is trusted only after it has reproduced the general one: once per process and factor count, two SGD
+// and two Adam steps of a small seeded problem run through both and must agree (loss 1e-5 relative, tables 1e-5 absolute).
+// A mismatch switches the lean body off for that factor count (a line on stderr says so) -- never a wrong table.
+static bool lean_selfcheck(int F)
+{
+    const int U = 96, I = 80, B = 384, K = 2;
+    const long long n = (long long)B * K;
+    StepKernel lean = pick_lean(F), gen = pick_kernel(F, false);
+    if (lean == nullptr || gen == nullptr) return false;
+    std::vector<float> hP((size_t)U * F), hQ((size_t)I * F);
+    std::vector<int32_t> hu(n), hi(n), hj(n);
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { x = x * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(x >> 33); };
+    for (auto &v : hP) v = ((float)(rnd() % 20001) - 10000.f) * 2e-5f;
+    for (auto &v : hQ) v = ((float)(rnd() % 20001) - 10000.f) * 2e-5f;
+    for (long long t = 0; t < n; ++t) { hu[t] = rnd() % (U / 4); hi[t] = rnd() % I; hj[t] = rnd() % I; }   // hot user rows
+    bool ok = true;
+    for (int opt = DRB_OPT_SGD; opt <= DRB_OPT_ADAM && ok; ++opt) {
+        const size_t wsb = carve(nullptr, U, I, F, opt, nullptr);
+        std::vector<float> outP[2], outQ[2];
+        double loss[2][K];
+        for (int v = 0; v < 2 && ok; ++v) {
+            float *dP = nullptr, *dQ = nullptr;
+            void *dws = nullptr;
+            int32_t *du = nullptr, *di = nullptr, *dj = nullptr;
+            double *dl = nullptr;
+            bool good = cudaMalloc(&dP, hP.size() * 4) == cudaSuccess && cudaMalloc(&dQ, hQ.size() * 4) == cudaSuccess &&
+                        cudaMalloc(&dws, wsb) == cudaSuccess && cudaMalloc(&du, n * 4) == cudaSuccess &&
+                        cudaMalloc(&di, n * 4) == cudaSuccess && cudaMalloc(&dj, n * 4) == cudaSuccess &&
+                        cudaMalloc(&dl, K * 8) == cudaSuccess;
+            if (good) {
+                cudaMemcpy(dP, hP.data(), hP.size() * 4, cudaMemcpyHostToDevice);
+                cudaMemcpy(dQ, hQ.data(), hQ.size() * 4, cudaMemcpyHostToDevice);
+                cudaMemcpy(du, hu.data(), n * 4, cudaMemcpyHostToDevice);
+                cudaMemcpy(di, hi.data(), n * 4, cudaMemcpyHostToDevice);
+                cudaMemcpy(dj, hj.data(), n * 4, cudaMemcpyHostToDevice);
+                cudaMemset(dws, 0, wsb);
+                drb_hyper h = {0.05f, 0.001f, 0.001f, opt, 0.9f, 0.999f, 1e-8f, DRB_LOSS_BPR};
+                StepParams p;
+                good = fill_params(p, dP, dQ, dws, U, I, F, du, di, dj, n, B, 0, K, &h, 0, dl, 1) == DRB_OK &&
+                       launch_kernel(v == 0 ? gen : lean, p, (cudaStream_t)0, false) == DRB_OK &&
+                       cudaStreamSynchronize((cudaStream_t)0) == cudaSuccess;
+            }
+            if (good) {
+                outP[v].resize(hP.size());
+                outQ[v].resize(hQ.size());
+                good = cudaMemcpy(outP[v].data(), dP, hP.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                       cudaMemcpy(outQ[v].data(), dQ, hQ.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                       cudaMemcpy(loss[v], dl, K * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+            }
+            cudaFree(dP); cudaFree(dQ); cudaFree(dws); cudaFree(du); cudaFree(di); cudaFree(dj); cudaFree(dl);
+            ok = ok && good;
+        }
+        if (!ok) break;
+        double moved = 0.0;
+        for (int k = 0; k < K; ++k) ok = ok && fabs(loss[0][k] - loss[1][k]) <= 1e-5 * fabs(loss[0][k]) && loss[0][k] > 0.0;
+        // Adam turns a gradient that is pure rounding noise into a +-lr step of either sign: a few such elements may differ by up
+        // to 2 lr between ANY two runs (also of the same kernel); everything else agrees to 1e-5
+        int bad = 0;
+        float worst = 0.f;
+        for (size_t e = 0; e < hP.size(); ++e) {
+            const float dlt = fabsf(outP[0][e] - outP[1][e]);
+            if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
+            moved = fmax(moved, fabs((double)outP[0][e] - hP[e]));
+        }
+        for (size_t e = 0; e < hQ.size(); ++e) {
+            const float dlt = fabsf(outQ[0][e] - outQ[1][e]);
+            if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
+        }
+        ok = ok && (bad == 0 || (opt == DRB_OPT_ADAM && bad <= 4 && worst <= 0.11f));
+        ok = ok && moved > 1e-4;                                   // the steps did move the tables
+    }
+    cudaGetLastError();
+    if (!ok) fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d) did not reproduce the general instantiation: "
+                             "using the general one\n", F);
+    return ok;
+}
+
+// exported to p2p.cu: may the lean body be used for this factor count?  (runs the self-check on first use)
+bool lean_enabled(int F)
+{
+    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;   // developer switch: A/B the two instantiations
+    if (no_lean || pick_lean(F) == nullptr) return false;
+    static std::mutex mu;
+    static std::map<int, int> state;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = state.find(F);
+    if (it == state.end()) it = state.emplace(F, lean_selfcheck(F) ? 1 : 0).first;
+    return it->second == 1;
+}
+
+int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
+{
+    // lean: the MF hot path; GEN: any loss but BPR, Adagrad / RMSprop sweeps, FM biases, deterministic accumulation
+    StepKernel k = nullptr;
+    if (step_params_lean(p) && lean_enabled(p.F)) k = pick_lean(p.F);
+    if (k == nullptr) k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
+    DRB_REQUIRE(!p.det || (p.phases == 3 && p.ws.gP64 != nullptr), "deterministic accumulation: single-GPU fused steps with a "
+                "workspace from drb_mf_workspace_bytes_det");
+    DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
+    return launch_kernel(k, p, st, keep_status);
+}
+
 int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step)
 {
     WsHeader h;
@@ -181,6 +281,24 @@ using namespace drb;
 extern "C" size_t drb_mf_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_t opt)
 {
     return carve(nullptr, U, I, F, opt, nullptr);
+}
+
+// 1: BPR + SGD/Adam steps at this factor count run the lean instantiation (after its self-check), 0: the general one.
+// lanes / chunks (optional) receive the lane geometry of that instantiation.
+extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
+{
+    const bool lean = drb::lean_enabled(F);
+    int W = 0, NCH = 0;
+    if (lean) {
+        drb::lean_geom(F, W, NCH);
+    } else if (F > 0) {
+        drb::RowGeom g = drb::row_geom(F);
+        W = g.width;
+        NCH = g.nch;
+    }
+    if (lanes) *lanes = W;
+    if (chunks) *chunks = NCH;
+    return lean ? 1 : 0;
 }
 
 extern "C" int drb_mf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F, int32_t opt, void *stream)

@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_p2p_steps_kernel(St
 typedef void (*P2PKernel)(StepParams, P2PParams);
 
 void lean_geom(int F, int &W, int &NCH);   // mf_bpr.cu
+bool lean_enabled(int F);                  // mf_bpr.cu: self-checked once per factor count
 
 // lean = the MF hot body (32-bit row offsets, its own lane geometry; step_params_lean); the exchange policy is the same
 static P2PKernel pick_p2p(int F, bool lean = false)
@@ -407,8 +408,7 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     p.n = n_local;
     p.step_offsets = (const long long *)d_step_offsets;
     p.dense_hint = 1;
-    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;
-    P2PKernel k = pick_p2p(F, !no_lean && step_params_lean(p));
+    P2PKernel k = pick_p2p(F, step_params_lean(p) && lean_enabled(F));
     P2PParams x;
     for (int q = 0; q < kMaxPeers; ++q) x.peer[q] = q < world ? (char *)h_peer_bufs[q] : nullptr;
     x.rank = rank;

@@ -40,6 +40,14 @@ def device_query():
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), l2_bytes=l2.value)
 
 
+def mf_step_variant(factors):
+    """-> (lean, lanes_per_row, chunks_per_lane) of the BPR + SGD / Adam step kernel at this factor count (runs the lean
+    instantiation's one-off self-check if it has not run yet)."""
+    w, n = C.c_int32(0), C.c_int32(0)
+    lean = L.lib().drb_mf_step_variant(int(factors), C.byref(w), C.byref(n))
+    return bool(lean), int(w.value), int(n.value)
+
+
 def check_index_range(ids, bounds, what):
     """IndexError (what nn.Embedding raises in the reference) when a column of the device index array ``ids`` [n, len(bounds)]
     holds an id outside [0, bounds[c]).  One kernel + one 64-byte read-back."""

@@ -156,6 +156,8 @@ class ShardedTrainer:
             self.comm = "nccl"                                    # outside the peer kernel's instantiations
         if self.comm == "nccl":
             init_native_comm(group)
+        if self.comm in ("nccl", "p2p"):
+            ops.mf_step_variant(Q.shape[1])                       # the lean kernel's one-off self-check, before any peer waits on us
         self.ops = ops
         self.Q = Q
         self._xbuf = None

@@ -61,6 +61,7 @@ typedef struct drb_hyper {
     int32_t loss;             /* DRB_LOSS_*: config['loss_type'] of the pair-wise family              */
 } drb_hyper;
 
+
 /* ---- library / device ----------------------------------------------------------- */
 int drb_version(void);
 const char *drb_last_error(void);
@@ -72,6 +73,11 @@ int drb_device_query(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, in
  * array and raise the same exception.  Synchronises the stream. */
 int drb_index_range_check(const void *d_ids, int32_t elem_bytes, int64_t n_rows, int32_t n_cols, const int64_t *h_hi,
                           int64_t *h_bad, void *stream);
+/* Which instantiation of the BPR step kernel trains `factors`-wide tables with BPR + SGD / Adam (the path behind
+ * GeneralRecommender.fit, daisy/model/AbstractRecommender.py:112-128, for MF): returns 1 for the lean MF instantiation (its own
+ * lane geometry; checked once per process against the general instantiation on a small seeded problem before it is ever
+ * used), 0 for the general one.  lanes / chunks (optional) receive the lanes per row and chunks of 4 floats per lane. */
+int drb_mf_step_variant(int32_t factors, int32_t *lanes, int32_t *chunks);
 
 /* ---- pair-wise sampler: BasicNegtiveSampler.sampling(), uniform + BPR branch ------
  * daisy/utils/sampler.py:55-103 (js table :63,84-89; explode :91,99-101).
