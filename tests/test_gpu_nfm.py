@@ -103,8 +103,15 @@ def test_nfm_class_drop_in():
             # for it is cancellation noise, which Adam turns into +-lr steps (in the reference as well, with another sign
             # pattern).  The bias does not change any output, but it shifts the running MEAN of the BatchNorm behind it by
             # momentum x the accumulated bias drift: bounded, not comparable bit for bit.
-            drift = 0.0 if opt == 0 else 3e-3
-            np.testing.assert_allclose(m.running.cpu().numpy(), g[f"c{c}_R"][3], rtol=2e-4, atol=2e-5 + drift)
+            # Only the running MEANS of the BatchNorms that follow a Linear are affected (layout: per BatchNorm mean F, var F;
+            # BatchNorm 0 follows the bi-interaction, not a Linear); the rest compares as tightly as under SGD.
+            got_r, want_r = m.running.cpu().numpy().reshape(-1, 2, F), g[f"c{c}_R"][3].reshape(-1, 2, F)
+            loose = np.zeros(got_r.shape, bool)
+            if opt != 0:
+                loose[1:, 0, :] = True
+            np.testing.assert_allclose(got_r[~loose], want_r[~loose], rtol=2e-4, atol=2e-5)
+            if loose.any():
+                assert np.abs(got_r[loose] - want_r[loose]).max() <= 10 * float(lr), float(np.abs(got_r[loose] - want_r[loose]).max())
         m.load_state_dict({"embed_user.weight": g[f"c{c}_P"][3], "embed_item.weight": g[f"c{c}_Q"][3], "u_bias.weight": Bs[3][:U],
                            "i_bias.weight": Bs[3][U:U + I], "bias_": Bs[3][U + I:], "net": g[f"c{c}_N"][3],
                            "running": g[f"c{c}_R"][3]})
