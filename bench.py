@@ -18,7 +18,8 @@ Own arm
              host shares, H2D per step + loss D2H per step).  `fit_host_batches` (per-step H2D / D2H) is kept beside it.
   roofline   algorithmic bytes (24*F+12 per triple) / event-timed launch duration vs MEASURED_PEAKS.json.
   configs    driver-visible lines for the other BASELINE configs and the kernels either side of the step: C3 NeuMF bf16
-             tower, C4 LightGCN L=3, C5 shape on one GPU (and row-sharded when N > 1), rank / full_rank / sampling.
+             tower, C4 LightGCN L=3, C5 shape on one GPU (and row-sharded when N > 1), rank / full_rank / KPIs / sampling /
+             epoch permutation, and one step-time line each for FM, NFM, NGCF.
   parity_check (N > 1)  3 global steps on a 48 K-triple slice: sharded run vs the single-GPU kernel on the same batches.
   cpu_baseline  the REAL reference (oracle/_ref = /root/reference installed unmodified, oracle/build_ref.py) running
              daisy.model.MFRecommender.MF.fit over its own DataLoader on this host's cores, bounded sample, in a
@@ -531,6 +532,97 @@ def cfg_shuffle(args, dev, d):
                              "latency-bound by construction; reported for completeness")}
 
 
+# SURVEY 8(f) ranks 3-4 on the device, one step-time line each.  Random-init parameters of the reference's shapes; parity is
+# the business of tests/test_gpu_{fm,ngcf,nfm}.py.
+def cfg_f_fm(args, dev, d, planes):
+    """FM + BPR, ML-20M shape, F=64, SGD: the first-order terms ride in the GEN step instantiation."""
+    from daisyrec_b200 import ops
+    from daisyrec_b200.utils.synthetic import init_tables
+    bu, bi, bj = planes
+    U, I, F, B = d["user_num"], d["item_num"], 64, args.batch
+    P, Q = init_tables(U, I, F, args.seed + 3, dev)
+    bias = torch.zeros(U + I + 1, dtype=torch.float32, device=dev)
+    ws = ops.FMWorkspace(U, I, F, "sgd", dev)
+    hp = ops.hyper(0.01, 0.001, 0.001, "sgd")
+    nst, k = min(8, bu.numel() // B), [0]
+
+    def step():
+        ops.fm_train_steps(P, Q, bias, ws, bu, bi, bj, B, k[0] % nst, 1, hp, check=False)
+        k[0] += 1
+    ms = timed_ms(step, 3, 10)
+    alg = B * (24 * F + 12 + 24)
+    return {"workload": f"FM+BPR synthetic ml-20m shape, factors={F}, SGD", "value": B / ms * 1e3, "unit": UNIT,
+            "ms_per_step": ms, "batch": B,
+            "roofline": roof(alg / ms / 1e6, "mf_bpr_steps_kernel<GEN> with the packed bias vector", alg,
+                             "24 F + 12 B per triple + 3 bias scalars read and written")}
+
+
+def cfg_f_nfm(args, dev, d, planes):
+    """NFM + BPR, ML-20M shape, F=64, one hidden layer + BatchNorm, relu, Adam (fp32 layer-wise path)."""
+    from daisyrec_b200 import ops
+    from daisyrec_b200.utils.synthetic import init_tables
+    bu, bi, bj = planes
+    U, I, F = d["user_num"], d["item_num"], 64
+    Ln, bn, B = 1, True, min(args.batch, 1 << 18)
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    P, Q = init_tables(U, I, F, args.seed + 4, dev)
+    P.mul_(10.0); Q.mul_(10.0)
+    bias = torch.zeros(U + I + 1, dtype=torch.float32, device=dev)
+    N = (torch.randn(ops.nfm_param_count(F, Ln, bn), device=dev, generator=g) * 0.1).contiguous()
+    N[0:F] = 1.0                                        # BatchNorm 0 weight (layout: NFMRecommender module-registration order)
+    o = 2 * F + F * F + F
+    N[o:o + F] = 1.0                                    # BatchNorm 1 weight
+    R = torch.zeros(2 * 2 * F, dtype=torch.float32, device=dev)
+    R[F:2 * F] = 1.0; R[3 * F:4 * F] = 1.0              # running variances start at 1
+    ws = ops.NfmWorkspace(U, I, F, Ln, bn, "adam", 2 * B, dev)
+    hp = ops.hyper(0.001, 0.0, 0.001, "adam")
+    nst, k = min(8, bu.numel() // B), [0]
+
+    def step():
+        ops.nfm_bpr_train_steps(P, Q, bias, N, R, ws, ops.NFM_ACT["relu"], bu, bi, bj, B, k[0] % nst, 1, hp, adam_step0=k[0],
+                                check=False)
+        k[0] += 1
+    ms = timed_ms(step, 3, 10)
+    alg = B * (3 * 4 * F * 2 + 12) + 2 * B * 4 * F * 2 * (3 + 4 * Ln)
+    return {"workload": f"NFM+BPR synthetic ml-20m shape, factors={F}, num_layers={Ln}, batch_norm, relu, Adam", "value": B / ms * 1e3,
+            "unit": UNIT, "ms_per_step": ms, "batch": B,
+            "roofline": roof(alg / ms / 1e6, "nfm_* kernels: layer-wise, activations through HBM", alg,
+                             "row gathers / scatters + one read and one write of every [2B, F] activation and gradient")}
+
+
+def cfg_f_ngcf(args, dev):
+    """NGCF + BPR, Amazon-Book shape, widths 64/64/64/64, Adam, dropout 0."""
+    from daisyrec_b200 import ops
+    from daisyrec_b200.utils.synthetic import SHAPES, make_interactions
+    U, I, nnz = SHAPES["amazon-book"]
+    g = torch.Generator(device=dev); g.manual_seed(12)
+    da = make_interactions(U, I, nnz, seed=args.seed, device=dev)
+    adj = ops.lgcn_build_adj(da["coo_u"], da["coo_i"], U, I)
+    graph = ops.LgcnGraph(*adj, dev)
+    nnzA = int(adj[1].numel())
+    dims = [64, 64, 64, 64]
+    E0 = (torch.randn(U + I, dims[0], device=dev, generator=g) * 0.05).contiguous()
+    W = (torch.randn(ops.ngcf_param_count(dims), device=dev, generator=g) * 0.1).contiguous()
+    ws = ops.NgcfWorkspace(U, I, dims, "adam", dev)
+    B = 65536
+    idx = torch.randint(0, da["coo_u"].numel(), (4 * B,), device=dev, generator=g)
+    bu, bi = da["coo_u"][idx].contiguous(), da["coo_i"][idx].contiguous()
+    bj = torch.randint(0, I, (4 * B,), device=dev, dtype=torch.int32, generator=g)
+    hp = ops.hyper(0.001, 0.0, 0.001, "adam")
+    k = [0]
+
+    def step():
+        ops.ngcf_bpr_train_steps(E0, W, ws, graph, bu, bi, bj, B, k[0] % 4, 1, hp, adam_step0=k[0], check=False)
+        k[0] += 1
+    ms = timed_ms(step, 3, 10)
+    Lg = len(dims) - 1
+    alg = 2 * Lg * (nnzA * (8 + 4 * 64) + (U + I) * 4 * 64 * 6) + B * (24 * sum(dims) + 12)
+    return {"workload": f"NGCF+BPR synthetic amazon-book shape ({U}x{I}, nnz={da['nnz']}), widths {dims}, Adam, dropout 0",
+            "value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": B, "adjacency_nnz": nnzA,
+            "roofline": roof(alg / ms / 1e6, "spmm_seg_kernel + BiGNN GEMMs / row kernels x 2L + BPR phases + Adam", alg,
+                             "upper-bound algorithmic bytes (sparse products + 6 [N, F] streams per layer and direction)")}
+
+
 def run_configs(args, dev, d, planes, P, Q, which):
     out = {}
 
@@ -549,6 +641,9 @@ def run_configs(args, dev, d, planes, P, Q, which):
     section("inference", lambda: cfg_inference(args, dev, d, P, Q))
     section("sampling", lambda: cfg_sampling(args, dev, d))
     section("shuffle", lambda: cfg_shuffle(args, dev, d))
+    section("f_fm", lambda: cfg_f_fm(args, dev, d, planes))
+    section("f_nfm", lambda: cfg_f_nfm(args, dev, d, planes))
+    section("f_ngcf", lambda: cfg_f_ngcf(args, dev))
     return out
 
 
@@ -940,7 +1035,7 @@ def main():
     ap.add_argument("--num-ng", dest="num_ng", type=int, default=4)
     ap.add_argument("--seed", type=int, default=2022)
     ap.add_argument("--e2e-reps", dest="e2e_reps", type=int, default=3)
-    ap.add_argument("--configs", default="all", help="all | none | comma list of c3_neumf,c4_lightgcn,c5_netflix_1gpu,inference,sampling")
+    ap.add_argument("--configs", default="all", help="all | none | comma list of c3_neumf,c4_lightgcn,c5_netflix_1gpu,inference,sampling,shuffle,f_fm,f_nfm,f_ngcf")
     ap.add_argument("--c5", default="auto", choices=["auto", "on", "off"], help="N > 1: also run config 5 (netflix F=128)")
     ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"],
                     help="N > 1: auto = in-kernel peer exchange on 2 GPUs (validated), the NCCL step beyond; or force one")
