@@ -301,6 +301,24 @@ extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
     return lean ? 1 : 0;
 }
 
+// host-only: the lane geometry of the lean (lean != 0) or the canonical instantiation for `factors`, and the tile size the
+// launcher picks for `per_cta` triples per CTA and step (no device needed)
+extern "C" int drb_mf_step_geometry(int32_t F, int32_t lean, int32_t *lanes, int32_t *chunks, int64_t per_cta, int32_t *tile)
+{
+    int W = 0, NCH = 0;
+    if (lean) {
+        drb::lean_geom(F, W, NCH);
+    } else if (F > 0) {
+        drb::RowGeom g = drb::row_geom(F);
+        W = g.width;
+        NCH = g.nch;
+    }
+    if (lanes) *lanes = W;
+    if (chunks) *chunks = NCH;
+    if (tile) *tile = drb::pick_tile(per_cta);
+    return W > 0 ? DRB_OK : DRB_ERR_INVALID;
+}
+
 extern "C" int drb_mf_workspace_init(void *d_ws, int32_t U, int32_t I, int32_t F, int32_t opt, void *stream)
 {
     DRB_REQUIRE(d_ws != nullptr && U > 0 && I > 0 && F > 0, "workspace_init: bad arguments");

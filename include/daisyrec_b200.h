@@ -78,6 +78,9 @@ int drb_index_range_check(const void *d_ids, int32_t elem_bytes, int64_t n_rows,
  * lane geometry; checked once per process against the general instantiation on a small seeded problem before it is ever
  * used), 0 for the general one.  lanes / chunks (optional) receive the lanes per row and chunks of 4 floats per lane. */
 int drb_mf_step_variant(int32_t factors, int32_t *lanes, int32_t *chunks);
+/* Host-only companion (no device): lane geometry of the lean (lean != 0) or canonical instantiation, and the tile size the
+ * launcher picks for `per_cta` triples per CTA and step.  DRB_ERR_INVALID when no instantiation exists for `factors`. */
+int drb_mf_step_geometry(int32_t factors, int32_t lean, int32_t *lanes, int32_t *chunks, int64_t per_cta, int32_t *tile);
 
 /* ---- pair-wise sampler: BasicNegtiveSampler.sampling(), uniform + BPR branch ------
  * daisy/utils/sampler.py:55-103 (js table :63,84-89; explode :91,99-101).

@@ -278,3 +278,30 @@ def test_reference_arm_times_the_installed_reference(tmp_path):
     assert line["steps"] == 3 and line["gpu_launches"] == 0
     ns = type("A", (), dict(shape="tiny", num_ng=4, factors=64, batch=2048))
     assert line["config"] == bench.workload_config(ns, 1)                  # same_config with the own arm
+
+
+def test_step_kernel_geometry_and_tiles():
+    """Host logic of the step-kernel launcher: the lean instantiation's lane geometry (W lanes x NCH chunks of 4 floats cover the
+    row, W a power of two <= 32, as few lanes as the instantiated chunk counts allow) and the equal-tile choice."""
+    import ctypes as C
+    from daisyrec_b200 import _lib as L
+    lib = L.lib()
+    w, n, t = C.c_int32(), C.c_int32(), C.c_int32()
+    for F in range(4, 516, 4):
+        rc = lib.drb_mf_step_geometry(F, 1, C.byref(w), C.byref(n), 3543, C.byref(t))
+        if rc != 0:                                            # rows the lean body has no geometry for take the general kernel
+            ch = F // 4
+            assert ch > 32 and not any(ch % k == 0 and (ch // k) & (ch // k - 1) == 0 and ch // k <= 32 for k in (4, 2, 1)), F
+            continue
+        W, N = w.value, n.value
+        assert W in (1, 2, 4, 8, 16, 32) and N in (1, 2, 4) and W * N * 4 >= F, (F, W, N)
+        if F % 16 == 0 and (F // 16) & (F // 16 - 1) == 0 and F // 16 <= 32:
+            assert (W, N) == (F // 16, 4), (F, W, N)           # 64 B per lane: F = 64 -> 4 lanes, F = 128 -> 8 lanes
+        assert t.value == 512
+    assert lib.drb_mf_step_geometry(64, 0, C.byref(w), C.byref(n), 3543, C.byref(t)) == 0 and (w.value, n.value) == (16, 1)
+    assert lib.drb_mf_step_geometry(6, 1, C.byref(w), C.byref(n), 1, C.byref(t)) != 0          # not a multiple of 4: general kernel
+    for per_cta, want in ((1, 16), (16, 16), (17, 32), (512, 512), (513, 272), (3543, 512), (1024, 512), (1025, 352)):
+        lib.drb_mf_step_geometry(64, 1, None, None, per_cta, C.byref(t))
+        assert t.value == want, (per_cta, t.value, want)
+        k = -(-per_cta // t.value)
+        assert t.value % 16 == 0 and k * t.value >= per_cta and (k - 1) * t.value < per_cta
