@@ -67,15 +67,16 @@ static StepKernel pick_kernel_v(int W, int NCH)
     return nullptr;
 }
 
-// The lean MF instantiation.  Its lane geometry is its own: a group of W = F / 16 lanes owns a row, every lane 4 chunks of
-// 4 floats (F = 64: 4 lanes x 64 B).  The index loads, address arithmetic, loss chain and counter updates of a triple are
-// replicated across the lanes of its group, the row arithmetic is not -- so fewer lanes per row means fewer issue slots per
-// triple (8 triples per warp at F = 64 instead of 2) and more rows in flight per warp.  Only the fp32 summation order of the
-// two dot products differs from the canonical geometry (row_geom) that rank / predict / the oracle share.
+// The lean MF instantiation.  Its lane geometry is its own: a group of 8 lanes owns a row and every lane F/32 chunks of 4 floats
+// (F = 64: 2 chunks, F = 128: 4), so that one 128-bit access of the group covers exactly one 128-byte line of the row -- the same
+// request granularity towards L2 as the canonical geometry -- while the index loads, address arithmetic, loss chain and counter
+// updates of a triple, which every lane of its group replays, are replayed by 8 lanes instead of F/4.  A warp carries 4 rows per
+// access instead of 2 (F = 64) or 1 (F = 128).  Only the fp32 summation order of the two dot products differs from the
+// canonical geometry (row_geom) that rank / predict / the oracle share.
 static int lean_nch()
 {
     static const int v = [] {
-        const char *e = getenv("DRB_LEAN_NCH");   // developer switch: 1 | 2 | 4 chunks per lane
+        const char *e = getenv("DRB_LEAN_NCH");   // developer switch: at most 1 | 2 | 4 chunks per lane
         int n = e ? atoi(e) : 4;
         return (n == 1 || n == 2 || n == 4) ? n : 4;
     }();
@@ -90,6 +91,7 @@ void lean_geom(int F, int &W, int &NCH)
         if (chunks % n != 0) continue;
         const int w = chunks / n;
         if (w > 32 || (w & (w - 1)) != 0) continue;
+        if (w < 8 && n > 1) continue;     // keep whole 128-byte lines per access (rows shorter than a line: one chunk per lane)
         W = w;
         NCH = n;
         return;

@@ -246,7 +246,7 @@ __device__ __forceinline__ void bpr_steps_body(StepParams &p, XCH &xch)
     using RowOff = typename RowOffset<LEAN>::type;
     constexpr int GPW = 32 / W;                  // lane groups per warp
     constexpr int GROUPS = (kThreads / 32) * GPW;  // lane groups per CTA
-    constexpr int UNR = (NCH * VEC <= 4) ? DRB_UNR : 1;  // triples in flight per group
+    constexpr int UNR = (NCH * VEC <= (LEAN ? 8 : 4)) ? DRB_UNR : 1;  // triples in flight per group
 
     __shared__ __align__(128) int32_t s_idx[2][3][kTileMax];
     __shared__ uint64_t s_bar[2];

@@ -282,7 +282,7 @@ def test_reference_arm_times_the_installed_reference(tmp_path):
 
 def test_step_kernel_geometry_and_tiles():
     """Host logic of the step-kernel launcher: the lean instantiation's lane geometry (W lanes x NCH chunks of 4 floats cover the
-    row, W a power of two <= 32, as few lanes as the instantiated chunk counts allow) and the equal-tile choice."""
+    row, W a power of two <= 32, 8 lanes = one 128-byte line per access where the row is long enough) and the equal-tile choice."""
     import ctypes as C
     from daisyrec_b200 import _lib as L
     lib = L.lib()
@@ -295,8 +295,10 @@ def test_step_kernel_geometry_and_tiles():
             continue
         W, N = w.value, n.value
         assert W in (1, 2, 4, 8, 16, 32) and N in (1, 2, 4) and W * N * 4 >= F, (F, W, N)
-        if F % 16 == 0 and (F // 16) & (F // 16 - 1) == 0 and F // 16 <= 32:
-            assert (W, N) == (F // 16, 4), (F, W, N)           # 64 B per lane: F = 64 -> 4 lanes, F = 128 -> 8 lanes
+        if N > 1:
+            assert W >= 8, (F, W, N)                           # a group's 128-bit access covers whole 128-byte lines
+    for F, want in ((16, (4, 1)), (32, (8, 1)), (64, (8, 2)), (128, (8, 4)), (256, (16, 4)), (100, (32, 1)), (48, (16, 1))):
+        assert lib.drb_mf_step_geometry(F, 1, C.byref(w), C.byref(n), 3543, C.byref(t)) == 0 and (w.value, n.value) == want, F
         assert t.value == 512
     assert lib.drb_mf_step_geometry(64, 0, C.byref(w), C.byref(n), 3543, C.byref(t)) == 0 and (w.value, n.value) == (16, 1)
     assert lib.drb_mf_step_geometry(6, 1, C.byref(w), C.byref(n), 1, C.byref(t)) != 0          # not a multiple of 4: general kernel
