@@ -159,82 +159,146 @@ static int launch_kernel(StepKernel k, StepParams &p, cudaStream_t st, bool keep
     return DRB_OK;
 }
 
-// The lean instantiation is trusted only after it has reproduced the general one: once per process and factor count, two SGD
-// and two Adam steps of a small seeded problem run through both and must agree (loss 1e-5 relative, tables 1e-5 absolute).
-// A mismatch switches the lean body off for that factor count (a line on stderr says so) -- never a wrong table.
-static bool lean_selfcheck(int F)
+// The lean instantiation is used only after it has (1) reproduced the general one and (2) beaten it on this device: once per
+// process and factor count, two SGD and two Adam steps of a small seeded problem run through both and must agree (loss 1e-5
+// relative, tables 1e-5 absolute); then both are timed on an L2-regime problem of the bench's index statistics and the lean
+// one is kept only if it is faster.  A mismatch or a slower lean body leaves the general instantiation in place (a line on
+// stderr says which) -- never a wrong table, never a slower step.
+struct CheckProblem {
+    int U, I, F, B, K;
+    std::vector<float> hP, hQ;
+    std::vector<int32_t> hu, hi, hj;
+};
+static void make_check_problem(CheckProblem &c, int U, int I, int F, int B, int K, bool hot_users)
 {
-    const int U = 96, I = 80, B = 384, K = 2;
+    c.U = U; c.I = I; c.F = F; c.B = B; c.K = K;
+    c.hP.resize((size_t)U * F);
+    c.hQ.resize((size_t)I * F);
     const long long n = (long long)B * K;
-    StepKernel lean = pick_lean(F), gen = pick_kernel(F, false);
-    if (lean == nullptr || gen == nullptr) return false;
-    std::vector<float> hP((size_t)U * F), hQ((size_t)I * F);
-    std::vector<int32_t> hu(n), hi(n), hj(n);
+    c.hu.resize(n); c.hi.resize(n); c.hj.resize(n);
     unsigned long long x = 0x9E3779B97F4A7C15ull;
     auto rnd = [&]() { x = x * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(x >> 33); };
-    for (auto &v : hP) v = ((float)(rnd() % 20001) - 10000.f) * 2e-5f;
-    for (auto &v : hQ) v = ((float)(rnd() % 20001) - 10000.f) * 2e-5f;
-    for (long long t = 0; t < n; ++t) { hu[t] = rnd() % (U / 4); hi[t] = rnd() % I; hj[t] = rnd() % I; }   // hot user rows
+    for (auto &v : c.hP) v = ((float)(rnd() % 20001) - 10000.f) * 2e-5f;
+    for (auto &v : c.hQ) v = ((float)(rnd() % 20001) - 10000.f) * 2e-5f;
+    for (long long t = 0; t < n; ++t) {
+        c.hu[t] = (int32_t)(rnd() % (uint32_t)(hot_users ? U / 4 : U));
+        const unsigned long long a = rnd() % (uint32_t)I;
+        c.hi[t] = (int32_t)(hot_users ? a : a * a / (unsigned)I);      // timing problem: popular items, like the bench's planes
+        c.hj[t] = (int32_t)(rnd() % (uint32_t)I);
+    }
+}
+// one launch of K steps of instantiation k on a fresh copy of the problem; optional outputs: tables, losses, milliseconds of a
+// second (warm) launch
+static bool run_check_variant(const CheckProblem &c, StepKernel k, int opt, float lr, std::vector<float> *outP,
+                              std::vector<float> *outQ, double *loss, float *ms)
+{
+    const long long n = (long long)c.B * c.K;
+    const size_t wsb = carve(nullptr, c.U, c.I, c.F, opt, nullptr);
+    float *dP = nullptr, *dQ = nullptr;
+    void *dws = nullptr;
+    int32_t *du = nullptr, *di = nullptr, *dj = nullptr;
+    double *dl = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool good = cudaMalloc(&dP, c.hP.size() * 4) == cudaSuccess && cudaMalloc(&dQ, c.hQ.size() * 4) == cudaSuccess &&
+                cudaMalloc(&dws, wsb) == cudaSuccess && cudaMalloc(&du, n * 4) == cudaSuccess &&
+                cudaMalloc(&di, n * 4) == cudaSuccess && cudaMalloc(&dj, n * 4) == cudaSuccess &&
+                cudaMalloc(&dl, c.K * 8) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess &&
+                cudaEventCreate(&e1) == cudaSuccess;
+    if (good) {
+        cudaMemcpy(dP, c.hP.data(), c.hP.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dQ, c.hQ.data(), c.hQ.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(du, c.hu.data(), n * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(di, c.hi.data(), n * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dj, c.hj.data(), n * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dws, 0, wsb);
+        drb_hyper h = {lr, 0.001f, 0.001f, opt, 0.9f, 0.999f, 1e-8f, DRB_LOSS_BPR};
+        StepParams p;
+        good = fill_params(p, dP, dQ, dws, c.U, c.I, c.F, du, di, dj, n, c.B, 0, c.K, &h, 0, dl, 1) == DRB_OK &&
+               launch_kernel(k, p, (cudaStream_t)0, false) == DRB_OK && cudaStreamSynchronize((cudaStream_t)0) == cudaSuccess;
+        if (good && ms != nullptr) {
+            *ms = 0.f;
+            for (int rep = 0; rep < 2 && good; ++rep) {            // best of two warm launches
+                float t = 0.f;
+                cudaEventRecord(e0, (cudaStream_t)0);
+                good = launch_kernel(k, p, (cudaStream_t)0, false) == DRB_OK;
+                cudaEventRecord(e1, (cudaStream_t)0);
+                good = good && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess;
+                if (good && (rep == 0 || t < *ms)) *ms = t;
+            }
+        }
+    }
+    if (good && outP != nullptr) {
+        outP->resize(c.hP.size());
+        outQ->resize(c.hQ.size());
+        good = cudaMemcpy(outP->data(), dP, c.hP.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(outQ->data(), dQ, c.hQ.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(loss, dl, c.K * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaFree(dP); cudaFree(dQ); cudaFree(dws); cudaFree(du); cudaFree(di); cudaFree(dj); cudaFree(dl);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return good;
+}
+
+static float g_lean_ms[2] = {0.f, 0.f};   // last self-check: ms of the timed launch, general / lean (reported by the C API)
+
+static bool lean_selfcheck(int F)
+{
+    StepKernel lean = pick_lean(F), gen = pick_kernel(F, false);
+    if (lean == nullptr || gen == nullptr) return false;
+    // (1) same results
     bool ok = true;
-    for (int opt = DRB_OPT_SGD; opt <= DRB_OPT_ADAM && ok; ++opt) {
-        const size_t wsb = carve(nullptr, U, I, F, opt, nullptr);
-        std::vector<float> outP[2], outQ[2];
-        double loss[2][K];
-        for (int v = 0; v < 2 && ok; ++v) {
-            float *dP = nullptr, *dQ = nullptr;
-            void *dws = nullptr;
-            int32_t *du = nullptr, *di = nullptr, *dj = nullptr;
-            double *dl = nullptr;
-            bool good = cudaMalloc(&dP, hP.size() * 4) == cudaSuccess && cudaMalloc(&dQ, hQ.size() * 4) == cudaSuccess &&
-                        cudaMalloc(&dws, wsb) == cudaSuccess && cudaMalloc(&du, n * 4) == cudaSuccess &&
-                        cudaMalloc(&di, n * 4) == cudaSuccess && cudaMalloc(&dj, n * 4) == cudaSuccess &&
-                        cudaMalloc(&dl, K * 8) == cudaSuccess;
-            if (good) {
-                cudaMemcpy(dP, hP.data(), hP.size() * 4, cudaMemcpyHostToDevice);
-                cudaMemcpy(dQ, hQ.data(), hQ.size() * 4, cudaMemcpyHostToDevice);
-                cudaMemcpy(du, hu.data(), n * 4, cudaMemcpyHostToDevice);
-                cudaMemcpy(di, hi.data(), n * 4, cudaMemcpyHostToDevice);
-                cudaMemcpy(dj, hj.data(), n * 4, cudaMemcpyHostToDevice);
-                cudaMemset(dws, 0, wsb);
-                drb_hyper h = {0.05f, 0.001f, 0.001f, opt, 0.9f, 0.999f, 1e-8f, DRB_LOSS_BPR};
-                StepParams p;
-                good = fill_params(p, dP, dQ, dws, U, I, F, du, di, dj, n, B, 0, K, &h, 0, dl, 1) == DRB_OK &&
-                       launch_kernel(v == 0 ? gen : lean, p, (cudaStream_t)0, false) == DRB_OK &&
-                       cudaStreamSynchronize((cudaStream_t)0) == cudaSuccess;
+    {
+        CheckProblem c;
+        make_check_problem(c, 96, 80, F, 384, 2, true);
+        for (int opt = DRB_OPT_SGD; opt <= DRB_OPT_ADAM && ok; ++opt) {
+            std::vector<float> outP[2], outQ[2];
+            double loss[2][2];
+            for (int v = 0; v < 2 && ok; ++v)
+                ok = run_check_variant(c, v == 0 ? gen : lean, opt, 0.05f, &outP[v], &outQ[v], loss[v], nullptr);
+            if (!ok) break;
+            double moved = 0.0;
+            for (int k = 0; k < c.K; ++k) ok = ok && fabs(loss[0][k] - loss[1][k]) <= 1e-5 * fabs(loss[0][k]) && loss[0][k] > 0.0;
+            // Adam turns a gradient that is pure rounding noise into a +-lr step of either sign: a few such elements may differ by
+            // up to 2 lr between ANY two runs (also of the same kernel); everything else agrees to 1e-5
+            int bad = 0;
+            float worst = 0.f;
+            for (size_t e = 0; e < c.hP.size(); ++e) {
+                const float dlt = fabsf(outP[0][e] - outP[1][e]);
+                if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
+                moved = fmax(moved, fabs((double)outP[0][e] - c.hP[e]));
             }
-            if (good) {
-                outP[v].resize(hP.size());
-                outQ[v].resize(hQ.size());
-                good = cudaMemcpy(outP[v].data(), dP, hP.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
-                       cudaMemcpy(outQ[v].data(), dQ, hQ.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
-                       cudaMemcpy(loss[v], dl, K * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+            for (size_t e = 0; e < c.hQ.size(); ++e) {
+                const float dlt = fabsf(outQ[0][e] - outQ[1][e]);
+                if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
             }
-            cudaFree(dP); cudaFree(dQ); cudaFree(dws); cudaFree(du); cudaFree(di); cudaFree(dj); cudaFree(dl);
-            ok = ok && good;
+            ok = ok && (bad == 0 || (opt == DRB_OPT_ADAM && bad <= 4 && worst <= 0.11f));
+            ok = ok && moved > 1e-4;                               // the steps did move the tables
         }
-        if (!ok) break;
-        double moved = 0.0;
-        for (int k = 0; k < K; ++k) ok = ok && fabs(loss[0][k] - loss[1][k]) <= 1e-5 * fabs(loss[0][k]) && loss[0][k] > 0.0;
-        // Adam turns a gradient that is pure rounding noise into a +-lr step of either sign: a few such elements may differ by up
-        // to 2 lr between ANY two runs (also of the same kernel); everything else agrees to 1e-5
-        int bad = 0;
-        float worst = 0.f;
-        for (size_t e = 0; e < hP.size(); ++e) {
-            const float dlt = fabsf(outP[0][e] - outP[1][e]);
-            if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
-            moved = fmax(moved, fabs((double)outP[0][e] - hP[e]));
-        }
-        for (size_t e = 0; e < hQ.size(); ++e) {
-            const float dlt = fabsf(outQ[0][e] - outQ[1][e]);
-            if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
-        }
-        ok = ok && (bad == 0 || (opt == DRB_OPT_ADAM && bad <= 4 && worst <= 0.11f));
-        ok = ok && moved > 1e-4;                                   // the steps did move the tables
     }
     cudaGetLastError();
-    if (!ok) fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d) did not reproduce the general instantiation: "
-                             "using the general one\n", F);
-    return ok;
+    if (!ok) {
+        fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d) did not reproduce the general instantiation: using the "
+                        "general one\n", F);
+        return false;
+    }
+    // (2) faster on this device (tables + accumulators of the timing problem stay inside L2, like BASELINE config 2)
+    {
+        CheckProblem c;
+        const int rows = F <= 64 ? 131072 : 65536;
+        make_check_problem(c, rows, rows / 4, F, 1 << 19, 3, false);
+        float ms[2] = {0.f, 0.f};
+        for (int v = 0; v < 2 && ok; ++v) ok = run_check_variant(c, v == 0 ? gen : lean, DRB_OPT_SGD, 0.01f, nullptr, nullptr, nullptr, &ms[v]);
+        cudaGetLastError();
+        g_lean_ms[0] = ms[0];
+        g_lean_ms[1] = ms[1];
+        if (!ok || !(ms[1] > 0.f) || !(ms[1] < 0.98f * ms[0])) {
+            fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d): %.3f ms against %.3f ms of the general instantiation "
+                            "on the timing problem: keeping the general one\n", F, ms[1], ms[0]);
+            return false;
+        }
+    }
+    return true;
 }
 
 // exported to p2p.cu: may the lean body be used for this factor count?  (runs the self-check on first use)
@@ -301,6 +365,14 @@ extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
     if (lanes) *lanes = W;
     if (chunks) *chunks = NCH;
     return lean ? 1 : 0;
+}
+
+// milliseconds of the timed launch (3 steps of 524 288 triples) of the last lean self-check: general / lean instantiation
+extern "C" int drb_mf_step_selfcheck_ms(float *ms_general, float *ms_lean)
+{
+    if (ms_general) *ms_general = drb::g_lean_ms[0];
+    if (ms_lean) *ms_lean = drb::g_lean_ms[1];
+    return DRB_OK;
 }
 
 // host-only: the lane geometry of the lean (lean != 0) or the canonical instantiation for `factors`, and the tile size the

@@ -48,6 +48,13 @@ def mf_step_variant(factors):
     return bool(lean), int(w.value), int(n.value)
 
 
+def mf_step_selfcheck_ms():
+    """-> (ms_general, ms_lean) of the last self-check's timed launch (zeros if none ran)."""
+    a, b = C.c_float(0), C.c_float(0)
+    L.lib().drb_mf_step_selfcheck_ms(C.byref(a), C.byref(b))
+    return float(a.value), float(b.value)
+
+
 def check_index_range(ids, bounds, what):
     """IndexError (what nn.Embedding raises in the reference) when a column of the device index array ``ids`` [n, len(bounds)]
     holds an id outside [0, bounds[c]).  One kernel + one 64-byte read-back."""

@@ -75,9 +75,12 @@ int drb_index_range_check(const void *d_ids, int32_t elem_bytes, int64_t n_rows,
                           int64_t *h_bad, void *stream);
 /* Which instantiation of the BPR step kernel trains `factors`-wide tables with BPR + SGD / Adam (the path behind
  * GeneralRecommender.fit, daisy/model/AbstractRecommender.py:112-128, for MF): returns 1 for the lean MF instantiation (its own
- * lane geometry; checked once per process against the general instantiation on a small seeded problem before it is ever
- * used), 0 for the general one.  lanes / chunks (optional) receive the lanes per row and chunks of 4 floats per lane. */
+ * lane geometry; checked once per process against the general instantiation -- same losses and tables on a small seeded problem,
+ * and faster on an L2-regime timing problem -- before it is ever used), 0 for the general one.  lanes / chunks (optional) receive the lanes per row and chunks of 4 floats per lane. */
 int drb_mf_step_variant(int32_t factors, int32_t *lanes, int32_t *chunks);
+/* The timing half of that check: milliseconds the general / the lean instantiation took for the same 3 steps of 524 288 triples
+ * (the lean one is kept only when it is faster on this device); zeros before any check has run. */
+int drb_mf_step_selfcheck_ms(float *ms_general, float *ms_lean);
 /* Host-only companion (no device): lane geometry of the lean (lean != 0) or canonical instantiation, and the tile size the
  * launcher picks for `per_cta` triples per CTA and step.  DRB_ERR_INVALID when no instantiation exists for `factors`. */
 int drb_mf_step_geometry(int32_t factors, int32_t lean, int32_t *lanes, int32_t *chunks, int64_t per_cta, int32_t *tile);
