@@ -357,12 +357,14 @@ def step_kernel_info(F):
     """Which instantiation of the step kernel the timed steps ran (the lean one only after its on-device self-check)."""
     from daisyrec_b200 import ops
     lean, lanes, chunks = ops.mf_step_variant(F)
-    ms_gen, ms_lean = ops.mf_step_selfcheck_ms()
+    ms_gen, ms_lean, tile_cap = ops.mf_step_selfcheck_ms(F)
     return {"instantiation": "mf_bpr_steps_lean_kernel" if lean else "mf_bpr_steps_kernel", "lanes_per_row": lanes,
             "chunks_per_lane": chunks,
-            "selfcheck": "on-device, once per process: lean == general on a seeded problem (loss 1e-5 rel, tables 1e-5 abs), then "
-                         "both timed on 3 steps x 524 288 triples; the lean one is used only if both hold",
-            "selfcheck_ms": {"general": ms_gen, "lean": ms_lean}}
+            "index_tile_cap": tile_cap,
+            "selection": "on-device, once per process: every lean candidate geometry must equal the general instantiation on a "
+                         "seeded problem (loss 1e-5 rel, tables 1e-5 abs); candidates and the general kernel are timed on 3 steps "
+                         "x 524 288 triples; the fastest correct candidate runs only if it beats the general one",
+            "selection_ms": {"general": ms_gen, "best_lean": ms_lean}}
 
 
 def roof(achieved_gbs, kernel, alg_bytes, note=None):

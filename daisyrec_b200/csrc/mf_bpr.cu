@@ -67,42 +67,58 @@ static StepKernel pick_kernel_v(int W, int NCH)
     return nullptr;
 }
 
-// The lean MF instantiation.  Its lane geometry is its own: a group of 8 lanes owns a row and every lane F/32 chunks of 4 floats
-// (F = 64: 2 chunks, F = 128: 4), so that one 128-bit access of the group covers exactly one 128-byte line of the row -- the same
-// request granularity towards L2 as the canonical geometry -- while the index loads, address arithmetic, loss chain and counter
-// updates of a triple, which every lane of its group replays, are replayed by 8 lanes instead of F/4.  A warp carries 4 rows per
-// access instead of 2 (F = 64) or 1 (F = 128).  Only the fp32 summation order of the two dot products differs from the
-// canonical geometry (row_geom) that rank / predict / the oracle share.
-static int lean_nch()
+// The lean MF instantiation.  Its lane geometry is its own: the index loads, address arithmetic, loss chain and counter updates
+// of a triple are replayed by every lane of the row's group, the row arithmetic is not -- so fewer lanes per row (more chunks of
+// 4 floats per lane) means fewer issue slots per triple and more rows in flight per warp.  Candidates for a factor count are
+// every (W lanes, NCH in {4, 2, 1} chunks per lane) with W a power of two; the preferred one keeps 8 lanes per row, so that one
+// 128-bit access of a group still covers exactly one 128-byte line (F = 64: 8 lanes x 2 chunks, F = 128: 8 x 4).  Which
+// candidate runs is decided on the device (lean_autotune).  Only the fp32 summation order of the two dot products differs from
+// the canonical geometry (row_geom) that rank / predict / the oracle share.
+static int lean_nch_only()
 {
     static const int v = [] {
-        const char *e = getenv("DRB_LEAN_NCH");   // developer switch: at most 1 | 2 | 4 chunks per lane
-        int n = e ? atoi(e) : 4;
-        return (n == 1 || n == 2 || n == 4) ? n : 4;
+        const char *e = getenv("DRB_LEAN_NCH");   // developer switch: restrict the candidates to 1 | 2 | 4 chunks per lane
+        int n = e ? atoi(e) : 0;
+        return (n == 1 || n == 2 || n == 4) ? n : 0;
     }();
     return v;
 }
-void lean_geom(int F, int &W, int &NCH)
+// candidates in order of preference; returns their number (at most 3)
+static int lean_candidates(int F, int (&cw)[3], int (&cn)[3])
 {
-    W = NCH = 0;
-    if (F <= 0 || F % 4 != 0) return;
+    int count = 0;
+    if (F <= 0 || F % 4 != 0) return 0;
     const int chunks = F / 4;
-    for (int n = lean_nch(); n >= 1; n >>= 1) {
-        if (chunks % n != 0) continue;
+    auto valid = [&](int n) {
+        if (chunks % n != 0) return false;
         const int w = chunks / n;
-        if (w > 32 || (w & (w - 1)) != 0) continue;
-        if (w < 8 && n > 1) continue;     // keep whole 128-byte lines per access (rows shorter than a line: one chunk per lane)
-        W = w;
-        NCH = n;
-        return;
+        return w <= 32 && (w & (w - 1)) == 0;
+    };
+    auto push = [&](int n) {
+        for (int k = 0; k < count; ++k) if (cn[k] == n) return;
+        if (lean_nch_only() != 0 && n != lean_nch_only()) return;
+        cw[count] = chunks / n;
+        cn[count] = n;
+        ++count;
+    };
+    for (int n = 4; n >= 1; n >>= 1)                       // preferred: the most chunks per lane that keep whole lines (W >= 8)
+        if (valid(n) && (chunks / n >= 8 || n == 1)) { push(n); break; }
+    for (int n = 4; n >= 1; n >>= 1)
+        if (valid(n)) push(n);
+    if (count == 0 && lean_nch_only() == 0) {              // e.g. F = 100: 25 chunks on 32 lanes
+        RowGeom g = row_geom(F);
+        if (g.vec == 4 && g.nch == 1) { cw[0] = g.width; cn[0] = 1; count = 1; }
     }
-    RowGeom g = row_geom(F);              // e.g. F = 100: 25 chunks on 32 lanes
-    if (g.vec == 4 && g.nch == 1) { W = g.width; NCH = 1; }
+    return count;
 }
-static StepKernel pick_lean(int F)
+void lean_default_geom(int F, int &W, int &NCH)            // host-only: the preferred candidate
 {
-    int W, NCH;
-    lean_geom(F, W, NCH);
+    int cw[3], cn[3];
+    W = NCH = 0;
+    if (lean_candidates(F, cw, cn) > 0) { W = cw[0]; NCH = cn[0]; }
+}
+static StepKernel pick_lean_wn(int W, int NCH)
+{
 #define DRB_LEAN(w, n) \
     if (W == w && NCH == n) return mf_bpr_steps_lean_kernel<4, w, n>;
     DRB_LEAN(1, 1) DRB_LEAN(2, 1) DRB_LEAN(4, 1) DRB_LEAN(8, 1) DRB_LEAN(16, 1) DRB_LEAN(32, 1)
@@ -128,7 +144,7 @@ static StepKernel pick_kernel(int F, bool gen)
 }
 
 // grid / tile choice and the cooperative launch of one chosen instantiation
-static int launch_kernel(StepKernel k, StepParams &p, cudaStream_t st, bool keep_status)
+static int launch_kernel(StepKernel k, StepParams &p, cudaStream_t st, bool keep_status, int tile_cap = kTileDefault)
 {
     // occupancy of the chosen instantiation, cached (the query costs microseconds and this runs once per step in the
     // split multi-GPU / LightGCN / NeuMF paths)
@@ -144,7 +160,7 @@ static int launch_kernel(StepKernel k, StepParams &p, cudaStream_t st, bool keep
     DRB_REQUIRE(per_sm > 0, "step kernel does not fit on an SM");
     const int max_grid = per_sm * sm_count();
     // tile: equal tiles of at most kTileMax triples, every CTA the same number of them
-    const int tile = pick_tile((p.batch + max_grid - 1) / max_grid);
+    const int tile = pick_tile((p.batch + max_grid - 1) / max_grid, tile_cap);
     p.tile = tile;
     long long tiles = (p.batch + tile - 1) / tile;
     long long rows_work = ((long long)p.U + p.I + 63) / 64;
@@ -159,11 +175,7 @@ static int launch_kernel(StepKernel k, StepParams &p, cudaStream_t st, bool keep
     return DRB_OK;
 }
 
-// The lean instantiation is used only after it has (1) reproduced the general one and (2) beaten it on this device: once per
-// process and factor count, two SGD and two Adam steps of a small seeded problem run through both and must agree (loss 1e-5
-// relative, tables 1e-5 absolute); then both are timed on an L2-regime problem of the bench's index statistics and the lean
-// one is kept only if it is faster.  A mismatch or a slower lean body leaves the general instantiation in place (a line on
-// stderr says which) -- never a wrong table, never a slower step.
+// ---- on-device selection of the step instantiation (lean_autotune below): seeded problems built on the host
 struct CheckProblem {
     int U, I, F, B, K;
     std::vector<float> hP, hQ;
@@ -190,7 +202,7 @@ static void make_check_problem(CheckProblem &c, int U, int I, int F, int B, int 
 // one launch of K steps of instantiation k on a fresh copy of the problem; optional outputs: tables, losses, milliseconds of a
 // second (warm) launch
 static bool run_check_variant(const CheckProblem &c, StepKernel k, int opt, float lr, std::vector<float> *outP,
-                              std::vector<float> *outQ, double *loss, float *ms)
+                              std::vector<float> *outQ, double *loss, float *ms, int tile_cap = kTileDefault)
 {
     const long long n = (long long)c.B * c.K;
     const size_t wsb = carve(nullptr, c.U, c.I, c.F, opt, nullptr);
@@ -214,13 +226,14 @@ static bool run_check_variant(const CheckProblem &c, StepKernel k, int opt, floa
         drb_hyper h = {lr, 0.001f, 0.001f, opt, 0.9f, 0.999f, 1e-8f, DRB_LOSS_BPR};
         StepParams p;
         good = fill_params(p, dP, dQ, dws, c.U, c.I, c.F, du, di, dj, n, c.B, 0, c.K, &h, 0, dl, 1) == DRB_OK &&
-               launch_kernel(k, p, (cudaStream_t)0, false) == DRB_OK && cudaStreamSynchronize((cudaStream_t)0) == cudaSuccess;
+               launch_kernel(k, p, (cudaStream_t)0, false, tile_cap) == DRB_OK &&
+               cudaStreamSynchronize((cudaStream_t)0) == cudaSuccess;
         if (good && ms != nullptr) {
             *ms = 0.f;
             for (int rep = 0; rep < 2 && good; ++rep) {            // best of two warm launches
                 float t = 0.f;
                 cudaEventRecord(e0, (cudaStream_t)0);
-                good = launch_kernel(k, p, (cudaStream_t)0, false) == DRB_OK;
+                good = launch_kernel(k, p, (cudaStream_t)0, false, tile_cap) == DRB_OK;
                 cudaEventRecord(e1, (cudaStream_t)0);
                 good = good && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess;
                 if (good && (rep == 0 || t < *ms)) *ms = t;
@@ -240,90 +253,141 @@ static bool run_check_variant(const CheckProblem &c, StepKernel k, int opt, floa
     return good;
 }
 
-static float g_lean_ms[2] = {0.f, 0.f};   // last self-check: ms of the timed launch, general / lean (reported by the C API)
+// what the BPR + SGD / Adam steps of one factor count run with
+struct LeanChoice {
+    int W = 0, NCH = 0;               // lanes per row, chunks per lane of the lean instantiation; W == 0: the general one
+    int tile_cap = kTileDefault;
+    float ms_general = 0.f, ms_lean = 0.f;   // timed launch of the autotune (best lean candidate)
+};
 
-static bool lean_selfcheck(int F)
+// same losses (1e-5 rel) and tables (1e-5 abs) as the reference outputs of the general instantiation
+static bool same_results(const CheckProblem &c, int opt, const std::vector<float> &P0, const std::vector<float> &Q0,
+                         const double *l0, const std::vector<float> &P1, const std::vector<float> &Q1, const double *l1)
 {
-    StepKernel lean = pick_lean(F), gen = pick_kernel(F, false);
-    if (lean == nullptr || gen == nullptr) return false;
-    // (1) same results
     bool ok = true;
-    {
-        CheckProblem c;
-        make_check_problem(c, 96, 80, F, 384, 2, true);
-        for (int opt = DRB_OPT_SGD; opt <= DRB_OPT_ADAM && ok; ++opt) {
-            std::vector<float> outP[2], outQ[2];
-            double loss[2][2];
-            for (int v = 0; v < 2 && ok; ++v)
-                ok = run_check_variant(c, v == 0 ? gen : lean, opt, 0.05f, &outP[v], &outQ[v], loss[v], nullptr);
-            if (!ok) break;
-            double moved = 0.0;
-            for (int k = 0; k < c.K; ++k) ok = ok && fabs(loss[0][k] - loss[1][k]) <= 1e-5 * fabs(loss[0][k]) && loss[0][k] > 0.0;
-            // Adam turns a gradient that is pure rounding noise into a +-lr step of either sign: a few such elements may differ by
-            // up to 2 lr between ANY two runs (also of the same kernel); everything else agrees to 1e-5
-            int bad = 0;
-            float worst = 0.f;
-            for (size_t e = 0; e < c.hP.size(); ++e) {
-                const float dlt = fabsf(outP[0][e] - outP[1][e]);
-                if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
-                moved = fmax(moved, fabs((double)outP[0][e] - c.hP[e]));
-            }
-            for (size_t e = 0; e < c.hQ.size(); ++e) {
-                const float dlt = fabsf(outQ[0][e] - outQ[1][e]);
-                if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
-            }
-            ok = ok && (bad == 0 || (opt == DRB_OPT_ADAM && bad <= 4 && worst <= 0.11f));
-            ok = ok && moved > 1e-4;                               // the steps did move the tables
+    for (int k = 0; k < c.K; ++k) ok = ok && fabs(l0[k] - l1[k]) <= 1e-5 * fabs(l0[k]) && l0[k] > 0.0;
+    // Adam turns a gradient that is pure rounding noise into a +-lr step of either sign: a few such elements may differ by up to
+    // 2 lr between ANY two runs (also of the same kernel); everything else agrees to 1e-5
+    int bad = 0;
+    float worst = 0.f;
+    double moved = 0.0;
+    for (size_t e = 0; e < P0.size(); ++e) {
+        const float dlt = fabsf(P0[e] - P1[e]);
+        if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
+        moved = fmax(moved, fabs((double)P0[e] - c.hP[e]));
+    }
+    for (size_t e = 0; e < Q0.size(); ++e) {
+        const float dlt = fabsf(Q0[e] - Q1[e]);
+        if (!(dlt <= 1e-5f)) { ++bad; worst = fmaxf(worst, dlt); }
+    }
+    ok = ok && (bad == 0 || (opt == DRB_OPT_ADAM && bad <= 4 && worst <= 0.11f));
+    return ok && moved > 1e-4;                                   // and the steps did move the tables
+}
+
+// The lean instantiations were written after the last GPU slot of their round, so nothing about them is assumed: once per
+// process and factor count every candidate geometry (1) must reproduce the general instantiation on a small seeded problem
+// (two SGD and two Adam steps), and (2) is timed against it on an L2-regime problem with the bench's index statistics
+// (3 steps x 524 288 triples, best of two warm launches).  The fastest correct candidate is used if it beats the general
+// instantiation, and a larger index tile if that helps it further; otherwise the general kernel stays.  Never a wrong table,
+// never a slower step.
+static LeanChoice lean_autotune(int F)
+{
+    LeanChoice best;
+    StepKernel gen = pick_kernel(F, false);
+    int cw[3], cn[3];
+    const int ncand = lean_candidates(F, cw, cn);
+    if (gen == nullptr || ncand == 0) return best;
+    CheckProblem small, big;
+    make_check_problem(small, 96, 80, F, 384, 2, true);
+    const int rows = F <= 64 ? 131072 : 65536;                    // tables + accumulators stay inside L2, like BASELINE config 2
+    make_check_problem(big, rows, rows / 4, F, 1 << 19, 3, false);
+    std::vector<float> refP[2], refQ[2];
+    double refl[2][2];
+    bool ok = true;
+    for (int opt = DRB_OPT_SGD; opt <= DRB_OPT_ADAM && ok; ++opt)
+        ok = run_check_variant(small, gen, opt, 0.05f, &refP[opt], &refQ[opt], refl[opt], nullptr);
+    ok = ok && run_check_variant(big, gen, DRB_OPT_SGD, 0.01f, nullptr, nullptr, nullptr, &best.ms_general);
+    float best_ms = 0.f;
+    for (int k = 0; k < ncand && ok; ++k) {
+        StepKernel lean = pick_lean_wn(cw[k], cn[k]);
+        if (lean == nullptr) continue;
+        bool same = true;
+        for (int opt = DRB_OPT_SGD; opt <= DRB_OPT_ADAM && same; ++opt) {
+            std::vector<float> P1, Q1;
+            double l1[2];
+            same = run_check_variant(small, lean, opt, 0.05f, &P1, &Q1, l1, nullptr) &&
+                   same_results(small, opt, refP[opt], refQ[opt], refl[opt], P1, Q1, l1);
         }
+        cudaGetLastError();
+        if (!same) {
+            fprintf(stderr, "[daisyrec_b200] lean step kernel %d lanes x %d chunks (factors=%d) did not reproduce the general "
+                            "instantiation: not used\n", cw[k], cn[k], F);
+            continue;
+        }
+        float ms = 0.f;
+        if (!run_check_variant(big, lean, DRB_OPT_SGD, 0.01f, nullptr, nullptr, nullptr, &ms) || !(ms > 0.f)) continue;
+        if (best_ms == 0.f || ms < best_ms) { best_ms = ms; best.W = cw[k]; best.NCH = cn[k]; }
     }
     cudaGetLastError();
-    if (!ok) {
-        fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d) did not reproduce the general instantiation: using the "
-                        "general one\n", F);
-        return false;
+    best.ms_lean = best_ms;
+    if (!ok || best.W == 0 || !(best_ms < 0.98f * best.ms_general)) {
+        if (ok && best.W != 0)
+            fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d): %.3f ms against %.3f ms of the general instantiation on "
+                            "the timing problem: keeping the general one\n", F, best_ms, best.ms_general);
+        best.W = best.NCH = 0;
+        return best;
     }
-    // (2) faster on this device (tables + accumulators of the timing problem stay inside L2, like BASELINE config 2)
-    {
-        CheckProblem c;
-        const int rows = F <= 64 ? 131072 : 65536;
-        make_check_problem(c, rows, rows / 4, F, 1 << 19, 3, false);
-        float ms[2] = {0.f, 0.f};
-        for (int v = 0; v < 2 && ok; ++v) ok = run_check_variant(c, v == 0 ? gen : lean, DRB_OPT_SGD, 0.01f, nullptr, nullptr, nullptr, &ms[v]);
-        cudaGetLastError();
-        g_lean_ms[0] = ms[0];
-        g_lean_ms[1] = ms[1];
-        if (!ok || !(ms[1] > 0.f) || !(ms[1] < 0.98f * ms[0])) {
-            fprintf(stderr, "[daisyrec_b200] lean step kernel (factors=%d): %.3f ms against %.3f ms of the general instantiation "
-                            "on the timing problem: keeping the general one\n", F, ms[1], ms[0]);
-            return false;
-        }
+    float ms_big_tile = 0.f;                                      // a larger index tile for the chosen candidate?
+    if (run_check_variant(big, pick_lean_wn(best.W, best.NCH), DRB_OPT_SGD, 0.01f, nullptr, nullptr, nullptr, &ms_big_tile,
+                          kTileMax) && ms_big_tile > 0.f && ms_big_tile < 0.98f * best_ms) {
+        best.tile_cap = kTileMax;
+        best.ms_lean = ms_big_tile;
     }
-    return true;
+    cudaGetLastError();
+    return best;
 }
 
-// exported to p2p.cu: may the lean body be used for this factor count?  (runs the self-check on first use)
-bool lean_enabled(int F)
+static const LeanChoice &lean_choice(int F)
 {
-    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;   // developer switch: A/B the two instantiations
-    if (no_lean || pick_lean(F) == nullptr) return false;
+    static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;   // developer switch: A/B the instantiations
     static std::mutex mu;
-    static std::map<int, int> state;
+    static std::map<int, LeanChoice> state;
     std::lock_guard<std::mutex> lock(mu);
     auto it = state.find(F);
-    if (it == state.end()) it = state.emplace(F, lean_selfcheck(F) ? 1 : 0).first;
-    return it->second == 1;
+    if (it == state.end()) it = state.emplace(F, no_lean ? LeanChoice() : lean_autotune(F)).first;
+    return it->second;
 }
+
+// exported to p2p.cu: the lean geometry and index-tile cap chosen for this factor count (W == 0: general instantiation)
+bool lean_enabled(int F) { return lean_choice(F).W > 0; }
+void lean_geom(int F, int &W, int &NCH)
+{
+    const LeanChoice &c = lean_choice(F);
+    W = c.W;
+    NCH = c.NCH;
+}
+int lean_tile_cap(int F) { return lean_choice(F).tile_cap; }
 
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
     // lean: the MF hot path; GEN: any loss but BPR, Adagrad / RMSprop sweeps, FM biases, deterministic accumulation
     StepKernel k = nullptr;
-    if (step_params_lean(p) && lean_enabled(p.F)) k = pick_lean(p.F);
-    if (k == nullptr) k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
+    int tile_cap = kTileDefault;
+    if (step_params_lean(p)) {
+        const LeanChoice &c = lean_choice(p.F);
+        if (c.W > 0) {
+            k = pick_lean_wn(c.W, c.NCH);
+            tile_cap = c.tile_cap;
+        }
+    }
+    if (k == nullptr) {
+        k = pick_kernel(p.F, p.loss != DRB_LOSS_BPR || p.opt > DRB_OPT_ADAM || p.bias != nullptr || p.det != 0);
+        tile_cap = kTileDefault;
+    }
     DRB_REQUIRE(!p.det || (p.phases == 3 && p.ws.gP64 != nullptr), "deterministic accumulation: single-GPU fused steps with a "
                 "workspace from drb_mf_workspace_bytes_det");
     DRB_REQUIRE(k != nullptr, "unsupported factors=%d (row too long for 32 lanes x 8 chunks)", p.F);
-    return launch_kernel(k, p, st, keep_status);
+    return launch_kernel(k, p, st, keep_status, tile_cap);
 }
 
 int check_nan(void *d_ws, cudaStream_t st, int64_t *nan_step)
@@ -353,11 +417,10 @@ extern "C" size_t drb_mf_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_
 // lanes / chunks (optional) receive the lane geometry of that instantiation.
 extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
 {
-    const bool lean = drb::lean_enabled(F);
     int W = 0, NCH = 0;
-    if (lean) {
-        drb::lean_geom(F, W, NCH);
-    } else if (F > 0) {
+    drb::lean_geom(F, W, NCH);
+    const bool lean = W > 0;
+    if (!lean && F > 0) {
         drb::RowGeom g = drb::row_geom(F);
         W = g.width;
         NCH = g.nch;
@@ -367,11 +430,14 @@ extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
     return lean ? 1 : 0;
 }
 
-// milliseconds of the timed launch (3 steps of 524 288 triples) of the last lean self-check: general / lean instantiation
-extern "C" int drb_mf_step_selfcheck_ms(float *ms_general, float *ms_lean)
+// the timing half of the on-device selection for `factors`: milliseconds of the timed launch (3 steps of 524 288 triples) of the
+// general instantiation and of the best lean candidate, and the index-tile cap in use (runs the selection if it has not run)
+extern "C" int drb_mf_step_selfcheck_ms(int32_t F, float *ms_general, float *ms_lean, int32_t *tile_cap)
 {
-    if (ms_general) *ms_general = drb::g_lean_ms[0];
-    if (ms_lean) *ms_lean = drb::g_lean_ms[1];
+    const drb::LeanChoice &c = drb::lean_choice(F);
+    if (ms_general) *ms_general = c.ms_general;
+    if (ms_lean) *ms_lean = c.ms_lean;
+    if (tile_cap) *tile_cap = c.tile_cap;
     return DRB_OK;
 }
 
@@ -381,7 +447,7 @@ extern "C" int drb_mf_step_geometry(int32_t F, int32_t lean, int32_t *lanes, int
 {
     int W = 0, NCH = 0;
     if (lean) {
-        drb::lean_geom(F, W, NCH);
+        drb::lean_default_geom(F, W, NCH);
     } else if (F > 0) {
         drb::RowGeom g = drb::row_geom(F);
         W = g.width;

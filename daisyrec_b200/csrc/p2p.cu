@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_p2p_steps_kernel(St
 
 typedef void (*P2PKernel)(StepParams, P2PParams);
 
-void lean_geom(int F, int &W, int &NCH);   // mf_bpr.cu
-bool lean_enabled(int F);                  // mf_bpr.cu: self-checked once per factor count
+void lean_geom(int F, int &W, int &NCH);   // mf_bpr.cu: the geometry chosen on the device for this factor count (W == 0: none)
+bool lean_enabled(int F);
+int lean_tile_cap(int F);
 
 // lean = the MF hot body (32-bit row offsets, its own lane geometry; step_params_lean); the exchange policy is the same
 static P2PKernel pick_p2p(int F, bool lean = false)
@@ -408,7 +409,8 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     p.n = n_local;
     p.step_offsets = (const long long *)d_step_offsets;
     p.dense_hint = 1;
-    P2PKernel k = pick_p2p(F, step_params_lean(p) && lean_enabled(F));
+    const bool lean_k = step_params_lean(p) && lean_enabled(F);
+    P2PKernel k = pick_p2p(F, lean_k);
     P2PParams x;
     for (int q = 0; q < kMaxPeers; ++q) x.peer[q] = q < world ? (char *)h_peer_bufs[q] : nullptr;
     x.rank = rank;
@@ -429,7 +431,7 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     }
     DRB_REQUIRE(cached_per_sm > 0, "p2p step kernel does not fit on an SM");
     const int max_grid = cached_per_sm * sm_count();
-    const int tile = pick_tile((batch_per_rank + max_grid - 1) / max_grid);
+    const int tile = pick_tile((batch_per_rank + max_grid - 1) / max_grid, lean_k ? lean_tile_cap(F) : kTileDefault);
     p.tile = tile;
     cudaStream_t st = (cudaStream_t)stream;
     DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, sizeof(WsHeader), st));

@@ -14,15 +14,20 @@ namespace drb {
 constexpr int kThreads = 256;
 constexpr int kTileMax = 1024;  // triples per staged index tile
 
+constexpr int kTileDefault = 512;
+
 // Tile size for `per_cta` triples per CTA and step: the fewest equal tiles of at most `cap` triples (a multiple of 16), so every
-// CTA walks the same number of full tiles (default cap 512: 3 543 per CTA -> 7 tiles of 512; DRB_TILE_CAP=1024 -> 4 tiles of 896).
-inline int pick_tile(long long per_cta)
+// CTA walks the same number of full tiles (cap 512: 3 543 per CTA -> 7 tiles of 512; cap 1 024 -> 4 tiles of 896).
+inline int pick_tile(long long per_cta, int cap = kTileDefault)
 {
-    static const int cap = [] {
+    static const int forced = [] {
         const char *e = getenv("DRB_TILE_CAP");   // developer switch
-        int c = e ? atoi(e) : 512;
-        return (c >= 16 && c <= kTileMax) ? c / 16 * 16 : 512;
+        int c = e ? atoi(e) : 0;
+        return (c >= 16 && c <= kTileMax) ? c / 16 * 16 : 0;
     }();
+    if (forced) cap = forced;
+    if (cap > kTileMax) cap = kTileMax;
+    if (cap < 16) cap = 16;
     if (per_cta < 16) return 16;
     const long long k = (per_cta + cap - 1) / cap;
     long long tile = ((per_cta + k - 1) / k + 15) / 16 * 16;

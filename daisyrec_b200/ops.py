@@ -48,11 +48,11 @@ def mf_step_variant(factors):
     return bool(lean), int(w.value), int(n.value)
 
 
-def mf_step_selfcheck_ms():
-    """-> (ms_general, ms_lean) of the last self-check's timed launch (zeros if none ran)."""
-    a, b = C.c_float(0), C.c_float(0)
-    L.lib().drb_mf_step_selfcheck_ms(C.byref(a), C.byref(b))
-    return float(a.value), float(b.value)
+def mf_step_selfcheck_ms(factors):
+    """-> (ms_general, ms_lean, tile_cap) of the on-device selection for this factor count."""
+    a, b, t = C.c_float(0), C.c_float(0), C.c_int32(0)
+    L.lib().drb_mf_step_selfcheck_ms(int(factors), C.byref(a), C.byref(b), C.byref(t))
+    return float(a.value), float(b.value), int(t.value)
 
 
 def check_index_range(ids, bounds, what):

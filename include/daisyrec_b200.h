@@ -74,13 +74,14 @@ int drb_device_query(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, in
 int drb_index_range_check(const void *d_ids, int32_t elem_bytes, int64_t n_rows, int32_t n_cols, const int64_t *h_hi,
                           int64_t *h_bad, void *stream);
 /* Which instantiation of the BPR step kernel trains `factors`-wide tables with BPR + SGD / Adam (the path behind
- * GeneralRecommender.fit, daisy/model/AbstractRecommender.py:112-128, for MF): returns 1 for the lean MF instantiation (its own
- * lane geometry; checked once per process against the general instantiation -- same losses and tables on a small seeded problem,
- * and faster on an L2-regime timing problem -- before it is ever used), 0 for the general one.  lanes / chunks (optional) receive the lanes per row and chunks of 4 floats per lane. */
+ * GeneralRecommender.fit, daisy/model/AbstractRecommender.py:112-128, for MF): returns 1 for a lean MF instantiation (its own
+ * lane geometry; selected once per process on the device: every candidate geometry must reproduce the general instantiation's
+ * losses and tables on a small seeded problem, the fastest one on an L2-regime timing problem is used if it beats the general
+ * instantiation), 0 for the general one.  lanes / chunks (optional) receive the lanes per row and chunks of 4 floats per lane. */
 int drb_mf_step_variant(int32_t factors, int32_t *lanes, int32_t *chunks);
-/* The timing half of that check: milliseconds the general / the lean instantiation took for the same 3 steps of 524 288 triples
- * (the lean one is kept only when it is faster on this device); zeros before any check has run. */
-int drb_mf_step_selfcheck_ms(float *ms_general, float *ms_lean);
+/* The timing half of that selection: milliseconds the general instantiation and the best lean candidate took for the same 3
+ * steps of 524 288 triples, and the index-tile cap (512 or 1 024 triples) the chosen one runs with. */
+int drb_mf_step_selfcheck_ms(int32_t factors, float *ms_general, float *ms_lean, int32_t *tile_cap);
 /* Host-only companion (no device): lane geometry of the lean (lean != 0) or canonical instantiation, and the tile size the
  * launcher picks for `per_cta` triples per CTA and step.  DRB_ERR_INVALID when no instantiation exists for `factors`. */
 int drb_mf_step_geometry(int32_t factors, int32_t lean, int32_t *lanes, int32_t *chunks, int64_t per_cta, int32_t *tile);
