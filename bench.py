@@ -353,11 +353,11 @@ def cpu_baseline_subprocess(args, rows, steps=2, warmup=1):
 
 
 # ------------------------------------------------------------------------------- secondary configs (driver-visible)
-def step_kernel_info(F):
-    """Which instantiation of the step kernel the timed steps ran (the lean one only after its on-device self-check)."""
+def step_kernel_info(F, table_rows=0):
+    """Which instantiation of the step kernel the timed steps ran (a lean one only after its on-device selection)."""
     from daisyrec_b200 import ops
-    lean, lanes, chunks = ops.mf_step_variant(F)
-    ms_gen, ms_lean, tile_cap = ops.mf_step_selfcheck_ms(F)
+    lean, lanes, chunks = ops.mf_step_variant(F, table_rows)
+    ms_gen, ms_lean, tile_cap = ops.mf_step_selfcheck_ms(F, table_rows)
     return {"instantiation": "mf_bpr_steps_lean_kernel" if lean else "mf_bpr_steps_kernel", "lanes_per_row": lanes,
             "chunks_per_lane": chunks,
             "index_tile_cap": tile_cap,
@@ -465,7 +465,8 @@ def cfg_c5_single(args, dev, steps=24):
     ms = timed_ms(lambda: ops.mf_bpr_train_steps(P, Q, ws, bu, bi, bj, B, 4, steps, hp, check=False), 1, 2) / steps
     bpt = 24 * F + 12
     return {"workload": workload_config(a5, 1)["workload"], "value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
-            "batch": B, "n_gpus": 1, "roofline": roof(B * bpt / ms / 1e6, "mf_bpr_steps_kernel", bpt)}
+            "batch": B, "n_gpus": 1, "roofline": roof(B * bpt / ms / 1e6, "mf_bpr_steps_kernel", bpt),
+            "step_kernel": step_kernel_info(F, U + I)}
 
 
 def cfg_inference(args, dev, d, P, Q):
@@ -802,7 +803,7 @@ def run_own(args):
                                                 "kernel + D2H of the loss, copy of batch s+1 under the kernel of batch s"}},
             "gpu_launches": launches,
             "gpu_launches_note": "persistent cooperative kernel: one launch runs up to steps_per_epoch synchronous steps",
-            "step_kernel": step_kernel_info(F),
+            "step_kernel": step_kernel_info(F, U + I),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if traffic is None else traffic * (args.steps / len(evs)),
                          "traffic_note": f"dram__bytes_read+write per step ({traffic_src}) x steps per launch; the 85 MB "
@@ -987,7 +988,8 @@ def run_sharded(args, rank, local, world, dev):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": main["cfg"],
                 "steps_per_epoch": main["spe"], "exchange": exchange, "comm": comm,
                 "clocks": clk, "e2e": main.get("e2e"), "parity_check": main["parity"],
-                "gpu_launches": 2 * args.steps if comm == "nccl" else 1, "step_kernel": step_kernel_info(F),
+                "gpu_launches": 2 * args.steps if comm == "nccl" else 1,
+                "step_kernel": step_kernel_info(F, main["d"]["user_num"] // world + main["d"]["item_num"]),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_triple": bpt,
                              "kernel": "mf_bpr_steps_kernel (per GPU)"}}

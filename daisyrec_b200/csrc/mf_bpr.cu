@@ -290,7 +290,7 @@ static bool same_results(const CheckProblem &c, int opt, const std::vector<float
 // (3 steps x 524 288 triples, best of two warm launches).  The fastest correct candidate is used if it beats the general
 // instantiation, and a larger index tile if that helps it further; otherwise the general kernel stays.  Never a wrong table,
 // never a slower step.
-static LeanChoice lean_autotune(int F)
+static LeanChoice lean_autotune(int F, bool hbm)
 {
     LeanChoice best;
     StepKernel gen = pick_kernel(F, false);
@@ -299,8 +299,9 @@ static LeanChoice lean_autotune(int F)
     if (gen == nullptr || ncand == 0) return best;
     CheckProblem small, big;
     make_check_problem(small, 96, 80, F, 384, 2, true);
-    const int rows = F <= 64 ? 131072 : 65536;                    // tables + accumulators stay inside L2, like BASELINE config 2
-    make_check_problem(big, rows, rows / 4, F, 1 << 19, 3, false);
+    // timing problem: tables + accumulators inside L2 (like BASELINE config 2) or, for the HBM regime, 2 x 134 MB of user rows
+    const int rows = hbm ? 33554432 / F : (F <= 64 ? 131072 : 65536);
+    make_check_problem(big, rows, hbm ? 16384 : rows / 4, F, 1 << 19, 3, false);
     std::vector<float> refP[2], refQ[2];
     double refl[2][2];
     bool ok = true;
@@ -347,26 +348,42 @@ static LeanChoice lean_autotune(int F)
     return best;
 }
 
-static const LeanChoice &lean_choice(int F)
+// regime of a problem: do the two tables and their accumulators fit the L2 cache?
+static bool hbm_regime(long long table_rows, int F)
+{
+    static const long long l2 = [] {
+        int dev = 0, bytes = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&bytes, cudaDevAttrL2CacheSize, dev) != cudaSuccess) {
+            cudaGetLastError();
+            bytes = 0;
+        }
+        return (long long)(bytes > 0 ? bytes : 64 << 20);
+    }();
+    return table_rows * (long long)F * 8 > l2;
+}
+
+static const LeanChoice &lean_choice(int F, long long table_rows)
 {
     static const bool no_lean = getenv("DRB_NO_LEAN") != nullptr;   // developer switch: A/B the instantiations
     static std::mutex mu;
     static std::map<int, LeanChoice> state;
+    const bool hbm = hbm_regime(table_rows, F);
+    const int key = F * 2 + (hbm ? 1 : 0);
     std::lock_guard<std::mutex> lock(mu);
-    auto it = state.find(F);
-    if (it == state.end()) it = state.emplace(F, no_lean ? LeanChoice() : lean_autotune(F)).first;
+    auto it = state.find(key);
+    if (it == state.end()) it = state.emplace(key, no_lean ? LeanChoice() : lean_autotune(F, hbm)).first;
     return it->second;
 }
 
-// exported to p2p.cu: the lean geometry and index-tile cap chosen for this factor count (W == 0: general instantiation)
-bool lean_enabled(int F) { return lean_choice(F).W > 0; }
-void lean_geom(int F, int &W, int &NCH)
+// exported to p2p.cu: the lean geometry and index-tile cap chosen for this factor count and table size (W == 0: general)
+bool lean_enabled(int F, long long table_rows) { return lean_choice(F, table_rows).W > 0; }
+void lean_geom(int F, long long table_rows, int &W, int &NCH)
 {
-    const LeanChoice &c = lean_choice(F);
+    const LeanChoice &c = lean_choice(F, table_rows);
     W = c.W;
     NCH = c.NCH;
 }
-int lean_tile_cap(int F) { return lean_choice(F).tile_cap; }
+int lean_tile_cap(int F, long long table_rows) { return lean_choice(F, table_rows).tile_cap; }
 
 int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
 {
@@ -374,7 +391,7 @@ int launch_steps(StepParams &p, cudaStream_t st, bool keep_status)
     StepKernel k = nullptr;
     int tile_cap = kTileDefault;
     if (step_params_lean(p)) {
-        const LeanChoice &c = lean_choice(p.F);
+        const LeanChoice &c = lean_choice(p.F, (long long)p.U + p.I);
         if (c.W > 0) {
             k = pick_lean_wn(c.W, c.NCH);
             tile_cap = c.tile_cap;
@@ -415,10 +432,10 @@ extern "C" size_t drb_mf_workspace_bytes(int32_t U, int32_t I, int32_t F, int32_
 
 // 1: BPR + SGD/Adam steps at this factor count run the lean instantiation (after its self-check), 0: the general one.
 // lanes / chunks (optional) receive the lane geometry of that instantiation.
-extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
+extern "C" int drb_mf_step_variant(int32_t F, int64_t table_rows, int32_t *lanes, int32_t *chunks)
 {
     int W = 0, NCH = 0;
-    drb::lean_geom(F, W, NCH);
+    drb::lean_geom(F, table_rows, W, NCH);
     const bool lean = W > 0;
     if (!lean && F > 0) {
         drb::RowGeom g = drb::row_geom(F);
@@ -432,9 +449,9 @@ extern "C" int drb_mf_step_variant(int32_t F, int32_t *lanes, int32_t *chunks)
 
 // the timing half of the on-device selection for `factors`: milliseconds of the timed launch (3 steps of 524 288 triples) of the
 // general instantiation and of the best lean candidate, and the index-tile cap in use (runs the selection if it has not run)
-extern "C" int drb_mf_step_selfcheck_ms(int32_t F, float *ms_general, float *ms_lean, int32_t *tile_cap)
+extern "C" int drb_mf_step_selfcheck_ms(int32_t F, int64_t table_rows, float *ms_general, float *ms_lean, int32_t *tile_cap)
 {
-    const drb::LeanChoice &c = drb::lean_choice(F);
+    const drb::LeanChoice &c = drb::lean_choice(F, table_rows);
     if (ms_general) *ms_general = c.ms_general;
     if (ms_lean) *ms_lean = c.ms_lean;
     if (tile_cap) *tile_cap = c.tile_cap;

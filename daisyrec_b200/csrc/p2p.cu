@@ -303,18 +303,19 @@ __global__ void __launch_bounds__(kThreads, DRB_MINB) mf_bpr_p2p_steps_kernel(St
 
 typedef void (*P2PKernel)(StepParams, P2PParams);
 
-void lean_geom(int F, int &W, int &NCH);   // mf_bpr.cu: the geometry chosen on the device for this factor count (W == 0: none)
-bool lean_enabled(int F);
-int lean_tile_cap(int F);
+// mf_bpr.cu: the geometry / index-tile cap chosen on the device for this factor count and table size (W == 0: none)
+void lean_geom(int F, long long table_rows, int &W, int &NCH);
+bool lean_enabled(int F, long long table_rows);
+int lean_tile_cap(int F, long long table_rows);
 
 // lean = the MF hot body (32-bit row offsets, its own lane geometry; step_params_lean); the exchange policy is the same
-static P2PKernel pick_p2p(int F, bool lean = false)
+static P2PKernel pick_p2p(int F, bool lean = false, long long table_rows = 0)
 {
     RowGeom g = row_geom(F);
     if (g.vec != 4 || g.nch != 1 || g.width < 4) return nullptr;
     if (lean) {
         int W, NCH;
-        lean_geom(F, W, NCH);
+        lean_geom(F, table_rows, W, NCH);
 #define DRB_P2P(w, n) \
     if (W == w && NCH == n) return mf_bpr_p2p_steps_kernel<4, w, n, true>;
         DRB_P2P(4, 1) DRB_P2P(8, 1) DRB_P2P(16, 1) DRB_P2P(32, 1)
@@ -409,8 +410,9 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     p.n = n_local;
     p.step_offsets = (const long long *)d_step_offsets;
     p.dense_hint = 1;
-    const bool lean_k = step_params_lean(p) && lean_enabled(F);
-    P2PKernel k = pick_p2p(F, lean_k);
+    const long long table_rows = (long long)U_local + I;
+    const bool lean_k = step_params_lean(p) && lean_enabled(F, table_rows);
+    P2PKernel k = pick_p2p(F, lean_k, table_rows);
     P2PParams x;
     for (int q = 0; q < kMaxPeers; ++q) x.peer[q] = q < world ? (char *)h_peer_bufs[q] : nullptr;
     x.rank = rank;
@@ -431,7 +433,7 @@ extern "C" int drb_mf_bpr_train_steps_p2p(float *d_P_local, void *d_ws, int32_t 
     }
     DRB_REQUIRE(cached_per_sm > 0, "p2p step kernel does not fit on an SM");
     const int max_grid = cached_per_sm * sm_count();
-    const int tile = pick_tile((batch_per_rank + max_grid - 1) / max_grid, lean_k ? lean_tile_cap(F) : kTileDefault);
+    const int tile = pick_tile((batch_per_rank + max_grid - 1) / max_grid, lean_k ? lean_tile_cap(F, table_rows) : kTileDefault);
     p.tile = tile;
     cudaStream_t st = (cudaStream_t)stream;
     DRB_CUDA(cudaMemsetAsync(p.ws.hdr, 0, sizeof(WsHeader), st));

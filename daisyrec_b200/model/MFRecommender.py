@@ -59,7 +59,7 @@ class MF(GeneralRecommender):
         self._ws = None
         self._opt_steps = 0
         self._stage = None
-        self.step_variant = ops.mf_step_variant(self.factors)   # (lean, lanes per row, chunks per lane); runs the one-off self-check
+        self.step_variant = ops.mf_step_variant(self.factors, self.user_num + self.item_num)   # runs the one-off on-device selection
         # optional B200 key: True = every cross-thread sum of a step in fixed point (bitwise reproducible runs); single GPU
         self.deterministic = bool(config.get('deterministic', False))
         if self.deterministic and (self.world > 1 or str(config.get('neg_sampling', 'table')) == 'fused'):

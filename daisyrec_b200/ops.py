@@ -40,18 +40,18 @@ def device_query():
     return dict(sm_count=sm.value, cc=(ma.value, mi.value), l2_bytes=l2.value)
 
 
-def mf_step_variant(factors):
-    """-> (lean, lanes_per_row, chunks_per_lane) of the BPR + SGD / Adam step kernel at this factor count (runs the lean
-    instantiation's one-off self-check if it has not run yet)."""
+def mf_step_variant(factors, table_rows=0):
+    """-> (lean, lanes_per_row, chunks_per_lane) of the BPR + SGD / Adam step kernel for this factor count and table size
+    (user_num + item_num; 0 = the L2 regime).  Runs the one-off on-device selection if it has not run yet."""
     w, n = C.c_int32(0), C.c_int32(0)
-    lean = L.lib().drb_mf_step_variant(int(factors), C.byref(w), C.byref(n))
+    lean = L.lib().drb_mf_step_variant(int(factors), int(table_rows), C.byref(w), C.byref(n))
     return bool(lean), int(w.value), int(n.value)
 
 
-def mf_step_selfcheck_ms(factors):
-    """-> (ms_general, ms_lean, tile_cap) of the on-device selection for this factor count."""
+def mf_step_selfcheck_ms(factors, table_rows=0):
+    """-> (ms_general, ms_lean, tile_cap) of the on-device selection for this factor count and table size."""
     a, b, t = C.c_float(0), C.c_float(0), C.c_int32(0)
-    L.lib().drb_mf_step_selfcheck_ms(int(factors), C.byref(a), C.byref(b), C.byref(t))
+    L.lib().drb_mf_step_selfcheck_ms(int(factors), int(table_rows), C.byref(a), C.byref(b), C.byref(t))
     return float(a.value), float(b.value), int(t.value)
 
 

@@ -157,7 +157,7 @@ class ShardedTrainer:
         if self.comm == "nccl":
             init_native_comm(group)
         if self.comm in ("nccl", "p2p"):
-            ops.mf_step_variant(Q.shape[1])                       # the lean kernel's one-off self-check, before any peer waits on us
+            ops.mf_step_variant(Q.shape[1], P_local.shape[0] + Q.shape[0])   # the step kernel's one-off on-device selection, before any peer waits on us
         self.ops = ops
         self.Q = Q
         self._xbuf = None
