@@ -102,6 +102,10 @@ SIGNATURES = {
     "drb_nfm_bpr_train_steps": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                           C.POINTER(Hyper), C.c_int64, C.c_int32, C.c_int32, vp, C.c_int32, c_i64p, vp]),
+    "drb_nfm_bpr_train_steps_dropout": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                  C.c_int32, C.c_int64, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                                  C.POINTER(Hyper), C.c_int64, C.c_int32, C.c_int32, vp, C.c_float, vp, C.c_int32,
+                                                  c_i64p, vp]),
     "drb_nfm_scores": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int64, vp, vp, C.c_int64, C.c_int32, vp, vp]),
     "drb_comm_unique_id": (C.c_int, [vp]),

@@ -240,6 +240,23 @@ __global__ void nfm_act_kernel(const float *__restrict__ z, long long total, int
         h[k] = nfm_act(act, z[k]);
 }
 
+// nn.Dropout with the caller's masks (NFMRecommender.py:67,:88): x *= keep ? 1/(1-p) : 0, in place.  keep is laid out as torch
+// drew it: [forward call (pos, neg)][site][B][F] bytes; rows [0,B) belong to the positive call, [B,2B) to the negative one.
+__device__ __forceinline__ float nfm_keep_factor(const uint8_t *__restrict__ keep, long long k, long long B, int F, int site,
+                                                 int nsites, float scale)
+{
+    const long long r = k / F;
+    const int f = (int)(k - r * F);
+    const long long pass = r >= B ? 1 : 0, t = r - pass * B;
+    return keep[((pass * nsites + site) * B + t) * F + f] ? scale : 0.f;
+}
+__global__ void nfm_dropout_kernel(float *__restrict__ x, const uint8_t *__restrict__ keep, long long B, long long total, int F,
+                                   int site, int nsites, float scale)
+{
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
+        x[k] = x[k] * nfm_keep_factor(keep, k, B, F, site, nsites, scale);
+}
+
 // one warp per row: fm = h + ((u_bias + i_bias) + bias_), pred = <fm, wp>   (rows given by (bu, bi|bj) or by explicit pairs)
 __global__ void __launch_bounds__(256) nfm_head_kernel(const float *__restrict__ hin, const float *__restrict__ bias, int U, int I,
                                                        const int32_t *__restrict__ bu, const int32_t *__restrict__ bi,
@@ -384,6 +401,16 @@ __global__ void nfm_act_bwd_kernel(const float *__restrict__ dh, const float *__
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x)
         out[k] = dh[k] * nfm_act_grad(act, z[k], h[k]);
 }
+// the same behind a Dropout: tmp = (dh * keep factor) * act'(z, act(z))  (h holds the dropped activations, so act(z) is redone)
+__global__ void nfm_act_bwd_drop_kernel(const float *__restrict__ dh, const float *__restrict__ z, const uint8_t *__restrict__ keep,
+                                        long long B, long long total, int F, int site, int nsites, float scale, int act,
+                                        float *__restrict__ out)
+{
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const float zz = z[k];
+        out[k] = (dh[k] * nfm_keep_factor(keep, k, B, F, site, nsites, scale)) * nfm_act_grad(act, zz, nfm_act(act, zz));
+    }
+}
 
 // BatchNorm backward (per half): dx = inv_std / B * (B dxh - sum(dxh) - xhat sum(dxh xhat)), dxh = dy gamma;
 // dgamma += sum dy xhat, dbeta += sum dy (both halves).  stats[h][2] = sum dy, [3] = sum dy xhat.
@@ -524,7 +551,29 @@ extern "C" int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, fl
                                        int32_t tower_dtype, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step,
                                        void *stream)
 {
+    return drb_nfm_bpr_train_steps_dropout(d_P, d_Q, d_bias, d_N, d_Rs, d_ws, U, I, F, L, batch_norm, act, max_rows, d_bu, d_bi, d_bj,
+                                           n, batch, first_step, n_steps, h, adam_step0, apply, tower_dtype, nullptr, 0.f,
+                                           d_step_loss, sync_and_check, nan_step, stream);
+}
+
+// The same with nn.Dropout active (dropout = config['dropout'] > 0, the reference default 0.5).  d_keep: the masks torch's Dropout
+// modules draw, as bytes (0 / 1), for the n_steps steps in order: per step [forward call: pos, neg][site: FM_layers' Dropout, then
+// the one behind each activation][batch][F] (the caller draws them on torch's CPU generator in exactly that order; a ragged
+// last batch uses its own row count).  Every step must hold `batch` triples when n_steps > 1.
+extern "C" int drb_nfm_bpr_train_steps_dropout(float *d_P, float *d_Q, float *d_bias, float *d_N, float *d_Rs, void *d_ws, int32_t U,
+                                               int32_t I, int32_t F, int32_t L, int32_t batch_norm, int32_t act, int64_t max_rows,
+                                               const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
+                                               int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *h,
+                                               int64_t adam_step0, int32_t apply, int32_t tower_dtype, const uint8_t *d_keep,
+                                               float dropout, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step,
+                                               void *stream)
+{
     NfmDims d;
+    DRB_REQUIRE(d_keep == nullptr || (dropout > 0.f && dropout < 1.f), "nfm: dropout masks need 0 < dropout < 1");
+    DRB_REQUIRE(d_keep == nullptr || n_steps <= 1 || (first_step + n_steps) * batch <= n,
+                "nfm: with dropout masks every step of a multi-step call must be a full batch");
+    const int nsites = 1 + L;
+    const float drop_scale = d_keep ? 1.0f / (float)(1.0 - (double)dropout) : 1.f;
     DRB_REQUIRE(d_P && d_Q && d_bias && d_N && d_ws && d_bu && d_bi && d_bj && h && d_step_loss, "nfm_train_steps: null argument");
     DRB_REQUIRE(nfm_dims(d, U, I, F, L, batch_norm, act), "nfm_train_steps: bad dims (factors <= 256, 0 <= num_layers <= 8, act 0..2)");
     DRB_REQUIRE(!batch_norm || d_Rs, "nfm_train_steps: batch_norm needs the running-statistics block");
@@ -543,16 +592,22 @@ extern "C" int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, fl
         const int64_t base = (first_step + s) * batch, B = (n - base < batch) ? n - base : batch;
         const long long R = 2 * B, tot = R * F;
         const int32_t *bu = d_bu + base, *bi = d_bi + base, *bj = d_bj + base;
+        const uint8_t *keep = d_keep ? d_keep + (size_t)s * 2 * nsites * (size_t)batch * F : nullptr;   // this step's masks
         int rc = DRB_OK;
         // ---- forward (both calls at once; BatchNorm statistics per half)
         nfm_product_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(d_P, d_Q, bu, bi, bj, B, R, F, w.e);
         DRB_CUDA(cudaGetLastError());
-        const float *hin = w.e;
+        float *h_fm = w.e;                                                // output of FM_layers
         if (d.bn) {
             rc = nfm_bn_train(d, w, 0, w.e, B, d_N + d.o_bn0, d_N + d.o_bn0 + F, d_Rs, d_Rs + F, w.xh0, w.h0, st);
             if (rc != DRB_OK) return rc;
-            hin = w.h0;
+            h_fm = w.h0;
         }
+        if (keep) {
+            nfm_dropout_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(h_fm, keep, B, tot, F, 0, nsites, drop_scale);
+            DRB_CUDA(cudaGetLastError());
+        }
+        const float *hin = h_fm;
         for (int l = 0; l < L; ++l) {
             const float *W = d_N + d.oW[l], *b = W + (size_t)F * F;
             rc = gemm_nt(tower_dtype, R, F, F, hin, F, W, F, w.zpre[l], F, st);
@@ -566,6 +621,10 @@ extern "C" int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, fl
             }
             nfm_act_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(w.z[l], tot, d.act, w.h[l]);
             DRB_CUDA(cudaGetLastError());
+            if (keep) {
+                nfm_dropout_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(w.h[l], keep, B, tot, F, 1 + l, nsites, drop_scale);
+                DRB_CUDA(cudaGetLastError());
+            }
             hin = w.h[l];
         }
         nfm_head_kernel<<<nfm_grid(R * 32, 256), 256, 0, st>>>(hin, d_bias, U, I, bu, bi, bj, B, R, F, wp, w.fm, w.pred);
@@ -583,7 +642,11 @@ extern "C" int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, fl
             const float *W = d_N + d.oW[l];
             const float *hprev = l == 0 ? (d.bn ? w.h0 : w.e) : w.h[l - 1];
             float *gW = w.gN + d.oW[l], *gb = gW + (size_t)F * F;
-            nfm_act_bwd_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(w.dh, w.z[l], w.h[l], tot, d.act, w.tmp);   // d act input
+            if (keep)
+                nfm_act_bwd_drop_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(w.dh, w.z[l], keep, B, tot, F, 1 + l, nsites, drop_scale,
+                                                                          d.act, w.tmp);
+            else
+                nfm_act_bwd_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(w.dh, w.z[l], w.h[l], tot, d.act, w.tmp);   // d act input
             DRB_CUDA(cudaGetLastError());
             float *dz = w.tmp;                                            // d Linear output
             if (d.bn) {
@@ -597,6 +660,10 @@ extern "C" int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, fl
             if (rc == DRB_OK) rc = gemm_nn(tower_dtype, R, F, F, dz, F, W, F, dprev, F, st);               // d h_in = dz W
             if (rc != DRB_OK) return rc;
             if (dprev != w.dh) DRB_CUDA(cudaMemcpyAsync(w.dh, dprev, sizeof(float) * (size_t)tot, cudaMemcpyDeviceToDevice, st));
+        }
+        if (keep) {                                                       // backward of FM_layers' Dropout
+            nfm_dropout_kernel<<<nfm_grid(tot, 256), 256, 0, st>>>(w.dh, keep, B, tot, F, 0, nsites, drop_scale);
+            DRB_CUDA(cudaGetLastError());
         }
         if (d.bn) {
             rc = nfm_bn_backward(d, w, 0, w.dh, w.xh0, B, d_N + d.o_bn0, w.gN + d.o_bn0, w.gN + d.o_bn0 + F, w.tmp, st);

@@ -1,11 +1,17 @@
 """NFM + BPR on the B200 path, with the reference's class name, config keys and methods
-(daisy/model/NFMRecommender.py:14-209; dropout = 0).
+(daisy/model/NFMRecommender.py:14-209).
 
 Factor tables ``embed_user.weight`` / ``embed_item.weight``, the first-order terms in one packed vector (``u_bias.weight``,
 ``i_bias.weight``, ``bias_`` are views of it), the network (FM_layers' BatchNorm, the hidden Linear / BatchNorm layers and
 ``prediction.weight``) in one flat fp32 block ``net`` in module-registration order, the BatchNorm running statistics in
 ``running`` (mean, var per BatchNorm).  Training goes through ``drb_nfm_bpr_train_steps``; rank / full_rank / predict score
 in eval mode (running statistics) through ``drb_nfm_scores`` + ``drb_topk_from_scores``.
+
+Dropout (``config['dropout']``, reference default 0.5, :67,:88): in train mode the host draws exactly the masks torch's Dropout
+modules would -- ``bernoulli_(1 - p)`` on the global CPU generator, forward(user, pos) first (FM_layers' Dropout, then the one
+behind each activation), then forward(user, neg) -- and uploads them as bytes with the batch, so a step equals the reference's
+and the global RNG ends where the reference's does.  That is a parity mechanism (one byte per activation and step through the
+host); ``dropout = 0`` is the throughput configuration.
 
 Two reference behaviours are NOT mirrored because they are failures, not results: with ``dropout = 0`` today's torch makes
 the reference's own ``backward()`` raise (the in-place ``fm += ...`` of :120 aliases the activation output), and
@@ -28,8 +34,8 @@ class NFM(GeneralRecommender):
         self.num_layers = config['num_layers']
         self.batch_norm = bool(config['batch_norm'])
         self.dropout = float(config['dropout'] or 0.0)
-        if self.dropout != 0.0:
-            raise NotImplementedError('NFM on the B200 path runs with dropout = 0 (the reference draws its masks from the torch RNG)')
+        if not 0.0 <= self.dropout < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), but got {self.dropout}")
         if self.act_function not in ops.NFM_ACT:
             raise NotImplementedError(f"act_function={self.act_function!r}: expected one of {sorted(ops.NFM_ACT)}")
         self.lr = config['lr']
@@ -135,12 +141,50 @@ class NFM(GeneralRecommender):
         elif self._ws.max_rows < rows:
             self._workspace(rows, self._fit_opt)
 
+    def _host_keep(self, rows_per_step):
+        """The masks nn.Dropout would draw for steps of rows_per_step[k] triples, drawn by torch on the global CPU generator in
+        the reference's order -> uint8 CUDA tensor [step][forward call][site][rows][F] (drb_nfm_bpr_train_steps_dropout)."""
+        F, sites, keep = self.factors, 1 + self.num_layers, 1.0 - self.dropout
+        parts = []
+        for B in rows_per_step:
+            for _side in (0, 1):                                          # forward(user, pos) draws first, then forward(user, neg)
+                for _site in range(sites):
+                    parts.append(torch.empty(B, F, dtype=torch.float32).bernoulli_(keep).to(torch.uint8).reshape(-1))
+        return torch.cat(parts).to(self.device)
+
+    def _dropping(self):
+        return self.training and self.dropout > 0.0
+
+    def _steps(self, bu, bi, bj, batch, first, n_steps, apply=True):
+        """n_steps steps; in train mode with dropout > 0 the masks of every step are drawn first (in step order)."""
+        kw = dict(adam_step0=self._opt_steps, tower_dtype=self._tower_dtype, apply=apply)
+        args = (self.embed_user.weight, self.embed_item.weight, self.bias, self.net, self.running, self._ws, self._act)
+        if not self._dropping():
+            return ops.nfm_bpr_train_steps(*args, bu, bi, bj, batch, first, n_steps, self._hp, **kw)
+        n = bu.numel()
+        per_step = 2 * (1 + self.num_layers) * batch * self.factors
+        chunk = max(1, (64 << 20) // per_step)                           # at most 64 MB of masks per call
+        out, s = [], first
+        while s < first + n_steps:
+            k = min(chunk, first + n_steps - s)
+            full = k if (s + k) * batch <= n else k - 1                   # a ragged last batch gets its own masks + call
+            if full > 0:
+                out.append(ops.nfm_bpr_train_steps(*args, bu, bi, bj, batch, s, full, self._hp, dropout=self.dropout,
+                                                   keep=self._host_keep([batch] * full),
+                                                   **dict(kw, adam_step0=self._opt_steps + (s - first))))
+            if full < k:
+                base = (s + full) * batch
+                last = n - base
+                out.append(ops.nfm_bpr_train_steps(*args, bu[base:], bi[base:], bj[base:], last, 0, 1, self._hp, dropout=self.dropout,
+                                                   keep=self._host_keep([last]),
+                                                   **dict(kw, adam_step0=self._opt_steps + (s + full - first))))
+            s += k
+        return torch.cat(out)
+
     def _train_steps(self, bu, bi, bj, batch, first, n_steps):
         if self._ws is None:
             self._workspace(2 * batch, self._fit_opt, fresh=True)
-        losses = ops.nfm_bpr_train_steps(self.embed_user.weight, self.embed_item.weight, self.bias, self.net, self.running,
-                                         self._ws, self._act, bu, bi, bj, batch, first, n_steps, self._hp,
-                                         adam_step0=self._opt_steps, tower_dtype=self._tower_dtype)
+        losses = self._steps(bu, bi, bj, batch, first, n_steps)
         self._opt_steps += n_steps
         return losses
 
@@ -163,16 +207,19 @@ class NFM(GeneralRecommender):
         self._check_loss_type()
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         self._ensure(2 * bu.numel())
-        loss = ops.nfm_bpr_train_steps(self.embed_user.weight, self.embed_item.weight, self.bias, self.net, self.running, self._ws,
-                                       self._act, bu, bi, bj, bu.numel(), 0, 1, self._hp, adam_step0=self._opt_steps, apply=False,
-                                       tower_dtype=self._tower_dtype)
+        loss = self._steps(bu, bi, bj, bu.numel(), 0, 1, apply=False)
         return loss.to(torch.float32).reshape(())
 
     def train_step(self, batch):
         self._check_loss_type()
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         self._ensure(2 * bu.numel())
-        return float(self._train_steps(bu, bi, bj, bu.numel(), 0, 1).item())
+        was = self.training
+        self.train()                                                 # a training step runs in train mode (dropout on)
+        try:
+            return float(self._train_steps(bu, bi, bj, bu.numel(), 0, 1).item())
+        finally:
+            self.train(was)
 
     def predict(self, u, i):
         return float(self.forward([int(u)], [int(i)]).item())

@@ -634,18 +634,25 @@ class NfmWorkspace:
 
 
 def nfm_bpr_train_steps(P, Q, bias, N, Rs, ws, act, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True,
-                        check=True, tower_dtype=0):
+                        check=True, tower_dtype=0, dropout=0.0, keep=None):
+    """keep (with dropout > 0): uint8 CUDA tensor of the masks torch's Dropout modules draw, per step
+    [forward call][site][batch][F] (drb_nfm_bpr_train_steps_dropout)."""
     for t in (P, Q, bias, N):
         _dev(t, torch.float32, "parameter")
     for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
         _dev(t, torch.int32, nm)
+    if keep is not None:
+        _dev(keep, torch.uint8, "keep")
+        rows = batch if n_steps != 1 else min(batch, bu.numel() - first_step * batch)
+        if keep.numel() != max(1, n_steps) * 2 * (1 + ws.Ln) * rows * ws.F:
+            raise ValueError("keep must hold n_steps x 2 x (1 + num_layers) x batch x factors bytes")
     losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=P.device)
     nan_step = C.c_int64(-1)
-    rc = L.lib().drb_nfm_bpr_train_steps(_ptr(P), _ptr(Q), _ptr(bias), _ptr(N), None if Rs is None or Rs.numel() == 0 else _ptr(Rs),
-                                         _ptr(ws.buf), ws.U, ws.I, ws.F, ws.Ln, ws.bn, act, ws.max_rows, _ptr(bu), _ptr(bi),
-                                         _ptr(bj), bu.numel(), batch, first_step, n_steps, C.byref(hp), adam_step0,
-                                         1 if apply else 0, tower_dtype, _ptr(losses), 1 if check else 0, C.byref(nan_step),
-                                         _stream())
+    rc = L.lib().drb_nfm_bpr_train_steps_dropout(
+        _ptr(P), _ptr(Q), _ptr(bias), _ptr(N), None if Rs is None or Rs.numel() == 0 else _ptr(Rs), _ptr(ws.buf), ws.U, ws.I, ws.F,
+        ws.Ln, ws.bn, act, ws.max_rows, _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(), batch, first_step, n_steps, C.byref(hp), adam_step0,
+        1 if apply else 0, tower_dtype, None if keep is None else _ptr(keep), C.c_float(dropout if keep is not None else 0.0),
+        _ptr(losses), 1 if check else 0, C.byref(nan_step), _stream())
     if rc == L.DRB_ERR_NAN_LOSS:
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
     L.check(rc)

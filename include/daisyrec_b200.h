@@ -257,7 +257,7 @@ int drb_ngcf_bpr_train_steps(float *d_E0, float *d_W, void *d_ws, int32_t user_n
                              int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0, int32_t apply, int32_t tower_dtype,
                              double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 
-/* ---- NFM + BPR (daisy/model/NFMRecommender.py:14-209; dropout = 0) ------------------------------
+/* ---- NFM + BPR (daisy/model/NFMRecommender.py:14-209) ------------------------------------------
  * P [U,F], Q [I,F] factor tables; d_bias = packed [u_bias (U), i_bias (I), bias_];
  * N: flat fp32 block in module-registration order (:64-90): [gamma0, beta0] of FM_layers' BatchNorm1d (if batch_norm), per
  *    hidden layer W [F,F] (out,in), b [F], [gamma, beta], then prediction.weight [F];
@@ -265,6 +265,10 @@ int drb_ngcf_bpr_train_steps(float *d_E0, float *d_W, void *d_ws, int32_t user_n
  * drb_nfm_bpr_train_steps  calc_loss :125-151 + backward + optimizer.step: the pos and the neg forward are separate calls in the
  *    reference, so every BatchNorm takes the statistics of ITS half of the 2*batch rows and moves its running statistics
  *    twice per step (pos first); apply = 0 evaluates the loss of one batch (the running statistics still move, as under train()).
+ * drb_nfm_bpr_train_steps_dropout  the same with the Dropout modules of :67,:88 active (the reference default, assets/nfm.yaml:
+ *    dropout 0.5): d_keep holds the masks torch's modules draw, as bytes, per step [forward call: pos, neg][site: FM_layers'
+ *    Dropout, then the one behind each activation][batch][factors]; the host draws them on torch's CPU generator in that order
+ *    (model/NFMRecommender.py), so a step equals the reference's.  d_keep = NULL: no dropout.
  * drb_nfm_scores  forward() under model.eval() (running statistics) for (d_u[k], d_i[k]) pairs: rank / full_rank / predict
  *    (:153-209); feed the scores to drb_topk_from_scores.  max_rows: rows of activation scratch (>= 2 * batch). */
 int64_t drb_nfm_param_count(int32_t factors, int32_t num_layers, int32_t batch_norm);
@@ -278,6 +282,12 @@ int drb_nfm_bpr_train_steps(float *d_P, float *d_Q, float *d_bias, float *d_N, f
                             int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
                             int32_t apply, int32_t tower_dtype, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step,
                             void *stream);
+int drb_nfm_bpr_train_steps_dropout(float *d_P, float *d_Q, float *d_bias, float *d_N, float *d_Rs, void *d_ws, int32_t user_num,
+                                    int32_t item_num, int32_t factors, int32_t num_layers, int32_t batch_norm, int32_t act,
+                                    int64_t max_rows, const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n,
+                                    int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *hyper,
+                                    int64_t adam_step0, int32_t apply, int32_t tower_dtype, const uint8_t *d_keep, float dropout,
+                                    double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 int drb_nfm_scores(const float *d_P, const float *d_Q, const float *d_bias, const float *d_N, const float *d_Rs, void *d_ws,
                    int32_t user_num, int32_t item_num, int32_t factors, int32_t num_layers, int32_t batch_norm, int32_t act,
                    int32_t opt, int64_t max_rows, const int32_t *d_u, const int32_t *d_i, int64_t n, int32_t tower_dtype,

@@ -619,6 +619,83 @@ def gen_nfm():
     _save("nfm", **out)
 
 
+def gen_nfm_dropout():
+    """NFM at the reference's DEFAULT dropout (assets/nfm.yaml: 0.5; NFMRecommender.py:67,:88): the masks come from torch's
+    global CPU generator, one bernoulli_ per Dropout call -- forward(user, pos): FM_layers' Dropout, then the Dropout behind
+    each activation; forward(user, neg): the same.  With dropout > 0 the unmodified reference trains (no aliasing shim needed).
+    Per case: snapshots around 3 training steps, the RNG seed set right before them, losses, eval-mode ranking."""
+    import torch
+    from daisy.model.NFMRecommender import NFM
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [  # U, I, F, L, bn, act, B, lr, reg1, reg2, opt, dropout, seed
+        (40, 60, 30, 2, True, "relu", 128, 0.001, 0.0, 0.0, "sgd", 0.5, 61),          # assets/nfm.yaml
+        (30, 40, 12, 1, False, "tanh", 50, 0.01, 0.001, 0.001, "sgd", 0.3, 62),
+        (30, 45, 16, 3, True, "sigmoid", 96, 0.01, 0.0, 0.001, "sgd", 0.5, 63),
+        (25, 30, 8, 2, False, "relu", 40, 0.001, 0.001, 0.0, "adam", 0.2, 64),
+        (25, 30, 8, 0, True, "relu", 40, 0.01, 0.0, 0.0, "sgd", 0.5, 65),              # no hidden layer: only FM_layers' Dropout
+    ]
+    ACT = {"relu": 0, "sigmoid": 1, "tanh": 2}
+    for k, (U, I, F, L, bn, act, B, lr, r1, r2, opt, drop, seed) in enumerate(cases):
+        cfg = rh.make_config("nfm", user_num=U, item_num=I, factors=F, num_layers=L, batch_norm=bn, act_function=act, dropout=drop,
+                             lr=lr, reg_1=r1, reg_2=r2, optimizer=opt, epochs=1, topk=10, cand_num=40)
+        torch.manual_seed(seed)
+        model = NFM(cfg)
+        with torch.no_grad():
+            model.embed_user.weight.mul_(3.0)
+            model.embed_item.weight.mul_(3.0)
+            model.u_bias.weight.normal_(0, 0.3)
+            model.i_bias.weight.normal_(0, 0.3)
+            model.bias_.fill_(0.25)
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        bns = [m for m in list(model.FM_layers) + list(model.deep_layers) if isinstance(m, torch.nn.BatchNorm1d)]
+
+        def snap():
+            net = []
+            for m in list(model.FM_layers) + list(model.deep_layers):
+                if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.Linear)):
+                    net += [m.weight, m.bias]
+            net.append(model.prediction.weight)
+            return (model.embed_user.weight.detach().numpy().copy(), model.embed_item.weight.detach().numpy().copy(),
+                    np.concatenate([model.u_bias.weight.detach().numpy().ravel(), model.i_bias.weight.detach().numpy().ravel(),
+                                    model.bias_.detach().numpy().ravel()]).astype(np.float32),
+                    np.concatenate([w.detach().numpy().ravel() for w in net]).astype(np.float32),
+                    np.concatenate([np.concatenate([m.running_mean.numpy(), m.running_var.numpy()]) for m in bns]).astype(np.float32)
+                    if bns else np.zeros(0, np.float32))
+        snaps, batches, losses = [snap()], [], []
+        model.train()
+        torch.manual_seed(seed + 100)                                   # the dropout masks of the 3 steps come from here
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            snaps.append(snap())
+        rng_after = torch.get_rng_state().numpy().copy()
+        model.eval()
+        users = rng.permutation(U)[:9].astype(np.int64)
+        cands = rng.integers(I, size=(9, 40)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), c] for u, c in zip(users, cands)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        with torch.no_grad():
+            preds = model.rank(loader)
+        out.update({f"c{k}_P": np.stack([s_[0] for s_ in snaps]), f"c{k}_Q": np.stack([s_[1] for s_ in snaps]),
+                    f"c{k}_bias": np.stack([s_[2] for s_ in snaps]), f"c{k}_N": np.stack([s_[3] for s_ in snaps]),
+                    f"c{k}_R": np.stack([s_[4] for s_ in snaps]), f"c{k}_batches": np.stack(batches),
+                    f"c{k}_loss": np.array(losses, np.float64),
+                    f"c{k}_hyper": np.array([L, 1 if bn else 0, ACT[act], lr, r1, r2, 0 if opt == "sgd" else 1, drop, seed], np.float64),
+                    f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32), f"c{k}_preds": preds,
+                    f"c{k}_rng_after": rng_after})
+        print(f"nfm_dropout case {k} (L={L} bn={bn} {act}/{opt} p={drop}): losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("nfm_dropout", **out)
+
+
 # --------------------------------------------------------------------------- NeuMF
 def _neumf_flat(model):
     """4 tables + the flat tower block in module-registration order (layer weight, bias, ..., predict weight, bias)."""
@@ -845,7 +922,7 @@ def gen_sampler_pop():
     _save("sampler_pop", **out)
 
 
-ALL = {"neumf_modes": gen_neumf_modes, "nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+ALL = {"nfm_dropout": gen_nfm_dropout, "neumf_modes": gen_neumf_modes, "nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

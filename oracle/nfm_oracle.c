@@ -109,15 +109,19 @@ static void bn_backward(const float *dy, const float *xhat, const float *inv_std
 }
 
 typedef struct {
-    float *e, *h0;                         /* e = p*q, h0 = FM_layers(e) */
+    float *e, *h0;                         /* e = p*q, h0 = FM_layers(e) before its Dropout */
+    float *h0d, *hd[NFM_MAXL];             /* the Dropout outputs (what the next module reads); == h0 / h[l] without dropout */
     float *xh0, is0[512];
     float *zpre[NFM_MAXL], *z[NFM_MAXL], *h[NFM_MAXL], *xh[NFM_MAXL];   /* Linear out, (BN out =) act input, act out, BN xhat */
     float *is[NFM_MAXL];
     float *fm, *pred;
 } nfm_pass;
 
+/* keep (optional, training only): the factors nn.Dropout multiplies with, 0 or 1/(1-p), layout [site][B][F] with site 0 = the
+ * Dropout of FM_layers (:67) and site 1+l = the Dropout behind activation l (:88) */
 static void nfm_forward(const float *P, const float *Q, const float *bias, const float *N, float *R, int32_t U, int32_t I, int32_t F,
-                        int32_t L, int32_t bn, int32_t act, const int32_t *bu, const int32_t *bi, int64_t B, int train, nfm_pass *a)
+                        int32_t L, int32_t bn, int32_t act, const int32_t *bu, const int32_t *bi, int64_t B, int train, nfm_pass *a,
+                        const float *keep)
 {
     size_t sz = (size_t)B * F;
     const float *w = N;
@@ -134,7 +138,9 @@ static void nfm_forward(const float *P, const float *Q, const float *bias, const
     } else {
         memcpy(a->h0, a->e, sizeof(float) * sz);
     }
-    const float *hin = a->h0;
+    a->h0d = (float *)malloc(sizeof(float) * sz);
+    for (size_t k = 0; k < sz; k++) a->h0d[k] = keep ? a->h0[k] * keep[k] : a->h0[k];
+    const float *hin = a->h0d;
     for (int l = 0; l < L; l++) {
         const float *W = w, *b = w + (size_t)F * F;
         w = b + F;
@@ -157,7 +163,9 @@ static void nfm_forward(const float *P, const float *Q, const float *bias, const
             memcpy(a->z[l], a->zpre[l], sizeof(float) * sz);
         }
         for (size_t k = 0; k < sz; k++) a->h[l][k] = act_f(act, a->z[l][k]);
-        hin = a->h[l];
+        a->hd[l] = (float *)malloc(sizeof(float) * sz);
+        for (size_t k = 0; k < sz; k++) a->hd[l][k] = keep ? a->h[l][k] * keep[(size_t)(1 + l) * sz + k] : a->h[l][k];
+        hin = a->hd[l];
     }
     const float *wp = w;
     a->fm = (float *)malloc(sizeof(float) * sz);
@@ -175,8 +183,8 @@ static void nfm_forward(const float *P, const float *Q, const float *bias, const
 
 static void nfm_free(nfm_pass *a, int L)
 {
-    free(a->e); free(a->h0); free(a->xh0); free(a->fm); free(a->pred);
-    for (int l = 0; l < L; l++) { free(a->zpre[l]); free(a->z[l]); free(a->h[l]); free(a->xh[l]); free(a->is[l]); }
+    free(a->e); free(a->h0); free(a->h0d); free(a->xh0); free(a->fm); free(a->pred);
+    for (int l = 0; l < L; l++) { free(a->zpre[l]); free(a->z[l]); free(a->h[l]); free(a->hd[l]); free(a->xh[l]); free(a->is[l]); }
 }
 
 /* eval-mode scores of (users[k], items[k]) pairs: forward() under model.eval() (:153-209) */
@@ -191,7 +199,7 @@ void orc_nfm_scores(const float *P, const float *Q, const float *bias, const flo
         Rc = (float *)malloc(sizeof(float) * nr);
         memcpy(Rc, R, sizeof(float) * nr);
     }
-    nfm_forward(P, Q, bias, N, Rc, U, I, F, L, bn, act, users, items, n, 0, &a);
+    nfm_forward(P, Q, bias, N, Rc, U, I, F, L, bn, act, users, items, n, 0, &a, NULL);
     memcpy(scores, a.pred, sizeof(float) * (size_t)n);
     nfm_free(&a, L);
     free(Rc);
@@ -199,7 +207,7 @@ void orc_nfm_scores(const float *P, const float *Q, const float *bias, const flo
 
 static void nfm_backward(const float *P, const float *Q, const float *N, int32_t U, int32_t F, int32_t L, int32_t bn, int32_t act,
                          const int32_t *bu, const int32_t *bi, int64_t B, const nfm_pass *a, const float *dpred, double *gP,
-                         double *gQ, double *gbias, int32_t I, double *gN)
+                         double *gQ, double *gbias, int32_t I, double *gN, const float *keep)
 {
     size_t sz = (size_t)B * F;
     /* offsets inside N */
@@ -222,7 +230,9 @@ static void nfm_backward(const float *P, const float *Q, const float *N, int32_t
     }
     for (int l = L - 1; l >= 0; l--) {
         const float *W = N + oW[l];
-        const float *hin = l == 0 ? a->h0 : a->h[l - 1];
+        const float *hin = l == 0 ? a->h0d : a->hd[l - 1];
+        if (keep)                                                                                    /* Dropout backward */
+            for (size_t k = 0; k < sz; k++) dh[k] = dh[k] * keep[(size_t)(1 + l) * sz + k];
         for (size_t k = 0; k < sz; k++) tmp[k] = dh[k] * act_grad(act, a->z[l][k], a->h[l][k]);      /* d act input */
         if (bn) {
             bn_backward(tmp, a->xh[l], a->is[l], N + oBN[l], B, F, dh, gN + oBN[l], gN + oBN[l] + F);   /* dh := d Linear out */
@@ -244,6 +254,8 @@ static void nfm_backward(const float *P, const float *Q, const float *N, int32_t
             }
         memcpy(dh, tmp, sizeof(float) * sz);
     }
+    if (keep)
+        for (size_t k = 0; k < sz; k++) dh[k] = dh[k] * keep[k];
     if (bn) {
         bn_backward(dh, a->xh0, a->is0, N + o_bn0, B, F, tmp, gN + o_bn0, gN + o_bn0 + F);
         memcpy(dh, tmp, sizeof(float) * sz);
@@ -259,15 +271,30 @@ static void nfm_backward(const float *P, const float *Q, const float *N, int32_t
 
 /* One NFM BPR step == calc_loss (:125-151) + backward + optimizer.step.  state (optional): m then v over [P | Q | bias | N].
  * R (running statistics) is updated by the two training-mode forward calls.  Returns the fp32 loss. */
+double orc_nfm_bpr_step_ex(float *P, float *Q, float *bias, float *N, float *R, int32_t U, int32_t I, int32_t F, int32_t L,
+                           int32_t bn, int32_t act, const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B,
+                           const orc_hyper *h, int32_t apply, float *state, int64_t step_count, const float *keep_pos,
+                           const float *keep_neg);
+
 double orc_nfm_bpr_step(float *P, float *Q, float *bias, float *N, float *R, int32_t U, int32_t I, int32_t F, int32_t L,
                         int32_t bn, int32_t act, const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B,
                         const orc_hyper *h, int32_t apply, float *state, int64_t step_count)
 {
+    return orc_nfm_bpr_step_ex(P, Q, bias, N, R, U, I, F, L, bn, act, bu, bi, bj, B, h, apply, state, step_count, NULL, NULL);
+}
+
+/* keep_pos / keep_neg (optional): the Dropout factors of the positive / the negative forward call ([1 + L][B][F], 0 or 1/(1-p)),
+ * drawn by the caller in the reference's order (dropout = config['dropout'] > 0, :67,:88) */
+double orc_nfm_bpr_step_ex(float *P, float *Q, float *bias, float *N, float *R, int32_t U, int32_t I, int32_t F, int32_t L,
+                           int32_t bn, int32_t act, const int32_t *bu, const int32_t *bi, const int32_t *bj, int64_t B,
+                           const orc_hyper *h, int32_t apply, float *state, int64_t step_count, const float *keep_pos,
+                           const float *keep_neg)
+{
     const float gamma = 1e-10f;
     if (F > 512) return NAN;
     nfm_pass pa, na;
-    nfm_forward(P, Q, bias, N, R, U, I, F, L, bn, act, bu, bi, B, 1, &pa);
-    nfm_forward(P, Q, bias, N, bn ? R : NULL, U, I, F, L, bn, act, bu, bj, B, 1, &na);
+    nfm_forward(P, Q, bias, N, R, U, I, F, L, bn, act, bu, bi, B, 1, &pa, keep_pos);
+    nfm_forward(P, Q, bias, N, bn ? R : NULL, U, I, F, L, bn, act, bu, bj, B, 1, &na, keep_neg);
     float *c = (float *)malloc(sizeof(float) * (size_t)(B > 0 ? B : 1)), *cn = (float *)malloc(sizeof(float) * (size_t)(B > 0 ? B : 1));
     double bpr = 0, l1u = 0, l1i = 0, l1j = 0, s2u = 0, s2i = 0, s2j = 0;
     for (int64_t t = 0; t < B; t++) {
@@ -296,8 +323,8 @@ double orc_nfm_bpr_step(float *P, float *Q, float *bias, float *N, float *R, int
     const int64_t nP = (int64_t)U * F, nQ = (int64_t)I * F, nB = (int64_t)U + I + 1, nN = orc_nfm_param_count(F, L, bn);
     double *gP = (double *)calloc((size_t)nP, sizeof(double)), *gQ = (double *)calloc((size_t)nQ, sizeof(double));
     double *gb = (double *)calloc((size_t)nB, sizeof(double)), *gN = (double *)calloc((size_t)nN, sizeof(double));
-    nfm_backward(P, Q, N, U, F, L, bn, act, bu, bi, B, &pa, c, gP, gQ, gb, I, gN);
-    nfm_backward(P, Q, N, U, F, L, bn, act, bu, bj, B, &na, cn, gP, gQ, gb, I, gN);
+    nfm_backward(P, Q, N, U, F, L, bn, act, bu, bi, B, &pa, c, gP, gQ, gb, I, gN, keep_pos);
+    nfm_backward(P, Q, N, U, F, L, bn, act, bu, bj, B, &na, cn, gP, gQ, gb, I, gN, keep_neg);
     float inu = nu > 0 ? (float)(1.0 / nu) : 0.f, ini = ni > 0 ? (float)(1.0 / ni) : 0.f, inj = nj > 0 ? (float)(1.0 / nj) : 0.f;
     for (int64_t t = 0; t < B; t++) {
         const float *p = P + (int64_t)bu[t] * F, *qi = Q + (int64_t)bi[t] * F, *qj = Q + (int64_t)bj[t] * F;

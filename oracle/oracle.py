@@ -319,12 +319,28 @@ def nfm_param_count(F, L, bn):
     return int(lib().orc_nfm_param_count(F, L, 1 if bn else 0))
 
 
-def nfm_bpr_step(P, Q, bias, N, R, L, bn, act, bu, bi, bj, hp, apply=True, state=None, step_count=1):
-    """In place on P, Q, bias, N (net block) and R (BatchNorm running statistics).  Returns the loss."""
-    lib().orc_nfm_bpr_step.restype = C.c_double
-    return lib().orc_nfm_bpr_step(_f32(P), _f32(Q), _f32(bias), _f32(N), _f32(R) if R.size else None, P.shape[0], Q.shape[0],
-                                  P.shape[1], L, 1 if bn else 0, act, _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)),
-                                  C.byref(hp), 1 if apply else 0, None if state is None else _f32(state), C.c_int64(step_count))
+def nfm_dropout_keep(B, F, L, p):
+    """The factors NFM's Dropout modules multiply with during ONE training step of B triples (NFMRecommender.py:67,:88):
+    forward(user, pos) draws site 0 (FM_layers) and sites 1..L (behind each activation), then forward(user, neg) the same; one
+    bernoulli_ per Dropout call on torch's global CPU generator, scaled by 1 / (1 - p) -> (keep_pos, keep_neg), float32
+    [1 + L, B, F] each."""
+    import torch
+    scale = np.float32(1.0) / np.float32(1.0 - p)
+    sides = []
+    for _side in range(2):
+        sides.append(np.stack([torch.empty(B, F, dtype=torch.float32).bernoulli_(1.0 - p).numpy() * scale for _ in range(1 + L)]))
+    return np.ascontiguousarray(sides[0], np.float32), np.ascontiguousarray(sides[1], np.float32)
+
+
+def nfm_bpr_step(P, Q, bias, N, R, L, bn, act, bu, bi, bj, hp, apply=True, state=None, step_count=1, keep=None):
+    """In place on P, Q, bias, N (net block) and R (BatchNorm running statistics).  Returns the loss.
+    keep: nfm_dropout_keep(...) in train mode with dropout > 0."""
+    lib().orc_nfm_bpr_step_ex.restype = C.c_double
+    kp, kn = (None, None) if keep is None else (_f32(keep[0]), _f32(keep[1]))
+    return lib().orc_nfm_bpr_step_ex(_f32(P), _f32(Q), _f32(bias), _f32(N), _f32(R) if R.size else None, P.shape[0], Q.shape[0],
+                                     P.shape[1], L, 1 if bn else 0, act, _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)),
+                                     C.byref(hp), 1 if apply else 0, None if state is None else _f32(state),
+                                     C.c_int64(step_count), kp, kn)
 
 
 def nfm_scores(P, Q, bias, N, R, L, bn, act, users, items):

@@ -1,0 +1,114 @@
+"""NFM with nn.Dropout active (the reference default, assets/nfm.yaml: dropout 0.5) on the device against the reference-generated
+fixture tests/golden/nfm_dropout.npz: the host draws torch's own masks in the reference's order, the kernels apply them.
+(This file sorts last on purpose: its CUDA path was written after the round's last GPU slot.)"""
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+ACTS = ["relu", "sigmoid", "tanh"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _keep_bytes(B, F, L, p):
+    """torch's draws for one step, in the reference's order -> (uint8 CUDA tensor for the kernels, float factors for the oracle)."""
+    parts = []
+    for _side in (0, 1):
+        for _site in range(1 + L):
+            parts.append(torch.empty(B, F, dtype=torch.float32).bernoulli_(1.0 - p))
+    k = torch.stack(parts).reshape(2, 1 + L, B, F)
+    scale = np.float32(1.0) / np.float32(1.0 - p)
+    f = k.numpy() * scale
+    return k.to(torch.uint8).reshape(-1).cuda(), (np.ascontiguousarray(f[0], np.float32), np.ascontiguousarray(f[1], np.float32))
+
+
+def test_nfm_dropout_steps_match_reference_fixture(orc):
+    from daisyrec_b200 import ops
+    g = golden("nfm_dropout")
+    for c in range(int(g["ncases"])):
+        L, bn, act, lr, r1, r2, opt, drop, seed = g[f"c{c}_hyper"]
+        L, bn, act, seed, drop = int(L), bool(bn), int(act), int(seed), float(drop)
+        optn = "sgd" if opt == 0 else "adam"
+        Ps, Qs, Bs, Ns, Rs = g[f"c{c}_P"], g[f"c{c}_Q"], g[f"c{c}_bias"], g[f"c{c}_N"], g[f"c{c}_R"]
+        bs, losses = g[f"c{c}_batches"], g[f"c{c}_loss"]
+        U, F = Ps.shape[1:]
+        I = Qs.shape[1]
+        hp = ops.hyper(float(lr), float(r1), float(r2), optn)
+        ho = orc.hyper(lr=lr, reg_1=r1, reg_2=r2, opt=optn)
+        ws = ops.NfmWorkspace(U, I, F, L, bn, optn, 2 * bs.shape[2], "cuda")       # optimiser state carried across the steps
+        tot = Ps[0].size + Qs[0].size + Bs.shape[1] + Ns.shape[1]
+        state = None if opt == 0 else np.zeros(2 * tot, np.float32)
+        torch.manual_seed(seed + 100)
+        for s in range(bs.shape[0]):
+            P, Q, bias, N = dev(Ps[s]), dev(Qs[s]), dev(Bs[s]), dev(Ns[s])
+            R = dev(Rs[s]) if bn else None
+            b = [dev(bs[s][k]) for k in range(3)]
+            keep_d, keep_h = _keep_bytes(b[0].numel(), F, L, drop)
+            loss = ops.nfm_bpr_train_steps(P, Q, bias, N, R, ws, act, *b, b[0].numel(), 0, 1, hp, adam_step0=s, dropout=drop,
+                                           keep=keep_d).item()
+            assert abs(loss - losses[s]) <= 3e-5 * abs(losses[s]), (c, s, loss, losses[s])
+            # the oracle on the same masks (pinned on this fixture by tests/test_oracle_golden.py)
+            Po, Qo, bo, No, Ro = (a[s].copy() for a in (Ps, Qs, Bs, Ns, Rs))
+            bh = np.ascontiguousarray(bs[s])
+            lo = orc.nfm_bpr_step(Po, Qo, bo, No, Ro, L, bn, act, bh[0], bh[1], bh[2], ho, True, state, s + 1, keep=keep_h)
+            assert abs(loss - lo) <= 3e-5 * abs(lo), (c, s, loss, lo)
+            for got, want, nm in ((P, Ps[s + 1], "P"), (Q, Qs[s + 1], "Q"), (bias, Bs[s + 1], "bias"), (N, Ns[s + 1], "N")):
+                err = np.abs(got.cpu().numpy() - want)
+                tol = (1e-5 if optn == "sgd" else 1e-4) * max(1.0, np.abs(want).max())
+                assert (err <= tol).mean() >= 0.99 and err.max() <= 2.1 * float(lr) + tol, \
+                    (c, s, nm, float((err <= tol).mean()), float(err.max()))
+            if bn:
+                np.testing.assert_allclose(R.cpu().numpy(), Rs[s + 1], rtol=2e-5, atol=2e-6, err_msg=f"running stats {c} {s}")
+        assert np.array_equal(torch.get_rng_state().numpy(), g[f"c{c}_rng_after"]), c   # as many draws as the reference made
+
+
+def test_nfm_class_runs_the_reference_default_config():
+    """NFM(config) with the reference's default dropout: three train_step calls from the fixture's state reproduce the
+    reference's parameters and leave torch's global generator where the reference left it; eval-mode ranking has no dropout."""
+    from daisyrec_b200.model import NFM
+    from daisyrec_b200.utils.dataset import CandidatesDataset, get_dataloader
+    g = golden("nfm_dropout")
+    for c in range(int(g["ncases"])):
+        L, bn, act, lr, r1, r2, opt, drop, seed = g[f"c{c}_hyper"]
+        L, bn, act, seed = int(L), bool(bn), int(act), int(seed)
+        U, F = g[f"c{c}_P"].shape[1:]
+        I = g[f"c{c}_Q"].shape[1]
+        cfg = dict(gpu="", logger=logging.getLogger("t"), epochs=1, lr=float(lr), reg_1=float(r1), reg_2=float(r2), user_num=U,
+                   item_num=I, factors=F, num_layers=L, batch_norm=bn, act_function=ACTS[act], dropout=float(drop), loss_type="BPR",
+                   optimizer="sgd" if opt == 0 else "adam", init_method="default", early_stop=False, topk=10, progress=False)
+        torch.manual_seed(seed)
+        m = NFM(cfg)
+        Bs = g[f"c{c}_bias"]
+        sd = {"embed_user.weight": g[f"c{c}_P"][0], "embed_item.weight": g[f"c{c}_Q"][0], "u_bias.weight": Bs[0][:U],
+              "i_bias.weight": Bs[0][U:U + I], "bias_": Bs[0][U + I:], "net": g[f"c{c}_N"][0]}
+        if bn:
+            sd["running"] = g[f"c{c}_R"][0]
+        m.load_state_dict(sd)
+        b = g[f"c{c}_batches"]
+        torch.manual_seed(seed + 100)
+        for s in range(3):
+            loss = m.train_step([torch.from_numpy(b[s][k]) for k in range(3)])
+            assert abs(loss - g[f"c{c}_loss"][s]) <= (5e-5 if opt == 0 else 2e-3) * abs(g[f"c{c}_loss"][s]), (c, s, loss)
+        assert np.array_equal(torch.get_rng_state().numpy(), g[f"c{c}_rng_after"]), c
+        want = g[f"c{c}_P"][3]
+        err = np.abs(m.embed_user.weight.cpu().numpy() - want)
+        tol = (3e-5 if opt == 0 else 3e-4) * max(1.0, np.abs(want).max())
+        assert (err <= tol).mean() >= 0.98, (c, float((err <= tol).mean()))
+        # eval mode: no dropout, running statistics -- the reference's ranking on its own final state
+        m.load_state_dict({"embed_user.weight": g[f"c{c}_P"][3], "embed_item.weight": g[f"c{c}_Q"][3], "u_bias.weight": Bs[3][:U],
+                           "i_bias.weight": Bs[3][U:U + I], "bias_": Bs[3][U + I:], "net": g[f"c{c}_N"][3],
+                           **({"running": g[f"c{c}_R"][3]} if bn else {})})
+        m.eval()
+        users, cands = g[f"c{c}_users"], g[f"c{c}_cands"].astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), cands[r]] for r, u in enumerate(users)]), batch_size=128, shuffle=False)
+        preds = m.rank(loader)
+        assert (preds == g[f"c{c}_preds"]).mean() >= 0.97, c
+        with pytest.raises(ValueError):
+            NFM(dict(cfg, dropout=1.0))
