@@ -155,10 +155,12 @@ __global__ void ngcf_mix_kernel(const float *__restrict__ E, const float *__rest
 }
 
 // one warp per row: y = (Y1 + b1) + (Y2 + b2) (:59), z = LeakyReLU_0.2(y), rn = max(||z||_2, 1e-12), N = z / rn (F.normalize :165)
+// keep (optional): the mask nn.Dropout(mess_dropout) draws over this layer's [n, d] output (:164), bytes; z *= keep ? scale : 0
 __global__ void __launch_bounds__(256) ngcf_act_kernel(const float *__restrict__ Y1, const float *__restrict__ Y2,
                                                        const float *__restrict__ b1, const float *__restrict__ b2, long long n,
                                                        int d, float *__restrict__ Y, float *__restrict__ rn, float *__restrict__ N,
-                                                       float *__restrict__ ALL, int C, int coff)
+                                                       float *__restrict__ ALL, int C, int coff, const uint8_t *__restrict__ keep,
+                                                       float scale)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -166,7 +168,8 @@ __global__ void __launch_bounds__(256) ngcf_act_kernel(const float *__restrict__
         double ss = 0.0;
         for (int o = lane; o < d; o += 32) {
             const float y = (Y1[r * d + o] + b1[o]) + (Y2[r * d + o] + b2[o]);
-            const float z = y > 0.f ? y : 0.2f * y;
+            float z = y > 0.f ? y : 0.2f * y;
+            if (keep) z = z * (keep[r * d + o] ? scale : 0.f);
             Y[r * d + o] = y;
             ss += (double)(z * z);
         }
@@ -176,7 +179,8 @@ __global__ void __launch_bounds__(256) ngcf_act_kernel(const float *__restrict__
         if (lane == 0) rn[r] = (float)nr;
         for (int o = lane; o < d; o += 32) {
             const float y = Y[r * d + o];
-            const float z = y > 0.f ? y : 0.2f * y;
+            float z = y > 0.f ? y : 0.2f * y;
+            if (keep) z = z * (keep[r * d + o] ? scale : 0.f);
             const float v = (float)((double)z / nr);
             N[r * d + o] = v;
             ALL[r * C + coff + o] = v;
@@ -199,7 +203,8 @@ __global__ void ngcf_copy_block_kernel(const float *__restrict__ E, long long n,
 __global__ void __launch_bounds__(256) ngcf_act_bwd_kernel(const float *__restrict__ G, int C, int coff,
                                                            const float *__restrict__ dE, const float *__restrict__ N,
                                                            const float *__restrict__ Y, const float *__restrict__ rn,
-                                                           long long n, int d, float *__restrict__ dY)
+                                                           long long n, int d, float *__restrict__ dY,
+                                                           const uint8_t *__restrict__ keep, float scale)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -214,7 +219,9 @@ __global__ void __launch_bounds__(256) ngcf_act_bwd_kernel(const float *__restri
         for (int o = lane; o < d; o += 32) {
             const double dn = (double)G[r * C + coff + o] + (dE ? (double)dE[r * d + o] : 0.0);
             const double dz = (nr > 1e-12) ? (dn - (double)N[r * d + o] * dot) / nr : dn / nr;
-            dY[r * d + o] = (float)dz * (Y[r * d + o] > 0.f ? 1.f : 0.2f);
+            float dzf = (float)dz;
+            if (keep) dzf = dzf * (keep[r * d + o] ? scale : 0.f);        // Dropout backward
+            dY[r * d + o] = dzf * (Y[r * d + o] > 0.f ? 1.f : 0.2f);
         }
     }
 }
@@ -307,8 +314,9 @@ __global__ void ngcf_update_w_kernel(float *__restrict__ W, float *__restrict__ 
     }
 }
 
+// keep: masks of the L layers concatenated ([n, d[1]], [n, d[2]], ...), or nullptr
 static int ngcf_forward(const NgcfDims &q, const NgcfWs &w, const Adj &adj, const float *E0, const float *W, int dtype,
-                        cudaStream_t st)
+                        cudaStream_t st, const uint8_t *keep = nullptr, float scale = 1.f)
 {
     const long long n = q.n;
     ngcf_copy_block_kernel<<<ngcf_grid(n * q.d[0], 256), 256, 0, st>>>(E0, n, q.d[0], w.ALL, q.C, 0);
@@ -326,8 +334,9 @@ static int ngcf_forward(const NgcfDims &q, const NgcfWs &w, const Adj &adj, cons
         if (rc == DRB_OK) rc = gemm_nt(dtype, n, out, in, w.ST + in, 2 * in, W2, in, w.Y2, out, st);
         if (rc != DRB_OK) return rc;
         ngcf_act_kernel<<<ngcf_grid(n * 32, 256), 256, 0, st>>>(w.Y1, w.Y2, b1, b2, n, out, w.Y[l], w.rn[l], w.E[l + 1], w.ALL,
-                                                              q.C, q.off[l + 1]);
+                                                              q.C, q.off[l + 1], keep, scale);
         DRB_CUDA(cudaGetLastError());
+        if (keep) keep += (size_t)n * out;
         E = w.E[l + 1];
     }
     return DRB_OK;
@@ -365,7 +374,19 @@ extern "C" int drb_ngcf_forward(const float *d_E0, const float *d_W, void *d_ws,
                                 const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg, int32_t tower_dtype,
                                 float *d_out, void *stream)
 {
+    return drb_ngcf_forward_dropout(d_E0, d_W, d_ws, U, I, dims, L, d_row_ptr, d_col, d_val, d_seg_row, d_seg_ptr, nseg, tower_dtype,
+                                    nullptr, 0.f, d_out, stream);
+}
+
+// forward() with nn.Dropout(mess_dropout) active (:164; the reference's module is always in training mode, rank() included).
+// d_keep: the masks torch draws, one per layer over its [n, width] output, as bytes, layers concatenated; NULL = no dropout.
+extern "C" int drb_ngcf_forward_dropout(const float *d_E0, const float *d_W, void *d_ws, int32_t U, int32_t I, const int32_t *dims,
+                                        int32_t L, const int64_t *d_row_ptr, const int32_t *d_col, const float *d_val,
+                                        const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg, int32_t tower_dtype,
+                                        const uint8_t *d_keep, float dropout, float *d_out, void *stream)
+{
     NgcfDims q;
+    DRB_REQUIRE(d_keep == nullptr || (dropout > 0.f && dropout < 1.f), "ngcf: dropout masks need 0 < mess_dropout < 1");
     DRB_REQUIRE(d_E0 && d_W && d_ws && d_row_ptr && d_out && ngcf_dims(q, U, I, dims, L), "ngcf_forward: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     NgcfWs w;
@@ -373,7 +394,7 @@ extern "C" int drb_ngcf_forward(const float *d_E0, const float *d_W, void *d_ws,
     Adj adj;
     adj.row_ptr = d_row_ptr; adj.col = d_col; adj.val = d_val; adj.seg_row = d_seg_row; adj.seg_ptr = d_seg_ptr; adj.nseg = nseg;
     adj.n = q.n;
-    int rc = ngcf_forward(q, w, adj, d_E0, d_W, tower_dtype, st);
+    int rc = ngcf_forward(q, w, adj, d_E0, d_W, tower_dtype, st, d_keep, d_keep ? 1.0f / (float)(1.0 - (double)dropout) : 1.f);
     if (rc != DRB_OK) return rc;
     DRB_CUDA(cudaMemcpyAsync(d_out, w.ALL, sizeof(float) * (size_t)q.n * q.C, cudaMemcpyDeviceToDevice, st));
     return DRB_OK;
@@ -388,7 +409,25 @@ extern "C" int drb_ngcf_bpr_train_steps(float *d_E0, float *d_W, void *d_ws, int
                                         int32_t apply, int32_t tower_dtype, double *d_step_loss, int32_t sync_and_check,
                                         int64_t *nan_step, void *stream)
 {
+    return drb_ngcf_bpr_train_steps_dropout(d_E0, d_W, d_ws, U, I, dims, L, d_row_ptr, d_col, d_val, d_seg_row, d_seg_ptr, nseg, d_bu,
+                                            d_bi, d_bj, n_triples, batch, first_step, n_steps, h, adam_step0, apply, tower_dtype,
+                                            nullptr, 0.f, d_step_loss, sync_and_check, nan_step, stream);
+}
+
+// The same with the message dropout of :164 active (reference default mess_dropout 0.1).  d_keep: per step the masks of the one
+// forward() a step runs (layers concatenated, bytes), steps concatenated.
+extern "C" int drb_ngcf_bpr_train_steps_dropout(float *d_E0, float *d_W, void *d_ws, int32_t U, int32_t I, const int32_t *dims,
+                                                int32_t L, const int64_t *d_row_ptr, const int32_t *d_col, const float *d_val,
+                                                const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg,
+                                                const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n_triples,
+                                                int64_t batch, int64_t first_step, int64_t n_steps, const drb_hyper *h,
+                                                int64_t adam_step0, int32_t apply, int32_t tower_dtype, const uint8_t *d_keep,
+                                                float dropout, double *d_step_loss, int32_t sync_and_check, int64_t *nan_step,
+                                                void *stream)
+{
     NgcfDims q;
+    DRB_REQUIRE(d_keep == nullptr || (dropout > 0.f && dropout < 1.f), "ngcf: dropout masks need 0 < mess_dropout < 1");
+    const float drop_scale = d_keep ? 1.0f / (float)(1.0 - (double)dropout) : 1.f;
     DRB_REQUIRE(d_E0 && d_W && d_ws && d_row_ptr && d_bu && d_bi && d_bj && h && d_step_loss, "ngcf_train_steps: null argument");
     DRB_REQUIRE(ngcf_dims(q, U, I, dims, L), "ngcf_train_steps: bad layer widths (1..256, 1 <= layers <= 8)");
     DRB_REQUIRE(batch > 0 && n_steps >= 0 && (n_steps == 0 || (first_step + n_steps - 1) * batch < n_triples),
@@ -407,7 +446,10 @@ extern "C" int drb_ngcf_bpr_train_steps(float *d_E0, float *d_W, void *d_ws, int
     DRB_CUDA(cudaMemsetAsync(w.hdr, 0, sizeof(WsHeader), st));
     for (int64_t s = 0; s < n_steps; ++s) {
         const int64_t base = (first_step + s) * batch, nb = (n_triples - base < batch) ? n_triples - base : batch;
-        int rc = ngcf_forward(q, w, adj, d_E0, d_W, tower_dtype, st);
+        size_t keep_per_step = 0;
+        for (int l = 0; l < q.L; ++l) keep_per_step += (size_t)n * q.d[l + 1];
+        const uint8_t *keep = d_keep ? d_keep + (size_t)s * keep_per_step : nullptr;
+        int rc = ngcf_forward(q, w, adj, d_E0, d_W, tower_dtype, st, keep, drop_scale);
         if (rc != DRB_OK) return rc;
         // phase 1: scores on the concatenated representation, norms on the ego rows, G = dL / d(representation)
         StepParams p;
@@ -445,8 +487,10 @@ extern "C" int drb_ngcf_bpr_train_steps(float *d_E0, float *d_W, void *d_ws, int
             const float *El = l == 0 ? d_E0 : w.E[l];
             const float *W1 = d_W + q.w_off[l], *W2 = W1 + (size_t)in * out + out;
             float *gW1 = w.gW + q.w_off[l], *gb1 = gW1 + (size_t)in * out, *gW2 = gb1 + out, *gb2 = gW2 + (size_t)in * out;
+            const uint8_t *keep_l = keep;
+            if (keep_l) for (int k = 0; k < l; ++k) keep_l += (size_t)n * q.d[k + 1];
             ngcf_act_bwd_kernel<<<ngcf_grid(n * 32, 256), 256, 0, st>>>(w.G, C, q.off[l + 1], dE, w.E[l + 1], w.Y[l], w.rn[l], n, out,
-                                                                      w.dY);
+                                                                      w.dY, keep_l, drop_scale);
             DRB_CUDA(cudaGetLastError());
             rc = colsum_acc(w.dY, n, out, gb1, st);
             if (rc == DRB_OK) rc = colsum_acc(w.dY, n, out, gb2, st);

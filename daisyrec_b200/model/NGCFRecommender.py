@@ -1,5 +1,5 @@
 """NGCF + BPR on the B200 path, with the reference's class name, config keys and methods
-(daisy/model/NGCFRecommender.py:61-252; node_dropout = mess_dropout = 0).
+(daisy/model/NGCFRecommender.py:61-252; node_dropout = 0).
 
 The ego table E0 = cat(embed_user.weight, embed_item.weight) is one contiguous device tensor; the BiGNN layers live in
 one flat fp32 block (``gnn``: per layer W1, b1, W2, b2 in module-registration order); the normalised adjacency is
@@ -8,9 +8,12 @@ LightGCN's (``get_norm_adj_mat`` :125-146 is the same arithmetic) as segmented C
 optimiser phases); rank / full_rank / predict score the cached concatenated representation (``restore_user_e`` /
 ``restore_item_e``, :99-100) with the MF rank kernels.
 
-Dropout: the reference draws its node / message masks from torch's RNG and keeps the message dropout active even at
-rank() time (:164 builds a fresh nn.Dropout in training mode).  Non-zero ``node_dropout`` / ``mess_dropout`` are refused
-rather than approximated.
+Message dropout (``mess_dropout``, reference default 0.1): forward() builds ``nn.Dropout(mess_dropout)`` per layer (:164), a
+module in training mode, so the reference drops on EVERY forward() -- the one behind rank() / full_rank() / predict() as well.
+The host draws exactly those masks (one ``bernoulli_(1 - p)`` per layer over its [n, width] output, torch's global CPU
+generator) and uploads them as bytes; the kernels apply them between LeakyReLU and the row normalisation, forward and backward.
+That is a parity mechanism (one byte per node and width through the host per forward); ``mess_dropout = 0`` is the throughput
+configuration.  ``node_dropout`` (reference default 0; a sparse dropout of the adjacency) is refused when non-zero.
 """
 import numpy as np
 import torch
@@ -35,9 +38,12 @@ class NGCF(GeneralRecommender):
         self.hidden_size_list = [self.embedding_size] + list(hidden)
         self.node_dropout = config['node_dropout']
         self.message_dropout = config['mess_dropout']
-        if float(self.node_dropout or 0.0) != 0.0 or float(self.message_dropout or 0.0) != 0.0:
-            raise NotImplementedError('NGCF on the B200 path runs with node_dropout = mess_dropout = 0 (the reference draws '
-                                      'its masks from the torch RNG, also at rank() time)')
+        if float(self.node_dropout or 0.0) != 0.0:
+            raise NotImplementedError('NGCF on the B200 path runs with node_dropout = 0 (the reference default; a sparse dropout '
+                                      'of the adjacency drawn from the torch RNG)')
+        self.message_dropout = float(self.message_dropout or 0.0)
+        if not 0.0 <= self.message_dropout < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), but got {self.message_dropout}")
         self.reg_1 = config['reg_1']
         self.reg_2 = config['reg_2']
         self.loss_type = config['loss_type']
@@ -106,10 +112,32 @@ class NGCF(GeneralRecommender):
         if self._ws is None:
             self._begin_fit(self._optimizer_name())
 
+    def _host_keep(self, n_forwards):
+        """The masks nn.Dropout(mess_dropout) draws for n_forwards forward() calls: per call one bernoulli_ per layer over its
+        [n, width] output on torch's global CPU generator -> uint8 CUDA tensor (None without message dropout)."""
+        if self.message_dropout <= 0.0:
+            return None
+        n, keep = self.user_num + self.item_num, 1.0 - self.message_dropout
+        parts = []
+        for _ in range(n_forwards):
+            for width in self.hidden_size_list[1:]:
+                parts.append(torch.empty(n, int(width), dtype=torch.float32).bernoulli_(keep).to(torch.uint8).reshape(-1))
+        return torch.cat(parts).to(self.device)
+
     def _train_steps(self, bu, bi, bj, batch, first, n_steps):
         self.restore_user_e = self.restore_item_e = None             # NGCFRecommender.py:175-176
-        losses = ops.ngcf_bpr_train_steps(self.E0, self.gnn, self._ws, self.graph, bu, bi, bj, batch, first, n_steps, self._hp,
-                                          adam_step0=self._opt_steps, tower_dtype=self._tower_dtype)
+        kw = dict(tower_dtype=self._tower_dtype, dropout=self.message_dropout)
+        if self.message_dropout <= 0.0:
+            losses = ops.ngcf_bpr_train_steps(self.E0, self.gnn, self._ws, self.graph, bu, bi, bj, batch, first, n_steps, self._hp,
+                                              adam_step0=self._opt_steps, **kw)
+        else:                                                        # masks of at most 64 MB per call, drawn in step order
+            chunk = max(1, (64 << 20) // max(1, ops.ngcf_keep_bytes(self._ws)))
+            out = []
+            for s in range(first, first + n_steps, chunk):
+                k = min(chunk, first + n_steps - s)
+                out.append(ops.ngcf_bpr_train_steps(self.E0, self.gnn, self._ws, self.graph, bu, bi, bj, batch, s, k, self._hp,
+                                                    adam_step0=self._opt_steps + (s - first), keep=self._host_keep(k), **kw))
+            losses = torch.cat(out)
         self._opt_steps += n_steps
         return losses
 
@@ -117,7 +145,8 @@ class NGCF(GeneralRecommender):
     def forward(self):
         """NGCFRecommender.py:157-172 -> (user_all_embeddings, item_all_embeddings): the concatenated layer outputs."""
         self._ensure_ws()
-        rep = ops.ngcf_forward(self.E0, self.gnn, self._ws, self.graph, self._tower_dtype)
+        rep = ops.ngcf_forward(self.E0, self.gnn, self._ws, self.graph, self._tower_dtype, dropout=self.message_dropout,
+                               keep=self._host_keep(1))              # the reference's forward() always drops (:164)
         return rep[:self.user_num], rep[self.user_num:]
 
     def calc_loss(self, batch):
@@ -126,7 +155,8 @@ class NGCF(GeneralRecommender):
         self.restore_user_e = self.restore_item_e = None
         bu, bi, bj = (torch.as_tensor(b).to(self.device, torch.int32).contiguous() for b in batch[:3])
         loss = ops.ngcf_bpr_train_steps(self.E0, self.gnn, self._ws, self.graph, bu, bi, bj, bu.numel(), 0, 1, self._hp,
-                                        apply=False, tower_dtype=self._tower_dtype)
+                                        apply=False, tower_dtype=self._tower_dtype, dropout=self.message_dropout,
+                                        keep=self._host_keep(1))
         return loss.to(torch.float32).reshape(())
 
     def train_step(self, batch):

@@ -588,25 +588,42 @@ class NgcfWorkspace:
                                                 self.opt, _stream()))
 
 
-def ngcf_forward(E0, W, ws, graph, tower_dtype=0):
+def ngcf_keep_bytes(ws):
+    """bytes of dropout masks one forward() consumes: one per element of every layer output."""
+    return (ws.U + ws.I) * sum(ws.dims[1:])
+
+
+def ngcf_forward(E0, W, ws, graph, tower_dtype=0, dropout=0.0, keep=None):
+    """keep (with mess_dropout > 0): uint8 CUDA tensor, the masks torch's nn.Dropout draws per layer, layers concatenated."""
     _dev(E0, torch.float32, "E0"); _dev(W, torch.float32, "W")
+    if keep is not None:
+        _dev(keep, torch.uint8, "keep")
+        if keep.numel() != ngcf_keep_bytes(ws):
+            raise ValueError("keep must hold (user_num + item_num) x sum(hidden widths) bytes")
     out = torch.empty((ws.U + ws.I, sum(ws.dims)), dtype=torch.float32, device=E0.device)
-    L.check(L.lib().drb_ngcf_forward(_ptr(E0), _ptr(W), _ptr(ws.buf), ws.U, ws.I, _dims_arr(ws.dims), len(ws.dims) - 1,
-                                     *graph.args(), tower_dtype, _ptr(out), _stream()))
+    L.check(L.lib().drb_ngcf_forward_dropout(_ptr(E0), _ptr(W), _ptr(ws.buf), ws.U, ws.I, _dims_arr(ws.dims), len(ws.dims) - 1,
+                                             *graph.args(), tower_dtype, None if keep is None else _ptr(keep),
+                                             C.c_float(dropout if keep is not None else 0.0), _ptr(out), _stream()))
     return out
 
 
 def ngcf_bpr_train_steps(E0, W, ws, graph, bu, bi, bj, batch, first_step, n_steps, hp, adam_step0=0, apply=True, check=True,
-                         tower_dtype=0):
+                         tower_dtype=0, dropout=0.0, keep=None):
     _dev(E0, torch.float32, "E0"); _dev(W, torch.float32, "W")
     for t, nm in ((bu, "bu"), (bi, "bi"), (bj, "bj")):
         _dev(t, torch.int32, nm)
+    if keep is not None:
+        _dev(keep, torch.uint8, "keep")
+        if keep.numel() != max(1, n_steps) * ngcf_keep_bytes(ws):
+            raise ValueError("keep must hold n_steps x (user_num + item_num) x sum(hidden widths) bytes")
     losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=E0.device)
     nan_step = C.c_int64(-1)
-    rc = L.lib().drb_ngcf_bpr_train_steps(_ptr(E0), _ptr(W), _ptr(ws.buf), ws.U, ws.I, _dims_arr(ws.dims), len(ws.dims) - 1,
-                                          *graph.args(), _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(), batch, first_step, n_steps,
-                                          C.byref(hp), adam_step0, 1 if apply else 0, tower_dtype, _ptr(losses),
-                                          1 if check else 0, C.byref(nan_step), _stream())
+    rc = L.lib().drb_ngcf_bpr_train_steps_dropout(_ptr(E0), _ptr(W), _ptr(ws.buf), ws.U, ws.I, _dims_arr(ws.dims), len(ws.dims) - 1,
+                                                  *graph.args(), _ptr(bu), _ptr(bi), _ptr(bj), bu.numel(), batch, first_step,
+                                                  n_steps, C.byref(hp), adam_step0, 1 if apply else 0, tower_dtype,
+                                                  None if keep is None else _ptr(keep),
+                                                  C.c_float(dropout if keep is not None else 0.0), _ptr(losses),
+                                                  1 if check else 0, C.byref(nan_step), _stream())
     if rc == L.DRB_ERR_NAN_LOSS:
         raise ValueError("Loss=Nan or Infinity: current settings does not fit the recommender")
     L.check(rc)

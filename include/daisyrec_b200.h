@@ -234,13 +234,16 @@ int drb_fm_full_rank(const float *d_P, const float *d_Q, const float *d_bias, in
 int drb_fm_predict(const float *d_P, const float *d_Q, const float *d_bias, int32_t user_num, int32_t item_num,
                    int32_t factors, const int32_t *d_u, const int32_t *d_i, int64_t n, float *d_out, void *stream);
 
-/* ---- NGCF + BPR (daisy/model/NGCFRecommender.py:38-252; node_dropout = mess_dropout = 0) ----------
+/* ---- NGCF + BPR (daisy/model/NGCFRecommender.py:38-252; node_dropout = 0) -------------------------
  * E0: the ego table cat(embed_user, embed_item) [(U+I), dims[0]];  dims[0..L]: embedding size then hidden_size_list;
  * W: flat fp32 block, per BiGNN layer W1 [out,in], b1 [out], W2 [out,in], b2 [out] (linear, interact_transform; :46-47);
  * adjacency: the normalised CSR + segment list of drb_lgcn_* (get_norm_adj_mat :125-146 is LightGCN's).
  * drb_ngcf_forward      NGCF.forward :157-172 -> [(U+I), sum(dims)] = cat(E_0 .. E_L) (what rank / full_rank / predict score
  *                       with: feed its user / item halves to drb_mf_rank, drb_mf_full_rank, drb_mf_predict)
  * drb_ngcf_bpr_train_steps  calc_loss :174-205 + backward + optimizer.step for n_steps batches (apply = 0: loss of one batch).
+ * drb_ngcf_forward_dropout / drb_ngcf_bpr_train_steps_dropout  the same with nn.Dropout(mess_dropout) of :164 active (reference
+ *    default 0.1; the reference builds the module inside forward(), so it drops at rank() time too): d_keep = the masks torch
+ *    draws, one per layer over its [(U+I), width] output, as bytes, layers concatenated (train_steps: steps concatenated).
  * Layer widths: 1..256.  tower_dtype as for NeuMF (0 fp32, 1 bf16 tcgen05 GEMMs). */
 int64_t drb_ngcf_param_count(const int32_t *h_dims, int32_t num_layers);
 size_t drb_ngcf_workspace_bytes(int32_t user_num, int32_t item_num, const int32_t *h_dims, int32_t num_layers, int32_t opt);
@@ -250,6 +253,17 @@ int drb_ngcf_forward(const float *d_E0, const float *d_W, void *d_ws, int32_t us
                      int32_t num_layers, const int64_t *d_row_ptr, const int32_t *d_col, const float *d_val,
                      const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg, int32_t tower_dtype, float *d_out,
                      void *stream);
+int drb_ngcf_forward_dropout(const float *d_E0, const float *d_W, void *d_ws, int32_t user_num, int32_t item_num,
+                             const int32_t *h_dims, int32_t num_layers, const int64_t *d_row_ptr, const int32_t *d_col,
+                             const float *d_val, const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg,
+                             int32_t tower_dtype, const uint8_t *d_keep, float mess_dropout, float *d_out, void *stream);
+int drb_ngcf_bpr_train_steps_dropout(float *d_E0, float *d_W, void *d_ws, int32_t user_num, int32_t item_num,
+                                     const int32_t *h_dims, int32_t num_layers, const int64_t *d_row_ptr, const int32_t *d_col,
+                                     const float *d_val, const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg,
+                                     const int32_t *d_bu, const int32_t *d_bi, const int32_t *d_bj, int64_t n, int64_t batch,
+                                     int64_t first_step, int64_t n_steps, const drb_hyper *hyper, int64_t adam_step0,
+                                     int32_t apply, int32_t tower_dtype, const uint8_t *d_keep, float mess_dropout,
+                                     double *d_step_loss, int32_t sync_and_check, int64_t *nan_step, void *stream);
 int drb_ngcf_bpr_train_steps(float *d_E0, float *d_W, void *d_ws, int32_t user_num, int32_t item_num, const int32_t *h_dims,
                              int32_t num_layers, const int64_t *d_row_ptr, const int32_t *d_col, const float *d_val,
                              const int32_t *d_seg_row, const int64_t *d_seg_ptr, int64_t nseg, const int32_t *d_bu,

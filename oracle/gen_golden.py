@@ -535,6 +535,78 @@ def gen_ngcf():
     _save("ngcf", **out)
 
 
+def gen_ngcf_dropout():
+    """NGCF at the reference's DEFAULT message dropout (assets/ngcf.yaml: mess_dropout 0.1, node_dropout 0): forward() builds a
+    fresh nn.Dropout per layer (:164) -- a module in training mode, so the masks are drawn on EVERY forward(), the one behind
+    rank() / full_rank() / predict() included (one draw per layer over the [n, width] layer output, torch's global CPU generator).
+    Per case: the forward right after seeding, 3 training steps from a seeded generator, then rank() from another seed."""
+    import pandas as pd
+    import torch
+    from daisy.model.NGCFRecommender import NGCF
+    from daisy.utils.utils import get_inter_matrix
+    from daisy.utils.dataset import CandidatesDataset, get_dataloader
+    out = {}
+    cases = [  # U, I, nnz, F, hidden, B, lr, reg1, reg2, opt, mess_dropout, seed
+        (40, 50, 400, 36, [64, 64, 64], 256, 0.01, 0.0, 0.0, "default", 0.1, 71),        # assets/ngcf.yaml defaults
+        (30, 45, 300, 8, [12, 6], 64, 0.05, 0.001, 0.001, "sgd", 0.3, 72),
+        (25, 30, 200, 6, [10], 50, 0.01, 0.0, 0.001, "sgd", 0.5, 73),
+    ]
+    rng0 = np.random.default_rng(78)
+
+    def flat(model):
+        ws = []
+        for g in model.gnn_layers:
+            ws += [g.linear.weight, g.linear.bias, g.interact_transform.weight, g.interact_transform.bias]
+        return np.concatenate([w.detach().numpy().ravel() for w in ws]).astype(np.float32)
+    for k, (U, I, nnz, F, hidden, B, lr, r1, r2, opt, drop, seed) in enumerate(cases):
+        cu, ci = _synthetic_inter(rng0, U, I, nnz)
+        df = pd.DataFrame({"user": cu, "item": ci, "rating": 1.0, "timestamp": np.arange(len(cu))})
+        cfg = rh.make_config("ngcf", user_num=U, item_num=I, factors=F, hidden_size_list=hidden, node_dropout=0.0,
+                             mess_dropout=drop, lr=lr, reg_1=r1, reg_2=r2, optimizer=opt, epochs=1, topk=10, cand_num=40)
+        cfg["inter_matrix"] = get_inter_matrix(df, cfg)
+        torch.manual_seed(seed)
+        model = NGCF(cfg)
+        model.criterion = model._build_criterion(model.loss_type)
+        optim = model._build_optimizer(optimizer=model.optimizer, lr=model.lr)
+        rng = np.random.default_rng(seed)
+        E = [torch.cat([model.embed_user.weight, model.embed_item.weight]).detach().numpy().copy()]
+        Ws = [flat(model)]
+        torch.manual_seed(seed + 50)
+        with torch.no_grad():
+            eu, ei = model.forward()
+        all0 = torch.cat([eu, ei]).numpy().copy()
+        batches, losses = [], []
+        torch.manual_seed(seed + 100)                                   # the masks of the 3 steps come from here
+        for step in range(3):
+            b = np.stack([rng.integers(U, size=B), rng.integers(I, size=B), rng.integers(I, size=B)]).astype(np.int32)
+            batches.append(b)
+            model.zero_grad()
+            loss = model.calc_loss([torch.from_numpy(b[0]), torch.from_numpy(b[1]), torch.from_numpy(b[2])])
+            loss.backward()
+            optim.step()
+            losses.append(float(loss.item()))
+            E.append(torch.cat([model.embed_user.weight, model.embed_item.weight]).detach().numpy().copy())
+            Ws.append(flat(model))
+        rng_after = torch.get_rng_state().numpy().copy()
+        users = rng.permutation(U)[:9].astype(np.int64)
+        cands = rng.integers(I, size=(9, 40)).astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), c] for u, c in zip(users, cands)]), batch_size=128,
+                                shuffle=False, num_workers=0)
+        torch.manual_seed(seed + 200)                                   # rank() runs forward() once: masks from here
+        with torch.no_grad():
+            preds = model.rank(loader)
+            all_rank = torch.cat([model.restore_user_e, model.restore_item_e]).numpy().copy()
+        out.update({f"c{k}_coo_u": cu, f"c{k}_coo_i": ci, f"c{k}_E": np.stack(E), f"c{k}_W": np.stack(Ws), f"c{k}_all0": all0,
+                    f"c{k}_batches": np.stack(batches), f"c{k}_loss": np.array(losses, np.float64),
+                    f"c{k}_dims": np.array([F] + hidden, np.int32),
+                    f"c{k}_hyper": np.array([U, I, lr, r1, r2, 0 if opt == "sgd" else 1, drop, seed], np.float64),
+                    f"c{k}_users": users, f"c{k}_cands": cands.astype(np.int32), f"c{k}_preds": preds, f"c{k}_all_rank": all_rank,
+                    f"c{k}_rng_after": rng_after})
+        print(f"ngcf_dropout case {k} (p={drop}): losses {losses}")
+    out["ncases"] = np.array(len(cases))
+    _save("ngcf_dropout", **out)
+
+
 # --------------------------------------------------------------------------- NFM
 def gen_nfm():
     """NFM (NFMRecommender.py:14-209) with dropout = 0: bi-interaction + [BatchNorm] + MLP + broadcast biases + prediction;
@@ -922,7 +994,7 @@ def gen_sampler_pop():
     _save("sampler_pop", **out)
 
 
-ALL = {"nfm_dropout": gen_nfm_dropout, "neumf_modes": gen_neumf_modes, "nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
+ALL = {"ngcf_dropout": gen_ngcf_dropout, "nfm_dropout": gen_nfm_dropout, "neumf_modes": gen_neumf_modes, "nfm": gen_nfm, "ngcf": gen_ngcf, "fm": gen_fm, "mf_optim": gen_mf_optim, "mf_pointwise": gen_mf_pointwise, "metrics": gen_metrics, "sampler_pop": gen_sampler_pop, "neumf": gen_neumf, "lightgcn": gen_lightgcn, "sampler_small": gen_sampler_small, "ml100k": gen_ml100k_pipeline, "mf_steps": gen_mf_steps,
        "mf_rank": gen_mf_rank}
 
 if __name__ == "__main__":

@@ -60,10 +60,12 @@ typedef struct {
     double *rn[NGCF_MAXL];       /* max(||Z row||, 1e-12) */
 } ngcf_acts;
 
+/* keep (optional): the factors of nn.Dropout(mess_dropout) (:164), 0 or 1/(1-p), layers concatenated: [n, dims[1]], [n, dims[2]], ... */
 static void ngcf_forward(const float *E0, const float *W, int64_t n, const int32_t *dims, int32_t L, const int64_t *row_ptr,
-                         const int32_t *col, const float *val, ngcf_acts *a)
+                         const int32_t *col, const float *val, ngcf_acts *a, const float *keep)
 {
     const float *w = W;
+    const float *kp = keep;
     a->E[0] = (float *)E0;
     for (int l = 0; l < L; l++) {
         const int in = dims[l], out = dims[l + 1];
@@ -86,6 +88,7 @@ static void ngcf_forward(const float *E0, const float *W, int64_t n, const int32
                 }
                 float y = ((float)acc1 + b1[o]) + ((float)acc2 + b2[o]);       /* inter_part1 + inter_part2 (:59) */
                 float z = y > 0.f ? y : 0.2f * y;
+                if (kp) z = z * kp[r * out + o];                                /* message dropout (:164) */
                 a->Y[l][r * out + o] = y;
                 a->Z[l][r * out + o] = z;
                 ss += (double)(z * z);
@@ -95,6 +98,7 @@ static void ngcf_forward(const float *E0, const float *W, int64_t n, const int32
             a->rn[l][r] = nr;
             for (int o = 0; o < out; o++) a->E[l + 1][r * out + o] = (float)((double)a->Z[l][r * out + o] / nr);
         }
+        if (kp) kp += (size_t)n * out;
     }
 }
 
@@ -106,14 +110,24 @@ static void ngcf_free(ngcf_acts *a, int32_t L)
 }
 
 /* NGCF.forward (:157-172): out [n, sum(dims)] = cat(E_0 .. E_L, dim=1) */
+void orc_ngcf_forward_ex(const float *E0, const float *W, int32_t U, int32_t I, const int32_t *dims, int32_t L,
+                         const int64_t *row_ptr, const int32_t *col, const float *val, float *out, const float *keep);
+
 void orc_ngcf_forward(const float *E0, const float *W, int32_t U, int32_t I, const int32_t *dims, int32_t L,
                       const int64_t *row_ptr, const int32_t *col, const float *val, float *out)
+{
+    orc_ngcf_forward_ex(E0, W, U, I, dims, L, row_ptr, col, val, out, NULL);
+}
+
+/* keep: message-dropout factors (see ngcf_forward); the reference's forward() applies them whenever it runs, rank() included */
+void orc_ngcf_forward_ex(const float *E0, const float *W, int32_t U, int32_t I, const int32_t *dims, int32_t L,
+                         const int64_t *row_ptr, const int32_t *col, const float *val, float *out, const float *keep)
 {
     int64_t n = (int64_t)U + I;
     int C = 0;
     for (int l = 0; l <= L; l++) C += dims[l];
     ngcf_acts a;
-    ngcf_forward(E0, W, n, dims, L, row_ptr, col, val, &a);
+    ngcf_forward(E0, W, n, dims, L, row_ptr, col, val, &a, keep);
     for (int64_t r = 0; r < n; r++) {
         int o = 0;
         for (int l = 0; l <= L; l++) {
@@ -126,9 +140,20 @@ void orc_ngcf_forward(const float *E0, const float *W, int32_t U, int32_t I, con
 
 /* One NGCF BPR step == calc_loss (:174-205) + backward + optimizer.step.  state (optional): m then v, each the size of
  * [E0 | W] (Adam), in that order.  Returns the fp32 loss. */
+double orc_ngcf_bpr_step_ex(float *E0, float *W, int32_t U, int32_t I, const int32_t *dims, int32_t L, const int64_t *row_ptr,
+                            const int32_t *col, const float *val, const int32_t *bu, const int32_t *bi, const int32_t *bj,
+                            int64_t B, const orc_hyper *h, int32_t apply, float *state, int64_t step_count, const float *keep);
+
 double orc_ngcf_bpr_step(float *E0, float *W, int32_t U, int32_t I, const int32_t *dims, int32_t L, const int64_t *row_ptr,
                          const int32_t *col, const float *val, const int32_t *bu, const int32_t *bi, const int32_t *bj,
                          int64_t B, const orc_hyper *h, int32_t apply, float *state, int64_t step_count)
+{
+    return orc_ngcf_bpr_step_ex(E0, W, U, I, dims, L, row_ptr, col, val, bu, bi, bj, B, h, apply, state, step_count, NULL);
+}
+
+double orc_ngcf_bpr_step_ex(float *E0, float *W, int32_t U, int32_t I, const int32_t *dims, int32_t L, const int64_t *row_ptr,
+                            const int32_t *col, const float *val, const int32_t *bu, const int32_t *bi, const int32_t *bj,
+                            int64_t B, const orc_hyper *h, int32_t apply, float *state, int64_t step_count, const float *keep)
 {
     const float gamma = 1e-10f;
     const int64_t n = (int64_t)U + I;
@@ -136,7 +161,7 @@ double orc_ngcf_bpr_step(float *E0, float *W, int32_t U, int32_t I, const int32_
     int C = 0, off[NGCF_MAXL + 2];
     for (int l = 0; l <= L; l++) { off[l] = C; C += dims[l]; }
     ngcf_acts a;
-    ngcf_forward(E0, W, n, dims, L, row_ptr, col, val, &a);
+    ngcf_forward(E0, W, n, dims, L, row_ptr, col, val, &a, keep);
     float *all = (float *)malloc(sizeof(float) * (size_t)n * C);
     for (int64_t r = 0; r < n; r++)
         for (int l = 0; l <= L; l++) memcpy(all + r * C + off[l], a.E[l] + r * dims[l], sizeof(float) * (size_t)dims[l]);
@@ -181,8 +206,11 @@ double orc_ngcf_bpr_step(float *E0, float *W, int32_t U, int32_t I, const int32_
     float *dE = NULL;
     int64_t woff[NGCF_MAXL];
     { int64_t o = 0; for (int l = 0; l < L; l++) { woff[l] = o; o += 2 * ((int64_t)dims[l] * dims[l + 1] + dims[l + 1]); } }
+    int64_t koff[NGCF_MAXL];
+    { int64_t o = 0; for (int l = 0; l < L; l++) { koff[l] = o; o += n * dims[l + 1]; } }
     for (int l = L - 1; l >= 0; l--) {
         const int in = dims[l], out = dims[l + 1];
+        const float *kl = keep ? keep + koff[l] : NULL;
         const float *W1 = W + woff[l], *W2 = W1 + (size_t)in * out + out;
         double *gW1 = gW + woff[l], *gb1 = gW1 + (size_t)in * out, *gW2 = gb1 + out, *gb2 = gW2 + (size_t)in * out;
         float *dX = (float *)malloc(sizeof(float) * (size_t)n * in);
@@ -204,6 +232,7 @@ double orc_ngcf_bpr_step(float *E0, float *W, int32_t U, int32_t I, const int32_
                 /* normalize backward: (dN - N <N, dN>) / ||Z||  (||Z|| clamped at 1e-12: the clamp branch has no N-term) */
                 double dz = (nr > 1e-12) ? (dn - (double)nn[o] * dot) / nr : dn / nr;
                 (void)z;
+                if (kl) dz = (double)((float)dz * kl[r * out + o]);               /* Dropout backward */
                 float dy = (float)dz * (y[o] > 0.f ? 1.f : 0.2f);
                 dY[o] = dy;
                 if (dy != 0.f) any = 1;

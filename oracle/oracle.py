@@ -297,20 +297,31 @@ def ngcf_param_count(dims):
     return int(lib().orc_ngcf_param_count(_i32(dims), len(dims) - 1))
 
 
-def ngcf_forward(E0, W, U, I, dims, row_ptr, col, val):
-    """NGCF.forward: [U + I, sum(dims)] concatenated layer outputs."""
+def ngcf_dropout_keep(n, dims, p):
+    """The factors of NGCF's nn.Dropout(mess_dropout) (NGCFRecommender.py:164) for ONE forward(): one bernoulli_ per layer on
+    torch's global CPU generator over the [n, dims[l + 1]] layer output, scaled by 1 / (1 - p) -> float32, layers concatenated."""
+    import torch
+    scale = np.float32(1.0) / np.float32(1.0 - p)
+    return np.ascontiguousarray(np.concatenate([torch.empty(n, int(d), dtype=torch.float32).bernoulli_(1.0 - p).numpy().reshape(-1)
+                                                for d in list(dims)[1:]]) * scale, np.float32)
+
+
+def ngcf_forward(E0, W, U, I, dims, row_ptr, col, val, keep=None):
+    """NGCF.forward: [U + I, sum(dims)] concatenated layer outputs.  keep: ngcf_dropout_keep(...) when mess_dropout > 0."""
     dims = np.ascontiguousarray(dims, np.int32)
     out = np.empty((U + I, int(dims.sum())), np.float32)
-    lib().orc_ngcf_forward(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val), _f32(out))
+    lib().orc_ngcf_forward_ex(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val), _f32(out),
+                              None if keep is None else _f32(keep))
     return out
 
 
-def ngcf_bpr_step(E0, W, U, I, dims, row_ptr, col, val, bu, bi, bj, hp, apply=True, state=None, step_count=1):
+def ngcf_bpr_step(E0, W, U, I, dims, row_ptr, col, val, bu, bi, bj, hp, apply=True, state=None, step_count=1, keep=None):
     dims = np.ascontiguousarray(dims, np.int32)
-    lib().orc_ngcf_bpr_step.restype = C.c_double
-    return lib().orc_ngcf_bpr_step(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val),
-                                   _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), 1 if apply else 0,
-                                   None if state is None else _f32(state), C.c_int64(step_count))
+    lib().orc_ngcf_bpr_step_ex.restype = C.c_double
+    return lib().orc_ngcf_bpr_step_ex(_f32(E0), _f32(W), U, I, _i32(dims), len(dims) - 1, _i64(row_ptr), _i32(col), _f32(val),
+                                      _i32(bu), _i32(bi), _i32(bj), C.c_int64(len(bu)), C.byref(hp), 1 if apply else 0,
+                                      None if state is None else _f32(state), C.c_int64(step_count),
+                                      None if keep is None else _f32(keep))
 
 
 # ---------------------------------------------------------------- NFM (nfm_oracle.c)

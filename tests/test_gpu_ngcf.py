@@ -92,8 +92,8 @@ def test_ngcf_class_drop_in():
         full = np.stack([m.full_rank(int(u)) for u in users[:4]])
         assert (full == g[f"c{c}_full"]).mean() >= 0.9
         np.testing.assert_allclose(m.predict(int(users[0]), int(cands[0][0])), float(g[f"c{c}_pred_pair"][0]), rtol=3e-5, atol=3e-6)
-        with pytest.raises(NotImplementedError):
-            NGCF(dict(cfg, mess_dropout=0.1))
+        with pytest.raises(NotImplementedError):                          # sparse dropout of the adjacency (reference default 0)
+            NGCF(dict(cfg, node_dropout=0.1))                              # (mess_dropout > 0 runs: tests/test_gpu_zzz_dropout.py)
 
 
 def test_ngcf_vs_oracle_random(orc):

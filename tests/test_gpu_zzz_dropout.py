@@ -112,3 +112,89 @@ def test_nfm_class_runs_the_reference_default_config():
         assert (preds == g[f"c{c}_preds"]).mean() >= 0.97, c
         with pytest.raises(ValueError):
             NFM(dict(cfg, dropout=1.0))
+
+
+# ------------------------------------------------------------------ NGCF message dropout (reference default mess_dropout 0.1)
+def _ngcf_keep(n, dims, p):
+    parts = [torch.empty(n, int(d), dtype=torch.float32).bernoulli_(1.0 - p) for d in list(dims)[1:]]
+    flat = torch.cat([t.reshape(-1) for t in parts])
+    scale = np.float32(1.0) / np.float32(1.0 - p)
+    return flat.to(torch.uint8).cuda(), np.ascontiguousarray(flat.numpy() * scale, np.float32)
+
+
+def test_ngcf_message_dropout_matches_reference_fixture(orc):
+    from daisyrec_b200 import ops
+    g = golden("ngcf_dropout")
+    for c in range(int(g["ncases"])):
+        U, I, lr, r1, r2, opt, drop, seed = g[f"c{c}_hyper"]
+        U, I, seed, drop = int(U), int(I), int(seed), float(drop)
+        optn = "sgd" if opt == 0 else "adam"
+        dims = [int(d) for d in g[f"c{c}_dims"]]
+        row_ptr, col, val = ops.lgcn_norm_adj(g[f"c{c}_coo_u"], g[f"c{c}_coo_i"], U, I)
+        graph = ops.LgcnGraph(row_ptr, col, val, "cuda")
+        Es, Ws, bs, losses = g[f"c{c}_E"], g[f"c{c}_W"], g[f"c{c}_batches"], g[f"c{c}_loss"]
+        ws = ops.NgcfWorkspace(U, I, dims, optn, "cuda")
+        torch.manual_seed(seed + 50)
+        keep_d, _ = _ngcf_keep(U + I, dims, drop)
+        rep = ops.ngcf_forward(dev(Es[0]), dev(Ws[0]), ws, graph, dropout=drop, keep=keep_d).cpu().numpy()
+        np.testing.assert_allclose(rep, g[f"c{c}_all0"], rtol=0, atol=3e-6, err_msg=f"case {c} forward")
+        hp = ops.hyper(lr, r1, r2, optn)
+        ho = orc.hyper(lr=lr, reg_1=r1, reg_2=r2, opt=optn)
+        state = None if opt == 0 else np.zeros(2 * (Es[0].size + Ws.shape[1]), np.float32)
+        torch.manual_seed(seed + 100)
+        for s in range(bs.shape[0]):
+            E, W = dev(Es[s]), dev(Ws[s])
+            b = [dev(bs[s][k]) for k in range(3)]
+            keep_d, keep_h = _ngcf_keep(U + I, dims, drop)
+            l1 = ops.ngcf_bpr_train_steps(E, W, ws, graph, *b, b[0].numel(), 0, 1, hp, adam_step0=s, dropout=drop, keep=keep_d).item()
+            assert abs(l1 - losses[s]) <= 3e-5 * abs(losses[s]), (c, s, l1, losses[s])
+            Eo, Wo = Es[s].copy(), Ws[s].copy()
+            bh = np.ascontiguousarray(bs[s])
+            lo = orc.ngcf_bpr_step(Eo, Wo, U, I, np.asarray(dims, np.int32), row_ptr, col, val, bh[0], bh[1], bh[2], ho, True, state,
+                                   s + 1, keep=keep_h)
+            assert abs(l1 - lo) <= 3e-5 * abs(lo), (c, s, l1, lo)
+            for got, want, nm in ((E.cpu().numpy(), Es[s + 1], "E"), (W.cpu().numpy(), Ws[s + 1], "W")):
+                err = np.abs(got - want)
+                tol = (5e-6 if optn == "sgd" else 5e-5) * max(1.0, np.abs(want).max())
+                assert (err <= tol).mean() >= 0.99 and err.max() <= 2.1 * lr + tol, (c, s, nm, float((err <= tol).mean()), float(err.max()))
+        assert np.array_equal(torch.get_rng_state().numpy(), g[f"c{c}_rng_after"]), c
+
+
+def test_ngcf_class_runs_the_reference_default_config():
+    """NGCF(config) with the reference's default mess_dropout: train steps from the fixture's state, then rank() -- whose
+    forward() still drops, as the reference's does -- reproduce the reference from the same generator seeds."""
+    import pandas as pd
+    from daisyrec_b200.model import NGCF
+    from daisyrec_b200.utils.dataset import CandidatesDataset, get_dataloader
+    from daisyrec_b200.utils.utils import get_inter_matrix
+    g = golden("ngcf_dropout")
+    for c in range(int(g["ncases"])):
+        U, I, lr, r1, r2, opt, drop, seed = g[f"c{c}_hyper"]
+        U, I, seed = int(U), int(I), int(seed)
+        dims = [int(d) for d in g[f"c{c}_dims"]]
+        cu, ci = g[f"c{c}_coo_u"], g[f"c{c}_coo_i"]
+        df = pd.DataFrame({"user": cu, "item": ci, "rating": 1.0, "timestamp": np.arange(len(cu))})
+        cfg = dict(gpu="", logger=logging.getLogger("t"), epochs=1, lr=float(lr), reg_1=float(r1), reg_2=float(r2), user_num=U,
+                   item_num=I, factors=dims[0], hidden_size_list=dims[1:], node_dropout=0.0, mess_dropout=float(drop),
+                   loss_type="BPR", optimizer="sgd" if opt == 0 else "default", init_method="default", early_stop=False, topk=10,
+                   progress=False, UID_NAME="user", IID_NAME="item", INTER_NAME="rating")
+        cfg["inter_matrix"] = get_inter_matrix(df, cfg)
+        torch.manual_seed(seed)
+        m = NGCF(cfg)
+        assert np.array_equal(m.E0.cpu().numpy(), g[f"c{c}_E"][0]) and np.array_equal(m.gnn.cpu().numpy(), g[f"c{c}_W"][0]), c
+        torch.manual_seed(seed + 50)
+        eu, ei = m.forward()
+        np.testing.assert_allclose(torch.cat([eu, ei]).cpu().numpy(), g[f"c{c}_all0"], rtol=0, atol=3e-6)
+        b = g[f"c{c}_batches"]
+        torch.manual_seed(seed + 100)
+        for s in range(3):
+            loss = m.train_step([torch.from_numpy(b[s][k]) for k in range(3)])
+            assert abs(loss - g[f"c{c}_loss"][s]) <= (5e-5 if opt == 0 else 3e-3) * abs(g[f"c{c}_loss"][s]), (c, s, loss)
+        assert np.array_equal(torch.get_rng_state().numpy(), g[f"c{c}_rng_after"]), c
+        m.load_state_dict({"embed_user.weight": g[f"c{c}_E"][3][:U], "embed_item.weight": g[f"c{c}_E"][3][U:], "gnn": g[f"c{c}_W"][3]})
+        users, cands = g[f"c{c}_users"], g[f"c{c}_cands"].astype(np.int64)
+        loader = get_dataloader(CandidatesDataset([[int(u), cands[r]] for r, u in enumerate(users)]), batch_size=128, shuffle=False)
+        torch.manual_seed(seed + 200)
+        preds = m.rank(loader)
+        np.testing.assert_allclose(torch.cat([m.restore_user_e, m.restore_item_e]).cpu().numpy(), g[f"c{c}_all_rank"], rtol=0, atol=3e-6)
+        assert (preds == g[f"c{c}_preds"]).mean() >= 0.97, c
