@@ -532,10 +532,12 @@ def cfg_shuffle(args, dev, d):
     ref = torch.randperm(T, generator=g)
     t_cpu = time.perf_counter() - t0
     same = bool(torch.equal(ops.randperm_torch(args.seed, T, dev).cpu(), ref))
-    return {"n": T, "mt19937_stream_ms": ms_mt, "randperm_total_ms": ms_all, "fisher_yates_ms": ms_all - ms_mt,
+    variant = ops.mt19937_stream_variant(T)
+    return {"n": T, "mt19937_kernel": variant, "mt19937_stream_ms": ms_mt, "randperm_total_ms": ms_all, "fisher_yates_ms": ms_all - ms_mt,
             "torch_cpu_randperm_s": t_cpu, "equals_torch_randperm": same,
-            "roofline": roof(T * 4 / ms_mt / 1e6, "mt19937_stream_kernel (one CTA: the sequence is sequential across 624-word blocks)", T * 4,
-                             "latency-bound by construction; reported for completeness")}
+            "roofline": roof(T * 4 / ms_mt / 1e6, "mt19937_segments_kernel (one CTA per 1 680 blocks of 624 words, jump-ahead polynomials)"
+                             if variant == "segmented" else "mt19937_stream_kernel (one CTA)", T * 4,
+                             "bounded by the Horner jump (19 937 single steps per set bit of the segment index), not by bytes")}
 
 
 # SURVEY 8(f) ranks 3-4 on the device, one step-time line each.  Random-init parameters of the reference's shapes; parity is

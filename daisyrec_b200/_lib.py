@@ -67,6 +67,7 @@ SIGNATURES = {
                                               C.c_int64, C.c_int64, C.POINTER(Hyper), C.c_int64, vp, vp, vp, c_i64p, vp]),
     "drb_randperm_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "drb_mt19937_stream": (C.c_int, [C.c_uint64, C.c_int64, vp, vp]),
+    "drb_mt19937_stream_variant": (C.c_int, [C.c_int64]),
     "drb_randperm_torch": (C.c_int, [C.c_uint64, C.c_int64, vp, vp, vp]),
     "drb_fm_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "drb_fm_workspace_init": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]),

@@ -11,6 +11,9 @@
 //                           x[k+624] = x[k+397] ^ twist(x[k], x[k+1]) allows (0..226 | 227..453 | 454..623) and streams the
 //                           tempered words to HBM: the sequence is inherently sequential across 624-word blocks, parallel
 //                           inside one (about 0.2 us per block).
+//   mt19937_segments_kernel the same stream from MANY CTAs: CTA k jumps the seeded state ahead by k segments of 1 680 blocks with
+//                           precomputed jump polynomials (GF(2)-linear jump-ahead, see below) and regenerates only its segment.
+//                           Used after a one-off device check against the one-CTA kernel; that one stays as the fallback.
 //   fisher_yates_kernel     the SAME permutation as the sequential walk, computed in parallel with deterministic
 //                           reservations (Shun, Gu, Blelloch, Fineman, Gibbons: "Sequential random permutation, list
 //                           contraction and tree contraction are highly parallel", SODA 2015): iteration i touches cells i
@@ -21,6 +24,12 @@
 //                           result equals the sequential order.  ~70 rounds for 80 M elements, 1.2 n cell visits, one
 //                           persistent cooperative launch (two grid barriers per round).
 // Integer kernels: bit-exact by construction; tests compare against torch.randperm itself.
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace drb {
@@ -52,20 +61,11 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 // three outputs, ONE barrier -- instead of three load/barrier/store/barrier rounds (58 ms -> see profiles/r02b for 80 M words).
 constexpr int kMtThreads = 256;
 
-__global__ void __launch_bounds__(kMtThreads) mt19937_stream_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
+// regenerate 624-word blocks from the block state in x[] and stream the tempered words to out[0..n): the three-phase walk above
+__device__ __forceinline__ void mt_generate(uint32_t *x, long long n, uint32_t *__restrict__ out)
 {
-    __shared__ uint32_t x[kMtN + 1];
     constexpr int D = kMtN - kMtM;                   // 227
     const int t = threadIdx.x;
-    if (t == 0) {                                    // init_genrand: sequential, 624 steps, once
-        uint32_t s = seed;
-        x[0] = s;
-        for (int j = 1; j < kMtN; ++j) {
-            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)j;
-            x[j] = s;
-        }
-    }
-    __syncthreads();
     const bool a1 = t < D, a3 = t + 2 * D < kMtN, last = t + 2 * D == kMtN - 1;
     for (long long base = 0; base < n; base += kMtN) {
         uint32_t v1 = 0, v2 = 0, v3 = 0;
@@ -95,6 +95,114 @@ __global__ void __launch_bounds__(kMtThreads) mt19937_stream_kernel(uint32_t see
         }
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ void mt_init_genrand(uint32_t *x, uint32_t seed)   // sequential, 624 steps, once (thread 0)
+{
+    uint32_t s = seed;
+    x[0] = s;
+    for (int j = 1; j < kMtN; ++j) {
+        s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)j;
+        x[j] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kMtThreads) mt19937_stream_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t x[kMtN + 1];
+    if (threadIdx.x == 0) mt_init_genrand(x, seed);
+    __syncthreads();
+    mt_generate(x, n, out);
+}
+
+// ------------------------------------------------------------------ many CTAs, ONE stream: jump-ahead
+// The one-word transition T of MT19937 is linear over GF(2) with a primitive characteristic polynomial phi of degree 19937, so
+// T^J = g_J(T) with g_J(x) = x^J mod phi(x): the state J words ahead is sum_i g_i T^i s, a Horner walk of 19937 single steps and
+// conditional XORs instead of J steps (Haramoto, Matsumoto, Nishimura, Panneton, L'Ecuyer 2008).  mt_jump_table.inc holds g for
+// J = kMtSegBlocks * 624 * 2^m, m = 0 .. 7 (generated and checked against numpy by scripts/gen_mt_jump.py).  CTA k applies the
+// levels of the set bits of k to the seeded state and then regenerates blocks [k * kMtSegBlocks, (k + 1) * kMtSegBlocks): the
+// one-CTA kernel's 43 ms for 80 M words become one jump of at most popcount(k) passes (about half a millisecond each) plus
+// 1 680 blocks per CTA.
+#define DRB_MT_TABLE_QUAL __device__
+#include "mt_jump_table.inc"
+#undef DRB_MT_TABLE_QUAL
+constexpr long long kMtSegWords = (long long)kMtSegBlocks * kMtN;
+
+// x <- g(T) x for the polynomial of `level`; sv, hb: 624-word scratch.  All threads of the CTA call this.
+__device__ __forceinline__ void mt_jump(uint32_t *x, uint32_t *sv, uint32_t *hb, int level)
+{
+    const int t = threadIdx.x;
+    const unsigned long long *g = kMtJumpPoly[level];
+    __shared__ int s_top;
+    for (int j = t; j < kMtN; j += kMtThreads) { sv[j] = x[j]; hb[j] = x[j]; }      // the leading coefficient is 1: h = s
+    if (t == 0) {
+        int top = -1;
+        for (int wd = kMtPolyWords - 1; wd >= 0 && top < 0; --wd)
+            if (g[wd]) top = wd * 64 + 63 - __clzll((long long)g[wd]);
+        s_top = top;
+    }
+    __syncthreads();
+    const int top = s_top;
+    int p = 0;                                       // head of the circular buffer hb (logical word j at hb[(p + j) % 624])
+    unsigned long long word = 0;
+    for (int i = top - 1; i >= 0; --i) {
+        if ((i & 63) == 63 || i == top - 1) word = g[i >> 6];
+        if (t == 0) {                                // h <- T h: one word leaves at the head, the new one takes its slot
+            const int p1 = p + 1 < kMtN ? p + 1 : p + 1 - kMtN, pm = p + kMtM < kMtN ? p + kMtM : p + kMtM - kMtN;
+            hb[p] = hb[pm] ^ mt_twist(hb[p], hb[p1]);
+        }
+        p = p + 1 < kMtN ? p + 1 : 0;
+        if ((word >> (i & 63)) & 1ull) {             // uniform across the CTA: h <- h + s
+            __syncthreads();
+            for (int j = t; j < kMtN; j += kMtThreads) {
+                const int q = p + j < kMtN ? p + j : p + j - kMtN;
+                hb[q] ^= sv[j];
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int j = t; j < kMtN; j += kMtThreads) {
+        const int q = p + j < kMtN ? p + j : p + j - kMtN;
+        x[j] = hb[q];
+    }
+    __syncthreads();
+}
+
+// CTA k: words [k * kMtSegWords, min(n, (k + 1) * kMtSegWords)) of the stream of `seed`
+__global__ void __launch_bounds__(kMtThreads) mt19937_segments_kernel(uint32_t seed, long long n, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t x[kMtN + 1], sv[kMtN], hb[kMtN];
+    const long long k = blockIdx.x, first = k * kMtSegWords;
+    if (first >= n) return;
+    if (threadIdx.x == 0) mt_init_genrand(x, seed);
+    __syncthreads();
+    for (int level = 0; level < kMtJumpLevels; ++level)
+        if ((k >> level) & 1) mt_jump(x, sv, hb, level);
+    const long long cnt = n - first < kMtSegWords ? n - first : kMtSegWords;
+    mt_generate(x, cnt, out + first);
+}
+
+// one-off device check of the jump table and kernel: CTA m verifies g_{m+1}(T) s == g_m(T) g_m(T) s (levels chain up from
+// level 0, which the host compares against the sequential kernel); ok[m] = 1 when equal in all 19 937 state bits
+__global__ void __launch_bounds__(kMtThreads) mt19937_jump_check_kernel(uint32_t seed, int *__restrict__ ok)
+{
+    __shared__ uint32_t a[kMtN + 1], b[kMtN + 1], sv[kMtN], hb[kMtN];
+    __shared__ int s_bad;
+    const int m = blockIdx.x;
+    if (threadIdx.x == 0) { mt_init_genrand(a, seed + 17u * (uint32_t)m); s_bad = 0; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kMtN; j += kMtThreads) b[j] = a[j];
+    __syncthreads();
+    mt_jump(a, sv, hb, m + 1);
+    mt_jump(b, sv, hb, m);
+    mt_jump(b, sv, hb, m);
+    for (int j = threadIdx.x; j < kMtN; j += kMtThreads) {
+        const uint32_t d = (a[j] ^ b[j]) & (j == 0 ? 0x80000000u : 0xffffffffu);   // word 0 of a block state: only its top bit lives on
+        if (d) atomicExch(&s_bad, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ok[m] = s_bad ? 0 : 1;
 }
 
 struct FyParams {
@@ -210,14 +318,62 @@ using namespace drb;
 
 extern "C" size_t drb_randperm_workspace_bytes(int64_t n) { return rp_layout(n).total; }
 
+// The segmented kernel is used only after a one-off check on this device (per process): (1) the words of the first four
+// segments equal the sequential kernel's, (2) every higher jump level equals two applications of the level below.  Otherwise
+// the one-CTA kernel keeps running (a line on stderr says so).
+static bool mt_segments_verified()
+{
+    static const bool no_par = getenv("DRB_MT_SEQUENTIAL") != nullptr;   // developer switch
+    if (no_par) return false;
+    static std::mutex mu;
+    static int state = -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (state >= 0) return state == 1;
+    state = 0;
+    const long long n = 3 * kMtSegWords + 1234;
+    uint32_t *da = nullptr, *db = nullptr;
+    int *dok = nullptr;
+    bool good = cudaMalloc(&da, n * 4) == cudaSuccess && cudaMalloc(&db, n * 4) == cudaSuccess &&
+                cudaMalloc(&dok, sizeof(int) * kMtJumpLevels) == cudaSuccess;
+    if (good) {
+        const uint32_t seed = 20240229u;
+        mt19937_stream_kernel<<<1, kMtThreads, 0, (cudaStream_t)0>>>(seed, n, da);
+        mt19937_segments_kernel<<<4, kMtThreads, 0, (cudaStream_t)0>>>(seed, n, db);
+        mt19937_jump_check_kernel<<<kMtJumpLevels - 1, kMtThreads, 0, (cudaStream_t)0>>>(seed, dok);
+        std::vector<uint32_t> ha((size_t)n), hb((size_t)n);
+        int hok[kMtJumpLevels] = {0};
+        good = cudaMemcpy(ha.data(), da, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hb.data(), db, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+               cudaMemcpy(hok, dok, sizeof(int) * (kMtJumpLevels - 1), cudaMemcpyDeviceToHost) == cudaSuccess;
+        good = good && memcmp(ha.data(), hb.data(), (size_t)n * 4) == 0;
+        for (int m = 0; m < kMtJumpLevels - 1; ++m) good = good && hok[m] == 1;
+    }
+    cudaFree(da); cudaFree(db); cudaFree(dok);
+    cudaGetLastError();
+    if (good) state = 1;
+    else fprintf(stderr, "[daisyrec_b200] segmented MT19937 kernel did not reproduce the sequential stream: using the one-CTA kernel\n");
+    return state == 1;
+}
+
 // d_mt_words[0..n) = first n 32-bit outputs of MT19937 seeded like at::mt19937(seed) / numpy.random.seed(seed & 0xffffffff)
 extern "C" int drb_mt19937_stream(uint64_t seed, int64_t n, uint32_t *d_out, void *stream)
 {
     DRB_REQUIRE(d_out && n >= 0, "mt19937_stream: bad arguments");
     if (n == 0) return DRB_OK;
-    mt19937_stream_kernel<<<1, kMtThreads, 0, (cudaStream_t)stream>>>((uint32_t)(seed & 0xffffffffull), n, d_out);
+    const long long segs = (n + kMtSegWords - 1) / kMtSegWords;
+    if (segs >= 2 && segs <= (1ll << kMtJumpLevels) && mt_segments_verified())
+        mt19937_segments_kernel<<<(int)segs, kMtThreads, 0, (cudaStream_t)stream>>>((uint32_t)(seed & 0xffffffffull), n, d_out);
+    else
+        mt19937_stream_kernel<<<1, kMtThreads, 0, (cudaStream_t)stream>>>((uint32_t)(seed & 0xffffffffull), n, d_out);
     DRB_CUDA(cudaGetLastError());
     return DRB_OK;
+}
+
+// which kernel drb_mt19937_stream runs for n words: 1 = segmented (after its one-off device check), 0 = one CTA
+extern "C" int drb_mt19937_stream_variant(int64_t n)
+{
+    const long long segs = (n + kMtSegWords - 1) / kMtSegWords;
+    return (segs >= 2 && segs <= (1ll << kMtJumpLevels) && mt_segments_verified()) ? 1 : 0;
 }
 
 // d_perm[0..n) = torch.randperm(n, generator=G) for a CPU generator G with G.manual_seed(seed), computed on the device.

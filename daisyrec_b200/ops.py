@@ -271,6 +271,12 @@ def mt19937_stream(seed, n, device):
     return out[:n]
 
 
+def mt19937_stream_variant(n):
+    """'segmented' when drb_mt19937_stream runs the many-CTA jump-ahead kernel for n words (after its one-off device check),
+    'one-cta' otherwise."""
+    return "segmented" if L.lib().drb_mt19937_stream_variant(int(n)) else "one-cta"
+
+
 def randperm_workspace(n, device):
     """(perm int64 [n], scratch) for randperm_torch(out=...): lets a caller keep them across epochs."""
     return (torch.empty(max(n, 1), dtype=torch.int64, device=device),

@@ -199,6 +199,10 @@ int drb_mf_bpr_train_steps_host(float *d_P, float *d_Q, void *d_ws, int32_t user
  * drb_mt19937_stream: the first n tempered 32-bit outputs of at::mt19937(seed) (= numpy's legacy stream for the same seed). */
 size_t drb_randperm_workspace_bytes(int64_t n);
 int drb_mt19937_stream(uint64_t seed, int64_t n, uint32_t *d_out, void *stream);
+/* 1: drb_mt19937_stream runs the segmented kernel for n words (many CTAs generate disjoint segments of the ONE stream after
+ * jumping ahead with precomputed polynomials, csrc/mt_jump_table.inc; used only after a one-off device check against the
+ * sequential kernel), 0: the one-CTA kernel. */
+int drb_mt19937_stream_variant(int64_t n);
 int drb_randperm_torch(uint64_t seed, int64_t n, int64_t *d_perm, void *d_ws, void *stream);
 
 /* Deterministic accumulation (opt-in, SURVEY 7 hard part 3): drb_mf_bpr_train_steps with every cross-thread sum (gradient

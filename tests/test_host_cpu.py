@@ -307,3 +307,47 @@ def test_step_kernel_geometry_and_tiles():
         assert t.value == want, (per_cta, t.value, want)
         k = -(-per_cta // t.value)
         assert t.value % 16 == 0 and k * t.value >= per_cta and (k - 1) * t.value < per_cta
+
+
+def test_mt19937_jump_table_matches_numpy():
+    """csrc/mt_jump_table.inc (scripts/gen_mt_jump.py): g_m(x) = x^(1680 * 624 * 2^m) mod phi(x).  The Horner walk the segmented
+    kernel runs, restated on the host, must land on numpy's MT19937 state that many words ahead (levels 0 and 2 here; the
+    generator script checks all eight), and every level must be the square of the one below modulo the same phi -- checked
+    through the states: two jumps of level m == one jump of level m + 1."""
+    import os
+    import re
+    from daisyrec_b200 import _build
+    src = open(os.path.join(_build.CSRC, "mt_jump_table.inc")).read()
+    seg_blocks = int(re.search(r"kMtSegBlocks = (\d+)", src).group(1))
+    rows = re.findall(r"\{((?:0x[0-9a-f]{16}ull(?:, )?)+)\}", src)
+    assert seg_blocks == 1680 and len(rows) == 8
+    polys = []
+    for r in rows:
+        words = [int(w[:-3], 16) for w in r.split(", ")]
+        assert len(words) == 312
+        polys.append(sum(w << (64 * k) for k, w in enumerate(words)))
+    UPPER, LOWER, MAG = 0x80000000, 0x7FFFFFFF, 0x9908B0DF
+
+    def jump(g, s):
+        s = [int(v) for v in s]
+        h, p = list(s), 0
+        for i in range(g.bit_length() - 2, -1, -1):
+            y = (h[p] & UPPER) | (h[(p + 1) % 624] & LOWER)
+            h[p] = h[(p + 397) % 624] ^ (y >> 1) ^ (MAG if y & 1 else 0)
+            p = (p + 1) % 624
+            if (g >> i) & 1:
+                for j in range(624):
+                    h[(p + j) % 624] ^= s[j]
+        return np.array([h[(p + j) % 624] for j in range(624)], dtype=np.uint32)
+
+    def same(a, b):                                   # word 0 of a block state: only its top bit is ever read again
+        return (int(a[0]) ^ int(b[0])) & UPPER == 0 and np.array_equal(a[1:], b[1:])
+
+    for m in (0, 2):
+        rs = np.random.RandomState(77 + m)
+        s0 = rs.get_state()[1].copy()
+        rs.bytes(4 * seg_blocks * 624 * (1 << m))
+        assert same(jump(polys[m], s0), rs.get_state()[1]), m
+    s0 = np.random.RandomState(5).get_state()[1].copy()
+    for m in (3, 6):
+        assert same(jump(polys[m + 1], s0), jump(polys[m], jump(polys[m], s0))), m
