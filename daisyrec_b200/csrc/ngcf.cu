@@ -239,8 +239,8 @@ __global__ void ngcf_mix_bwd_kernel(const float *__restrict__ dS, const float *_
 }
 
 // out = a + b (+ c[:, coff : coff+d] of a [n, C] matrix when c != nullptr)
-__global__ void ngcf_add_kernel(const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c, int C,
-                                int coff, long long n, int d, float *__restrict__ out)
+__global__ void ngcf_add_kernel(const float *a, const float *__restrict__ b, const float *__restrict__ c, int C,
+                                int coff, long long n, int d, float *out)   // out may alias a (in-place accumulate)
 {
     const long long total = n * d;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
