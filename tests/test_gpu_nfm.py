@@ -128,4 +128,4 @@ def test_nfm_class_drop_in():
         else:
             assert isinstance(m.predict(int(users[0]), int(cands[0][0])), float)      # the reference's predict() cannot run here
         with pytest.raises(ValueError):                                    # nn.Dropout's own range check (dropout > 0 itself runs:
-            NFM(dict(cfg, dropout=1.5))                                    # tests/test_gpu_zzz_dropout.py)
+            NFM(dict(cfg, dropout=1.5))                                    # tests/test_gpu_zzz_late.py)

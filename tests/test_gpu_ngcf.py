@@ -93,7 +93,7 @@ def test_ngcf_class_drop_in():
         assert (full == g[f"c{c}_full"]).mean() >= 0.9
         np.testing.assert_allclose(m.predict(int(users[0]), int(cands[0][0])), float(g[f"c{c}_pred_pair"][0]), rtol=3e-5, atol=3e-6)
         with pytest.raises(NotImplementedError):                          # sparse dropout of the adjacency (reference default 0)
-            NGCF(dict(cfg, node_dropout=0.1))                              # (mess_dropout > 0 runs: tests/test_gpu_zzz_dropout.py)
+            NGCF(dict(cfg, node_dropout=0.1))                              # (mess_dropout > 0 runs: tests/test_gpu_zzz_late.py)
 
 
 def test_ngcf_vs_oracle_random(orc):

@@ -1,6 +1,8 @@
-"""NFM with nn.Dropout active (the reference default, assets/nfm.yaml: dropout 0.5) on the device against the reference-generated
-fixture tests/golden/nfm_dropout.npz: the host draws torch's own masks in the reference's order, the kernels apply them.
-(This file sorts last on purpose: its CUDA path was written after the round's last GPU slot.)"""
+"""Tests of CUDA paths written after the round's last GPU slot (this file sorts last on purpose):
+* NFM with nn.Dropout active (the reference default, assets/nfm.yaml: dropout 0.5) and NGCF with its message dropout (default
+  0.1) against reference-generated fixtures (tests/golden/nfm_dropout.npz, ngcf_dropout.npz): the host draws torch's own masks in
+  the reference's order, the kernels apply them;
+* the KPI impact of the fused bf16 NeuMF tower on a config-1-sized run."""
 import logging
 
 import numpy as np
@@ -198,3 +200,37 @@ def test_ngcf_class_runs_the_reference_default_config():
         preds = m.rank(loader)
         np.testing.assert_allclose(torch.cat([m.restore_user_e, m.restore_item_e]).cpu().numpy(), g[f"c{c}_all_rank"], rtol=0, atol=3e-6)
         assert (preds == g[f"c{c}_preds"]).mean() >= 0.97, c
+
+
+# ------------------------------------------------------------------ KPI impact of the bf16 / fused NeuMF tower (config-1-sized run)
+def test_neumf_fused_tower_kpi_impact_is_small():
+    """NeuMF (F = 32, tower 128 -> 64 -> 32, Adam, dropout 0) trained for two epochs on the ML-100K fixture triples (the config-1
+    data: 943 x 1 152, 313 452 triples, batch 256) from the same initial weights and the same batch order, once with the fp32
+    tower and once with the fused bf16 tcgen05 tower: NDCG@10 / HR@10 on the fixture's 304 test users x 1 000 candidates move by
+    less than the stated bound (bf16 rounds every product operand to 8 bits of mantissa; the gap is training noise, not bias)."""
+    from daisyrec_b200 import ops
+    from daisyrec_b200.model import NeuMF
+    from daisyrec_b200.utils.dataset import BasicDataset, CandidatesDataset, get_dataloader
+    gs, gr = golden("ml100k_sampler"), golden("ml100k_rank")
+    U, I, G, _seed = (int(v) for v in gs["meta"])
+    samples = np.stack([np.repeat(gs["coo_u"].astype(np.int32), G), np.repeat(gs["coo_i"].astype(np.int32), G),
+                        gs["triples_j"].astype(np.int32)], 1)
+    users, cands = gr["test_u"].astype(np.int64), gr["cands"].astype(np.int64)
+    test_loader = get_dataloader(CandidatesDataset([[int(u), cands[r]] for r, u in enumerate(users)]), batch_size=128, shuffle=False)
+    gt_ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(gr["gt_len"])]).astype(np.int64)).cuda()
+    off = np.concatenate([[0], np.cumsum(gr["gt_len"])])
+    gt_idx = torch.from_numpy(np.concatenate([np.sort(gr["gt_flat"][off[k]:off[k + 1]]) for k in range(len(users))]).astype(np.int32)).cuda()
+    kpi = {}
+    for tower in ("fp32", "fused"):
+        cfg = dict(gpu='', logger=logging.getLogger('t'), lr=0.001, epochs=2, reg_1=0.0, reg_2=0.0, dropout=0.0, model_name='NeuMF',
+                   GMF_model=None, MLP_model=None, user_num=U, item_num=I, factors=32, num_layers=2, loss_type='BPR',
+                   optimizer='default', init_method='default', early_stop=False, topk=10, progress=False, tower_dtype=tower)
+        torch.manual_seed(2022)
+        m = NeuMF(cfg)
+        m.fit(get_dataloader(BasicDataset(samples), batch_size=256, shuffle=True))
+        preds = torch.from_numpy(np.ascontiguousarray(m.rank(test_loader), np.float32)).cuda()
+        res = ops.rank_metrics(preds, gt_ptr, gt_idx, [10], I).cpu().numpy()[0]
+        kpi[tower] = {"ndcg": float(res[2]), "hr": float(res[3])}
+    print("NeuMF KPI impact (NDCG@10, HR@10):", kpi)
+    assert kpi["fp32"]["ndcg"] > 0.02 and kpi["fused"]["ndcg"] > 0.02, kpi        # both models learned something
+    assert abs(kpi["fp32"]["ndcg"] - kpi["fused"]["ndcg"]) <= 0.03 and abs(kpi["fp32"]["hr"] - kpi["fused"]["hr"]) <= 0.06, kpi
