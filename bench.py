@@ -788,6 +788,7 @@ def run_own(args):
     avg_launch_triples = done_triples / len(evs)
     achieved = avg_launch_triples * bytes_per_triple / (avg_launch_ms * 1e-3) / 1e9
     traffic, traffic_src = profiled_traffic(F, B)
+    sk = step_kernel_info(F, U + I)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1), "steps_per_epoch": spe,
@@ -805,14 +806,15 @@ def run_own(args):
                                                 "kernel + D2H of the loss, copy of batch s+1 under the kernel of batch s"}},
             "gpu_launches": launches,
             "gpu_launches_note": "persistent cooperative kernel: one launch runs up to steps_per_epoch synchronous steps",
-            "step_kernel": step_kernel_info(F, U + I),
+            "step_kernel": sk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if traffic is None else traffic * (args.steps / len(evs)),
-                         "traffic_note": f"dram__bytes_read+write per step ({traffic_src}) x steps per launch; the 85 MB "
-                                         "working set is L2-resident, so the limiter at this shape is L2/issue, not HBM -- "
-                                         "configs.c5_netflix_1gpu is the HBM-regime figure",
+                         "traffic_note": f"dram__bytes_read+write per step ({traffic_src}: ncu capture of the general "
+                                         "instantiation mf_bpr_steps_kernel<4,16,1>; a lean instantiation moves the same rows) x "
+                                         "steps per launch; the 85 MB working set is L2-resident, so the limiter at this shape is "
+                                         "L2/issue, not HBM -- configs.c5_netflix_1gpu is the HBM-regime figure",
                          "peak_source": peak_src, "algorithmic_bytes_per_triple": bytes_per_triple,
-                         "kernel": "mf_bpr_steps_kernel", "avg_launch_ms": avg_launch_ms},
+                         "kernel": sk["instantiation"], "avg_launch_ms": avg_launch_ms},
             "cpu_baseline": cpu,
             "configs": cfgs}
     print(json.dumps(line), flush=True)
