@@ -37,14 +37,18 @@ def test_nfm_steps_match_reference_fixture(orc):
             b = [dev(bs[s][k]) for k in range(3)]
             loss = ops.nfm_bpr_train_steps(P, Q, bias, N, R, ws, act, *b, b[0].numel(), 0, 1, hp, adam_step0=s).item()
             assert abs(loss - losses[s]) <= 3e-5 * abs(losses[s]), (c, s, loss, losses[s])
-            # a Linear bias in front of a BatchNorm has a mathematically zero gradient: what any implementation computes for it
-            # is cancellation noise, and Adam turns noise into +-lr steps (different signs here and in the reference).  Those F
-            # slots per layer are only required to stay within 2.1 lr; everything else must agree.
+            # A Linear bias in front of a BatchNorm has a mathematically zero gradient (the batch mean is removed), and so has the
+            # bias (beta) of FM_layers' BatchNorm when a Linear + BatchNorm follows it directly (dropout 0: a constant shift of
+            # the Linear's input is a constant shift of its output).  What any implementation computes for those slots is
+            # cancellation noise, and Adam turns noise into +-lr steps (different signs here and in the reference).  They are only
+            # required to stay within 2.1 lr; everything else must agree.
             noisy = np.zeros(Ns.shape[1], bool)
             if bn and optn == "adam":
+                if L >= 1:
+                    noisy[F:2 * F] = True                                 # beta of BatchNorm 0
                 o = 2 * F
                 for _l in range(L):
-                    noisy[o + F * F:o + F * F + F] = True
+                    noisy[o + F * F:o + F * F + F] = True                 # Linear bias
                     o += F * F + F + 2 * F
             for got, want, nm in ((P, Ps[s + 1], "P"), (Q, Qs[s + 1], "Q"), (bias, Bs[s + 1], "bias"), (N, Ns[s + 1], "N")):
                 err = np.abs(got.cpu().numpy() - want)
