@@ -355,9 +355,12 @@ def cpu_baseline_subprocess(args, rows, steps=2, warmup=1):
 # ------------------------------------------------------------------------------- secondary configs (driver-visible)
 def step_kernel_info(F, table_rows=0):
     """Which instantiation of the step kernel the timed steps ran (a lean one only after its on-device selection)."""
-    from daisyrec_b200 import ops
-    lean, lanes, chunks = ops.mf_step_variant(F, table_rows)
-    ms_gen, ms_lean, tile_cap = ops.mf_step_selfcheck_ms(F, table_rows)
+    try:
+        from daisyrec_b200 import ops
+        lean, lanes, chunks = ops.mf_step_variant(F, table_rows)
+        ms_gen, ms_lean, tile_cap = ops.mf_step_selfcheck_ms(F, table_rows)
+    except Exception as e:  # noqa: BLE001  (reporting only: never let it cost the line)
+        return {"instantiation": "mf_bpr_steps_kernel", "error": repr(e)}
     return {"instantiation": "mf_bpr_steps_lean_kernel" if lean else "mf_bpr_steps_kernel", "lanes_per_row": lanes,
             "chunks_per_lane": chunks,
             "index_tile_cap": tile_cap,
