@@ -234,3 +234,21 @@ def test_neumf_fused_tower_kpi_impact_is_small():
     print("NeuMF KPI impact (NDCG@10, HR@10):", kpi)
     assert kpi["fp32"]["ndcg"] > 0.02 and kpi["fused"]["ndcg"] > 0.02, kpi        # both models learned something
     assert abs(kpi["fp32"]["ndcg"] - kpi["fused"]["ndcg"]) <= 0.03 and abs(kpi["fp32"]["hr"] - kpi["fused"]["hr"]) <= 0.06, kpi
+
+
+# ------------------------------------------------------------------ MT19937 from many CTAs (jump-ahead), every table level
+def test_mt19937_stream_across_all_jump_levels():
+    """drb_mt19937_stream == numpy's MT19937 for a stream long enough to need every level of csrc/mt_jump_table.inc (129 segments
+    of 1 680 blocks: segment 128 takes level 7, segment 127 takes levels 0-6), whichever kernel the one-off device check selected."""
+    from daisyrec_b200 import ops
+    seg = 1680 * 624
+    n = 128 * seg + 5 * 624 + 77
+    print("mt19937 kernel for", n, "words:", ops.mt19937_stream_variant(n))
+    got = ops.mt19937_stream(424242, n, "cuda")
+    rs = np.random.RandomState(424242)
+    for lo in range(0, n, 1 << 24):
+        hi = min(n, lo + (1 << 24))
+        want = np.frombuffer(rs.bytes(4 * (hi - lo)), dtype="<u4")
+        assert np.array_equal(got[lo:hi].cpu().numpy().view(np.uint32), want), (lo, hi)
+    # and a short stream stays on the one-CTA kernel
+    assert ops.mt19937_stream_variant(1000) == "one-cta"
