@@ -1,5 +1,6 @@
 #!/bin/bash
-# dev tool: build A/B variants of the step kernel (launch bounds / unroll) into gpurun_out-free scratch libs
+# dev tool: build A/B variants of the step kernel (launch bounds / unroll: MINB_UNR, e.g. 2_2 3_1) into scratch libs;
+# run one with DRB_LIB_PATH=daisyrec_b200/lib/variants/lib_<cfg>.so
 set -e
 cd "$(dirname "$0")/.."
 python daisyrec_b200/_build.py >/dev/null
@@ -12,7 +13,7 @@ done
 wait
 for cfg in "$@"; do
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o daisyrec_b200/lib/variants/lib_${cfg}.so \
-       daisyrec_b200/lib/variants/mf_bpr_${cfg}.o daisyrec_b200/lib/capi.o daisyrec_b200/lib/sampler.o daisyrec_b200/lib/rank.o daisyrec_b200/lib/shard.o daisyrec_b200/lib/lightgcn.o daisyrec_b200/lib/neumf.o daisyrec_b200/lib/comm.o daisyrec_b200/lib/metrics.o -ldl
+       daisyrec_b200/lib/variants/mf_bpr_${cfg}.o $(ls daisyrec_b200/lib/*.o | grep -v '/mf_bpr.o$') -ldl
   rm daisyrec_b200/lib/variants/mf_bpr_${cfg}.o
 done
 ls daisyrec_b200/lib/variants
