@@ -335,8 +335,11 @@ class ShardedTrainer:
         main = torch.cuda.current_stream(self.dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.dev)
-        d_loss = torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
-        h_loss = torch.empty(max(1, n_steps), dtype=torch.float64).pin_memory()
+        # loss buffers live with the trainer: no device / pinned allocation while peers may already sit in their launch
+        if getattr(self, "_loss_bufs", None) is None or self._loss_bufs[0].numel() < max(1, n_steps):
+            self._loss_bufs = (torch.empty(max(64, n_steps), dtype=torch.float64, device=self.dev),
+                               torch.empty(max(64, n_steps), dtype=torch.float64).pin_memory())
+        d_loss, h_loss = self._loss_bufs
         self._copy_stream.wait_stream(main)
         spans = [(s, min(chunk, first + n_steps - s)) for s in range(first, first + n_steps, chunk)]
         ready = []
@@ -353,7 +356,7 @@ class ShardedTrainer:
             self.train_steps(s0, k, d_loss[s0 - first:])
             h_loss[s0 - first:s0 - first + k].copy_(d_loss[s0 - first:s0 - first + k], non_blocking=True)
         main.synchronize()
-        return h_loss[:n_steps]
+        return h_loss[:n_steps].clone()
 
     def step_host(self, h_bu, h_bi, h_bj, stage):
         """End-to-end step from pinned HOST arrays holding this rank's share of the global batch."""
