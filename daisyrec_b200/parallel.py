@@ -261,6 +261,13 @@ class ShardedTrainer:
         self.offsets_host = self.step_offsets.cpu().numpy()
         self.batch_global = int(batch_global)
         self.bu, self.bi, self.bj = self._planes[0], self._planes[1], self._planes[2]
+        if self.comm == "p2p":
+            # everything a launch needs is allocated here, and every rank has finished allocating before anyone can sit in a
+            # launch waiting for its peers (a device allocation in one process may have to touch its peers' mappings)
+            if getattr(self, "_losses", None) is None or self._losses.numel() < m + 1:
+                self._losses = torch.empty(m + 1, dtype=torch.float64, device=self.dev)
+            torch.cuda.synchronize()
+            dist.barrier(group=_host_group(self.group))
         return m
 
     # ---- one synchronous global step
@@ -282,7 +289,9 @@ class ShardedTrainer:
     def train_steps(self, first, n_steps, losses=None):
         """Global steps first .. first+n_steps-1 of the prepared epoch; returns the per-step global losses (device)."""
         if losses is None:
-            losses = torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
+            pre = getattr(self, "_losses", None)
+            losses = pre if (self.comm == "p2p" and pre is not None and pre.numel() >= n_steps) else \
+                torch.empty(max(1, n_steps), dtype=torch.float64, device=self.dev)
         if self.comm == "p2p":
             bad = C.c_int64(-1)
             per_rank = max(1, self.batch_global // self.world)
