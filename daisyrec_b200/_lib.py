@@ -167,6 +167,56 @@ def so_path():
     return os.environ.get("DRB_LIB_PATH") or _build.SO
 
 
+def _cuda_device_count():
+    """Devices the driver reports, without touching the runtime of this process (0 when there is no driver)."""
+    try:
+        cu = C.CDLL("libcuda.so.1")
+        n = C.c_int(0)
+        if cu.cuInit(0) != 0 or cu.cuDeviceGetCount(C.byref(n)) != 0:
+            return 0
+        return n.value
+    except OSError:
+        return 0
+
+
+_CANARY = r"""
+import ctypes, sys
+l = ctypes.CDLL(sys.argv[1])
+l.drb_mf_step_variant.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+l.drb_mt19937_stream_variant.argtypes = [ctypes.c_int64]
+a = l.drb_mf_step_variant(64, 0, None, None)                 # step-kernel selection, tables inside L2
+b = l.drb_mf_step_variant(128, 1 << 20, None, None)          # ... streamed from HBM
+c = l.drb_mt19937_stream_variant(3 << 20)                    # segmented MT19937 kernel's device check
+print("CANARY OK", a, b, c, flush=True)
+"""
+
+
+def _canary(path):
+    """The kernels that select themselves on the device (lean step instantiations, segmented MT19937) first run in a sacrificial
+    child process: if that child crashes or does not come back, this process keeps the kernels that have a GPU record
+    (DRB_NO_LEAN / DRB_MT_SEQUENTIAL are set before the library reads them).  Skipped without a device and under DRB_NO_CANARY."""
+    if os.environ.get("DRB_NO_CANARY") or os.environ.get("DRB_NO_LEAN") or _cuda_device_count() == 0:
+        return
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    local = int(env.get("LOCAL_RANK", "0") or 0)
+    vis = [v for v in env.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    env["CUDA_VISIBLE_DEVICES"] = vis[local] if local < len(vis) else (vis[0] if vis else str(local))
+    ok = False
+    try:
+        r = subprocess.run([sys.executable, "-c", _CANARY, path], env=env, capture_output=True, text=True, timeout=90)
+        ok = r.returncode == 0 and "CANARY OK" in r.stdout
+        why = (r.stdout + r.stderr)[-300:]
+    except Exception as e:  # noqa: BLE001  (timeout, spawn failure)
+        why = repr(e)
+    if not ok:
+        os.environ["DRB_NO_LEAN"] = "1"
+        os.environ["DRB_MT_SEQUENTIAL"] = "1"
+        sys.stderr.write(f"[daisyrec_b200] canary run of the self-selecting kernels failed ({why!r}): keeping the general step "
+                         "kernel and the one-CTA MT19937 kernel in this process\n")
+
+
 def lib():
     """Load (building first if the .so is absent and nvcc is present).  Fails loudly otherwise."""
     global _lib
@@ -184,6 +234,7 @@ def lib():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(L, name)          # AttributeError here == header and library out of sync
         fn.restype, fn.argtypes = res, args
+    _canary(path)
     _lib = L
     return L
 
