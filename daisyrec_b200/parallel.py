@@ -17,6 +17,7 @@ torch.distributed (NCCL on GPUs, gloo in the CPU tests of the host logic) is plu
 libdaisyrec_b200.so.
 """
 import ctypes as C
+import os
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -126,6 +127,8 @@ def _host_group(group=None):
     key = id(group)
     if key not in _HOST_GROUP:
         ranks = None if group is None else dist.get_process_group_ranks(group)
+        if os.environ.get("MASTER_ADDR", "127.0.0.1") in ("127.0.0.1", "localhost"):
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")   # one node: no hostname resolution (it may not resolve in a container)
         _HOST_GROUP[key] = dist.new_group(ranks=ranks, backend="gloo")
     return _HOST_GROUP[key]
 
