@@ -1053,7 +1053,7 @@ def main():
     ap.add_argument("--c5", default="auto", choices=["auto", "on", "off"], help="N > 1: also run config 5 (netflix F=128)")
     ap.add_argument("--comm", default="auto", choices=["auto", "nccl", "p2p"],
                     help="N > 1: auto = in-kernel peer exchange on 2 GPUs (validated), the NCCL step beyond; or force one")
-    ap.add_argument("--watchdog", type=float, default=600.0,
+    ap.add_argument("--watchdog", type=float, default=420.0,
                     help="N > 1: seconds after which rank 0 prints the line with what has been measured and every rank exits")
     ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=45.0)
     ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=330.0)
